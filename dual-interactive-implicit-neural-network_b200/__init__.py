@@ -1,0 +1,8 @@
+"""diinn_b200 -- B200-native (sm_100a) query decoder for DIINN (arch=diinn, mode=3, init_q=False).
+
+Drop-in for /root/reference/src/models/components/diinn.py:39-173 (``ImplicitDecoder``) behind a C-ABI CUDA
+library (include/diinn_b200.h). No CPU fallback: every compute entry needs the built CUDA library and a GPU.
+"""
+from . import synth  # noqa: F401  (pure numpy; safe without the CUDA library)
+
+__all__ = ["synth"]

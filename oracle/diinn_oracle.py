@@ -1,0 +1,242 @@
+"""CPU ORACLE for the DIINN query decoder -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may
+import this module, and only as the checker (or as the timed CPU baseline). The shipped path
+(``dual-interactive-implicit-neural-network_b200``) never imports it and has no CPU fallback.
+
+What it restates (numpy, fp32 unless ``fp64=True``): the reference ``ImplicitDecoder`` with ``mode=3,
+init_q=False`` -- /root/reference/src/models/components/diinn.py:39-173 -- whose arithmetic lives in
+PyTorch/ATen (not vendored in the reference tree; the reference pins no torch version, README.md:59-61):
+
+* ``nearest_exact_index``  <- F.interpolate(mode='nearest-exact'), ATen/native/UpSample.h
+  ``nearest_exact_idx`` = min(floorf((dst + 0.5) * scale), in - 1), scale = (float)in / out.
+* ``axis_centres`` / ``rel_axis`` / ``make_pos_encoding``  <- diinn.py:94-110.
+* ``syn_input``            <- diinn.py:165-167.
+* ``unfold3x3``            <- F.unfold(x, 3, padding=1).view(B, C*9, H, W), diinn.py:168.
+* ``step_mode3``           <- diinn.py:132-139 with K/Q/last_layer built at diinn.py:73-80,92.
+* ``decoder_forward``      <- diinn.py:163-173 (bsize chunking, diinn.py:149-160, is pure scheduling).
+* ``query``                <- the (feat, coord, cell) superset entry of SURVEY.md section 8(b); on a regular
+                              grid it reproduces ``decoder_forward`` (tested).
+
+PARITY PIN: the reference has no tests/golden vectors for this path, so the oracle is
+pinned against outputs of the reference itself, produced in the build container by importing
+/root/reference (tests/golden/make_golden.py) and committed under tests/golden/*.npz;
+tests/test_oracle_golden.py re-checks every fixture on CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+
+
+# --------------------------------------------------------------------------------------------------
+# a1: coordinates and nearest-exact indices (diinn.py:94-110)
+# --------------------------------------------------------------------------------------------------
+def nearest_exact_index(n_in: int, n_out: int) -> np.ndarray:
+    """Source index of every destination index for mode='nearest-exact' along one axis.
+
+    ATen: scale = (float)n_in / n_out; idx = min((int64)floorf((dst + 0.5) * scale), n_in - 1), the product
+    being formed in double on CPU and rounded to float by floorf's argument conversion (identical to the
+    CUDA kernel's float product because both factors have <= 24 significant bits)."""
+    scale = F32(n_in) / F32(n_out)
+    dst = np.arange(n_out, dtype=np.float64) + 0.5
+    prod = (dst * np.float64(scale)).astype(F32)
+    idx = np.floor(prod).astype(np.int64)
+    return np.minimum(idx, n_in - 1)
+
+
+def axis_centres(n: int) -> np.ndarray:
+    """-1 + 1/n + 2/n * arange(n).float(): python-double scalars rounded to fp32, mul then add, no FMA."""
+    a = F32(-1.0 + 1.0 / n)
+    b = F32(2.0 / n)
+    i = np.arange(n, dtype=F32)
+    return (a + (b * i).astype(F32)).astype(F32)
+
+
+def rel_axis(n_in: int, n_out: int):
+    """(idx, rel) along one axis: rel[j] = fl(fl(c_up[j] - c_in[idx[j]]) * fl(n_in))  (diinn.py:106-108)."""
+    idx = nearest_exact_index(n_in, n_out)
+    c_in = axis_centres(n_in)
+    c_up = axis_centres(n_out)
+    rel = ((c_up - c_in[idx]).astype(F32) * F32(n_in)).astype(F32)
+    return idx, rel
+
+
+def make_pos_encoding(H: int, W: int, H_up: int, W_up: int) -> np.ndarray:
+    """(2, H_up, W_up) fp32: channel 0 = rel_h (varies along rows), channel 1 = rel_w."""
+    _, rh = rel_axis(H, H_up)
+    _, rw = rel_axis(W, W_up)
+    out = np.empty((2, H_up, W_up), dtype=F32)
+    out[0] = rh[:, None]
+    out[1] = rw[None, :]
+    return out
+
+
+def ratio_value(H: int, W: int, H_up: int, W_up: int) -> np.float32:
+    """x.new_tensor([(H*W)/(H_up*W_up)]): python double rounded to fp32 (diinn.py:166)."""
+    return F32((H * W) / (H_up * W_up))
+
+
+def syn_input(H: int, W: int, H_up: int, W_up: int) -> np.ndarray:
+    """(3, H_up, W_up): [rel_h, rel_w, ratio] (diinn.py:165-167)."""
+    out = np.empty((3, H_up, W_up), dtype=F32)
+    out[:2] = make_pos_encoding(H, W, H_up, W_up)
+    out[2] = ratio_value(H, W, H_up, W_up)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# a3: 3x3 unfold (diinn.py:168)
+# --------------------------------------------------------------------------------------------------
+def unfold3x3(feat: np.ndarray) -> np.ndarray:
+    """(B,C,H,W) -> (B,C*9,H,W); channel c*9 + kh*3 + kw = feat[c, h+kh-1, w+kw-1], zero outside."""
+    B, C, H, W = feat.shape
+    pad = np.zeros((B, C, H + 2, W + 2), dtype=feat.dtype)
+    pad[:, :, 1:-1, 1:-1] = feat
+    out = np.empty((B, C, 9, H, W), dtype=feat.dtype)
+    for kh in range(3):
+        for kw in range(3):
+            out[:, :, kh * 3 + kw] = pad[:, :, kh:kh + H, kw:kw + W]
+    return out.reshape(B, C * 9, H, W)
+
+
+# --------------------------------------------------------------------------------------------------
+# a4: the dual-interactive MLP, mode 3 (diinn.py:132-139)
+# --------------------------------------------------------------------------------------------------
+def _w2d(w: np.ndarray) -> np.ndarray:
+    return w.reshape(w.shape[0], w.shape[1])
+
+
+def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False, taps: dict | None = None):
+    """x: (N,576) gathered unfolded features, syn: (N,3) -> (N,3) RGB.
+
+    k = relu(K0 x); q = k * sin(Q0 syn); for i in 1..3: k = relu(K_i [q,x]); q = k * sin(Q_i q);
+    out = last(q).  1x1 Conv2d == per-pixel affine map."""
+    dt = np.float64 if fp64 else F32
+    x = x.astype(dt)
+    syn = syn.astype(dt)
+    W = {k: v.astype(dt) for k, v in weights.items()}
+    n_layers = sum(1 for k in W if k.startswith("K.") and k.endswith("weight"))
+    k = np.maximum(x @ _w2d(W["K.0.0.weight"]).T + W["K.0.0.bias"], 0)
+    q = k * np.sin(syn @ _w2d(W["Q.0.0.weight"]).T + W["Q.0.0.bias"])
+    if taps is not None:
+        taps["k0"], taps["q0"] = k, q
+    for i in range(1, n_layers):
+        qx = np.concatenate([q, x], axis=1)
+        k = np.maximum(qx @ _w2d(W[f"K.{i}.0.weight"]).T + W[f"K.{i}.0.bias"], 0)
+        q = k * np.sin(q @ _w2d(W[f"Q.{i}.0.weight"]).T + W[f"Q.{i}.0.bias"])
+        if taps is not None:
+            taps[f"k{i}"], taps[f"q{i}"] = k, q
+    out = q @ _w2d(W["last_layer.weight"]).T + W["last_layer.bias"]
+    return out.astype(dt)
+
+
+# --------------------------------------------------------------------------------------------------
+# forward (diinn.py:163-173) and the row-band form used for sharding / large configs
+# --------------------------------------------------------------------------------------------------
+def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool = False,
+                    chunk: int = 1 << 16) -> np.ndarray:
+    """(B,64,H,W), size=(H_up,W_up) -> (B,3,rows,W_up); rows=(r0,r1) restricts to an HR row band."""
+    B, C, H, W = feat.shape
+    H_up, W_up = int(size[0]), int(size[1])
+    r0, r1 = (0, H_up) if rows is None else (int(rows[0]), int(rows[1]))
+    ih, rh = rel_axis(H, H_up)
+    iw, rw = rel_axis(W, W_up)
+    ratio = ratio_value(H, W, H_up, W_up)
+    u = unfold3x3(feat)                                   # (B,576,H,W)
+    u = np.ascontiguousarray(u.transpose(0, 2, 3, 1))     # (B,H,W,576)
+    nr = r1 - r0
+    out = np.empty((B, 3, nr, W_up), dtype=np.float64 if fp64 else F32)
+    rows_per_chunk = max(1, chunk // W_up)
+    for b in range(B):
+        for a in range(r0, r1, rows_per_chunk):
+            e = min(a + rows_per_chunk, r1)
+            x = u[b][ih[a:e]][:, iw].reshape(-1, C * 9)
+            syn = np.empty((e - a, W_up, 3), dtype=F32)
+            syn[..., 0] = rh[a:e, None]
+            syn[..., 1] = rw[None, :]
+            syn[..., 2] = ratio
+            y = step_mode3(weights, x, syn.reshape(-1, 3), fp64=fp64)
+            out[b, :, a - r0:e - r0] = y.reshape(e - a, W_up, 3).transpose(2, 0, 1)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# superset entry: query(feat, coord, cell) with DIINN semantics
+# --------------------------------------------------------------------------------------------------
+def query_index_rel(coord_axis: np.ndarray, n: int):
+    """Per-axis: idx = clamp(floor((c+1)*n/2), 0, n-1); rel = fl(fl(c - centre[idx]) * n).
+
+    All in fp32: t = fl(fl(c + 1) * fl(n * 0.5)); idx = floorf(t)."""
+    c = coord_axis.astype(F32)
+    t = ((c + F32(1.0)).astype(F32) * F32(n * 0.5)).astype(F32)
+    idx = np.clip(np.floor(t).astype(np.int64), 0, n - 1)
+    centre = axis_centres(n)
+    rel = ((c - centre[idx]).astype(F32) * F32(n)).astype(F32)
+    return idx, rel
+
+
+def query(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.ndarray, fp64: bool = False) -> np.ndarray:
+    """feat (B,64,H,W), coord (B,Q,2) as (h,w) in [-1,1], cell (B,Q,2) -> (B,Q,3).
+
+    ratio = fl(fl(fl(cell_h * cell_w) * fl(H*W)) * 0.25) -- for a regular grid cell=(2/H_up, 2/W_up)
+    this is (H*W)/(H_up*W_up) up to fp32 rounding."""
+    B, C, H, W = feat.shape
+    u = np.ascontiguousarray(unfold3x3(feat).transpose(0, 2, 3, 1))
+    out = np.empty(coord.shape[:2] + (3,), dtype=np.float64 if fp64 else F32)
+    for b in range(B):
+        ih, rh = query_index_rel(coord[b, :, 0], H)
+        iw, rw = query_index_rel(coord[b, :, 1], W)
+        ce = cell[b].astype(F32)
+        ratio = (((ce[:, 0] * ce[:, 1]).astype(F32) * F32(H * W)).astype(F32) * F32(0.25)).astype(F32)
+        syn = np.stack([rh, rw, ratio], axis=1).astype(F32)
+        out[b] = step_mode3(weights, u[b][ih, iw], syn, fp64=fp64)
+    return out
+
+
+def grid_coords(H_up: int, W_up: int):
+    """Cell-centre coords of the HR grid, as the reference builds them (diinn.py:101-102)."""
+    return axis_centres(H_up), axis_centres(W_up)
+
+
+def calc_psnr(sr: np.ndarray, hr: np.ndarray, rgb_range: float = 1.0) -> float:
+    """PSNR as in sr_module.py:21-38 with dataset=None (no shave, no gray conversion)."""
+    diff = (sr.astype(np.float64) - hr.astype(np.float64)) / rgb_range
+    mse = float(np.mean(diff ** 2))
+    return float(-10.0 * np.log10(mse))
+
+
+# --------------------------------------------------------------------------------------------------
+# torch-CPU timing port: the same algorithm (un-hoisted, materialising the (B,576,H_up,W_up) tensor like
+# diinn.py:168 does) on PyTorch CPU kernels with all host threads -- used ONLY as bench.py's cpu_baseline
+# / --impl reference arm, because /root/reference does not exist on the GPU box.
+# --------------------------------------------------------------------------------------------------
+def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None):
+    import torch
+    import torch.nn.functional as TF
+
+    with torch.no_grad():
+        x = torch.as_tensor(feat, dtype=torch.float32)
+        B, C, H, W = x.shape
+        H_up, W_up = int(size[0]), int(size[1])
+        syn = torch.from_numpy(syn_input(H, W, H_up, W_up)).unsqueeze(0).expand(B, -1, -1, -1)
+        ih = torch.from_numpy(nearest_exact_index(H, H_up))
+        iw = torch.from_numpy(nearest_exact_index(W, W_up))
+        u = TF.unfold(x, 3, padding=1).view(B, C * 9, H, W)
+        xu = u[:, :, ih][:, :, :, iw]                      # nearest-exact gather -> (B,576,H_up,W_up)
+        Wt = {k: torch.as_tensor(v) for k, v in weights.items()}
+
+        def step(xs, ss):
+            k = torch.relu(TF.conv2d(xs, Wt["K.0.0.weight"], Wt["K.0.0.bias"]))
+            q = k * torch.sin(TF.conv2d(ss, Wt["Q.0.0.weight"], Wt["Q.0.0.bias"]))
+            for i in range(1, 4):
+                k = torch.relu(TF.conv2d(torch.cat([q, xs], 1), Wt[f"K.{i}.0.weight"], Wt[f"K.{i}.0.bias"]))
+                q = k * torch.sin(TF.conv2d(q, Wt[f"Q.{i}.0.weight"], Wt[f"Q.{i}.0.bias"]))
+            return TF.conv2d(q, Wt["last_layer.weight"], Wt["last_layer.bias"])
+
+        if bsize is None:
+            return step(xu, syn).numpy()
+        strip = max(1, bsize // H_up)
+        outs = [step(xu[..., a:a + strip], syn[..., a:a + strip]) for a in range(0, W_up, strip)]
+        return torch.cat(outs, -1).numpy()

@@ -1,0 +1,109 @@
+"""CPU: pin the oracle (oracle/diinn_oracle.py) against the fixtures produced by the reference itself
+(tests/golden/make_golden.py ran /root/reference/src/models/components/diinn.py on torch CPU fp32)."""
+import numpy as np
+import pytest
+
+import diinn_b200  # noqa: F401
+from diinn_b200 import synth
+from oracle import diinn_oracle as orc
+
+POS_CASES = ["c1", "c2x2", "c2x3", "c2x4", "c3", "c4", "c5", "odd1", "odd2", "odd3", "down"]
+
+
+@pytest.mark.parametrize("name", POS_CASES)
+def test_index_and_rel_coords_bit_exact(golden_posenc, name):
+    H, W, H_up, W_up = (int(v) for v in golden_posenc[f"{name}.shape"])
+    ih, rh = orc.rel_axis(H, H_up)
+    iw, rw = orc.rel_axis(W, W_up)
+    assert np.array_equal(ih, golden_posenc[f"{name}.ih"])
+    assert np.array_equal(iw, golden_posenc[f"{name}.iw"])
+    # bit-exact: compare the raw fp32 bit patterns
+    assert np.array_equal(rh.view(np.uint32), golden_posenc[f"{name}.rel_h"].view(np.uint32))
+    assert np.array_equal(rw.view(np.uint32), golden_posenc[f"{name}.rel_w"].view(np.uint32))
+
+
+def _case(golden_decoder, name):
+    seed, fseed, B, H, W, H_up, W_up, bsize = (int(v) for v in golden_decoder[f"{name}.meta"])
+    kg, qg = (float(v) for v in golden_decoder[f"{name}.gains"])
+    weights = synth.make_weights(seed=seed, k_gain=kg, q_gain=qg)
+    feat = synth.make_feat(fseed, B, H, W)
+    return weights, feat, (H_up, W_up), golden_decoder[f"{name}.out"]
+
+
+@pytest.mark.parametrize("name,tol", [("c1", 2e-6), ("c1_bsize", 2e-6), ("odd2", 2e-6), ("x1_batch", 2e-6),
+                                      ("frac", 2e-6), ("stress", 2e-5)])
+def test_decoder_forward_matches_reference(golden_decoder, name, tol):
+    weights, feat, size, ref = _case(golden_decoder, name)
+    out = orc.decoder_forward(weights, feat, size)
+    assert out.shape == ref.shape and out.dtype == np.float32
+    assert float(np.abs(out - ref).max()) <= tol
+
+
+def test_fp64_oracle_brackets_reference(golden_decoder):
+    weights, feat, size, ref = _case(golden_decoder, "c1")
+    out64 = orc.decoder_forward(weights, feat, size, fp64=True)
+    assert float(np.abs(out64 - ref).max()) <= 1e-6
+
+
+def test_row_band_equals_full(golden_decoder):
+    weights, feat, size, ref = _case(golden_decoder, "odd2")
+    band = orc.decoder_forward(weights, feat, size, rows=(37, 61))
+    assert float(np.abs(band - ref[:, :, 37:61]).max()) <= 2e-6
+
+
+def test_layer_taps(golden_decoder):
+    weights = synth.make_weights(seed=0)
+    feat = synth.make_feat(1, 1, 48, 48)
+    r0, r1, c0, c1 = (int(v) for v in golden_decoder["taps.rows"])
+    ih, rh = orc.rel_axis(48, 192)
+    iw, rw = orc.rel_axis(48, 192)
+    u = orc.unfold3x3(feat)[0].transpose(1, 2, 0)
+    x = u[ih[r0:r1]][:, iw[c0:c1]].reshape(-1, 576)
+    syn = np.empty((r1 - r0, c1 - c0, 3), np.float32)
+    syn[..., 0] = rh[r0:r1, None]
+    syn[..., 1] = rw[None, c0:c1]
+    syn[..., 2] = orc.ratio_value(48, 48, 192, 192)
+    taps = {}
+    out = orc.step_mode3(weights, x, syn.reshape(-1, 3), taps=taps)
+    for key in ["k0", "q0", "k1", "q1", "k2", "q2", "k3", "q3"]:
+        ref = golden_decoder[f"taps.{key}"][0].transpose(1, 2, 0).reshape(-1, 256)
+        assert float(np.abs(taps[key] - ref).max()) <= 3e-6, key
+    ref = golden_decoder["taps.out"][0].transpose(1, 2, 0).reshape(-1, 3)
+    assert float(np.abs(out - ref).max()) <= 2e-6
+
+
+def test_query_on_regular_grid_equals_forward(golden_decoder):
+    """The (feat, coord, cell) superset entry reproduces forward() on the HR grid (integer and odd scales)."""
+    for name in ["x1_batch", "frac"]:
+        weights, feat, (H_up, W_up), ref = _case(golden_decoder, name)
+        B, _, H, W = feat.shape
+        ch, cw = orc.grid_coords(H_up, W_up)
+        coord = np.stack(np.meshgrid(ch, cw, indexing="ij"), -1).reshape(1, -1, 2).repeat(B, 0)
+        # indices must agree exactly with nearest-exact
+        ih, _ = orc.query_index_rel(ch, H)
+        iw, _ = orc.query_index_rel(cw, W)
+        assert np.array_equal(ih, orc.nearest_exact_index(H, H_up))
+        assert np.array_equal(iw, orc.nearest_exact_index(W, W_up))
+        cell = np.empty_like(coord)
+        cell[..., 0], cell[..., 1] = 2.0 / H_up, 2.0 / W_up
+        out = orc.query(weights, feat, coord, cell)
+        out = out.reshape(B, H_up, W_up, 3).transpose(0, 3, 1, 2)
+        assert float(np.abs(out - ref).max()) <= 5e-6
+
+
+def test_torch_cpu_port_matches(golden_decoder):
+    weights, feat, size, ref = _case(golden_decoder, "frac")
+    out = orc.decoder_forward_torch_cpu(weights, feat, size)
+    assert float(np.abs(out - ref).max()) <= 2e-6
+    out_b = orc.decoder_forward_torch_cpu(weights, feat, size, bsize=300)
+    assert float(np.abs(out_b - ref).max()) <= 2e-6
+
+
+def test_synth_is_stable():
+    """The synthetic generator is the other half of every golden pin: freeze a few values."""
+    w = synth.make_weights(seed=0)
+    assert w["K.1.0.weight"].shape == (256, 832, 1, 1) and w["last_layer.weight"].shape == (3, 256, 1, 1)
+    f = synth.make_feat(1, 1, 4, 4)
+    chk = float(np.float64(f.astype(np.float64).sum()))
+    assert abs(float(f.std()) - 0.34) < 0.05
+    assert chk == pytest.approx(float(synth.make_feat(1, 1, 4, 4).astype(np.float64).sum()), abs=0)
