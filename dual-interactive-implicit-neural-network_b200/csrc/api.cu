@@ -1,0 +1,387 @@
+// extern "C" entry points of libdiinn_b200.so (declared in include/diinn_b200.h) and the host-side planning that
+// sits between them and the kernels: argument validation, workspace carving, TMA descriptor encoding.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "handle.h"
+
+using namespace diinn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t kAlign = 1024;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+// host twin of axis_index() in common.cuh (one rounded fp32 multiply, then floorf)
+inline int host_axis_index(const AxisParams& p, int j) {
+  volatile float t = (static_cast<float>(j) + 0.5f) * p.scale;
+  int i = static_cast<int>(floorf(t));
+  return i < p.n_in - 1 ? i : p.n_in - 1;
+}
+
+struct DecodePlan {
+  int lr_row0 = 0, lr_rows = 0;  // LR rows P must hold
+  int fr0 = 0, frows = 0;        // LR rows (with +-1 halo, clipped) of the NHWC bf16 copy
+  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, total = 0;
+  int64_t chunk = 0;
+};
+
+constexpr int64_t kFp32Chunk = 1 << 17;  // HR pixels per activation ping-pong pass of the fp32 path
+
+DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int row1, int compute) {
+  DecodePlan p;
+  const AxisParams ah = make_axis(H, H_up);
+  p.lr_row0 = host_axis_index(ah, row0);
+  p.lr_rows = host_axis_index(ah, row1 - 1) - p.lr_row0 + 1;
+  p.fr0 = p.lr_row0 > 0 ? p.lr_row0 - 1 : 0;
+  const int fr1 = (p.lr_row0 + p.lr_rows + 1 < H) ? p.lr_row0 + p.lr_rows + 1 : H;
+  p.frows = fr1 - p.fr0;
+  size_t off = 0;
+  p.off_P = off;
+  off += align_up(static_cast<size_t>(B) * p.lr_rows * W * kPCols * sizeof(float));
+  if (compute == DIINN_COMPUTE_FP32) {
+    const int64_t total = static_cast<int64_t>(B) * (row1 - row0) * W_up;
+    p.chunk = total < kFp32Chunk ? total : kFp32Chunk;
+    p.off_q0 = off;
+    off += align_up(static_cast<size_t>(p.chunk) * kD * sizeof(float));
+    p.off_q1 = off;
+    off += align_up(static_cast<size_t>(p.chunk) * kD * sizeof(float));
+  } else {
+    p.off_nhwc = off;
+    off += align_up(static_cast<size_t>(B) * p.frows * W * kC * sizeof(__nv_bfloat16));
+  }
+  p.total = off;
+  return p;
+}
+
+int check_common(Handle* h, int B, int C, int H, int W, int io_dtype, int compute) {
+  if (!h) return DIINN_ERR_BAD_ARG;
+  if (!h->has_weights) return fail(h, DIINN_ERR_NO_WEIGHTS, "diinn_set_weights has not been called");
+  if (C != kC) return fail(h, DIINN_ERR_BAD_SHAPE, "feat must have 64 channels");
+  if (B < 1 || H < 1 || W < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "empty feature map");
+  if (io_dtype != DIINN_IO_F32 && io_dtype != DIINN_IO_BF16) return fail(h, DIINN_ERR_BAD_DTYPE, "io_dtype");
+  if (compute != DIINN_COMPUTE_FP32 && compute != DIINN_COMPUTE_BF16)
+    return fail(h, DIINN_ERR_BAD_DTYPE, "compute must be DIINN_COMPUTE_FP32 or DIINN_COMPUTE_BF16");
+  return DIINN_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+namespace diinn {
+
+int make_tmap_2d_bf16(Handle* h, CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                      uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(h, DIINN_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  const cuuint64_t dims[2] = {inner, rows};
+  const cuuint64_t strides[1] = {inner * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {box_inner, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, DIINN_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: " + std::to_string(r));
+  return DIINN_OK;
+}
+
+int make_tmap_4d_bf16(Handle* h, CUtensorMap* map, const void* base, const uint64_t dims_[4],
+                      const uint64_t strides_bytes[3], const uint32_t box_[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(h, DIINN_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) dims[i] = dims_[i], box[i] = box_[i];
+  for (int i = 0; i < 3; ++i) strides[i] = strides_bytes[i];
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, DIINN_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string(r));
+  return DIINN_OK;
+}
+
+}  // namespace diinn
+
+extern "C" {
+
+const char* diinn_version(void) { return "diinn_b200 0.1 (sm_100a)"; }
+
+int diinn_create(diinn_handle** out, const diinn_config* cfg) {
+  if (!out || !cfg) {
+    g_create_error = "null argument";
+    return DIINN_ERR_BAD_ARG;
+  }
+  *out = nullptr;
+  if (cfg->mode != 3 || cfg->init_q != 0 || cfg->in_channels != kC || cfg->hidden != kD ||
+      cfg->n_layers != kLayers) {
+    g_create_error =
+        "only mode=3, init_q=False, in_channels=64, hidden_dims=[256]*4 is implemented (diinn.py:73-80)";
+    return DIINN_ERR_UNSUPPORTED_MODE;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    return DIINN_ERR_UNSUPPORTED_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "bad device ordinal";
+    return DIINN_ERR_BAD_ARG;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    return DIINN_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                     "; this library is built for sm_100a (B200) only";
+    return DIINN_ERR_UNSUPPORTED_DEVICE;
+  }
+  diinn_handle* h = new (std::nothrow) diinn_handle();
+  if (!h) {
+    g_create_error = "out of host memory";
+    return DIINN_ERR_BAD_ARG;
+  }
+  h->cfg = *cfg;
+  h->sm_count = prop.multiProcessorCount;
+  cudaSetDevice(cfg->device);
+  *out = h;
+  return DIINN_OK;
+}
+
+void diinn_destroy(diinn_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->WA32);
+  cudaFree(h->bA);
+  cudaFree(h->bq_dev);
+  cudaFree(h->WB32);
+  cudaFree(h->WA16);
+  cudaFree(h->WB16);
+  cudaFree(h->host_feat_dev);
+  cudaFree(h->host_out_dev);
+  cudaFree(h->host_ws);
+  delete h;
+}
+
+const char* diinn_last_error(const diinn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t diinn_launch_count(const diinn_handle* h) { return h ? h->launches : 0; }
+
+int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream) {
+  if (!h || !w) return DIINN_ERR_BAD_ARG;
+  for (int i = 0; i < 4; ++i)
+    if (!w->k_weight[i] || !w->k_bias[i] || !w->q_weight[i] || !w->q_bias[i])
+      return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
+  if (!w->last_weight || !w->last_bias) return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
+  cudaSetDevice(h->cfg.device);
+  return pack_weights(h, w, static_cast<cudaStream_t>(stream));
+}
+
+size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_up, int W_up, int row0, int row1,
+                             int compute) {
+  (void)h;
+  if (B < 1 || H < 1 || W < 1 || H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1) return 0;
+  return plan_decode(B, H, W, H_up, W_up, row0, row1, compute).total;
+}
+
+int diinn_decode(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
+                 int row1, void* out, int64_t out_batch_stride, int64_t out_chan_stride, int64_t out_row_stride,
+                 void* workspace, size_t workspace_bytes, int io_dtype, int compute, void* stream) {
+  int rc = check_common(h, B, C, H, W, io_dtype, compute);
+  if (rc) return rc;
+  if (!feat || !out) return fail(h, DIINN_ERR_BAD_ARG, "null feat/out");
+  if (H_up < 1 || W_up < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "size must be positive");
+  if (row0 < 0 || row1 > H_up || row0 >= row1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad row range");
+  if (static_cast<int64_t>(B) * H * W >= (1ll << 31) / kPCols * 512)
+    return fail(h, DIINN_ERR_BAD_SHAPE, "feature map too large");
+  const DecodePlan plan = plan_decode(B, H, W, H_up, W_up, row0, row1, compute);
+  if (!workspace || workspace_bytes < plan.total)
+    return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL,
+                "workspace too small: need " + std::to_string(plan.total) + " bytes");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* P = reinterpret_cast<float*>(ws + plan.off_P);
+
+  PixelSource src{};
+  src.mode = 0;
+  src.ax_h = make_axis(H, H_up);
+  src.ax_w = make_axis(W, W_up);
+  src.ratio = static_cast<float>((static_cast<double>(H) * W) / (static_cast<double>(H_up) * W_up));
+  src.B = B, src.H = H, src.W = W, src.H_up = H_up, src.W_up = W_up, src.row0 = row0, src.row1 = row1;
+  src.lr_row0 = plan.lr_row0, src.lr_rows = plan.lr_rows;
+  OutSpec o{out, out_batch_stride, out_chan_stride, out_row_stride, io_dtype};
+
+  if (compute == DIINN_COMPUTE_FP32) {
+    if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, plan.lr_row0, plan.lr_rows, P, s))) return rc;
+    return run_stage_b_fp32(h, src, o, P, reinterpret_cast<float*>(ws + plan.off_q0),
+                            reinterpret_cast<float*>(ws + plan.off_q1), plan.chunk, s);
+  }
+  __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + plan.off_nhwc);
+  if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, s)))
+    return rc;
+  if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s)))
+    return rc;
+  return launch_stage_b_umma(h, src, o, P, 0, s);
+}
+
+int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int H, int W, int H_up, int W_up,
+                      int row0, int row1, void* out_host, int io_dtype, int compute, void* stream) {
+  int rc = check_common(h, B, C, H, W, io_dtype, compute);
+  if (rc) return rc;
+  if (!feat_host || !out_host) return fail(h, DIINN_ERR_BAD_ARG, "null feat/out");
+  if (H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1)
+    return fail(h, DIINN_ERR_BAD_SHAPE, "bad size / row range");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t esz = io_dtype == DIINN_IO_F32 ? 4 : 2;
+  const size_t feat_bytes = static_cast<size_t>(B) * C * H * W * esz;
+  const int nrows = row1 - row0;
+  const size_t out_bytes = static_cast<size_t>(B) * 3 * nrows * W_up * esz;
+  const size_t ws_bytes = diinn_workspace_bytes(h, B, H, W, H_up, W_up, row0, row1, compute);
+  auto grow = [&](void** p, size_t* have, size_t need) -> cudaError_t {
+    if (*have >= need) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+  };
+  DIINN_CUDA_OK(h, grow(&h->host_feat_dev, &h->host_feat_bytes, feat_bytes));
+  DIINN_CUDA_OK(h, grow(&h->host_out_dev, &h->host_out_bytes, out_bytes));
+  DIINN_CUDA_OK(h, grow(&h->host_ws, &h->host_ws_bytes, ws_bytes));
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(h->host_feat_dev, feat_host, feat_bytes, cudaMemcpyHostToDevice, s));
+  rc = diinn_decode(h, h->host_feat_dev, B, C, H, W, H_up, W_up, row0, row1, h->host_out_dev,
+                    static_cast<int64_t>(3) * nrows * W_up, static_cast<int64_t>(nrows) * W_up, W_up, h->host_ws,
+                    h->host_ws_bytes, io_dtype, compute, s);
+  if (rc) return rc;
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(out_host, h->host_out_dev, out_bytes, cudaMemcpyDeviceToHost, s));
+  DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
+  return DIINN_OK;
+}
+
+size_t diinn_query_workspace_bytes(const diinn_handle* h, int B, int H, int W, int Q, int compute) {
+  (void)h;
+  if (B < 1 || H < 1 || W < 1 || Q < 1) return 0;
+  // same carving as a full-image decode whose "grid" has B*Q pixels
+  size_t off = align_up(static_cast<size_t>(B) * H * W * kPCols * sizeof(float));
+  if (compute == DIINN_COMPUTE_FP32) {
+    const int64_t total = static_cast<int64_t>(B) * Q;
+    const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;
+    off += 2 * align_up(static_cast<size_t>(chunk) * kD * sizeof(float));
+  } else {
+    off += align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+  }
+  return off;
+}
+
+static PixelSource make_query_source(int B, int H, int W, const float* coord, const float* cell, int Q) {
+  PixelSource src{};
+  src.mode = 1;
+  src.ax_h = make_axis(H, H);
+  src.ax_w = make_axis(W, W);
+  src.B = B, src.H = H, src.W = W;
+  src.lr_row0 = 0, src.lr_rows = H;
+  src.coord = coord, src.cell = cell, src.Q = Q;
+  src.hw_f = static_cast<float>(H * W);
+  return src;
+}
+
+int diinn_query(diinn_handle* h, const void* feat, int B, int C, int H, int W, const float* coord, const float* cell,
+                int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype, int compute, void* stream) {
+  int rc = check_common(h, B, C, H, W, io_dtype, compute);
+  if (rc) return rc;
+  if (!feat || !out || !coord || !cell) return fail(h, DIINN_ERR_BAD_ARG, "null pointer");
+  if (Q < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "Q must be positive");
+  const size_t need = diinn_query_workspace_bytes(h, B, H, W, Q, compute);
+  if (!workspace || workspace_bytes < need)
+    return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL, "workspace too small: need " + std::to_string(need) + " bytes");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* P = reinterpret_cast<float*>(ws);
+  size_t off = align_up(static_cast<size_t>(B) * H * W * kPCols * sizeof(float));
+  const PixelSource src = make_query_source(B, H, W, coord, cell, Q);
+  OutSpec o{out, 0, 0, 0, io_dtype};
+  if (compute == DIINN_COMPUTE_FP32) {
+    const int64_t total = static_cast<int64_t>(B) * Q;
+    const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;
+    float* q0 = reinterpret_cast<float*>(ws + off);
+    float* q1 = reinterpret_cast<float*>(ws + off + align_up(static_cast<size_t>(chunk) * kD * sizeof(float)));
+    if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, 0, H, P, s))) return rc;
+    return run_stage_b_fp32(h, src, o, P, q0, q1, chunk, s);
+  }
+  __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + off);
+  if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
+  if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s))) return rc;
+  return launch_stage_b_umma(h, src, o, P, 0, s);
+}
+
+int diinn_debug_gather(diinn_handle* h, int H, int W, int H_up, int W_up, int32_t* ih, int32_t* iw, float* rel_h,
+                       float* rel_w, void* stream) {
+  if (!h || !ih || !iw || !rel_h || !rel_w) return DIINN_ERR_BAD_ARG;
+  if (H < 1 || W < 1 || H_up < 1 || W_up < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad shape");
+  cudaSetDevice(h->cfg.device);
+  return launch_axis_tables(h, make_axis(H, H_up), make_axis(W, W_up), ih, iw, rel_h, rel_w,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int diinn_debug_query_gather(diinn_handle* h, int B, int H, int W, const float* coord, const float* cell, int Q,
+                             int32_t* idx, float* rel, float* ratio, void* stream) {
+  if (!h || !coord || !cell || !idx || !rel || !ratio) return DIINN_ERR_BAD_ARG;
+  if (B < 1 || H < 1 || W < 1 || Q < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad shape");
+  cudaSetDevice(h->cfg.device);
+  return launch_query_gather(h, make_query_source(B, H, W, coord, cell, Q), idx, rel, ratio,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, int W, float* P, void* workspace,
+                        size_t workspace_bytes, int io_dtype, int compute, void* stream) {
+  int rc = check_common(h, B, C, H, W, io_dtype, compute);
+  if (rc) return rc;
+  if (!feat || !P) return fail(h, DIINN_ERR_BAD_ARG, "null pointer");
+  cudaSetDevice(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (compute == DIINN_COMPUTE_FP32) return launch_stage_a_fp32(h, feat, io_dtype, B, H, W, 0, H, P, s);
+  const size_t need = align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+  if (!workspace || workspace_bytes < need)
+    return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL, "workspace too small: need " + std::to_string(need) + " bytes");
+  __nv_bfloat16* nhwc = static_cast<__nv_bfloat16*>(workspace);
+  if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
+  return launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s);
+}
+
+int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
+                          int cta_group, void* stream) {
+  if (!h || !A || !B || !D) return DIINN_ERR_BAD_ARG;
+  if (M < 128 || M % 128 || N < 256 || N % 256 || K < 64 || K % 64 || (cta_group != 1 && cta_group != 2))
+    return fail(h, DIINN_ERR_BAD_SHAPE, "need M%128==0, N%256==0, K%64==0, cta_group in {1,2}");
+  if (cta_group == 2 && M % 256) return fail(h, DIINN_ERR_BAD_SHAPE, "cta_group 2 needs M%256==0");
+  cudaSetDevice(h->cfg.device);
+  return launch_umma_selftest(h, A, B, D, M, N, K, cta_group, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

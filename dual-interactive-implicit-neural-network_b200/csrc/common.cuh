@@ -1,0 +1,101 @@
+// Internal types shared by the .cu files of libdiinn_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/diinn_b200.h"
+
+namespace diinn {
+
+constexpr int kC = 64;          // encoder channels (in_channels, diinn.py:40)
+constexpr int kUnfold = 576;    // 3x3 unfold of 64 channels (diinn.py:168)
+constexpr int kD = 256;         // hidden width
+constexpr int kLayers = 4;      // K/Q layer pairs
+constexpr int kPCols = 1024;    // hoisted LR-resolution pre-activations per LR pixel: [k0 | kx1 | kx2 | kx3]
+
+// ---------------------------------------------------------------------------------------------------------
+// Coordinates (diinn.py:94-110). Per axis with n source and n_up destination samples the reference computes, in
+// fp32 with separately rounded mul/add (no FMA):
+//   c(i, n)  = fl(a_n + fl(b_n * i)),      a_n = fp32(-1 + 1/n), b_n = fp32(2/n)   (python doubles -> fp32)
+//   idx(j)   = min(floorf(fl((j + 0.5) * scale)), n - 1),  scale = fp32(n) / fp32(n_up)   (nearest-exact)
+//   rel(j)   = fl(fl(c(j, n_up) - c(idx(j), n)) * fp32(n))
+// The host fills AxisParams with the rounded constants so host and device agree bit for bit.
+// ---------------------------------------------------------------------------------------------------------
+struct AxisParams {
+  float a_in, b_in, a_up, b_up, scale, n_in_f;
+  int n_in, n_up;
+};
+
+__host__ inline AxisParams make_axis(int n_in, int n_up) {
+  AxisParams p;
+  p.a_in = static_cast<float>(-1.0 + 1.0 / n_in);
+  p.b_in = static_cast<float>(2.0 / n_in);
+  p.a_up = static_cast<float>(-1.0 + 1.0 / n_up);
+  p.b_up = static_cast<float>(2.0 / n_up);
+  p.scale = static_cast<float>(n_in) / static_cast<float>(n_up);
+  p.n_in_f = static_cast<float>(n_in);
+  p.n_in = n_in;
+  p.n_up = n_up;
+  return p;
+}
+
+__device__ __forceinline__ int axis_index(const AxisParams& p, int j) {
+  const float t = __fmul_rn(static_cast<float>(j) + 0.5f, p.scale);
+  const int i = static_cast<int>(floorf(t));
+  return min(i, p.n_in - 1);
+}
+__device__ __forceinline__ float axis_centre_in(const AxisParams& p, int i) {
+  return __fadd_rn(p.a_in, __fmul_rn(p.b_in, static_cast<float>(i)));
+}
+__device__ __forceinline__ float axis_rel(const AxisParams& p, int j, int i) {
+  const float cu = __fadd_rn(p.a_up, __fmul_rn(p.b_up, static_cast<float>(j)));
+  return __fmul_rn(__fsub_rn(cu, axis_centre_in(p, i)), p.n_in_f);
+}
+// query entry: idx = clamp(floorf(fl(fl(c + 1) * fl(n/2)))), rel = fl(fl(c - centre) * n)
+__device__ __forceinline__ int query_index(const AxisParams& p, float c) {
+  const float t = __fmul_rn(__fadd_rn(c, 1.0f), p.n_in_f * 0.5f);
+  const int i = static_cast<int>(floorf(t));
+  return max(0, min(i, p.n_in - 1));
+}
+__device__ __forceinline__ float query_rel(const AxisParams& p, float c, int i) {
+  return __fmul_rn(__fsub_rn(c, axis_centre_in(p, i)), p.n_in_f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// How the fused kernels enumerate "HR query pixels". Two sources: the regular grid of forward(x, size) and the
+// explicit (coord, cell) list of query().
+// ---------------------------------------------------------------------------------------------------------
+struct PixelSource {
+  int mode;  // 0 = grid rows [row0,row1) x [0,W_up) per batch image, 1 = query list
+  // grid
+  AxisParams ax_h, ax_w;
+  float ratio;
+  int B, H, W, H_up, W_up, row0, row1;
+  int lr_row0, lr_rows;  // P holds LR rows [lr_row0, lr_row0 + lr_rows) of every batch image
+  // query
+  const float* coord;  // (B,Q,2)
+  const float* cell;   // (B,Q,2)
+  int Q;
+  float hw_f;  // fp32(H*W)
+};
+
+struct OutSpec {
+  void* ptr;
+  int64_t batch_stride, chan_stride, row_stride;  // grid mode (elements); query mode: out[(b*Q+q)*3 + c]
+  int io_dtype;
+};
+
+// small fp32 parameters every path needs in registers/constant bank (passed by value as kernel params)
+struct SmallParams {
+  float bq[kLayers][kD];   // Q biases (layer 0..3)
+  float wq0[kD][4];        // per feature: Q.0 weight row + bias = (w_relh, w_relw, w_ratio, bq0)  -> one LDC.128
+  float wl_t[kD][4];       // per feature: last_layer.weight column = (wl[0][f], wl[1][f], wl[2][f], 0)
+  float bl[4];             // last_layer.bias (+pad)
+};
+
+struct Handle;  // defined in handle.h
+
+}  // namespace diinn

@@ -1,0 +1,82 @@
+// diinn_handle: library-owned state (repacked weights, TMA descriptors, cached host-entry scratch).
+#pragma once
+#include <cuda.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace diinn {
+
+struct Handle {
+  diinn_config cfg{};
+  int sm_count = 0;
+  bool has_weights = false;
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- fp32 CUDA-core path ----
+  float* WA32 = nullptr;  // (1024, 576): rows [0,256) K.0; rows 256*i.. K.i[:,256:832]; reference k order c*9+tap
+  float* bA = nullptr;    // (1024): K biases of layers 0..3
+  float* bq_dev = nullptr;  // (4, 256): Q biases (device copy of small.bq)
+  float* WB32 = nullptr;  // (3, 512, 256): layer i=1..3: rows [0,256) K.i[:, :256], rows [256,512) Q.i
+  // ---- tcgen05 path (bf16) ----
+  __nv_bfloat16* WA16 = nullptr;  // (4 n-blocks, 9 taps, 256 rows, 64 ch): K index permuted to tap*64 + c
+  __nv_bfloat16* WB16 = nullptr;  // (3 layers, 2 halves, 4 k-chunks, 256 rows, 64): rows [0,128) K-part, [128,256) Q-part
+  CUtensorMap tmapWA{};           // 2-D (64, 9216 rows), box (64, 256|128), 128B swizzle
+  CUtensorMap tmapWA_half{};
+  CUtensorMap tmapWB{};           // 2-D (64, 6144 rows)
+  CUtensorMap tmapWB_half{};
+  SmallParams small{};            // host copy; passed by value to kernels
+
+  // ---- cached device scratch for diinn_decode_host ----
+  void* host_feat_dev = nullptr;
+  size_t host_feat_bytes = 0;
+  void* host_out_dev = nullptr;
+  size_t host_out_bytes = 0;
+  void* host_ws = nullptr;
+  size_t host_ws_bytes = 0;
+};
+
+inline int fail(Handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define DIINN_CUDA_OK(h, expr)                                                                       \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::diinn::fail((h), DIINN_ERR_CUDA, std::string(#expr ": ") + cudaGetErrorString(_e));   \
+  } while (0)
+
+// ---- implemented across the .cu files -------------------------------------------------------------------
+// pack.cu
+int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s);
+int launch_feat_to_nhwc_bf16(Handle* h, const void* feat, int io_dtype, int B, int H, int W, int r0, int r1,
+                             __nv_bfloat16* dst, cudaStream_t s);
+// simt.cu
+int launch_axis_tables(Handle* h, const AxisParams& ah, const AxisParams& aw, int32_t* ih, int32_t* iw,
+                       float* rel_h, float* rel_w, cudaStream_t s);
+int launch_query_gather(Handle* h, const PixelSource& src, int32_t* idx, float* rel, float* ratio, cudaStream_t s);
+int launch_stage_a_fp32(Handle* h, const void* feat, int io_dtype, int B, int H, int W, int lr_row0, int lr_rows,
+                        float* P, cudaStream_t s);
+int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,
+                     float* qbuf1, int64_t chunk, cudaStream_t s);
+// stage_a_umma.cu / stage_b_umma.cu
+int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H, int W, int fr0, int frows,
+                        int lr_row0, int lr_rows, float* P, cudaStream_t s);
+int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group,
+                        cudaStream_t s);
+// umma_selftest.cu
+int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
+                         cudaStream_t s);
+// tensor maps (api.cu)
+int make_tmap_2d_bf16(Handle* h, CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                      uint32_t box_inner, uint32_t box_rows);
+int make_tmap_4d_bf16(Handle* h, CUtensorMap* map, const void* base, const uint64_t dims[4],
+                      const uint64_t strides_bytes[3], const uint32_t box[4]);
+
+}  // namespace diinn
+
+struct diinn_handle : public diinn::Handle {};

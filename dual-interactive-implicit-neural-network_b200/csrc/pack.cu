@@ -1,0 +1,184 @@
+// Weight repacking (reference state_dict layout -> library layouts) and the NCHW -> NHWC bf16 feature pass.
+//
+// Reference layout (diinn.py:73-80,92):
+//   K.0 (256,576)   K.i (256,832) with input channels [0,256) <- q and [256,832) <- x   (torch.cat([q,x]), diinn.py:136)
+//   Q.0 (256,3)     Q.i (256,256)      last (3,256)
+//   x channel c*9 + kh*3 + kw = feat[c, h+kh-1, w+kw-1]                                   (F.unfold, diinn.py:168)
+//
+// Because every term multiplying x depends only on the LR pixel, the four x-facing blocks are stacked into one
+// (1024 x 576) matrix evaluated once per LR pixel ("stage A"); the per-HR-pixel work ("stage B") keeps only the
+// 256x256 q-facing blocks of K.1..3 next to Q.1..3.
+#include "handle.h"
+
+namespace diinn {
+
+struct RefPtrs {
+  const float* kw[4];
+  const float* kb[4];
+  const float* qw[4];
+  const float* qb[4];
+  const float* lw;
+  const float* lb;
+};
+
+__global__ void pack_stage_a_kernel(RefPtrs r, float* __restrict__ WA32, float* __restrict__ bA,
+                                    __nv_bfloat16* __restrict__ WA16) {
+  const int n = blockIdx.x;  // 0..1023
+  const int layer = n >> 8, row = n & 255;
+  const int stride = layer == 0 ? kUnfold : kD + kUnfold;
+  const int off = layer == 0 ? 0 : kD;
+  const float* src = r.kw[layer] + static_cast<size_t>(row) * stride + off;
+  for (int k = threadIdx.x; k < kUnfold; k += blockDim.x) {
+    const float v = src[k];
+    WA32[static_cast<size_t>(n) * kUnfold + k] = v;
+    const int c = k / 9, tap = k % 9;
+    // (n-block, tap, row, c)
+    WA16[((static_cast<size_t>(layer) * 9 + tap) * 256 + row) * kC + c] = __float2bfloat16_rn(v);
+  }
+  if (threadIdx.x == 0) bA[n] = r.kb[layer][row];
+}
+
+__global__ void pack_stage_b_kernel(RefPtrs r, float* __restrict__ WB32, __nv_bfloat16* __restrict__ WB16) {
+  const int n = blockIdx.x;   // 0..511
+  const int li = blockIdx.y;  // 0..2 -> reference layer li+1
+  const bool is_q = n >= kD;
+  const int row = is_q ? n - kD : n;
+  const float* src = is_q ? r.qw[li + 1] + static_cast<size_t>(row) * kD
+                          : r.kw[li + 1] + static_cast<size_t>(row) * (kD + kUnfold);
+  const int half = row >> 7;                              // which 128-feature half of the layer output
+  const int tile_row = (is_q ? 128 : 0) + (row & 127);    // K-part rows [0,128), Q-part rows [128,256)
+  for (int k = threadIdx.x; k < kD; k += blockDim.x) {
+    const float v = src[k];
+    WB32[(static_cast<size_t>(li) * 512 + n) * kD + k] = v;
+    const int kc = k >> 6, e = k & 63;
+    WB16[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row) * 64 + e] = __float2bfloat16_rn(v);
+  }
+}
+
+int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
+  RefPtrs r{};
+  float* staging = nullptr;
+  const size_t sizes_kw[4] = {256 * 576, 256 * 832, 256 * 832, 256 * 832};
+  const size_t sizes_qw[4] = {256 * 3, 256 * 256, 256 * 256, 256 * 256};
+  size_t total = 0;
+  for (int i = 0; i < 4; ++i) total += sizes_kw[i] + sizes_qw[i] + 512;
+  total += 3 * 256 + 4;
+  if (!w->on_device) {
+    DIINN_CUDA_OK(h, cudaMalloc(&staging, total * sizeof(float)));
+    float* p = staging;
+    auto up = [&](const float* src, size_t n) -> const float* {
+      cudaMemcpyAsync(p, src, n * sizeof(float), cudaMemcpyHostToDevice, s);
+      const float* d = p;
+      p += n;
+      return d;
+    };
+    for (int i = 0; i < 4; ++i) {
+      r.kw[i] = up(w->k_weight[i], sizes_kw[i]);
+      r.kb[i] = up(w->k_bias[i], 256);
+      r.qw[i] = up(w->q_weight[i], sizes_qw[i]);
+      r.qb[i] = up(w->q_bias[i], 256);
+    }
+    r.lw = up(w->last_weight, 768);
+    r.lb = up(w->last_bias, 3);
+  } else {
+    for (int i = 0; i < 4; ++i) {
+      r.kw[i] = w->k_weight[i];
+      r.kb[i] = w->k_bias[i];
+      r.qw[i] = w->q_weight[i];
+      r.qb[i] = w->q_bias[i];
+    }
+    r.lw = w->last_weight;
+    r.lb = w->last_bias;
+  }
+  if (!h->WA32) {
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WA32, sizeof(float) * kPCols * kUnfold));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->bA, sizeof(float) * kPCols));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WB32, sizeof(float) * 3 * 512 * kD));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->bq_dev, sizeof(float) * kLayers * kD));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WA16, sizeof(__nv_bfloat16) * kPCols * kUnfold));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WB16, sizeof(__nv_bfloat16) * 3 * 512 * kD));
+  }
+  pack_stage_a_kernel<<<kPCols, 192, 0, s>>>(r, h->WA32, h->bA, h->WA16);
+  pack_stage_b_kernel<<<dim3(512, 3), 128, 0, s>>>(r, h->WB32, h->WB16);
+  h->launches += 2;
+  DIINN_CUDA_OK(h, cudaGetLastError());
+
+  // small fp32 parameters -> host struct (they travel to the kernels as by-value parameters / constant bank)
+  SmallParams& sp = h->small;
+  const cudaMemcpyKind kind = w->on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+  for (int i = 0; i < 4; ++i)
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(sp.bq[i], w->q_bias[i], sizeof(float) * kD, kind, s));
+  static thread_local float tmp_q0[kD * 3];
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_q0, w->q_weight[0], sizeof(float) * kD * 3, kind, s));
+  static thread_local float tmp_wl[3 * kD];
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_wl, w->last_weight, sizeof(float) * 3 * kD, kind, s));
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(sp.bl, w->last_bias, sizeof(float) * 3, kind, s));
+  DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
+  sp.bl[3] = 0.f;
+  for (int f = 0; f < kD; ++f) {
+    sp.wq0[f][0] = tmp_q0[f * 3 + 0];
+    sp.wq0[f][1] = tmp_q0[f * 3 + 1];
+    sp.wq0[f][2] = tmp_q0[f * 3 + 2];
+    sp.wq0[f][3] = sp.bq[0][f];
+    sp.wl_t[f][0] = tmp_wl[f];
+    sp.wl_t[f][1] = tmp_wl[kD + f];
+    sp.wl_t[f][2] = tmp_wl[2 * kD + f];
+    sp.wl_t[f][3] = 0.f;
+  }
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bq_dev, sp.bq, sizeof(float) * kLayers * kD, cudaMemcpyHostToDevice, s));
+  DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
+  if (staging) cudaFree(staging);
+
+  // TMA descriptors over the bf16 tiles (rows of 64 bf16 = 128 B, 128B swizzle applied by TMA on the way in)
+  int rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWA, h->WA16, 64, 4 * 9 * 256, 64, 256))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWA_half, h->WA16, 64, 4 * 9 * 256, 64, 128))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB, h->WB16, 64, 3 * 2 * 4 * 256, 64, 256))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB_half, h->WB16, 64, 3 * 2 * 4 * 256, 64, 128))) return rc;
+  h->has_weights = true;
+  return DIINN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// feat (B,64,H,W) NCHW fp32|bf16, LR rows [r0,r1) -> (B, r1-r0, W, 64) bf16, the layout stage A's TMA im2col
+// boxes read (one 128-byte row per LR pixel and tap). Coalesced both ways through a padded smem tile.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void feat_to_nhwc_bf16_kernel(const T* __restrict__ feat, __nv_bfloat16* __restrict__ dst, int H, int W,
+                                         int r0, int rows) {
+  __shared__ float tile[kC][33];
+  const int w0 = blockIdx.x * 32;
+  const int row = blockIdx.y;  // relative to r0
+  const int b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: 8 warps
+  for (int c = ty; c < kC; c += 8) {
+    const int w = w0 + tx;
+    float v = 0.f;
+    if (w < W) v = static_cast<float>(feat[((static_cast<size_t>(b) * kC + c) * H + (r0 + row)) * W + w]);
+    tile[c][tx] = v;
+  }
+  __syncthreads();
+  // each thread writes 2 channels of one pixel: 32 threads cover one pixel's 64 channels (128 B)
+  for (int p = ty; p < 32; p += 8) {
+    const int w = w0 + p;
+    if (w < W) {
+      __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * tx][p], tile[2 * tx + 1][p]);
+      reinterpret_cast<__nv_bfloat162*>(dst + ((static_cast<size_t>(b) * rows + row) * W + w) * kC)[tx] = v;
+    }
+  }
+}
+
+int launch_feat_to_nhwc_bf16(Handle* h, const void* feat, int io_dtype, int B, int H, int W, int r0, int r1,
+                             __nv_bfloat16* dst, cudaStream_t s) {
+  dim3 grid((W + 31) / 32, r1 - r0, B);
+  if (io_dtype == DIINN_IO_F32)
+    feat_to_nhwc_bf16_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(feat), dst, H, W, r0, r1 - r0);
+  else
+    feat_to_nhwc_bf16_kernel<__nv_bfloat16>
+        <<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), dst, H, W, r0, r1 - r0);
+  h->launches += 1;
+  DIINN_CUDA_OK(h, cudaGetLastError());
+  return DIINN_OK;
+}
+
+}  // namespace diinn

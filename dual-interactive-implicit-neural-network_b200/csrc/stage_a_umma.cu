@@ -1,0 +1,274 @@
+// Stage A of the DIINN query decoder on tcgen05 tensor cores: everything in the K branch that multiplies the
+// unfolded feature x_l depends only on the LR pixel l (diinn.py:133,136 with x = unfold3x3(feat), diinn.py:168), and
+// "unfold 3x3 -> 1x1 conv" is a 3x3 zero-padded convolution. So per LR pixel, once:
+//
+//   P[l] (1024 fp32) = [ relu(K0 x_l + b0) | K_i[:, 256:] x_l + b_i , i = 1..3 ]      (implicit GEMM, K = 9 taps x 64 ch)
+//
+// A operand: feat as NHWC bf16; for tap (kh,kw) the K-chunk of LR pixel (h,w) is the 128-byte channel vector of pixel
+// (h+kh-1, w+kw-1), fetched as one TMA 4-D box (64 ch x 16 w x 8 h x 1 b) per tap whose out-of-bounds zero fill IS the
+// unfold's zero padding. B operand: the stacked weight matrix, K re-ordered to tap*64 + c (pack.cu), streamed from L2
+// in [256 x 64] bf16 stages. D: two 256-column TMEM slots, one N-block each, drained by 4 epilogue warps that add the
+// bias, apply ReLU to N-block 0, transpose through padded shared memory and write P with 128-byte coalesced rows.
+//
+// 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA), warp 2 = TMEM allocator, warps 4..7 = epilogue.
+// CG=2 runs CTA pairs (cta_group::2, M = 256 = two 8x16 LR patches, B split by N halves between the CTAs).
+#include <cstdlib>
+
+#include "handle.h"
+#include "ptx.cuh"
+
+namespace diinn {
+using namespace ptx;
+
+namespace sa {
+constexpr int kPatchH = 8, kPatchW = 16;
+constexpr int kTapBytes = 128 * 128;            // 16 KB per tap
+constexpr int kABytes = 9 * kTapBytes;          // 144 KB: the whole K extent of one 128-pixel tile
+constexpr int kWBytesTotal = 64 * 1024;
+constexpr int kThreads = 256;
+constexpr int kXposeFloats = 32 * 33;           // per epilogue warp
+
+template <int CG>
+struct Cfg {
+  static constexpr int kStageRows = 256 / CG;
+  static constexpr int kStageBytes = kStageRows * 128;
+  static constexpr int kStages = kWBytesTotal / kStageBytes;  // 2 (CG=1) or 4 (CG=2)
+};
+
+struct Smem {
+  float xpose[4][kXposeFloats];
+  uint64_t w_full[4];
+  uint64_t w_empty[4];
+  uint64_t a_full;
+  uint64_t a_empty;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_ptr;
+};
+constexpr size_t kSmemBytes = kABytes + kWBytesTotal + sizeof(Smem);
+static_assert(kSmemBytes <= 232448, "exceeds 227 KB of dynamic shared memory");
+
+struct Geo {
+  int B, H, W;            // feature map
+  int fr0;                // first LR row held by the NHWC copy
+  int lr_row0, lr_rows;   // LR rows to produce (rows of P per image)
+  int tiles_y, n_txp, n_work;
+};
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmW,
+                    const float* __restrict__ bA, float* __restrict__ P, const Geo g, int* __restrict__ err_flag) {
+  using C = Cfg<CG>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_a = smem;
+  uint8_t* s_w = smem + kABytes;
+  Smem& sm = *reinterpret_cast<Smem*>(smem + kABytes + kWBytesTotal);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = rank == 0;
+  const int unit_id = blockIdx.x / CG, n_units = gridDim.x / CG;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) atomicExch(err_flag, 2);
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmF);
+    prefetch_tensormap(&tmW);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&sm.w_full[i], 1);
+      mbar_init(&sm.w_empty[i], 1);
+    }
+    mbar_init(&sm.a_full, 1);
+    mbar_init(&sm.a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.tmem_full[i], 1);
+      mbar_init(&sm.tmem_empty[i], 4 * CG);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(&sm.tmem_ptr, 512);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_ptr;
+  const int per_img = g.tiles_y * g.n_txp;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int t = 0;
+      for (int work = unit_id; work < g.n_work; work += n_units, ++t) {
+        const int b = work / per_img;
+        const int rem = work - b * per_img;
+        const int ty = rem / g.n_txp, txp = rem - ty * g.n_txp;
+        const int h0 = g.lr_row0 + ty * kPatchH;
+        const int w0 = (txp * CG + rank) * kPatchW;
+        mbar_wait(&sm.a_empty, (t & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(&sm.a_full, kABytes * CG);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
+          if constexpr (CG == 1) tma_load_4d(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
+          else tma_load_4d_2sm(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
+        }
+#pragma unroll 1
+        for (int s36 = 0; s36 < 36; ++s36, ++it) {  // (n-block, tap)
+          const int st = it % C::kStages;
+          mbar_wait(&sm.w_empty[st], ((it / C::kStages) & 1) ^ 1);
+          if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
+          void* dst = s_w + st * C::kStageBytes;
+          if constexpr (CG == 1) tma_load_2d(dst, &tmW, &sm.w_full[st], 0, s36 * 256);
+          else tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s36 * 256 + rank * 128);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, 256);
+      uint32_t it = 0, slot_use = 0;
+      int t = 0;
+      for (int work = unit_id; work < g.n_work; work += n_units, ++t) {
+        mbar_wait(&sm.a_full, t & 1);
+#pragma unroll 1
+        for (int nb = 0; nb < 4; ++nb, ++slot_use) {
+          const int slot = nb & 1;
+          const uint32_t use = slot_use >> 1;  // how many times this slot was used before
+          if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[slot], (use & 1) ^ 1);
+          else mbar_wait(&sm.tmem_empty[slot], (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + slot * 256;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++it) {
+            const int st = it % C::kStages;
+            mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(s_a + tap * kTapBytes);
+            const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
+                            (tap | k) != 0 ? 1u : 0u);
+            umma_commit<CG>(&sm.w_empty[st]);
+          }
+          umma_commit<CG>(&sm.tmem_full[slot]);
+        }
+        umma_commit<CG>(&sm.a_empty);  // all MMAs reading this tile's A have completed when this fires
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
+    float* xp = sm.xpose[quarter];
+    uint32_t slot_use = 0;
+    for (int work = unit_id; work < g.n_work; work += n_units) {
+      const int b = work / per_img;
+      const int rem = work - b * per_img;
+      const int ty = rem / g.n_txp, txp = rem - ty * g.n_txp;
+      const int h0 = ty * kPatchH;                       // relative to lr_row0
+      const int w0 = (txp * CG + rank) * kPatchW;
+#pragma unroll 1
+      for (int nb = 0; nb < 4; ++nb, ++slot_use) {
+        const int slot = nb & 1;
+        mbar_wait(&sm.tmem_full[slot], (slot_use >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tslot = tmem_base + lane_bits + slot * 256;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v0[16], v1[16];
+          tmem_ld16(tslot + c0, v0);
+          tmem_ld16(tslot + c0 + 16, v1);
+          tmem_ld_wait();
+          __syncwarp();  // previous block's readers are done with xp
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            xp[lane * 33 + j] = __uint_as_float(v0[j]);
+            xp[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
+          }
+          __syncwarp();
+          const int n = nb * 256 + c0 + lane;
+          const float bias = __ldg(bA + n);
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r = quarter * 32 + rr;
+            const int hh = h0 + (r >> 4), ww = w0 + (r & 15);
+            if (hh < g.lr_rows && ww < g.W) {
+              float v = xp[rr * 33 + lane] + bias;
+              if (nb == 0) v = fmaxf(v, 0.f);
+              P[(static_cast<size_t>(b) * g.lr_rows + hh) * g.W * kPCols + static_cast<size_t>(ww) * kPCols + n] = v;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(&sm.tmem_empty[slot], 0);
+          else mbar_arrive(&sm.tmem_empty[slot]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+}  // namespace sa
+
+int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H, int W, int fr0, int frows,
+                        int lr_row0, int lr_rows, float* P, cudaStream_t s) {
+  using namespace sa;
+  static int env_cg = -1;
+  if (env_cg < 0) {
+    const char* e = getenv("DIINN_CTA_GROUP_A");
+    env_cg = (e && e[0] == '1') ? 1 : 2;
+  }
+  const int cta_group = env_cg;
+  static int* err_flag = nullptr;
+  if (!err_flag) {
+    DIINN_CUDA_OK(h, cudaMalloc(&err_flag, sizeof(int)));
+    DIINN_CUDA_OK(h, cudaMemset(err_flag, 0, sizeof(int)));
+  }
+  CUtensorMap tmF;
+  const uint64_t dims[4] = {static_cast<uint64_t>(kC), static_cast<uint64_t>(W), static_cast<uint64_t>(frows),
+                            static_cast<uint64_t>(B)};
+  const uint64_t strides[3] = {kC * 2ull, static_cast<uint64_t>(W) * kC * 2ull,
+                               static_cast<uint64_t>(frows) * W * kC * 2ull};
+  const uint32_t box[4] = {kC, kPatchW, kPatchH, 1};
+  int rc = make_tmap_4d_bf16(h, &tmF, feat_nhwc, dims, strides, box);
+  if (rc) return rc;
+  Geo g{};
+  g.B = B, g.H = H, g.W = W, g.fr0 = fr0, g.lr_row0 = lr_row0, g.lr_rows = lr_rows;
+  const int tiles_x = (W + kPatchW - 1) / kPatchW;
+  g.tiles_y = (lr_rows + kPatchH - 1) / kPatchH;
+  g.n_txp = (tiles_x + cta_group - 1) / cta_group;
+  g.n_work = B * g.tiles_y * g.n_txp;
+  int units = h->sm_count / cta_group;
+  if (units > g.n_work) units = g.n_work;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * cta_group, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cta_group == 1) {
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(kSmemBytes)));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<1>, tmF, h->tmapWA, h->bA, P, g, err_flag));
+  } else {
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(kSmemBytes)));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<2>, tmF, h->tmapWA_half, h->bA, P, g, err_flag));
+  }
+  h->launches += 1;
+  return DIINN_OK;
+}
+
+}  // namespace diinn

@@ -1,0 +1,453 @@
+// Stage B of the DIINN query decoder on tcgen05 tensor cores: the per-HR-pixel dual-interactive MLP
+// (diinn.py:134-138 after hoisting the x-facing terms to LR resolution, see pack.cu / stage_a_umma.cu):
+//
+//   q0  = P[l][0:256] * sin(Wq0 s_p + bq0)                                        CUDA cores (K = 3)
+//   k_i = relu(Wk_i[:, :256] q_{i-1} + P[l][256i:256i+256]),  q_i = k_i * sin(Wq_i q_{i-1} + bq_i),  i = 1..3
+//   rgb = Wl q_3 + bl                                                              fused into layer 3's epilogue
+//
+// One persistent CTA per SM (CG=2: CTA pairs with cta_group::2 MMA, M = 256 across the pair, B operand split by N
+// halves), 128 HR pixels (an 8x16 patch, or 128 consecutive queries) per CTA tile. Nothing per-pixel ever touches
+// HBM except the 12 B/px output: activations live in two 64 KB shared-memory A-operand buffers (bf16, K-major,
+// 128B swizzle) and the fp32 accumulators in TMEM.
+//
+// Per layer the [128 x 512] pre-activation is produced as two "half slots" of N = 256: TMEM columns
+// [256h, 256h+128) = K-branch and [256h+128, 256h+256) = Q-branch of output features [128h, 128h+128). The
+// epilogue of half h writes exactly K-chunks 2h, 2h+1 (64 features = one 128-byte swizzle row) of the next A
+// operand and signals each chunk separately, so the next layer's MMAs start while the previous epilogue is still
+// running, and layer 0 of the NEXT tile is interleaved into the epilogue warps during layer 3.
+//
+// Warp roles (384 threads): warp 0 = TMA producer (streams the 3 x 2 x 4 weight stages of [256 x 64] bf16 from L2),
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..11 = 8 epilogue warps
+// (two per TMEM lane quarter; the pair splits every 64-feature chunk 32/32).
+#include <cstdlib>
+
+#include "handle.h"
+#include "ptx.cuh"
+
+namespace diinn {
+using namespace ptx;
+
+namespace sb {
+constexpr int kTileM = 128;
+constexpr int kPatchH = 8, kPatchW = 16;
+constexpr int kActBytes = kTileM * kD * 2;       // 64 KB: one activation buffer (4 K-chunks x 16 KB)
+constexpr int kChunkBytes = kTileM * 128;        // 16 KB: 128 rows x 128 B
+constexpr int kWBytesTotal = 96 * 1024;          // weight stages
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
+
+template <int CG>
+struct Cfg {
+  static constexpr int kStageRows = 256 / CG;
+  static constexpr int kStageBytes = kStageRows * 128;
+  static constexpr int kStages = kWBytesTotal / kStageBytes;  // 3 (CG=1) or 6 (CG=2)
+};
+
+struct Smem {  // after the big buffers
+  uint64_t w_full[6];
+  uint64_t w_empty[6];
+  uint64_t act_ready[2][4];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_ptr;
+  uint32_t pad[3];
+  float partial[kTileM][3];
+};
+constexpr size_t kSmemBytes = 2 * kActBytes + kWBytesTotal + sizeof(Smem);
+static_assert(kSmemBytes <= 232448, "exceeds 227 KB of dynamic shared memory");
+
+struct Work {
+  int n_work;          // work items per CTA pair (CG=2) / CTA (CG=1)
+  int tiles_y, n_txp;  // grid mode
+};
+
+struct RowCtx {
+  const float* prow;  // P row of this pixel's LR cell
+  float rel_h, rel_w, ratio;
+  int64_t out_off;  // offset of channel 0
+  bool valid;
+};
+
+template <int CG>
+__device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& o, const float* __restrict__ P,
+                                           const Work& wk, int work, int rank, int r) {
+  RowCtx rc;
+  if (s.mode == 0) {
+    const int per_img = wk.tiles_y * wk.n_txp;
+    const int b = work / per_img;
+    const int rem = work - b * per_img;
+    const int ty = rem / wk.n_txp, txp = rem - ty * wk.n_txp;
+    const int oh = s.row0 + ty * kPatchH + (r >> 4);
+    const int ow = (txp * CG + rank) * kPatchW + (r & 15);
+    rc.valid = oh < s.row1 && ow < s.W_up;
+    const int ohc = min(oh, s.row1 - 1), owc = min(ow, s.W_up - 1);
+    const int ih = axis_index(s.ax_h, ohc), iw = axis_index(s.ax_w, owc);
+    rc.prow = P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw) * kPCols;
+    rc.rel_h = axis_rel(s.ax_h, ohc, ih);
+    rc.rel_w = axis_rel(s.ax_w, owc, iw);
+    rc.ratio = s.ratio;
+    rc.out_off = b * o.batch_stride + static_cast<int64_t>(ohc - s.row0) * o.row_stride + owc;
+  } else {
+    const int64_t total = static_cast<int64_t>(s.B) * s.Q;
+    const int64_t g = (static_cast<int64_t>(work) * CG + rank) * kTileM + r;
+    rc.valid = g < total;
+    const int64_t gc = rc.valid ? g : total - 1;
+    const int b = static_cast<int>(gc / s.Q);
+    const float ch = __ldg(s.coord + gc * 2), cw = __ldg(s.coord + gc * 2 + 1);
+    const int ih = query_index(s.ax_h, ch), iw = query_index(s.ax_w, cw);
+    rc.prow = P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kPCols;
+    rc.rel_h = query_rel(s.ax_h, ch, ih);
+    rc.rel_w = query_rel(s.ax_w, cw, iw);
+    rc.ratio = __fmul_rn(__fmul_rn(__fmul_rn(__ldg(s.cell + gc * 2), __ldg(s.cell + gc * 2 + 1)), s.hw_f), 0.25f);
+    rc.out_off = gc * 3;
+  }
+  return rc;
+}
+
+// 16-byte unit `unit` (0..7) of row r inside a [128 x 128 B] SWIZZLE_128B chunk
+__device__ __forceinline__ uint32_t swz(uint32_t chunk_base, int r, int unit) {
+  return chunk_base + r * 128 + ((unit ^ (r & 7)) << 4);
+}
+
+template <int CG>
+__device__ __forceinline__ void signal(uint64_t* bar) {
+  if constexpr (CG == 2) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar);
+}
+
+// layer 0 for K-chunk kc of the tile described by rc, features [64kc + 32wg, +32) of row r -> act buffer
+__device__ __forceinline__ void layer0_chunk(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
+                                             const SmallParams& sp) {
+  const uint32_t chunk_base = act_base + kc * kChunkBytes;
+#pragma unroll
+  for (int step = 0; step < 2; ++step) {
+    const int f0 = kc * 64 + wg * 32 + step * 16;
+    float k0[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(rc.prow + f0 + j));
+      k0[j] = v.x, k0[j + 1] = v.y, k0[j + 2] = v.z, k0[j + 3] = v.w;
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      float q[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float4 w = *reinterpret_cast<const float4*>(&sp.wq0[f0 + j + e][0]);
+        float t = fmaf(w.x, rc.rel_h, w.w);
+        t = fmaf(w.y, rc.rel_w, t);
+        t = fmaf(w.z, rc.ratio, t);
+        q[e] = k0[j + e] * __sinf(t);
+      }
+      pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+    }
+    const int unit = wg * 4 + step * 2;
+    st_shared_v4(swz(chunk_base, r, unit), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(swz(chunk_base, r, unit + 1), pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// epilogue of 32 features [128h + 64c + 32wg, +32) of row r for reference layer `layer` (1..3).
+// kLast: accumulate the RGB projection instead of writing the next A operand.
+template <bool kLast>
+__device__ __forceinline__ void epi_chunk(uint32_t tslot, uint32_t out_base, int layer, int h, int c, int wg, int r,
+                                          const RowCtx& rc, const SmallParams& sp, float (&rgb)[3]) {
+  const uint32_t chunk_base = out_base + (2 * h + c) * kChunkBytes;
+#pragma unroll
+  for (int step = 0; step < 2; ++step) {
+    const int col = c * 64 + wg * 32 + step * 16;
+    const int f0 = h * 128 + col;
+    uint32_t vk[16], vq[16];
+    tmem_ld16(tslot + col, vk);
+    tmem_ld16(tslot + 128 + col, vq);
+    float kx[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(rc.prow + layer * kD + f0 + j));
+      kx[j] = v.x, kx[j + 1] = v.y, kx[j + 2] = v.z, kx[j + 3] = v.w;
+    }
+    tmem_ld_wait();
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      float q[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float k = fmaxf(__uint_as_float(vk[j + e]) + kx[j + e], 0.f);
+        const float sn = __sinf(__uint_as_float(vq[j + e]) + sp.bq[layer][f0 + j + e]);
+        q[e] = k * sn;
+        if constexpr (kLast) {
+          const float4 w = *reinterpret_cast<const float4*>(&sp.wl_t[f0 + j + e][0]);
+          rgb[0] = fmaf(w.x, q[e], rgb[0]);
+          rgb[1] = fmaf(w.y, q[e], rgb[1]);
+          rgb[2] = fmaf(w.z, q[e], rgb[2]);
+        }
+      }
+      if constexpr (!kLast) pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+    }
+    if constexpr (!kLast) {
+      const int unit = wg * 4 + step * 2;
+      st_shared_v4(swz(chunk_base, r, unit), pk[0], pk[1], pk[2], pk[3]);
+      st_shared_v4(swz(chunk_base, r, unit + 1), pk[4], pk[5], pk[6], pk[7]);
+    }
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SmallParams sp,
+                    const PixelSource src, const OutSpec out, const float* __restrict__ P, const Work wk,
+                    int* __restrict__ err_flag) {
+  using C = Cfg<CG>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_act = smem;                     // 2 x 64 KB
+  uint8_t* s_w = smem + 2 * kActBytes;       // 96 KB of weight stages
+  Smem& sm = *reinterpret_cast<Smem*>(smem + 2 * kActBytes + kWBytesTotal);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = rank == 0;
+  const int unit_id = blockIdx.x / CG;        // CTA pair (or CTA) index
+  const int n_units = gridDim.x / CG;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) atomicExch(err_flag, 1);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmW);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&sm.w_full[i], 1);
+      mbar_init(&sm.w_empty[i], 1);
+    }
+    for (int i = 0; i < 8; ++i) mbar_init(&sm.act_ready[0][0] + i, kEpiWarps * CG);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.tmem_full[i], 1);
+      mbar_init(&sm.tmem_empty[i], kEpiWarps * CG);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(&sm.tmem_ptr, 512);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_ptr;
+  const uint32_t act0 = smem_u32(s_act);
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int work = unit_id; work < wk.n_work; work += n_units) {
+        for (int s24 = 0; s24 < 24; ++s24, ++it) {  // (layer-1, half, kc) in MMA consumption order
+          const int st = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&sm.w_empty[st], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
+          void* dst = s_w + st * C::kStageBytes;
+          if constexpr (CG == 1)
+            tma_load_2d(dst, &tmW, &sm.w_full[st], 0, s24 * 256);
+          else
+            tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s24 * 256 + rank * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, 256);
+      uint32_t it = 0;            // weight stage counter
+      uint32_t act_phase = 0;     // bit b: parity to wait for on act_ready[b][*]
+      uint32_t slot_uses = 0;     // completed uses per TMEM slot (same for both slots at layer granularity)
+      int t = 0;
+      for (int work = unit_id; work < wk.n_work; work += n_units, ++t) {
+        const int X = t & 1;
+#pragma unroll 1
+        for (int layer = 1; layer <= 3; ++layer) {
+          const int bin = (layer == 2) ? (X ^ 1) : X;  // L1: buf X, L2: buf X^1, L3: buf X
+          const uint32_t a_base = act0 + bin * kActBytes;
+          const uint32_t aph = (act_phase >> bin) & 1;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            // slot h must have been drained by the epilogue of its previous use
+            if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
+            else mbar_wait(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + h * 256;
+#pragma unroll 1
+            for (int kc = 0; kc < 4; ++kc, ++it) {
+              if constexpr (CG == 2) mbar_wait_cluster(&sm.act_ready[bin][kc], aph);
+              else mbar_wait(&sm.act_ready[bin][kc], aph);
+              const int st = it % C::kStages;
+              mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
+              tc_fence_after();
+              const uint32_t a0 = a_base + kc * kChunkBytes;
+              const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
+                              (kc | k) != 0 ? 1u : 0u);
+              umma_commit<CG>(&sm.w_empty[st]);
+            }
+            umma_commit<CG>(&sm.tmem_full[h]);
+          }
+          act_phase ^= 1u << bin;
+          ++slot_uses;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 4;
+    const int wg = ew >> 2;             // which 32-feature half of each 64-feature chunk
+    const int quarter = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;  // tile row == TMEM lane
+    const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t full_uses = 0;             // completed uses per TMEM slot (layer granularity)
+    int t = 0;
+    int work = unit_id;
+    RowCtx rc{};
+    if (work < wk.n_work) {
+      rc = make_row<CG>(src, out, P, wk, work, rank, r);
+      // layer 0 of the first tile -> buf 0
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc) {
+        layer0_chunk(act0, kc, wg, r, rc, sp);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) signal<CG>(&sm.act_ready[0][kc]);
+      }
+    }
+    for (; work < wk.n_work; work += n_units, ++t) {
+      const int X = t & 1;
+      const int next_work = work + n_units;
+      const bool has_next = next_work < wk.n_work;
+      RowCtx rc_next{};
+      float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int layer = 1; layer <= 3; ++layer) {
+        const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
+        const uint32_t out_base = act0 + bout * kActBytes;
+        if (layer == 3 && has_next) rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (layer == 3 && has_next) {
+            // layer 0 of the next tile, two K-chunks ahead of each layer-3 half (buffer X^1 is free: layer 2's
+            // MMAs, its last readers, completed before tmem_full of layer 2 half 1 was observed)
+#pragma unroll 1
+            for (int kc = 2 * h; kc < 2 * h + 2; ++kc) {
+              layer0_chunk(act0 + (X ^ 1) * kActBytes, kc, wg, r, rc_next, sp);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) signal<CG>(&sm.act_ready[X ^ 1][kc]);
+            }
+          }
+          mbar_wait(&sm.tmem_full[h], full_uses & 1);
+          tc_fence_after();
+          const uint32_t tslot = tmem_base + lane_bits + h * 256;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            if (layer < 3) {
+              epi_chunk<false>(tslot, out_base, layer, h, c, wg, r, rc, sp, rgb);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + c]);
+            } else {
+              epi_chunk<true>(tslot, out_base, layer, h, c, wg, r, rc, sp, rgb);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+        }
+        ++full_uses;
+      }
+      // combine the two feature halves of the RGB projection and store
+      if (wg == 1) {
+        if (t > 0) named_bar_sync(2, 256);  // warp-group 0 finished reading the previous tile's partials
+        sm.partial[r][0] = rgb[0];
+        sm.partial[r][1] = rgb[1];
+        sm.partial[r][2] = rgb[2];
+        __threadfence_block();
+        asm volatile("bar.arrive 1, 256;" ::: "memory");
+      } else {
+        named_bar_sync(1, 256);
+        const float o0 = rgb[0] + sm.partial[r][0] + sp.bl[0];
+        const float o1 = rgb[1] + sm.partial[r][1] + sp.bl[1];
+        const float o2 = rgb[2] + sm.partial[r][2] + sp.bl[2];
+        __threadfence_block();
+        if (has_next) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        if (rc.valid) {
+          const int64_t cs = src.mode == 0 ? out.chan_stride : 1;
+          if (out.io_dtype == DIINN_IO_F32) {
+            float* o = static_cast<float*>(out.ptr) + rc.out_off;
+            o[0] = o0, o[cs] = o1, o[2 * cs] = o2;
+          } else {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out.ptr) + rc.out_off;
+            o[0] = __float2bfloat16_rn(o0), o[cs] = __float2bfloat16_rn(o1), o[2 * cs] = __float2bfloat16_rn(o2);
+          }
+        }
+      }
+      rc = rc_next;
+    }
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+}  // namespace sb
+
+int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group,
+                        cudaStream_t s) {
+  using namespace sb;
+  if (cta_group == 0) {
+    static int env_cg = -1;
+    if (env_cg < 0) {
+      const char* e = getenv("DIINN_CTA_GROUP");
+      env_cg = (e && e[0] == '1') ? 1 : 2;
+    }
+    cta_group = env_cg;
+  }
+  static int* err_flag = nullptr;
+  if (!err_flag) {
+    DIINN_CUDA_OK(h, cudaMalloc(&err_flag, sizeof(int)));
+    DIINN_CUDA_OK(h, cudaMemset(err_flag, 0, sizeof(int)));
+  }
+  Work wk{};
+  if (src.mode == 0) {
+    const int tiles_x = (src.W_up + kPatchW - 1) / kPatchW;
+    wk.tiles_y = (src.row1 - src.row0 + kPatchH - 1) / kPatchH;
+    wk.n_txp = (tiles_x + cta_group - 1) / cta_group;
+    wk.n_work = src.B * wk.tiles_y * wk.n_txp;
+  } else {
+    const int64_t total = static_cast<int64_t>(src.B) * src.Q;
+    wk.n_work = static_cast<int>((total + kTileM * cta_group - 1) / (kTileM * cta_group));
+  }
+  int units = h->sm_count / cta_group;
+  if (units > wk.n_work) units = wk.n_work;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * cta_group, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cta_group == 1) {
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(kSmemBytes)));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_b_umma_kernel<1>, h->tmapWB, h->small, src, out, P, wk, err_flag));
+  } else {
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(kSmemBytes)));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_b_umma_kernel<2>, h->tmapWB_half, h->small, src, out, P, wk,
+                                        err_flag));
+  }
+  h->launches += 1;
+  return DIINN_OK;
+}
+
+}  // namespace diinn

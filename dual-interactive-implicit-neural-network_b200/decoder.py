@@ -1,0 +1,279 @@
+"""Host-side mirror of the reference decoder interface on top of the C ABI.
+
+``FusedImplicitDecoder`` is a drop-in for ``ImplicitDecoder`` (/root/reference/src/models/components/diinn.py:39-173):
+same constructor arguments (diinn.py:40), same parameter names/shapes -- so ``load_state_dict(strict=True)`` and
+``SRLitModule.load_from_checkpoint`` (demo2.py:34) work unchanged -- and the same ``forward(x, size, bsize=None)``
+(diinn.py:163). ``DIINN.forward`` (diinn.py:16-19) / ``SRLitModule.forward`` (sr_module.py:104-105) call it as before;
+``swap_decoder`` performs the replacement on an existing model. PyTorch here only supplies device memory, streams and
+parameter bookkeeping; all arithmetic runs in libdiinn_b200.so. There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_PRECISIONS = {"fp32": _lib.COMPUTE_FP32, "bf16": _lib.COMPUTE_BF16}
+
+
+class SineAct(nn.Module):
+    """Parameter-free placeholder so Q.i is a 2-element Sequential like the reference (diinn.py:21-26, 59)."""
+
+    def forward(self, x):
+        return torch.sin(x)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class FusedImplicitDecoder(nn.Module):
+    """B200-native DIINN query decoder (mode=3, init_q=False).
+
+    precision: "bf16" -> tcgen05 tensor cores, bf16 operands / fp32 accumulation (throughput path);
+               "fp32" -> fp32 FMA on CUDA cores end to end (exact-fp32 parity path).
+    The I/O dtype follows ``x.dtype`` (float32 or bfloat16), as in the reference where out.dtype == x.dtype.
+    """
+
+    def __init__(self, in_channels: int = 64, hidden_dims: Sequence[int] = (256, 256, 256, 256), mode: int = 1,
+                 init_q: bool = False, precision: str = "bf16"):
+        super().__init__()
+        hidden_dims = list(hidden_dims)
+        if mode != 3 or init_q:
+            raise NotImplementedError(
+                "FusedImplicitDecoder implements the paper's final model only: mode=3, init_q=False "
+                "(diinn.py:73-80); other wirings are SURVEY.md section 8(f) 'next' rows")
+        if in_channels != 64 or hidden_dims != [256] * 4:
+            raise NotImplementedError("only in_channels=64, hidden_dims=[256]*4 is implemented")
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
+        self.mode, self.init_q, self.precision = mode, init_q, precision
+        # identical module tree (hence state_dict keys and default init / RNG consumption) to diinn.py:53-92
+        self.K = nn.ModuleList()
+        self.Q = nn.ModuleList()
+        last_k, last_q = in_channels * 9, 3
+        for hd in hidden_dims:
+            self.K.append(nn.Sequential(nn.Conv2d(last_k, hd, 1), nn.ReLU()))
+            self.Q.append(nn.Sequential(nn.Conv2d(last_q, hd, 1), SineAct()))
+            last_k, last_q = hd + in_channels * 9, hd
+        self.last_layer = nn.Conv2d(hidden_dims[-1], 3, 1)
+        self._handle = None
+        self._handle_device = None
+        self._packed_versions = None
+        self._workspace = None
+
+    # ------------------------------------------------------------------ handle / weights
+    def _ref_tensors(self):
+        ts = []
+        for i in range(4):
+            ts += [self.K[i][0].weight, self.K[i][0].bias, self.Q[i][0].weight, self.Q[i][0].bias]
+        return ts + [self.last_layer.weight, self.last_layer.bias]
+
+    def _ensure_handle(self, device: torch.device):
+        lib = _lib.load()
+        if device.type != "cuda":
+            raise RuntimeError("FusedImplicitDecoder runs on CUDA (sm_100a) only; there is no CPU fallback")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._handle is None or self._handle_device != idx:
+            self.release()
+            cfg = _lib.Config(64, 256, 4, 3, 0, idx)
+            h = C.c_void_p()
+            _lib.check(lib, None, lib.diinn_create(C.byref(h), C.byref(cfg)))
+            self._handle, self._handle_device, self._packed_versions = h, idx, None
+        tensors = self._ref_tensors()
+        versions = tuple((t.data_ptr(), t._version) for t in tensors)
+        if versions != self._packed_versions:
+            for t in tensors:
+                if t.device.type != "cuda" or t.device.index != idx:
+                    raise RuntimeError("decoder parameters must live on the same CUDA device as the input")
+            ws = [t.detach().to(torch.float32).contiguous() for t in tensors]
+            w = _lib.WeightsF32()
+            for i in range(4):
+                w.k_weight[i], w.k_bias[i] = ws[4 * i].data_ptr(), ws[4 * i + 1].data_ptr()
+                w.q_weight[i], w.q_bias[i] = ws[4 * i + 2].data_ptr(), ws[4 * i + 3].data_ptr()
+            w.last_weight, w.last_bias, w.on_device = ws[16].data_ptr(), ws[17].data_ptr(), 1
+            _lib.check(lib, self._handle, lib.diinn_set_weights(self._handle, C.byref(w), _stream(device)))
+            self._packed_versions = versions
+        return lib, self._handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.load().diinn_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def _get_workspace(self, nbytes: int, device) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
+            self._workspace = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        return self._workspace
+
+    @staticmethod
+    def _io_dtype(x: torch.Tensor) -> int:
+        if x.dtype == torch.float32:
+            return _lib.IO_F32
+        if x.dtype == torch.bfloat16:
+            return _lib.IO_BF16
+        raise TypeError(f"unsupported dtype {x.dtype}: the decoder takes float32 or bfloat16 feature maps")
+
+    def _check_input(self, x: torch.Tensor):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if x.requires_grad:
+                raise RuntimeError("FusedImplicitDecoder is forward-only: call it under torch.no_grad()")
+        if x.dim() != 4 or x.shape[1] != 64:
+            raise ValueError(f"expected a (B,64,H,W) feature map, got {tuple(x.shape)}")
+
+    # ------------------------------------------------------------------ reference interface
+    def forward(self, x: torch.Tensor, size, bsize: Optional[int] = None) -> torch.Tensor:
+        """(B,64,H,W), size=(H_up,W_up) -> (B,3,H_up,W_up). ``bsize`` (the reference's query-chunk size,
+        diinn.py:149-160) is accepted and ignored: no per-pixel intermediate is ever materialised."""
+        H_up, W_up = int(size[0]), int(size[1])
+        return self.forward_rows(x, (H_up, W_up), 0, H_up)
+
+    def forward_rows(self, x: torch.Tensor, size, row0: int, row1: int, out: Optional[torch.Tensor] = None):
+        """HR rows [row0,row1) only -> (B,3,row1-row0,W_up), or written in place into rows [row0,row1) of a full
+        (B,3,H_up,W_up) ``out``. Row tiles are how the query grid shards across GPUs."""
+        self._check_input(x)
+        lib, h = self._ensure_handle(x.device)
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        H_up, W_up = int(size[0]), int(size[1])
+        io = self._io_dtype(x)
+        comp = _PRECISIONS[self.precision]
+        nbytes = lib.diinn_workspace_bytes(h, B, H, W, H_up, W_up, row0, row1, comp)
+        if nbytes == 0:
+            raise _lib.DiinnError(-2, f"bad shape/rows: feat {tuple(x.shape)}, size {(H_up, W_up)}, rows {(row0, row1)}")
+        ws = self._get_workspace(nbytes, x.device)
+        if out is None:
+            res = torch.empty((B, 3, row1 - row0, W_up), dtype=x.dtype, device=x.device)
+            base, bs, cs, rs = res, 3 * (row1 - row0) * W_up, (row1 - row0) * W_up, W_up
+            ptr = res.data_ptr()
+        else:
+            if out.shape != (B, 3, H_up, W_up) or out.dtype != x.dtype or not out.is_contiguous():
+                raise ValueError("out must be a contiguous (B,3,H_up,W_up) tensor of x.dtype")
+            res, bs, cs, rs = out, 3 * H_up * W_up, H_up * W_up, W_up
+            ptr = out.data_ptr() + row0 * W_up * out.element_size()
+        _lib.check(lib, h, lib.diinn_decode(h, _ptr(x), B, Cc, H, W, H_up, W_up, row0, row1, C.c_void_p(ptr), bs, cs,
+                                            rs, _ptr(ws), ws.numel(), io, comp, _stream(x.device)))
+        return res
+
+    def query(self, feat: torch.Tensor, coord: torch.Tensor, cell: torch.Tensor) -> torch.Tensor:
+        """(feat, coord, cell) superset entry named by north_star (signature of LIIF.query_rgb, liif.py:59):
+        coord (B,Q,2) as (h,w) in [-1,1], cell (B,Q,2) -> (B,Q,3), DIINN semantics."""
+        self._check_input(feat)
+        lib, h = self._ensure_handle(feat.device)
+        feat = feat.contiguous()
+        B, Cc, H, W = feat.shape
+        Q = coord.shape[1]
+        coord = coord.to(torch.float32).contiguous()
+        cell = cell.to(torch.float32).contiguous()
+        if coord.shape != (B, Q, 2) or cell.shape != (B, Q, 2):
+            raise ValueError("coord and cell must be (B,Q,2)")
+        io = self._io_dtype(feat)
+        comp = _PRECISIONS[self.precision]
+        nbytes = lib.diinn_query_workspace_bytes(h, B, H, W, Q, comp)
+        ws = self._get_workspace(nbytes, feat.device)
+        out = torch.empty((B, Q, 3), dtype=feat.dtype, device=feat.device)
+        _lib.check(lib, h, lib.diinn_query(h, _ptr(feat), B, Cc, H, W, _ptr(coord), _ptr(cell), Q, _ptr(out), _ptr(ws),
+                                           ws.numel(), io, comp, _stream(feat.device)))
+        return out
+
+    def decode_host(self, feat_host: torch.Tensor, size, row0: int = 0, row1: Optional[int] = None,
+                    out_host: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+        """End-to-end call on HOST tensors (what a CPU-side caller such as demo2.py:40 does): H2D copy of the feature
+        map, decode, D2H copy of the result, stream-synchronised. Use pinned tensors for full PCIe bandwidth."""
+        if feat_host.device.type != "cpu":
+            raise ValueError("decode_host takes CPU tensors")
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        lib, h = self._ensure_handle(device)
+        feat_host = feat_host.contiguous()
+        B, Cc, H, W = feat_host.shape
+        H_up, W_up = int(size[0]), int(size[1])
+        row1 = H_up if row1 is None else row1
+        if out_host is None:
+            out_host = torch.empty((B, 3, row1 - row0, W_up), dtype=feat_host.dtype).pin_memory()
+        io = self._io_dtype(feat_host)
+        comp = _PRECISIONS[self.precision]
+        _lib.check(lib, h, lib.diinn_decode_host(h, _ptr(feat_host), B, Cc, H, W, H_up, W_up, row0, row1,
+                                                 _ptr(out_host), io, comp, _stream(device)))
+        return out_host
+
+    # ------------------------------------------------------------------ debug taps (bit-exact tests)
+    def debug_gather(self, H: int, W: int, H_up: int, W_up: int, device):
+        device = torch.device(device)
+        lib, h = self._ensure_handle(device)
+        ih = torch.empty(H_up, dtype=torch.int32, device=device)
+        iw = torch.empty(W_up, dtype=torch.int32, device=device)
+        rh = torch.empty(H_up, dtype=torch.float32, device=device)
+        rw = torch.empty(W_up, dtype=torch.float32, device=device)
+        _lib.check(lib, h, lib.diinn_debug_gather(h, H, W, H_up, W_up, _ptr(ih), _ptr(iw), _ptr(rh), _ptr(rw),
+                                                  _stream(device)))
+        return ih, iw, rh, rw
+
+    def debug_query_gather(self, H: int, W: int, coord: torch.Tensor, cell: torch.Tensor):
+        device = coord.device
+        lib, h = self._ensure_handle(device)
+        B, Q = coord.shape[:2]
+        coord = coord.to(torch.float32).contiguous()
+        cell = cell.to(torch.float32).contiguous()
+        idx = torch.empty((B, Q), dtype=torch.int32, device=device)
+        rel = torch.empty((B, Q, 2), dtype=torch.float32, device=device)
+        ratio = torch.empty((B, Q), dtype=torch.float32, device=device)
+        _lib.check(lib, h, lib.diinn_debug_query_gather(h, B, H, W, _ptr(coord), _ptr(cell), Q, _ptr(idx), _ptr(rel),
+                                                        _ptr(ratio), _stream(device)))
+        return idx, rel, ratio
+
+    def debug_stage_a(self, x: torch.Tensor) -> torch.Tensor:
+        """Hoisted LR-resolution pre-activations P (B*H*W, 1024) fp32."""
+        lib, h = self._ensure_handle(x.device)
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        P = torch.empty((B * H * W, 1024), dtype=torch.float32, device=x.device)
+        ws = self._get_workspace(B * H * W * 64 * 2 + 4096, x.device)
+        _lib.check(lib, h, lib.diinn_debug_stage_a(h, _ptr(x), B, Cc, H, W, _ptr(P), _ptr(ws), ws.numel(),
+                                                   self._io_dtype(x), _PRECISIONS[self.precision], _stream(x.device)))
+        return P
+
+    def debug_umma_gemm(self, A: torch.Tensor, Bm: torch.Tensor, cta_group: int = 2) -> torch.Tensor:
+        """tcgen05 self-test: (M,K) bf16 x (N,K) bf16 ^T -> (M,N) fp32."""
+        lib, h = self._ensure_handle(A.device)
+        M, K = A.shape
+        N = Bm.shape[0]
+        D = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        _lib.check(lib, h, lib.diinn_debug_umma_gemm(h, _ptr(A.contiguous()), _ptr(Bm.contiguous()), _ptr(D), M, N, K,
+                                                     cta_group, _stream(A.device)))
+        return D
+
+    def launch_count(self) -> int:
+        return int(_lib.load().diinn_launch_count(self._handle)) if self._handle is not None else 0
+
+
+def load_numpy_weights(decoder: FusedImplicitDecoder, weights: dict) -> FusedImplicitDecoder:
+    """Load a reference-layout dict of numpy arrays (e.g. diinn_b200.synth.make_weights) with strict key checking."""
+    sd = {k: torch.from_numpy(v.copy()) for k, v in weights.items()}
+    decoder.load_state_dict(sd, strict=True)
+    return decoder
+
+
+def swap_decoder(model: nn.Module, precision: str = "bf16") -> nn.Module:
+    """Replace the reference decoder inside a ``DIINN`` (diinn.py:8-19) or an ``SRLitModule`` (``.net``,
+    sr_module.py:93) by a FusedImplicitDecoder carrying the same parameters. Call sites stay unchanged."""
+    net = model.net if hasattr(model, "net") and hasattr(model.net, "decoder") else model
+    old = net.decoder
+    new = FusedImplicitDecoder(mode=getattr(old, "mode", 3), init_q=getattr(old, "init_q", False), precision=precision)
+    new.load_state_dict(old.state_dict(), strict=True)
+    p = next(old.parameters())
+    net.decoder = new.to(p.device)
+    return model

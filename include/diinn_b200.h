@@ -1,0 +1,144 @@
+/*
+ * diinn_b200.h -- C ABI of the B200-native (sm_100a) DIINN query decoder.
+ *
+ * One shared library (libdiinn_b200.so) replaces the hot path of the reference:
+ *   ImplicitDecoder.forward / _make_pos_encoding / step (mode 3, init_q=False),
+ *   /root/reference/src/models/components/diinn.py:94-110 (coordinates), :163-173 (forward),
+ *   :132-139 (dual-interactive K/Q MLP), reached from DIINN.forward (diinn.py:18),
+ *   SRLitModule.forward (src/models/sr_module.py:104-105) and demo2.py:40.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every function returns DIINN_OK (0) or a negative diinn_status; nothing throws, nothing exits.
+ *     diinn_last_error() returns a human-readable message for the last failure on that handle
+ *     (or, with a NULL handle, of the calling thread's last failed diinn_create).
+ *   - device pointers unless the name says "host"; the caller owns feat / out / workspace, the library owns
+ *     the repacked weights and its TMA descriptors. No allocation happens inside decode/query once the
+ *     handle has weights, so the calls are CUDA-graph capturable.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). All work is asynchronous on
+ *     that stream except the *_host entry, which synchronises the stream before returning.
+ *   - there is NO CPU fallback: a device that is not sm_100 yields DIINN_ERR_UNSUPPORTED_DEVICE.
+ */
+#ifndef DIINN_B200_H
+#define DIINN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct diinn_handle diinn_handle;
+
+typedef enum diinn_status {
+  DIINN_OK = 0,
+  DIINN_ERR_BAD_ARG = -1,
+  DIINN_ERR_BAD_SHAPE = -2,
+  DIINN_ERR_BAD_DTYPE = -3,
+  DIINN_ERR_UNSUPPORTED_MODE = -4,   /* anything but mode=3, init_q=False, 64 channels, 4x256 hidden */
+  DIINN_ERR_WORKSPACE_TOO_SMALL = -5,
+  DIINN_ERR_CUDA = -6,
+  DIINN_ERR_NO_WEIGHTS = -7,
+  DIINN_ERR_UNSUPPORTED_DEVICE = -8
+} diinn_status;
+
+/* arithmetic path */
+typedef enum diinn_compute {
+  DIINN_COMPUTE_FP32 = 0, /* fp32 FMA on CUDA cores end to end (exact-fp32 path; slow, used for fp32 parity)   */
+  DIINN_COMPUTE_BF16 = 1  /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation, fp32 bias/sin/relu     */
+} diinn_compute;
+
+/* element type of the feat / out buffers */
+typedef enum diinn_io_dtype { DIINN_IO_F32 = 0, DIINN_IO_BF16 = 1 } diinn_io_dtype;
+
+/* Constructor arguments of the reference ImplicitDecoder (diinn.py:40). */
+typedef struct diinn_config {
+  int in_channels; /* 64 */
+  int hidden;      /* 256 (hidden_dims = [256]*n_layers) */
+  int n_layers;    /* 4 */
+  int mode;        /* 3 */
+  int init_q;      /* 0 */
+  int device;      /* CUDA device ordinal the handle lives on */
+} diinn_config;
+
+/* The 18 tensors of the reference state_dict, fp32, contiguous, reference layout:
+ *   k_weight[0] (256,576)  k_weight[1..3] (256,832)  q_weight[0] (256,3)  q_weight[1..3] (256,256)
+ *   *_bias (256)           last_weight (3,256)       last_bias (3)
+ * on_device != 0: pointers are device pointers on the handle's device; otherwise host pointers. */
+typedef struct diinn_weights_f32 {
+  const float* k_weight[4];
+  const float* k_bias[4];
+  const float* q_weight[4];
+  const float* q_bias[4];
+  const float* last_weight;
+  const float* last_bias;
+  int on_device;
+} diinn_weights_f32;
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+int diinn_create(diinn_handle** out, const diinn_config* cfg);
+void diinn_destroy(diinn_handle* h);
+const char* diinn_last_error(const diinn_handle* h);
+
+/* Repack the reference-layout weights into the library's layouts (fp32 hoisted matrices for the CUDA-core
+ * path; bf16, K-permuted, 128B-swizzle tiles for the tcgen05 path). Replaces ImplicitDecoder.__init__ /
+ * load_state_dict (diinn.py:40-92). */
+int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------------- */
+/* Scratch needed by diinn_decode for HR rows [row0,row1) of a (B,C,H,W)->(B,3,H_up,W_up) decode. */
+size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_up, int W_up,
+                             int row0, int row1, int compute);
+
+/* ImplicitDecoder.forward(x, size, bsize) for HR rows [row0,row1) (diinn.py:163-173; bsize is pure scheduling,
+ * diinn.py:149-160, and has no equivalent here because no per-pixel intermediate is ever materialised).
+ *   feat : (B,C,H,W) contiguous NCHW, io_dtype
+ *   out  : element (b,c,row,col) is written at out[b*out_batch_stride + c*out_chan_stride +
+ *          (row-row0)*out_row_stride + col] (strides in elements, io_dtype); for a full contiguous
+ *          (B,3,H_up,W_up) tensor pass out + row0*W_up, 3*H_up*W_up, H_up*W_up, W_up.
+ * row0=0,row1=H_up decodes the whole image; row tiles are how the query grid shards across GPUs. */
+int diinn_decode(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up,
+                 int row0, int row1, void* out, int64_t out_batch_stride, int64_t out_chan_stride,
+                 int64_t out_row_stride, void* workspace, size_t workspace_bytes, int io_dtype, int compute,
+                 void* stream);
+
+/* Same call with HOST buffers: copies feat H2D, decodes, copies the (B,3,row1-row0,W_up) band D2H into
+ * out_host (contiguous), synchronises `stream`. Device scratch is owned and cached by the handle. This is the
+ * call a CPU-side caller such as demo2.py:40 makes; bench.py's `e2e` times it. */
+int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int H, int W, int H_up, int W_up,
+                      int row0, int row1, void* out_host, int io_dtype, int compute, void* stream);
+
+/* Superset entry with the (feat, coord, cell) signature north_star names (LIIF.query_rgb's, liif.py:59):
+ *   coord (B,Q,2) fp32 (h,w) in [-1,1], cell (B,Q,2) fp32, out (B,Q,3) io_dtype.
+ * DIINN semantics per axis: idx = clamp(floor((c+1)*n/2)), rel = (c - centre[idx])*n,
+ * ratio = cell_h*cell_w*H*W/4. On the regular HR grid it reproduces diinn_decode bit for bit. */
+size_t diinn_query_workspace_bytes(const diinn_handle* h, int B, int H, int W, int Q, int compute);
+int diinn_query(diinn_handle* h, const void* feat, int B, int C, int H, int W, const float* coord,
+                const float* cell, int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype,
+                int compute, void* stream);
+
+/* ---- debug taps for the bit-exact tests -------------------------------------------------------------- */
+/* Per-axis nearest-exact source index and scaled relative coordinate, exactly the values
+ * _make_pos_encoding (diinn.py:94-110) produces: ih[H_up], iw[W_up] int32; rel_h[H_up], rel_w[W_up] fp32. */
+int diinn_debug_gather(diinn_handle* h, int H, int W, int H_up, int W_up, int32_t* ih, int32_t* iw,
+                       float* rel_h, float* rel_w, void* stream);
+/* Same for the query entry: idx[B*Q] = ih*W+iw, rel[B*Q*2], ratio[B*Q]. */
+int diinn_debug_query_gather(diinn_handle* h, int B, int H, int W, const float* coord, const float* cell, int Q,
+                             int32_t* idx, float* rel, float* ratio, void* stream);
+/* LR-resolution hoisted pre-activations P (B*H*W, 1024) fp32 = [relu(K0 x) | K_i[:,256:] x + b_i, i=1..3]. */
+int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, int W, float* P, void* workspace,
+                        size_t workspace_bytes, int io_dtype, int compute, void* stream);
+/* tcgen05 self-test: D(M x N fp32) = A(M x K bf16, row-major) * B(N x K bf16, row-major)^T through the same
+ * TMA / UMMA-descriptor / TMEM plumbing the fused kernels use. M%128==0, N%256==0, K%64==0. cta_group 1|2. */
+int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
+                          int cta_group, void* stream);
+
+/* Number of kernels this library launched on the handle since creation (bench.py's gpu_launches). */
+int64_t diinn_launch_count(const diinn_handle* h);
+const char* diinn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIINN_B200_H */

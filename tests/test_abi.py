@@ -1,0 +1,128 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/diinn_b200.h declares; the host-side mirror
+of the reference interface keeps the reference's names, shapes and error behaviour. No compute calls (no GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import diinn_b200
+from diinn_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+def test_header_symbols_are_exported():
+    _ensure_built()
+    header = open(os.path.join(ROOT, "include", "diinn_b200.h")).read()
+    declared = set(re.findall(r"\b(diinn_[a-z_0-9]+)\s*\(", header))
+    declared -= {"diinn_status", "diinn_compute", "diinn_io_dtype"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_version_and_create_errors_without_gpu():
+    _ensure_built()
+    lib = _lib.load()
+    assert b"sm_100a" in lib.diinn_version()
+    h = ctypes.c_void_p()
+    bad = _lib.Config(64, 256, 4, 1, 0, 0)  # mode 1 is not implemented
+    assert lib.diinn_create(ctypes.byref(h), ctypes.byref(bad)) == -4
+    assert b"mode=3" in lib.diinn_last_error(None)
+    if not torch.cuda.is_available():
+        ok = _lib.Config(64, 256, 4, 3, 0, 0)
+        assert lib.diinn_create(ctypes.byref(h), ctypes.byref(ok)) == -8  # no CPU fallback
+        assert not h.value
+    assert lib.diinn_workspace_bytes(None, 1, 48, 48, 192, 192, 0, 192, 1) > 48 * 48 * 1024 * 4
+    assert lib.diinn_workspace_bytes(None, 1, 48, 48, 192, 192, 10, 5, 1) == 0
+
+
+def test_module_mirrors_reference_state_dict():
+    dec = diinn_b200.FusedImplicitDecoder(mode=3, init_q=False)
+    shapes = {k: tuple(v.shape) for k, v in dec.state_dict().items()}
+    assert shapes == synth.weight_shapes()
+    assert sorted(shapes) == sorted(synth.weight_names())
+    # strict round trip with reference-layout tensors
+    w = synth.make_weights(seed=3)
+    diinn_b200.load_numpy_weights(dec, w)
+    back = dec.state_dict()
+    for k, v in w.items():
+        assert np.array_equal(back[k].numpy(), v)
+    with pytest.raises(RuntimeError):
+        dec.load_state_dict({k: torch.zeros(1) for k in shapes}, strict=True)
+
+
+def test_same_default_init_as_reference_layout():
+    """Same module tree => same RNG consumption as ImplicitDecoder(mode=3): seeded inits are reproducible."""
+    torch.manual_seed(0)
+    a = diinn_b200.FusedImplicitDecoder(mode=3).state_dict()
+    torch.manual_seed(0)
+    b = diinn_b200.FusedImplicitDecoder(mode=3).state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert sum(v.numel() for v in a.values()) == 986627
+
+
+def test_unsupported_wirings_raise():
+    for kw in (dict(mode=1), dict(mode=2), dict(mode=4), dict(mode=3, init_q=True),
+               dict(mode=3, in_channels=32), dict(mode=3, hidden_dims=[128] * 4)):
+        with pytest.raises(NotImplementedError):
+            diinn_b200.FusedImplicitDecoder(**kw)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    dec = diinn_b200.FusedImplicitDecoder(mode=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dec(torch.zeros(1, 64, 4, 4), (8, 8))
+
+
+def test_swap_decoder_keeps_call_site():
+    class RefLikeDecoder(torch.nn.Module):  # parameter container with the reference's key layout
+        def __init__(self):
+            super().__init__()
+            self.mode, self.init_q = 3, False
+            inner = diinn_b200.FusedImplicitDecoder(mode=3)
+            self.K, self.Q, self.last_layer = inner.K, inner.Q, inner.last_layer
+
+    class Net(torch.nn.Module):  # stand-in for DIINN (diinn.py:8-19)
+        def __init__(self):
+            super().__init__()
+            self.encoder = torch.nn.Identity()
+            self.decoder = RefLikeDecoder()
+
+        def forward(self, x, size, bsize=None):
+            return self.decoder(self.encoder(x), size, bsize)
+
+    class Lit(torch.nn.Module):  # stand-in for SRLitModule (sr_module.py:93,104-105)
+        def __init__(self):
+            super().__init__()
+            self.net = Net()
+
+        def forward(self, x, size, eval_bsize=None):
+            return self.net(x, size, eval_bsize)
+
+    m = Lit()
+    before = {k: v.clone() for k, v in m.net.decoder.state_dict().items()}
+    diinn_b200.swap_decoder(m, precision="fp32")
+    assert isinstance(m.net.decoder, diinn_b200.FusedImplicitDecoder)
+    after = m.net.decoder.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)
+
+
+def test_row_partition():
+    parts = diinn_b200.row_partition(1356, 8)
+    assert [b - a for a, b in parts] == [170, 170, 170, 170, 169, 169, 169, 169]
+    assert parts[0][0] == 0 and parts[-1][1] == 1356
+    assert all(parts[i][1] == parts[i + 1][0] for i in range(7))
+    assert diinn_b200.row_partition(4320, 8) == [(540 * i, 540 * (i + 1)) for i in range(8)]
+    assert diinn_b200.row_partition(3, 8)[3:] == [(3, 3)] * 5
