@@ -24,7 +24,8 @@ STATUS_NAMES = {
 SYMBOLS = [
     "diinn_create", "diinn_destroy", "diinn_last_error", "diinn_set_weights", "diinn_workspace_bytes",
     "diinn_decode", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_debug_gather",
-    "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_launch_count",
+    "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace",
+    "diinn_launch_count",
     "diinn_version",
 ]
 
@@ -79,6 +80,8 @@ def load() -> C.CDLL:
     lib.diinn_debug_stage_a.restype = i
     lib.diinn_debug_umma_gemm.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]
     lib.diinn_debug_umma_gemm.restype = i
+    lib.diinn_debug_read_trace.argtypes = [vp, vp, i]
+    lib.diinn_debug_read_trace.restype = i
     lib.diinn_launch_count.argtypes = [vp]
     lib.diinn_launch_count.restype = i64
     lib.diinn_version.argtypes = []

@@ -374,6 +374,15 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
   return launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s);
 }
 
+int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n) {
+  if (!h || !host_out || n < 1 || n > 1024) return DIINN_ERR_BAD_ARG;
+  if (!h->trace_dev) return fail(h, DIINN_ERR_BAD_ARG, "no trace: run a bf16 decode with DIINN_TRACE=1 first");
+  cudaSetDevice(h->cfg.device);
+  DIINN_CUDA_OK(h, cudaDeviceSynchronize());
+  DIINN_CUDA_OK(h, cudaMemcpy(host_out, h->trace_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+  return DIINN_OK;
+}
+
 int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
                           int cta_group, void* stream) {
   if (!h || !A || !B || !D) return DIINN_ERR_BAD_ARG;

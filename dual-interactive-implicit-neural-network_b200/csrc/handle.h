@@ -14,6 +14,7 @@ struct Handle {
   bool has_weights = false;
   std::string err;
   int64_t launches = 0;
+  long long* trace_dev = nullptr;  // DIINN_TRACE=1: 1024 clock64 samples of the last stage-B launch
 
   // ---- fp32 CUDA-core path ----
   float* WA32 = nullptr;  // (1024, 576): rows [0,256) K.0; rows 256*i.. K.i[:,256:832]; reference k order c*9+tap

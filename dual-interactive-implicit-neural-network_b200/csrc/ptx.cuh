@@ -127,6 +127,12 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* ma
       : "memory");
 }
 
+// bring [p, p+bytes) into L2 (bytes % 16 == 0); no destination, no completion tracking
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p)), "r"(bytes)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 template <int kCtaGroup>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

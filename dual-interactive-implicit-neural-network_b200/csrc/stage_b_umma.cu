@@ -16,9 +16,10 @@
 // operand and signals each chunk separately, so the next layer's MMAs start while the previous epilogue is still
 // running, and layer 0 of the NEXT tile is interleaved into the epilogue warps during layer 3.
 //
-// Warp roles (384 threads): warp 0 = TMA producer (streams the 3 x 2 x 4 weight stages of [256 x 64] bf16 from L2),
-// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..11 = 8 epilogue warps
-// (two per TMEM lane quarter; the pair splits every 64-feature chunk 32/32).
+// Warp roles (640 threads): warp 0 = TMA producer (streams the 3 x 2 x 4 weight stages of [256 x 64] bf16 from L2),
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps
+// (four per TMEM lane quarter; they split every 64-feature chunk 16/16/16/16). The control warpgroup gives its
+// registers away (setmaxnreg) so each epilogue thread can hold a prefetched slice of P next to its accumulators.
 #include <cstdlib>
 
 #include "handle.h"
@@ -33,8 +34,10 @@ constexpr int kPatchH = 8, kPatchW = 16;
 constexpr int kActBytes = kTileM * kD * 2;       // 64 KB: one activation buffer (4 K-chunks x 16 KB)
 constexpr int kChunkBytes = kTileM * 128;        // 16 KB: 128 rows x 128 B
 constexpr int kWBytesTotal = 96 * 1024;          // weight stages
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
+constexpr int kThreads = 640;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kRegsCtrl = 40, kRegsEpi = 104;
 
 template <int CG>
 struct Cfg {
@@ -51,7 +54,6 @@ struct Smem {  // after the big buffers
   uint64_t tmem_empty[2];
   uint32_t tmem_ptr;
   uint32_t pad[3];
-  float partial[kTileM][3];
 };
 constexpr size_t kSmemBytes = 2 * kActBytes + kWBytesTotal + sizeof(Smem);
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of dynamic shared memory");
@@ -104,6 +106,42 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
   return rc;
 }
 
+// P is produced by stage A right before this kernel and is far larger than L2 for real images, so a tile's first
+// touch of its P rows would be an HBM-latency load in the middle of the epilogue. The producer warp therefore pulls
+// the P rows of the tile two work items ahead into L2 (whole 4 KB rows, one bulk prefetch per LR row segment).
+template <int CG>
+__device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const float* __restrict__ P, const Work& wk,
+                                                   int work, int rank, int lane) {
+  if (s.mode == 0) {
+    const int per_img = wk.tiles_y * wk.n_txp;
+    const int b = work / per_img;
+    const int rem = work - b * per_img;
+    const int ty = rem / wk.n_txp, txp = rem - ty * wk.n_txp;
+    const int oh0 = min(s.row0 + ty * kPatchH, s.row1 - 1), oh1 = min(oh0 + kPatchH - 1, s.row1 - 1);
+    const int ow0 = min((txp * CG + rank) * kPatchW, s.W_up - 1), ow1 = min(ow0 + kPatchW - 1, s.W_up - 1);
+    const int ih0 = axis_index(s.ax_h, oh0), ih1 = axis_index(s.ax_h, oh1);
+    const int iw0 = axis_index(s.ax_w, ow0), iw1 = axis_index(s.ax_w, ow1);
+    const int ncols = iw1 - iw0 + 1;
+    const int segs = (ncols + 3) >> 2;  // <= 16 KB per prefetch
+    const int n = (ih1 - ih0 + 1) * segs;
+    for (int i = lane; i < n; i += 32) {
+      const int ih = ih0 + i / segs, c0 = (i % segs) * 4;
+      const int nc = min(4, ncols - c0);
+      prefetch_l2_bulk(P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw0 + c0) * kPCols,
+                       static_cast<uint32_t>(nc) * kPCols * 4u);
+    }
+  } else {
+    const int64_t total = static_cast<int64_t>(s.B) * s.Q;
+    for (int rr = lane; rr < kTileM; rr += 32) {
+      const int64_t g = (static_cast<int64_t>(work) * CG + rank) * kTileM + rr;
+      if (g >= total) break;
+      const int b = static_cast<int>(g / s.Q);
+      const int ih = query_index(s.ax_h, __ldg(s.coord + g * 2)), iw = query_index(s.ax_w, __ldg(s.coord + g * 2 + 1));
+      prefetch_l2_bulk(P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kPCols, kPCols * 4u);
+    }
+  }
+}
+
 // 16-byte unit `unit` (0..7) of row r inside a [128 x 128 B] SWIZZLE_128B chunk
 __device__ __forceinline__ uint32_t swz(uint32_t chunk_base, int r, int unit) {
   return chunk_base + r * 128 + ((unit ^ (r & 7)) << 4);
@@ -114,82 +152,73 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
   if constexpr (CG == 2) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar);
 }
 
-// layer 0 for K-chunk kc of the tile described by rc, features [64kc + 32wg, +32) of row r -> act buffer
-__device__ __forceinline__ void layer0_chunk(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
-                                             const SmallParams& sp) {
-  const uint32_t chunk_base = act_base + kc * kChunkBytes;
+__device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[4]) {
 #pragma unroll
-  for (int step = 0; step < 2; ++step) {
-    const int f0 = kc * 64 + wg * 32 + step * 16;
-    float k0[16];
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(rc.prow + f0 + j));
-      k0[j] = v.x, k0[j + 1] = v.y, k0[j + 2] = v.z, k0[j + 3] = v.w;
-    }
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      float q[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float4 w = *reinterpret_cast<const float4*>(&sp.wq0[f0 + j + e][0]);
-        float t = fmaf(w.x, rc.rel_h, w.w);
-        t = fmaf(w.y, rc.rel_w, t);
-        t = fmaf(w.z, rc.ratio, t);
-        q[e] = k0[j + e] * __sinf(t);
-      }
-      pk[j >> 1] = pack_bf16x2(q[0], q[1]);
-    }
-    const int unit = wg * 4 + step * 2;
-    st_shared_v4(swz(chunk_base, r, unit), pk[0], pk[1], pk[2], pk[3]);
-    st_shared_v4(swz(chunk_base, r, unit + 1), pk[4], pk[5], pk[6], pk[7]);
-  }
+  for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p) + j);
 }
 
-// epilogue of 32 features [128h + 64c + 32wg, +32) of row r for reference layer `layer` (1..3).
-// kLast: accumulate the RGB projection instead of writing the next A operand.
+// layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
+__device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
+                                            const SmallParams& sp, const float4 (&k0v)[4]) {
+  const uint32_t chunk_base = act_base + kc * kChunkBytes;
+  const int f0 = kc * 64 + wg * 16;
+  const float* k0 = reinterpret_cast<const float*>(k0v);
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    float q[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float4 w = *reinterpret_cast<const float4*>(&sp.wq0[f0 + j + e][0]);
+      float t = fmaf(w.x, rc.rel_h, w.w);
+      t = fmaf(w.y, rc.rel_w, t);
+      t = fmaf(w.z, rc.ratio, t);
+      q[e] = k0[j + e] * __sinf(t);
+    }
+    pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+  }
+  st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
+  st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
+}
+
+// epilogue of 16 features [128h + 64c + 16wg, +16) of row r for reference layer `layer` (1..3); kx = the matching
+// slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
 template <bool kLast>
-__device__ __forceinline__ void epi_chunk(uint32_t tslot, uint32_t out_base, int layer, int h, int c, int wg, int r,
-                                          const RowCtx& rc, const SmallParams& sp, float (&rgb)[3]) {
-  const uint32_t chunk_base = out_base + (2 * h + c) * kChunkBytes;
+__device__ __forceinline__ void epi_step(uint32_t tslot, uint32_t out_base, int layer, int h, int c, int wg, int r,
+                                         const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3],
+                                         long long* tr = nullptr) {
+  const int col = c * 64 + wg * 16;
+  const int f0 = h * 128 + col;
+  const float* kx = reinterpret_cast<const float*>(kxv);
+  uint32_t vk[16], vq[16];
+  tmem_ld16(tslot + col, vk);
+  tmem_ld16(tslot + 128 + col, vq);
+  tmem_ld_wait();
+  if (tr) tr[0] = clock64();
+  uint32_t pk[8];
 #pragma unroll
-  for (int step = 0; step < 2; ++step) {
-    const int col = c * 64 + wg * 32 + step * 16;
-    const int f0 = h * 128 + col;
-    uint32_t vk[16], vq[16];
-    tmem_ld16(tslot + col, vk);
-    tmem_ld16(tslot + 128 + col, vq);
-    float kx[16];
+  for (int j = 0; j < 16; j += 2) {
+    float q[2];
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(rc.prow + layer * kD + f0 + j));
-      kx[j] = v.x, kx[j + 1] = v.y, kx[j + 2] = v.z, kx[j + 3] = v.w;
-    }
-    tmem_ld_wait();
-    uint32_t pk[8];
-#pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-      float q[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float k = fmaxf(__uint_as_float(vk[j + e]) + kx[j + e], 0.f);
-        const float sn = __sinf(__uint_as_float(vq[j + e]) + sp.bq[layer][f0 + j + e]);
-        q[e] = k * sn;
-        if constexpr (kLast) {
-          const float4 w = *reinterpret_cast<const float4*>(&sp.wl_t[f0 + j + e][0]);
-          rgb[0] = fmaf(w.x, q[e], rgb[0]);
-          rgb[1] = fmaf(w.y, q[e], rgb[1]);
-          rgb[2] = fmaf(w.z, q[e], rgb[2]);
-        }
+    for (int e = 0; e < 2; ++e) {
+      const float k = fmaxf(__uint_as_float(vk[j + e]) + kx[j + e], 0.f);
+      const float sn = __sinf(__uint_as_float(vq[j + e]) + sp.bq[layer][f0 + j + e]);
+      q[e] = k * sn;
+      if constexpr (kLast) {
+        const float4 w = *reinterpret_cast<const float4*>(&sp.wl_t[f0 + j + e][0]);
+        rgb[0] = fmaf(w.x, q[e], rgb[0]);
+        rgb[1] = fmaf(w.y, q[e], rgb[1]);
+        rgb[2] = fmaf(w.z, q[e], rgb[2]);
       }
-      if constexpr (!kLast) pk[j >> 1] = pack_bf16x2(q[0], q[1]);
     }
-    if constexpr (!kLast) {
-      const int unit = wg * 4 + step * 2;
-      st_shared_v4(swz(chunk_base, r, unit), pk[0], pk[1], pk[2], pk[3]);
-      st_shared_v4(swz(chunk_base, r, unit + 1), pk[4], pk[5], pk[6], pk[7]);
-    }
+    if constexpr (!kLast) pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+  }
+  if constexpr (!kLast) {
+    const uint32_t chunk_base = out_base + (2 * h + c) * kChunkBytes;
+    if (tr) tr[1] = clock64();
+    st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
+    if (tr) tr[2] = clock64();
   }
 }
 
@@ -197,18 +226,24 @@ template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SmallParams sp,
                     const PixelSource src, const OutSpec out, const float* __restrict__ P, const Work wk,
-                    int* __restrict__ err_flag) {
+                    int* __restrict__ err_flag, long long* __restrict__ trace) {
   using C = Cfg<CG>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_act = smem;                     // 2 x 64 KB
   uint8_t* s_w = smem + 2 * kActBytes;       // 96 KB of weight stages
   Smem& sm = *reinterpret_cast<Smem*>(smem + 2 * kActBytes + kWBytesTotal);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: ptxas then knows it is warp-uniform, so everything indexed by it (feature offsets
+  // into the constant-bank parameters, TMEM columns) goes through uniform registers / LDCU instead of the ADU
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
   const int unit_id = blockIdx.x / CG;        // CTA pair (or CTA) index
   const int n_units = gridDim.x / CG;
+  // optional timeline capture (DIINN_TRACE=1): leader CTA of unit 0, first 8 tiles, clock64 at pipeline events
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+#define DIINN_TR(tile, idx) do { if (tracing && (tile) < 8) trace[(tile) * 128 + (idx)] = clock64(); } while (0)
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) atomicExch(err_flag, 1);
 
@@ -232,11 +267,16 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const uint32_t tmem_base = sm.tmem_ptr;
   const uint32_t act0 = smem_u32(s_act);
 
+  if (warp < 4) {
+  setmaxnreg_dec<kRegsCtrl>();
   if (warp == 0) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int work = unit_id; work < wk.n_work; work += n_units) {
+    // ===================== weight producer (+ L2 prefetch of upcoming tiles' P rows) =====================
+    uint32_t it = 0;
+    if (unit_id + n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, unit_id + n_units, rank, lane);
+    for (int work = unit_id; work < wk.n_work; work += n_units) {
+      if (work + 2 * n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, work + 2 * n_units, rank, lane);
+      __syncwarp();
+      if (lane == 0) {
         for (int s24 = 0; s24 < 24; ++s24, ++it) {  // (layer-1, half, kc) in MMA consumption order
           const int st = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
@@ -249,7 +289,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s24 * 256 + rank * 128);
         }
       }
+      it = __shfl_sync(0xffffffffu, it, 0);
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
     if (lane == 0 && leader) {
@@ -271,14 +313,19 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
             else mbar_wait(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
             tc_fence_after();
+            DIINN_TR(t, (layer - 1) * 20 + h * 10);
             const uint32_t d_tmem = tmem_base + h * 256;
 #pragma unroll 1
             for (int kc = 0; kc < 4; ++kc, ++it) {
-              if constexpr (CG == 2) mbar_wait_cluster(&sm.act_ready[bin][kc], aph);
-              else mbar_wait(&sm.act_ready[bin][kc], aph);
+              if (h == 0) {  // half 1 re-reads chunks whose readiness half 0 already observed
+                if constexpr (CG == 2) mbar_wait_cluster(&sm.act_ready[bin][kc], aph);
+                else mbar_wait(&sm.act_ready[bin][kc], aph);
+              }
+              DIINN_TR(t, (layer - 1) * 20 + h * 10 + 1 + 2 * kc);
               const int st = it % C::kStages;
               mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
               tc_fence_after();
+              DIINN_TR(t, (layer - 1) * 20 + h * 10 + 2 + 2 * kc);
               const uint32_t a0 = a_base + kc * kChunkBytes;
               const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
 #pragma unroll
@@ -288,16 +335,20 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
               umma_commit<CG>(&sm.w_empty[st]);
             }
             umma_commit<CG>(&sm.tmem_full[h]);
+            DIINN_TR(t, (layer - 1) * 20 + h * 10 + 9);
           }
           act_phase ^= 1u << bin;
           ++slot_uses;
         }
       }
     }
-  } else if (warp >= 4) {
+    __syncwarp();
+  }
+  } else {
     // ===================== epilogue warps =====================
+    setmaxnreg_inc<kRegsEpi>();
     const int ew = warp - 4;
-    const int wg = ew >> 2;             // which 32-feature half of each 64-feature chunk
+    const int wg = ew >> 2;             // which 16-feature quarter of each 64-feature chunk
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
     const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
@@ -308,12 +359,20 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     if (work < wk.n_work) {
       rc = make_row<CG>(src, out, P, wk, work, rank, r);
       // layer 0 of the first tile -> buf 0
+      float4 ka[4], kb[4];
+      load16(rc.prow + wg * 16, ka);
 #pragma unroll 1
-      for (int kc = 0; kc < 4; ++kc) {
-        layer0_chunk(act0, kc, wg, r, rc, sp);
+      for (int kc = 0; kc < 4; kc += 2) {
+        load16(rc.prow + (kc + 1) * 64 + wg * 16, kb);
+        layer0_step(act0, kc, wg, r, rc, sp, ka);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) signal<CG>(&sm.act_ready[0][kc]);
+        if (kc + 2 < 4) load16(rc.prow + (kc + 2) * 64 + wg * 16, ka);
+        layer0_step(act0, kc + 1, wg, r, rc, sp, kb);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) signal<CG>(&sm.act_ready[0][kc + 1]);
       }
     }
     for (; work < wk.n_work; work += n_units, ++t) {
@@ -327,62 +386,84 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
         const uint32_t out_base = act0 + bout * kActBytes;
         if (layer == 3 && has_next) rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
+        const float* pl = rc.prow + layer * kD + wg * 16;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+          float4 ka[4], kb[4];
           if (layer == 3 && has_next) {
             // layer 0 of the next tile, two K-chunks ahead of each layer-3 half (buffer X^1 is free: layer 2's
             // MMAs, its last readers, completed before tmem_full of layer 2 half 1 was observed)
-#pragma unroll 1
-            for (int kc = 2 * h; kc < 2 * h + 2; ++kc) {
-              layer0_chunk(act0 + (X ^ 1) * kActBytes, kc, wg, r, rc_next, sp);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) signal<CG>(&sm.act_ready[X ^ 1][kc]);
-            }
+            const float* pn = rc_next.prow + wg * 16;
+            load16(pn + (2 * h) * 64, ka);
+            load16(pn + (2 * h + 1) * 64, kb);
+            layer0_step(act0 + (X ^ 1) * kActBytes, 2 * h, wg, r, rc_next, sp, ka);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.act_ready[X ^ 1][2 * h]);
+            load16(pl + h * 128, ka);  // kx of this half's first chunk, in flight across the second layer-0 step
+            layer0_step(act0 + (X ^ 1) * kActBytes, 2 * h + 1, wg, r, rc_next, sp, kb);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.act_ready[X ^ 1][2 * h + 1]);
+          } else {
+            load16(pl + h * 128, ka);  // in flight while waiting for the accumulators
           }
+          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
           mbar_wait(&sm.tmem_full[h], full_uses & 1);
           tc_fence_after();
+          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
+          load16(pl + h * 128 + 64, kb);
           const uint32_t tslot = tmem_base + lane_bits + h * 256;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            if (layer < 3) {
-              epi_chunk<false>(tslot, out_base, layer, h, c, wg, r, rc, sp, rgb);
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + c]);
-            } else {
-              epi_chunk<true>(tslot, out_base, layer, h, c, wg, r, rc, sp, rgb);
-            }
+          if (layer < 3) {
+            long long* tr = (tracing && warp == 4 && lane == 0 && layer == 2 && t < 8) ? trace + t * 128 + 96 + h * 8 : nullptr;
+            epi_step<false>(tslot, out_base, layer, h, 0, wg, r, sp, ka, rgb, tr);
+            fence_proxy_async_smem();
+            if (tr) tr[3] = clock64();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h]);
+            if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
+            epi_step<false>(tslot, out_base, layer, h, 1, wg, r, sp, kb, rgb, tr ? tr + 4 : nullptr);
+            fence_proxy_async_smem();
+            if (tr) tr[7] = clock64();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + 1]);
+          } else {
+            epi_step<true>(tslot, out_base, layer, h, 0, wg, r, sp, ka, rgb);
+            epi_step<true>(tslot, out_base, layer, h, 1, wg, r, sp, kb, rgb);
           }
+          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
         }
         ++full_uses;
       }
-      // combine the two feature halves of the RGB projection and store
-      if (wg == 1) {
-        if (t > 0) named_bar_sync(2, 256);  // warp-group 0 finished reading the previous tile's partials
-        sm.partial[r][0] = rgb[0];
-        sm.partial[r][1] = rgb[1];
-        sm.partial[r][2] = rgb[2];
-        __threadfence_block();
-        asm volatile("bar.arrive 1, 256;" ::: "memory");
+      // Combine the four feature quarters of the RGB projection in a fixed order (bit-reproducible) and store.
+      // Scratch = the first bytes of activation buffer X: its last readers (layer 3's MMAs) have completed, and its
+      // next writers (layer 1 epilogue of the next tile) wait on named barrier 2 below.
+      float* scratch = reinterpret_cast<float*>(s_act + X * kActBytes);
+      if (wg != 0) {
+        float* p = scratch + ((wg - 1) * kTileM + r) * 3;
+        p[0] = rgb[0], p[1] = rgb[1], p[2] = rgb[2];
+        named_bar_arrive(1, kEpiThreads);
+        if (has_next) named_bar_sync(2, kEpiThreads);
       } else {
-        named_bar_sync(1, 256);
-        const float o0 = rgb[0] + sm.partial[r][0] + sp.bl[0];
-        const float o1 = rgb[1] + sm.partial[r][1] + sp.bl[1];
-        const float o2 = rgb[2] + sm.partial[r][2] + sp.bl[2];
-        __threadfence_block();
-        if (has_next) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        named_bar_sync(1, kEpiThreads);
+        float o[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          o[ch] = ((rgb[ch] + scratch[r * 3 + ch]) + scratch[(kTileM + r) * 3 + ch]) +
+                  scratch[(2 * kTileM + r) * 3 + ch] + sp.bl[ch];
+        if (has_next) named_bar_sync(2, kEpiThreads);
         if (rc.valid) {
           const int64_t cs = src.mode == 0 ? out.chan_stride : 1;
           if (out.io_dtype == DIINN_IO_F32) {
-            float* o = static_cast<float*>(out.ptr) + rc.out_off;
-            o[0] = o0, o[cs] = o1, o[2 * cs] = o2;
+            float* op = static_cast<float*>(out.ptr) + rc.out_off;
+            op[0] = o[0], op[cs] = o[1], op[2 * cs] = o[2];
           } else {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out.ptr) + rc.out_off;
-            o[0] = __float2bfloat16_rn(o0), o[cs] = __float2bfloat16_rn(o1), o[2 * cs] = __float2bfloat16_rn(o2);
+            __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out.ptr) + rc.out_off;
+            op[0] = __float2bfloat16_rn(o[0]), op[cs] = __float2bfloat16_rn(o[1]), op[2 * cs] = __float2bfloat16_rn(o[2]);
           }
         }
       }
@@ -412,6 +493,18 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
     DIINN_CUDA_OK(h, cudaMalloc(&err_flag, sizeof(int)));
     DIINN_CUDA_OK(h, cudaMemset(err_flag, 0, sizeof(int)));
   }
+  static long long* trace = nullptr;
+  static int want_trace = -1;
+  if (want_trace < 0) {
+    const char* e = getenv("DIINN_TRACE");
+    want_trace = (e && e[0] == '1') ? 1 : 0;
+    if (want_trace) {
+      DIINN_CUDA_OK(h, cudaMalloc(&trace, 1024 * sizeof(long long)));
+      DIINN_CUDA_OK(h, cudaMemset(trace, 0, 1024 * sizeof(long long)));
+    }
+  }
+  h->trace_dev = trace;
+
   Work wk{};
   if (src.mode == 0) {
     const int tiles_x = (src.W_up + kPatchW - 1) / kPatchW;
@@ -439,12 +532,12 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   if (cta_group == 1) {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(kSmemBytes)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_b_umma_kernel<1>, h->tmapWB, h->small, src, out, P, wk, err_flag));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_b_umma_kernel<1>, h->tmapWB, h->small, src, out, P, wk, err_flag, trace));
   } else {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(kSmemBytes)));
     DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_b_umma_kernel<2>, h->tmapWB_half, h->small, src, out, P, wk,
-                                        err_flag));
+                                        err_flag, trace));
   }
   h->launches += 1;
   return DIINN_OK;

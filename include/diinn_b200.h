@@ -134,6 +134,10 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
 int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
                           int cta_group, void* stream);
 
+/* DIINN_TRACE=1 in the environment makes the fused stage-B kernel record clock64() at its pipeline events (leader
+ * CTA of the first CTA pair, first 8 tiles); this copies the first n (<=1024) samples to host_out. */
+int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n);
+
 /* Number of kernels this library launched on the handle since creation (bench.py's gpu_launches). */
 int64_t diinn_launch_count(const diinn_handle* h);
 const char* diinn_version(void);

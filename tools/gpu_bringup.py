@@ -175,6 +175,37 @@ def timing():
         break  # cta_group is latched per process on first use
 
 
+@stage
+def mma_rate():
+    np, torch, diinn_b200, synth, orc = _setup()
+    dec = diinn_b200.FusedImplicitDecoder(mode=3).cuda()
+    M, N, K = 8192, 2048, 4096
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda").to(torch.bfloat16)
+    for cg in (1, 2):
+        for _ in range(2):
+            dec.debug_umma_gemm(A, B, cta_group=cg)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dec.debug_umma_gemm(A, B, cta_group=cg)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"mma_rate cg={cg}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    C = A @ B.t()
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(10):
+        C = A @ B.t()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 10
+    print(f"cuBLAS same shape: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+
+
 def main():
     names = sys.argv[1:] or list(STAGES)
     if len(names) == 1 and names[0].startswith("--run="):
