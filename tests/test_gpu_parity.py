@@ -1,0 +1,376 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI (libdiinn_b200.so via
+ctypes); the checker is the CPU oracle (oracle/diinn_oracle.py) and the golden vectors the reference itself produced
+(tests/golden). Tolerances are BASELINE.json's: gather indices / relative coordinates bit-exact, fp32 path <= 1e-4
+max-abs, bf16 path <= 1e-2 max-abs and < 0.01 dB PSNR delta."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import diinn_b200
+from diinn_b200 import synth
+from oracle import diinn_oracle as orc
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a GPU")]
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+# regression guards well inside the contract (measured: fp32 ~5e-8, bf16 ~3e-5 on the default-init weight set)
+TIGHT = {"fp32": 2e-6, "bf16": 2e-4}
+POS_CASES = ["c1", "c2x2", "c2x3", "c2x4", "c3", "c4", "c5", "odd1", "odd2", "odd3", "down"]
+GOLDEN_CASES = ["c1", "c1_bsize", "odd2", "x1_batch", "frac"]
+
+
+def _decoder(weights, precision):
+    dec = diinn_b200.FusedImplicitDecoder(mode=3, init_q=False, precision=precision)
+    return diinn_b200.load_numpy_weights(dec, weights).cuda()
+
+
+def _case(golden_decoder, name):
+    seed, fseed, B, H, W, H_up, W_up, bsize = (int(v) for v in golden_decoder[f"{name}.meta"])
+    kg, qg = (float(v) for v in golden_decoder[f"{name}.gains"])
+    weights = synth.make_weights(seed=seed, k_gain=kg, q_gain=qg)
+    return weights, synth.make_feat(fseed, B, H, W), (H_up, W_up), golden_decoder[f"{name}.out"], (None if bsize < 0 else bsize)
+
+
+def _psnr_delta(a, ref, seed=2):
+    hr = synth.uniform(seed, 3, ref.shape, 0.0, 1.0)
+    return abs(orc.calc_psnr(a, hr) - orc.calc_psnr(ref, hr))
+
+
+@pytest.fixture(scope="module")
+def w0():
+    return synth.make_weights(seed=0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 plumbing
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 512, 576)])
+def test_umma_selftest(cg, shape):
+    M, N, K = shape
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    D = diinn_b200.FusedImplicitDecoder(mode=3).cuda().debug_umma_gemm(A, B, cta_group=cg)
+    ref = A.float() @ B.float().t()
+    assert float((D - ref).abs().max()) <= 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a1: indices and relative coordinates, bit-exact
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", POS_CASES)
+def test_gather_bit_exact(golden_posenc, name):
+    H, W, H_up, W_up = (int(v) for v in golden_posenc[f"{name}.shape"])
+    dec = diinn_b200.FusedImplicitDecoder(mode=3).cuda()
+    ih, iw, rh, rw = dec.debug_gather(H, W, H_up, W_up, "cuda")
+    assert np.array_equal(ih.cpu().numpy(), golden_posenc[f"{name}.ih"])
+    assert np.array_equal(iw.cpu().numpy(), golden_posenc[f"{name}.iw"])
+    assert np.array_equal(rh.cpu().numpy().view(np.uint32), golden_posenc[f"{name}.rel_h"].view(np.uint32))
+    assert np.array_equal(rw.cpu().numpy().view(np.uint32), golden_posenc[f"{name}.rel_w"].view(np.uint32))
+
+
+@pytest.mark.parametrize("shape", [(48, 48, 192, 192), (37, 53, 100, 211), (339, 510, 1356, 2040)])
+def test_query_gather_reproduces_grid(shape):
+    """The (feat, coord, cell) entry fed with the HR grid's cell centres yields the nearest-exact indices bit for bit."""
+    H, W, H_up, W_up = shape
+    ch, cw = orc.grid_coords(H_up, W_up)
+    coord = np.stack(np.meshgrid(ch, cw, indexing="ij"), -1).reshape(1, -1, 2)
+    cell = np.empty_like(coord)
+    cell[..., 0], cell[..., 1] = 2.0 / H_up, 2.0 / W_up
+    dec = diinn_b200.FusedImplicitDecoder(mode=3).cuda()
+    idx, rel, ratio = dec.debug_query_gather(H, W, torch.from_numpy(coord).cuda(), torch.from_numpy(cell).cuda())
+    ih, rh = orc.rel_axis(H, H_up)
+    iw, rw = orc.rel_axis(W, W_up)
+    ref_idx = (ih[:, None] * W + iw[None, :]).reshape(-1)
+    assert np.array_equal(idx.cpu().numpy().reshape(-1), ref_idx)
+    qi, qr = orc.query_index_rel(coord[0, :, 0], H)
+    assert np.array_equal(rel.cpu().numpy()[0, :, 0].view(np.uint32), qr.view(np.uint32))
+    assert abs(float(ratio[0, 0]) - float(orc.ratio_value(H, W, H_up, W_up))) <= 3e-7 * float(ratio[0, 0])  # one or two fp32 roundings
+
+
+def test_query_gather_random_coords():
+    H, W, B, Q = 48, 40, 3, 5000
+    coord, cell = synth.make_query(3, B, Q)
+    dec = diinn_b200.FusedImplicitDecoder(mode=3).cuda()
+    idx, rel, ratio = dec.debug_query_gather(H, W, torch.from_numpy(coord).cuda(), torch.from_numpy(cell).cuda())
+    for b in range(B):
+        ih, rh = orc.query_index_rel(coord[b, :, 0], H)
+        iw, rw = orc.query_index_rel(coord[b, :, 1], W)
+        assert np.array_equal(idx[b].cpu().numpy(), (ih * W + iw).astype(np.int32))
+        assert np.array_equal(rel[b, :, 0].cpu().numpy().view(np.uint32), rh.view(np.uint32))
+        assert np.array_equal(rel[b, :, 1].cpu().numpy().view(np.uint32), rw.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a3/a4: stage A (hoisted LR-resolution pre-activations) and the full decode against the reference's outputs
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 2e-2)])
+def test_stage_a_matches_oracle(w0, precision, tol):
+    feat = synth.make_feat(9, 2, 21, 37)
+    u = orc.unfold3x3(feat).transpose(0, 2, 3, 1).reshape(-1, 576).astype(np.float64)
+    ref = np.empty((u.shape[0], 1024))
+    ref[:, :256] = np.maximum(u @ w0["K.0.0.weight"].reshape(256, 576).T.astype(np.float64) + w0["K.0.0.bias"], 0)
+    for i in range(1, 4):
+        wk = w0[f"K.{i}.0.weight"].reshape(256, 832)[:, 256:].astype(np.float64)
+        ref[:, 256 * i:256 * (i + 1)] = u @ wk.T + w0[f"K.{i}.0.bias"]
+    P = _decoder(w0, precision).debug_stage_a(torch.from_numpy(feat).cuda()).cpu().numpy()
+    assert float(np.abs(P - ref).max()) <= tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_decode_matches_reference_golden(golden_decoder, precision, name):
+    weights, feat, size, ref, bsize = _case(golden_decoder, name)
+    dec = _decoder(weights, precision)
+    with torch.no_grad():
+        out = dec(torch.from_numpy(feat).cuda(), list(size), bsize)
+    assert out.shape == ref.shape and out.dtype == torch.float32 and out.is_contiguous()
+    out = out.cpu().numpy()
+    err = float(np.abs(out - ref).max())
+    assert err <= TOL[precision], err
+    assert err <= TIGHT[precision], err
+    assert _psnr_delta(out, ref) < 0.01
+
+
+@pytest.mark.parametrize("precision,rel_tol", [("fp32", 2e-5), ("bf16", 5e-2)])
+def test_decode_stress_weights(golden_decoder, precision, rel_tol):
+    """Gain-scaled weights (activations O(0.3) instead of being dominated by last_layer.bias):
+    report the error relative to the output range; fp32 path must still meet the absolute 1e-4."""
+    weights, feat, size, ref, _ = _case(golden_decoder, "stress")
+    with torch.no_grad():
+        out = _decoder(weights, precision)(torch.from_numpy(feat).cuda(), size).cpu().numpy()
+    err = float(np.abs(out - ref).max())
+    assert err <= rel_tol * float(np.abs(ref).max()), err
+    if precision == "fp32":
+        assert err <= 1e-4
+    assert _psnr_delta(out, ref) < 0.01
+
+
+def test_bf16_io(golden_decoder):
+    """bf16 feature map in, bf16 image out (config c2 'bf16'): compare with the fp32 reference output."""
+    weights, feat, size, ref, _ = _case(golden_decoder, "c1")
+    with torch.no_grad():
+        out = _decoder(weights, "bf16")(torch.from_numpy(feat).cuda().to(torch.bfloat16), size)
+    assert out.dtype == torch.bfloat16
+    out = out.float().cpu().numpy()
+    assert float(np.abs(out - ref).max()) <= 1e-2
+    assert _psnr_delta(out, ref) < 0.01
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_bsize_is_pure_scheduling(w0, precision):
+    x = torch.from_numpy(synth.make_feat(5, 1, 20, 24)).cuda()
+    dec = _decoder(w0, precision)
+    with torch.no_grad():
+        assert torch.equal(dec(x, (60, 96)), dec(x, (60, 96), 30000))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# sharding: row tiles are bit-identical to the full decode
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_row_tiles_bit_identical(w0, precision, world):
+    x = torch.from_numpy(synth.make_feat(6, 2, 23, 31)).cuda()
+    size = (91, 125)
+    dec = _decoder(w0, precision)
+    with torch.no_grad():
+        full = dec(x, size)
+        tiled = torch.empty_like(full)
+        for r0, r1 in diinn_b200.row_partition(size[0], world):
+            if r1 > r0:
+                dec.forward_rows(x, size, r0, r1, out=tiled)
+        parts = torch.cat([dec.forward_rows(x, size, r0, r1) for r0, r1 in diinn_b200.row_partition(size[0], world)
+                           if r1 > r0], dim=2)
+    assert torch.equal(full, tiled)
+    assert torch.equal(full, parts)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the (feat, coord, cell) superset entry
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_query_random_coords_vs_oracle(w0, precision):
+    """Config c5, sampled form: 16 patches of 48x48, 2304 sampled coords each."""
+    B, H, W, Q = 16, 48, 48, 2304
+    feat = synth.make_feat(8, B, H, W)
+    coord, cell = synth.make_query(3, B, Q)
+    ref = orc.query(w0, feat, coord, cell)
+    with torch.no_grad():
+        out = _decoder(w0, precision).query(torch.from_numpy(feat).cuda(), torch.from_numpy(coord).cuda(),
+                                           torch.from_numpy(cell).cuda())
+    assert out.shape == (B, Q, 3)
+    err = float(np.abs(out.cpu().numpy() - ref).max())
+    assert err <= TOL[precision] and err <= TIGHT[precision], err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_query_on_grid_equals_forward(w0, precision):
+    B, H, W, H_up, W_up = 2, 16, 20, 37, 51
+    feat = synth.make_feat(4, B, H, W)
+    ch, cw = orc.grid_coords(H_up, W_up)
+    coord = np.stack(np.meshgrid(ch, cw, indexing="ij"), -1).reshape(1, -1, 2).repeat(B, 0)
+    cell = np.empty_like(coord)
+    cell[..., 0], cell[..., 1] = 2.0 / H_up, 2.0 / W_up
+    dec = _decoder(w0, precision)
+    x = torch.from_numpy(feat).cuda()
+    with torch.no_grad():
+        grid = dec(x, (H_up, W_up))
+        q = dec.query(x, torch.from_numpy(coord).cuda(), torch.from_numpy(cell).cuda())
+    q = q.reshape(B, H_up, W_up, 3).permute(0, 3, 1, 2)
+    # same indices and relative coordinates; only `ratio` is formed differently (one fp32 rounding)
+    assert float((grid - q).abs().max()) <= 1e-6
+
+
+def test_c5_grid_form(w0):
+    """Config c5, grid form: 16 patches 48x48 decoded on the x1 grid (2304 queries per patch, ratio = 1)."""
+    B, H, W, H_up, W_up = synth.CONFIGS["c5"]
+    feat = synth.make_feat(8, B, H, W)
+    ref = orc.decoder_forward(w0, feat, (H_up, W_up))
+    x = torch.from_numpy(feat).cuda()
+    with torch.no_grad():
+        for precision in ("fp32", "bf16"):
+            out = _decoder(w0, precision)(x, (H_up, W_up)).cpu().numpy()
+            err = float(np.abs(out - ref).max())
+            assert err <= TIGHT[precision], (precision, err)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-buffer entry (what bench.py's e2e times) and the call-site contract
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decode_host_equals_device(w0, precision):
+    feat = torch.from_numpy(synth.make_feat(2, 1, 37, 53))
+    dec = _decoder(w0, precision)
+    with torch.no_grad():
+        dev = dec(feat.cuda(), (100, 211)).cpu()
+        host = dec.decode_host(feat.pin_memory(), (100, 211))
+        band = dec.decode_host(feat.pin_memory(), (100, 211), 40, 77)
+    assert torch.equal(dev, host)
+    assert torch.equal(dev[:, :, 40:77], band)
+
+
+def test_swap_decoder_call_site(w0):
+    """DIINN.forward (diinn.py:16-19) / SRLitModule.forward (sr_module.py:104-105) stand-ins keep working after the
+    decoder is swapped: model(lr, size) with a python list size, as demo2.py:40 calls it."""
+
+    class Net(torch.nn.Module):
+        def __init__(self, dec):
+            super().__init__()
+            self.encoder = torch.nn.Conv2d(3, 64, 3, padding=1)
+            self.decoder = dec
+
+        def forward(self, x, size, bsize=None):
+            return self.decoder(self.encoder(x), size, bsize)
+
+    class Lit(torch.nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.net = net
+
+        def forward(self, x, size, eval_bsize=None):
+            return self.net(x, size, eval_bsize)
+
+    ref_like = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="fp32"), w0)
+    model = Lit(Net(ref_like)).cuda()
+    diinn_b200.swap_decoder(model, precision="bf16")
+    lr = torch.rand(1, 3, 24, 24, device="cuda")
+    with torch.no_grad():
+        sr = model(lr, [96, 96])
+        feat = model.net.encoder(lr)
+    ref = orc.decoder_forward(w0, feat.cpu().numpy(), (96, 96))
+    assert sr.shape == (1, 3, 96, 96)
+    assert float(np.abs(sr.cpu().numpy() - ref).max()) <= 1e-2
+
+
+def test_error_behaviour(w0):
+    dec = _decoder(w0, "bf16")
+    with torch.no_grad():
+        with pytest.raises(ValueError):
+            dec(torch.zeros(1, 32, 8, 8, device="cuda"), (16, 16))
+        with pytest.raises(TypeError):
+            dec(torch.zeros(1, 64, 8, 8, device="cuda", dtype=torch.float16), (16, 16))
+        with pytest.raises(RuntimeError):
+            dec(torch.zeros(1, 64, 8, 8), (16, 16))  # CPU tensor: no fallback
+        with pytest.raises(diinn_b200._lib.DiinnError):
+            dec.forward_rows(torch.zeros(1, 64, 8, 8, device="cuda"), (16, 16), 5, 3)
+    x = torch.zeros(1, 64, 8, 8, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        dec(x, (16, 16))
+
+
+def test_weight_update_is_picked_up(w0):
+    dec = _decoder(w0, "fp32")
+    x = torch.from_numpy(synth.make_feat(1, 1, 8, 8)).cuda()
+    with torch.no_grad():
+        a = dec(x, (16, 16)).clone()
+        dec.last_layer.bias.add_(1.0)
+        b = dec(x, (16, 16))
+    assert float((b - a - 1.0).abs().max()) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: band oracle + cross-path + size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+def _band_check(weights, feat, size, out_np, bands, tol):
+    for r0, r1 in bands:
+        ref = orc.decoder_forward(weights, feat, size, rows=(r0, r1))
+        err = float(np.abs(out_np[:, :, r0:r1] - ref).max())
+        assert err <= tol, (r0, r1, err)
+
+
+@pytest.mark.parametrize("name", ["c2x2", "c2x3", "c2x4"])
+def test_config_c2(w0, name):
+    B, H, W, H_up, W_up = synth.CONFIGS[name]
+    feat = synth.make_feat(1, B, H, W)
+    x = torch.from_numpy(feat).cuda()
+    with torch.no_grad():
+        o32 = _decoder(w0, "fp32")(x, (H_up, W_up))
+        o16 = _decoder(w0, "bf16")(x, (H_up, W_up))
+        o16b = _decoder(w0, "bf16")(x.to(torch.bfloat16), (H_up, W_up)).float()
+    assert float((o16 - o32).abs().max()) <= TIGHT["bf16"]
+    assert float((o16b - o32).abs().max()) <= 1e-2
+    o32n = o32.cpu().numpy()
+    assert _psnr_delta(o16.cpu().numpy(), o32n) < 0.01 and _psnr_delta(o16b.cpu().numpy(), o32n) < 0.01
+    bands = [(0, 2), (H_up // 2 - 1, H_up // 2 + 1), (H_up - 2, H_up)]
+    _band_check(w0, feat, (H_up, W_up), o32n, bands, TIGHT["fp32"])
+
+
+def test_config_c3_div2k(w0):
+    B, H, W, H_up, W_up = synth.CONFIGS["c3"]
+    feat = synth.make_feat(1, B, H, W)
+    x = torch.from_numpy(feat).cuda()
+    with torch.no_grad():
+        dec16 = _decoder(w0, "bf16")
+        o16 = dec16(x, (H_up, W_up))
+        o32 = _decoder(w0, "fp32")(x, (H_up, W_up))
+        # 8-rank row tiling (170,170,170,170,169,169,169,169) is bit-identical to the single decode
+        tiled = torch.empty_like(o16)
+        for r0, r1 in diinn_b200.row_partition(H_up, 8):
+            dec16.forward_rows(x, (H_up, W_up), r0, r1, out=tiled)
+    assert torch.equal(o16, tiled)
+    assert float((o16 - o32).abs().max()) <= TIGHT["bf16"]
+    assert _psnr_delta(o16.cpu().numpy(), o32.cpu().numpy()) < 0.01
+    bands = [(0, 1), (169, 171), (677, 679), (1355, 1356)]  # first/last rows and shard boundaries
+    _band_check(w0, feat, (H_up, W_up), o32.cpu().numpy(), bands, TIGHT["fp32"])
+
+
+def test_config_c4_8k(w0):
+    B, H, W, H_up, W_up = synth.CONFIGS["c4"]
+    feat = synth.make_feat(1, B, H, W)
+    x = torch.from_numpy(feat).cuda()
+    dec16 = _decoder(w0, "bf16")
+    with torch.no_grad():
+        o16 = dec16(x, (H_up, W_up))
+        # shard invariance on two of the eight 540-row tiles
+        for r0, r1 in (diinn_b200.row_partition(H_up, 8)[i] for i in (0, 5)):
+            assert torch.equal(o16[:, :, r0:r1], dec16.forward_rows(x, (H_up, W_up), r0, r1))
+        # fp32 path on a band straddling a shard boundary
+        o32 = _decoder(w0, "fp32").forward_rows(x, (H_up, W_up), 536, 544)
+    assert float((o16[:, :, 536:544] - o32).abs().max()) <= TIGHT["bf16"]
+    o16n = o16[:, :, :, :].cpu().numpy()
+    assert np.isfinite(o16n).all()
+    _band_check(w0, feat, (H_up, W_up), o16n, [(0, 1), (539, 541), (4319, 4320)], TIGHT["bf16"])
