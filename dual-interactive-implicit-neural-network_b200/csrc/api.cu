@@ -182,6 +182,7 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->host_feat_dev);
   cudaFree(h->host_out_dev);
   cudaFree(h->host_ws);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
 }
 
@@ -240,11 +241,24 @@ int diinn_decode(diinn_handle* h, const void* feat, int B, int C, int H, int W, 
                             reinterpret_cast<float*>(ws + plan.off_q1), plan.chunk, s);
   }
   __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + plan.off_nhwc);
+  auto mark = [&]() {
+    if (!h->profiling) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, s);
+      h->prof_events.push_back(e);
+    }
+  };
+  mark();
   if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, s)))
     return rc;
+  mark();
   if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s)))
     return rc;
-  return launch_stage_b_umma(h, src, o, P, 0, s);
+  mark();
+  rc = launch_stage_b_umma(h, src, o, P, 0, s);
+  mark();
+  return rc;
 }
 
 int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int H, int W, int H_up, int W_up,
@@ -372,6 +386,36 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
   __nv_bfloat16* nhwc = static_cast<__nv_bfloat16*>(workspace);
   if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
   return launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s);
+}
+
+int diinn_set_profiling(diinn_handle* h, int enable) {
+  if (!h) return DIINN_ERR_BAD_ARG;
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear();
+  h->profiling = enable != 0;
+  return DIINN_OK;
+}
+
+int diinn_get_kernel_times(diinn_handle* h, double* ms_layout, double* ms_stage_a, double* ms_stage_b,
+                           int64_t* n_decodes) {
+  if (!h || !ms_layout || !ms_stage_a || !ms_stage_b || !n_decodes) return DIINN_ERR_BAD_ARG;
+  cudaSetDevice(h->cfg.device);
+  *ms_layout = *ms_stage_a = *ms_stage_b = 0.0;
+  *n_decodes = 0;
+  const size_t n = h->prof_events.size() / 4;
+  for (size_t i = 0; i < n; ++i) {
+    cudaEvent_t* e = &h->prof_events[4 * i];
+    DIINN_CUDA_OK(h, cudaEventSynchronize(e[3]));
+    float a = 0, b = 0, c = 0;
+    DIINN_CUDA_OK(h, cudaEventElapsedTime(&a, e[0], e[1]));
+    DIINN_CUDA_OK(h, cudaEventElapsedTime(&b, e[1], e[2]));
+    DIINN_CUDA_OK(h, cudaEventElapsedTime(&c, e[2], e[3]));
+    *ms_layout += a, *ms_stage_a += b, *ms_stage_b += c;
+  }
+  *n_decodes = static_cast<int64_t>(n);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear();
+  return DIINN_OK;
 }
 
 int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n) {

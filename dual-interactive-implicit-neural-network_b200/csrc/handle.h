@@ -3,6 +3,7 @@
 #include <cuda.h>
 
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -14,6 +15,9 @@ struct Handle {
   bool has_weights = false;
   std::string err;
   int64_t launches = 0;
+  // optional per-kernel timing of the tcgen05 path (diinn_set_profiling): 4 events per decode
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
   long long* trace_dev = nullptr;  // DIINN_TRACE=1: 1024 clock64 samples of the last stage-B launch
 
   // ---- fp32 CUDA-core path ----

@@ -256,6 +256,20 @@ class FusedImplicitDecoder(nn.Module):
                                                      cta_group, _stream(A.device)))
         return D
 
+    def set_profiling(self, enable: bool, device=None):
+        """Record CUDA events around the three kernels of every bf16-path decode (see diinn_set_profiling)."""
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        lib, h = self._ensure_handle(device)
+        _lib.check(lib, h, lib.diinn_set_profiling(h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """-> dict(layout_ms, stage_a_ms, stage_b_ms, decodes): summed device time since the last call."""
+        lib = _lib.load()
+        a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(lib, self._handle, lib.diinn_get_kernel_times(self._handle, C.byref(a), C.byref(b), C.byref(c),
+                                                                 C.byref(n)))
+        return dict(layout_ms=a.value, stage_a_ms=b.value, stage_b_ms=c.value, decodes=n.value)
+
     def launch_count(self) -> int:
         return int(_lib.load().diinn_launch_count(self._handle)) if self._handle is not None else 0
 

@@ -46,10 +46,9 @@ def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessG
         tile[:, :, : r1 - r0] = decoder.forward_rows(x, (H_up, W_up), r0, r1)
     if gather == "none" or world == 1:
         return tile[:, :, : r1 - r0] if gather == "none" else tile[:, :, :H_up]
-    gathered = torch.empty((world,) + tuple(tile.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(gathered, tile, group=group)
-    out = torch.empty((B, 3, H_up, W_up), dtype=x.dtype, device=x.device)
-    for r, (a, b) in enumerate(parts):
-        if b > a:
-            out[:, :, a:b] = gathered[r, :, :, : b - a]
-    return out
+    # output laid out as the dim-0 concatenation of the per-rank tiles (the form both NCCL and gloo accept)
+    flat = torch.empty((world * B, 3, max_rows, W_up), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(flat, tile, group=group)
+    gathered = flat.view(world, B, 3, max_rows, W_up)
+    # one concatenation kernel re-interleaves the rank-major tiles into NCHW and drops the padding rows
+    return torch.cat([gathered[r, :, :, : b - a] for r, (a, b) in enumerate(parts) if b > a], dim=2)

@@ -134,6 +134,14 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
 int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
                           int cta_group, void* stream);
 
+/* Per-kernel device timing of the tcgen05 path, measured with CUDA events recorded on the caller's stream around
+ * the three kernels of every diinn_decode (layout pass, stage A, stage B) while enabled. diinn_get_kernel_times
+ * synchronises on the recorded events, returns the summed milliseconds and the number of decodes, and resets.
+ * bench.py uses it for the roofline of the dominant kernel (stage B). */
+int diinn_set_profiling(diinn_handle* h, int enable);
+int diinn_get_kernel_times(diinn_handle* h, double* ms_layout, double* ms_stage_a, double* ms_stage_b,
+                           int64_t* n_decodes);
+
 /* DIINN_TRACE=1 in the environment makes the fused stage-B kernel record clock64() at its pipeline events (leader
  * CTA of the first CTA pair, first 8 tiles); this copies the first n (<=1024) samples to host_out. */
 int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n);

@@ -212,7 +212,9 @@ def calc_psnr(sr: np.ndarray, hr: np.ndarray, rgb_range: float = 1.0) -> float:
 # diinn.py:168 does) on PyTorch CPU kernels with all host threads -- used ONLY as bench.py's cpu_baseline
 # / --impl reference arm, because /root/reference does not exist on the GPU box.
 # --------------------------------------------------------------------------------------------------
-def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None):
+def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None, rows=None):
+    """rows=(r0,r1) restricts the work to an HR row band (the bounded sample bench.py times); everything else is the
+    reference's algorithm at full arithmetic cost per pixel (1.97 MFLOP/px, nothing hoisted)."""
     import torch
     import torch.nn.functional as TF
 
@@ -220,8 +222,15 @@ def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None):
         x = torch.as_tensor(feat, dtype=torch.float32)
         B, C, H, W = x.shape
         H_up, W_up = int(size[0]), int(size[1])
-        syn = torch.from_numpy(syn_input(H, W, H_up, W_up)).unsqueeze(0).expand(B, -1, -1, -1)
-        ih = torch.from_numpy(nearest_exact_index(H, H_up))
+        r0, r1 = (0, H_up) if rows is None else (int(rows[0]), int(rows[1]))
+        _, rh = rel_axis(H, H_up)
+        _, rw = rel_axis(W, W_up)
+        syn_np = np.empty((3, r1 - r0, W_up), dtype=F32)
+        syn_np[0] = rh[r0:r1, None]
+        syn_np[1] = rw[None, :]
+        syn_np[2] = ratio_value(H, W, H_up, W_up)
+        syn = torch.from_numpy(syn_np).unsqueeze(0).expand(B, -1, -1, -1)
+        ih = torch.from_numpy(nearest_exact_index(H, H_up)[r0:r1])
         iw = torch.from_numpy(nearest_exact_index(W, W_up))
         u = TF.unfold(x, 3, padding=1).view(B, C * 9, H, W)
         xu = u[:, :, ih][:, :, :, iw]                      # nearest-exact gather -> (B,576,H_up,W_up)
@@ -237,6 +246,6 @@ def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None):
 
         if bsize is None:
             return step(xu, syn).numpy()
-        strip = max(1, bsize // H_up)
+        strip = max(1, bsize // (r1 - r0))
         outs = [step(xu[..., a:a + strip], syn[..., a:a + strip]) for a in range(0, W_up, strip)]
         return torch.cat(outs, -1).numpy()
