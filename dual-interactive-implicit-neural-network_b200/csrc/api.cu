@@ -103,8 +103,20 @@ int make_tmap_2d_bf16(Handle* h, CUtensorMap* map, const void* base, uint64_t in
   return DIINN_OK;
 }
 
+static int make_tmap_4d(Handle* h, CUtensorMap* map, const void* base, CUtensorMapDataType dt, const uint64_t dims_[4],
+                        const uint64_t strides_bytes[3], const uint32_t box_[4]);
+
 int make_tmap_4d_bf16(Handle* h, CUtensorMap* map, const void* base, const uint64_t dims_[4],
                       const uint64_t strides_bytes[3], const uint32_t box_[4]) {
+  return make_tmap_4d(h, map, base, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, dims_, strides_bytes, box_);
+}
+int make_tmap_4d_f32(Handle* h, CUtensorMap* map, const void* base, const uint64_t dims_[4],
+                     const uint64_t strides_bytes[3], const uint32_t box_[4]) {
+  return make_tmap_4d(h, map, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, dims_, strides_bytes, box_);
+}
+
+static int make_tmap_4d(Handle* h, CUtensorMap* map, const void* base, CUtensorMapDataType dt, const uint64_t dims_[4],
+                        const uint64_t strides_bytes[3], const uint32_t box_[4]) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(h, DIINN_ERR_CUDA, "cuTensorMapEncodeTiled not available");
   cuuint64_t dims[4], strides[3];
@@ -112,7 +124,7 @@ int make_tmap_4d_bf16(Handle* h, CUtensorMap* map, const void* base, const uint6
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   for (int i = 0; i < 4; ++i) dims[i] = dims_[i], box[i] = box_[i];
   for (int i = 0; i < 3; ++i) strides[i] = strides_bytes[i];
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, DIINN_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed: " + std::to_string(r));

@@ -23,6 +23,7 @@ struct Handle {
   // ---- fp32 CUDA-core path ----
   float* WA32 = nullptr;  // (1024, 576): rows [0,256) K.0; rows 256*i.. K.i[:,256:832]; reference k order c*9+tap
   float* bA = nullptr;    // (1024): K biases of layers 0..3
+  float bA_host[kPCols] = {};  // host copy: travels to the tcgen05 stage-A kernel as a by-value parameter
   float* bq_dev = nullptr;  // (4, 256): Q biases (device copy of small.bq)
   float* WB32 = nullptr;  // (3, 512, 256): layer i=1..3: rows [0,256) K.i[:, :256], rows [256,512) Q.i
   // ---- tcgen05 path (bf16) ----
@@ -81,6 +82,8 @@ int make_tmap_2d_bf16(Handle* h, CUtensorMap* map, const void* base, uint64_t in
                       uint32_t box_inner, uint32_t box_rows);
 int make_tmap_4d_bf16(Handle* h, CUtensorMap* map, const void* base, const uint64_t dims[4],
                       const uint64_t strides_bytes[3], const uint32_t box[4]);
+int make_tmap_4d_f32(Handle* h, CUtensorMap* map, const void* base, const uint64_t dims[4],
+                     const uint64_t strides_bytes[3], const uint32_t box[4]);
 
 }  // namespace diinn
 

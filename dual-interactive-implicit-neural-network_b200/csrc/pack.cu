@@ -113,6 +113,8 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   static thread_local float tmp_wl[3 * kD];
   DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_wl, w->last_weight, sizeof(float) * 3 * kD, kind, s));
   DIINN_CUDA_OK(h, cudaMemcpyAsync(sp.bl, w->last_bias, sizeof(float) * 3, kind, s));
+  for (int i = 0; i < 4; ++i)
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bA_host + i * kD, w->k_bias[i], sizeof(float) * kD, kind, s));
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
   sp.bl[3] = 0.f;
   for (int f = 0; f < kD; ++f) {

@@ -8,7 +8,8 @@
 // (h+kh-1, w+kw-1), fetched as one TMA 4-D box (64 ch x 16 w x 8 h x 1 b) per tap whose out-of-bounds zero fill IS the
 // unfold's zero padding. B operand: the stacked weight matrix, K re-ordered to tap*64 + c (pack.cu), streamed from L2
 // in [256 x 64] bf16 stages. D: two 256-column TMEM slots, one N-block each, drained by 4 epilogue warps that add the
-// bias, apply ReLU to N-block 0, transpose through padded shared memory and write P with 128-byte coalesced rows.
+// bias, apply ReLU to N-block 0, stage 32x32 fp32 blocks in 128B-swizzled shared memory and hand them to TMA stores
+// (4-D box over P = (1024 cols, W, LR rows, B): the store clips rows/columns outside the image by itself).
 //
 // 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA), warp 2 = TMEM allocator, warps 4..7 = epilogue.
 // CG=2 runs CTA pairs (cta_group::2, M = 256 = two 8x16 LR patches, B split by N halves between the CTAs).
@@ -26,7 +27,7 @@ constexpr int kTapBytes = 128 * 128;            // 16 KB per tap
 constexpr int kABytes = 9 * kTapBytes;          // 144 KB: the whole K extent of one 128-pixel tile
 constexpr int kWBytesTotal = 64 * 1024;
 constexpr int kThreads = 256;
-constexpr int kXposeFloats = 32 * 33;           // per epilogue warp
+constexpr int kStoreBytes = 32 * 128;            // per epilogue warp: 32 rows x 32 fp32, 128B swizzle
 
 template <int CG>
 struct Cfg {
@@ -35,8 +36,12 @@ struct Cfg {
   static constexpr int kStages = kWBytesTotal / kStageBytes;  // 2 (CG=1) or 4 (CG=2)
 };
 
+struct BiasParams {
+  float b[kPCols];
+};
+
 struct Smem {
-  float xpose[4][kXposeFloats];
+  uint8_t store[4][kStoreBytes];  // must stay first: 1024-byte aligned (kABytes + kWBytesTotal is a multiple of 1024)
   uint64_t w_full[4];
   uint64_t w_empty[4];
   uint64_t a_full;
@@ -58,14 +63,16 @@ struct Geo {
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmW,
-                    const float* __restrict__ bA, float* __restrict__ P, const Geo g, int* __restrict__ err_flag) {
+                    const __grid_constant__ CUtensorMap tmP, const __grid_constant__ BiasParams bias, const Geo g,
+                    int* __restrict__ err_flag) {
   using C = Cfg<CG>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_a = smem;
   uint8_t* s_w = smem + kABytes;
   Smem& sm = *reinterpret_cast<Smem*>(smem + kABytes + kWBytesTotal);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const bool leader = rank == 0;
   const int unit_id = blockIdx.x / CG, n_units = gridDim.x / CG;
@@ -74,6 +81,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmF);
     prefetch_tensormap(&tmW);
+    prefetch_tensormap(&tmP);
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&sm.w_full[i], 1);
       mbar_init(&sm.w_empty[i], 1);
@@ -160,13 +168,14 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
   } else if (warp >= 4) {
     const int quarter = warp & 3;
     const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
-    float* xp = sm.xpose[quarter];
+    const uint32_t sbuf = smem_u32(sm.store[quarter]);
+    const uint32_t srow = sbuf + lane * 128;  // this lane's tile row (TMEM lane) inside the warp's 32-row block
     uint32_t slot_use = 0;
     for (int work = unit_id; work < g.n_work; work += n_units) {
       const int b = work / per_img;
       const int rem = work - b * per_img;
       const int ty = rem / g.n_txp, txp = rem - ty * g.n_txp;
-      const int h0 = ty * kPatchH;                       // relative to lr_row0
+      const int h0 = ty * kPatchH + 2 * quarter;          // relative to lr_row0; this warp owns patch rows 2q, 2q+1
       const int w0 = (txp * CG + rank) * kPatchW;
 #pragma unroll 1
       for (int nb = 0; nb < 4; ++nb, ++slot_use) {
@@ -176,28 +185,28 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
         const uint32_t tslot = tmem_base + lane_bits + slot * 256;
 #pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t v0[16], v1[16];
-          tmem_ld16(tslot + c0, v0);
-          tmem_ld16(tslot + c0 + 16, v1);
+          uint32_t v[32];
+          tmem_ld16(tslot + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld16(tslot + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
           tmem_ld_wait();
-          __syncwarp();  // previous block's readers are done with xp
+          const int n0 = nb * 256 + c0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            xp[lane * 33 + j] = __uint_as_float(v0[j]);
-            xp[lane * 33 + 16 + j] = __uint_as_float(v1[j]);
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + bias.b[n0 + j];
+            if (nb == 0) x = fmaxf(x, 0.f);  // first 256 columns are k0 = relu(K0 x + b0)
+            v[j] = __float_as_uint(x);
           }
+          // the previous TMA store of this warp must have finished reading the staging block
+          if (lane == 0) bulk_wait_group_read0();
           __syncwarp();
-          const int n = nb * 256 + c0 + lane;
-          const float bias = __ldg(bA + n);
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int r = quarter * 32 + rr;
-            const int hh = h0 + (r >> 4), ww = w0 + (r & 15);
-            if (hh < g.lr_rows && ww < g.W) {
-              float v = xp[rr * 33 + lane] + bias;
-              if (nb == 0) v = fmaxf(v, 0.f);
-              P[(static_cast<size_t>(b) * g.lr_rows + hh) * g.W * kPCols + static_cast<size_t>(ww) * kPCols + n] = v;
-            }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            st_shared_v4(srow + ((u ^ (lane & 7)) << 4), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmP, sm.store[quarter], n0, w0, h0, b);
+            bulk_commit_group();
           }
         }
         tc_fence_before();
@@ -208,6 +217,8 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
         }
       }
     }
+    if (lane == 0) bulk_wait_group0();
+    __syncwarp();
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -238,6 +249,15 @@ int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H,
   const uint32_t box[4] = {kC, kPatchW, kPatchH, 1};
   int rc = make_tmap_4d_bf16(h, &tmF, feat_nhwc, dims, strides, box);
   if (rc) return rc;
+  CUtensorMap tmP;
+  const uint64_t pdims[4] = {static_cast<uint64_t>(kPCols), static_cast<uint64_t>(W), static_cast<uint64_t>(lr_rows),
+                             static_cast<uint64_t>(B)};
+  const uint64_t pstrides[3] = {kPCols * 4ull, static_cast<uint64_t>(W) * kPCols * 4ull,
+                                static_cast<uint64_t>(lr_rows) * W * kPCols * 4ull};
+  const uint32_t pbox[4] = {32, kPatchW, 2, 1};
+  if ((rc = make_tmap_4d_f32(h, &tmP, P, pdims, pstrides, pbox))) return rc;
+  static_assert(sizeof(BiasParams) == sizeof(float) * kPCols, "bias block");
+  const BiasParams& bias = *reinterpret_cast<const BiasParams*>(h->bA_host);
   Geo g{};
   g.B = B, g.H = H, g.W = W, g.fr0 = fr0, g.lr_row0 = lr_row0, g.lr_rows = lr_rows;
   const int tiles_x = (W + kPatchW - 1) / kPatchW;
@@ -261,11 +281,11 @@ int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H,
   if (cta_group == 1) {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(kSmemBytes)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<1>, tmF, h->tmapWA, h->bA, P, g, err_flag));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<1>, tmF, h->tmapWA, tmP, bias, g, err_flag));
   } else {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(kSmemBytes)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<2>, tmF, h->tmapWA_half, h->bA, P, g, err_flag));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<2>, tmF, h->tmapWA_half, tmP, bias, g, err_flag));
   }
   h->launches += 1;
   return DIINN_OK;
