@@ -24,7 +24,7 @@ STATUS_NAMES = {
 SYMBOLS = [
     "diinn_create", "diinn_destroy", "diinn_last_error", "diinn_set_weights", "diinn_workspace_bytes",
     "diinn_decode", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_debug_gather",
-    "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace", "diinn_set_profiling", "diinn_get_kernel_times",
+    "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace", "diinn_debug_umma_pace", "diinn_set_profiling", "diinn_get_kernel_times",
     "diinn_launch_count",
     "diinn_version",
 ]
@@ -82,6 +82,8 @@ def load() -> C.CDLL:
     lib.diinn_debug_umma_gemm.restype = i
     lib.diinn_debug_read_trace.argtypes = [vp, vp, i]
     lib.diinn_debug_read_trace.restype = i
+    lib.diinn_debug_umma_pace.argtypes = [vp, i, i, i, i, vp, i, vp]
+    lib.diinn_debug_umma_pace.restype = i
     lib.diinn_set_profiling.argtypes = [vp, i]
     lib.diinn_set_profiling.restype = i
     lib.diinn_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -400,6 +400,16 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
   return launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s);
 }
 
+int diinn_debug_umma_pace(diinn_handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma,
+                          int noise, void* stream) {
+  if (!h || !cyc_per_mma) return DIINN_ERR_BAD_ARG;
+  if ((cta_group != 1 && cta_group != 2) || n_cols < 16 || n_cols > 256 || n_cols % 16 || iters < 1 || n_ctas < cta_group ||
+      n_ctas % cta_group)
+    return fail(h, DIINN_ERR_BAD_SHAPE, "bad pace-probe arguments");
+  cudaSetDevice(h->cfg.device);
+  return launch_umma_pace(h, cta_group, n_cols, iters, n_ctas, cyc_per_mma, noise, static_cast<cudaStream_t>(stream));
+}
+
 int diinn_set_profiling(diinn_handle* h, int enable) {
   if (!h) return DIINN_ERR_BAD_ARG;
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);

@@ -77,6 +77,8 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
 // umma_selftest.cu
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
                          cudaStream_t s);
+int launch_umma_pace(Handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma, int noise,
+                     cudaStream_t s);
 // tensor maps (api.cu)
 int make_tmap_2d_bf16(Handle* h, CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
                       uint32_t box_inner, uint32_t box_rows);

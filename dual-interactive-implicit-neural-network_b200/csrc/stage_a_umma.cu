@@ -102,7 +102,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
   const int per_img = g.tiles_y * g.n_txp;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp walks the loops (uniform registers); one elected lane issues the TMA / expect_tx instructions
       uint32_t it = 0;
       int t = 0;
       for (int work = unit_id; work < g.n_work; work += n_units, ++t) {
@@ -112,28 +112,35 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
         const int h0 = g.lr_row0 + ty * kPatchH;
         const int w0 = (txp * CG + rank) * kPatchW;
         mbar_wait(&sm.a_empty, (t & 1) ^ 1);
-        if (leader) mbar_arrive_expect_tx(&sm.a_full, kABytes * CG);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&sm.a_full, kABytes * CG);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
-          if constexpr (CG == 1) tma_load_4d(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
-          else tma_load_4d_2sm(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
+            if constexpr (CG == 1) tma_load_4d(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
+            else tma_load_4d_2sm(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
+          }
         }
+        __syncwarp();
 #pragma unroll 1
         for (int s36 = 0; s36 < 36; ++s36, ++it) {  // (n-block, tap)
           const int st = it % C::kStages;
           mbar_wait(&sm.w_empty[st], ((it / C::kStages) & 1) ^ 1);
-          if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
-          void* dst = s_w + st * C::kStageBytes;
-          if constexpr (CG == 1) tma_load_2d(dst, &tmW, &sm.w_full[st], 0, s36 * 256);
-          else tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s36 * 256 + rank * 128);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
+            void* dst = s_w + st * C::kStageBytes;
+            if constexpr (CG == 1) tma_load_2d(dst, &tmW, &sm.w_full[st], 0, s36 * 256);
+            else tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s36 * 256 + rank * 128);
+          }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
+    if (leader) {  // whole warp loops, tcgen05 instructions under elect_one() (see stage_b_umma.cu)
       constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, 256);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0, slot_use = 0;
       int t = 0;
       for (int work = unit_id; work < g.n_work; work += n_units, ++t) {
@@ -145,7 +152,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
           if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[slot], (use & 1) ^ 1);
           else mbar_wait(&sm.tmem_empty[slot], (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + slot * 256;
+          const uint32_t d_tmem = tmem_u + slot * 256;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++it) {
             const int st = it % C::kStages;
@@ -153,15 +160,20 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
             tc_fence_after();
             const uint32_t a0 = smem_u32(s_a + tap * kTapBytes);
             const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
-                            (tap | k) != 0 ? 1u : 0u);
-            umma_commit<CG>(&sm.w_empty[st]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
+                              (tap | k) != 0 ? 1u : 0u);
+              umma_commit<CG>(&sm.w_empty[st]);
+              if (tap == 8) {
+                umma_commit<CG>(&sm.tmem_full[slot]);
+                if (nb == 3) umma_commit<CG>(&sm.a_empty);  // every MMA reading this tile's A has completed when this fires
+              }
+            }
+            __syncwarp();
           }
-          umma_commit<CG>(&sm.tmem_full[slot]);
         }
-        umma_commit<CG>(&sm.a_empty);  // all MMAs reading this tile's A have completed when this fires
       }
     }
     __syncwarp();

@@ -17,9 +17,10 @@
 // running, and layer 0 of the NEXT tile is interleaved into the epilogue warps during layer 3.
 //
 // Warp roles (640 threads): warp 0 = TMA producer (streams the 3 x 2 x 4 weight stages of [256 x 64] bf16 from L2),
-// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps
-// (four per TMEM lane quarter; they split every 64-feature chunk 16/16/16/16). The control warpgroup gives its
-// registers away (setmaxnreg) so each epilogue thread can hold a prefetched slice of P next to its accumulators.
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps in two groups of 8:
+// group g drains TMEM half slot g of every layer, so one half's epilogue runs under the other half's MMAs. The control
+// warpgroup gives its registers away (setmaxnreg) so each epilogue thread can hold a prefetched slice of P next to
+// its accumulators.
 #include <cstdlib>
 
 #include "handle.h"
@@ -33,7 +34,7 @@ constexpr int kTileM = 128;
 constexpr int kPatchH = 8, kPatchW = 16;
 constexpr int kActBytes = kTileM * kD * 2;       // 64 KB: one activation buffer (4 K-chunks x 16 KB)
 constexpr int kChunkBytes = kTileM * 128;        // 16 KB: 128 rows x 128 B
-constexpr int kWBytesTotal = 96 * 1024;          // weight stages
+constexpr int kWBytesTotal = 80 * 1024;          // weight stages
 constexpr int kThreads = 640;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
@@ -54,6 +55,7 @@ struct Smem {  // after the big buffers
   uint64_t tmem_empty[2];
   uint32_t tmem_ptr;
   uint32_t pad[3];
+  float partial[3][kTileM][3];  // RGB partial sums of the three non-reducing warp sets
 };
 constexpr size_t kSmemBytes = 2 * kActBytes + kWBytesTotal + sizeof(Smem);
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of dynamic shared memory");
@@ -253,10 +255,10 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_init(&sm.w_full[i], 1);
       mbar_init(&sm.w_empty[i], 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&sm.act_ready[0][0] + i, kEpiWarps * CG);
+    for (int i = 0; i < 8; ++i) mbar_init(&sm.act_ready[0][0] + i, (kEpiWarps / 2) * CG);  // one group per chunk
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.tmem_full[i], 1);
-      mbar_init(&sm.tmem_empty[i], kEpiWarps * CG);
+      mbar_init(&sm.tmem_empty[i], (kEpiWarps / 2) * CG);
     }
     fence_barrier_init();
   }
@@ -276,11 +278,13 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     for (int work = unit_id; work < wk.n_work; work += n_units) {
       if (work + 2 * n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, work + 2 * n_units, rank, lane);
       __syncwarp();
-      if (lane == 0) {
-        for (int s24 = 0; s24 < 24; ++s24, ++it) {  // (layer-1, half, kc) in MMA consumption order
-          const int st = it % C::kStages;
-          const uint32_t ph = (it / C::kStages) & 1;
-          mbar_wait(&sm.w_empty[st], ph ^ 1);
+      // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
+      // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues
+      for (int s24 = 0; s24 < 24; ++s24, ++it) {  // (layer-1, half, kc) in MMA consumption order
+        const int st = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
+        mbar_wait(&sm.w_empty[st], ph ^ 1);
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
           void* dst = s_w + st * C::kStageBytes;
           if constexpr (CG == 1)
@@ -288,14 +292,19 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           else
             tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s24 * 256 + rank * 128);
         }
+        __syncwarp();
       }
-      it = __shfl_sync(0xffffffffu, it, 0);
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (lane == 0 && leader) {
+    // The whole warp runs the loop and waits on the barriers; only the tcgen05 instructions sit under elect_one().
+    // With every operand derived from warp-uniform values ptxas builds the descriptors in uniform registers; issued
+    // from a divergent single-lane region instead, each UTCHMMA costs an ELECT + 5x R2UR.BROADCAST waterfall
+    // (~100 clk), which capped the tensor pipe at ~200 clk per MMA instead of 128.
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, 256);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0;            // weight stage counter
       uint32_t act_phase = 0;     // bit b: parity to wait for on act_ready[b][*]
       uint32_t slot_uses = 0;     // completed uses per TMEM slot (same for both slots at layer granularity)
@@ -313,29 +322,32 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
             else mbar_wait(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
             tc_fence_after();
-            DIINN_TR(t, (layer - 1) * 20 + h * 10);
-            const uint32_t d_tmem = tmem_base + h * 256;
+            if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10);
+            const uint32_t d_tmem = tmem_u + h * 256;
 #pragma unroll 1
             for (int kc = 0; kc < 4; ++kc, ++it) {
               if (h == 0) {  // half 1 re-reads chunks whose readiness half 0 already observed
                 if constexpr (CG == 2) mbar_wait_cluster(&sm.act_ready[bin][kc], aph);
                 else mbar_wait(&sm.act_ready[bin][kc], aph);
               }
-              DIINN_TR(t, (layer - 1) * 20 + h * 10 + 1 + 2 * kc);
+              if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 1 + 2 * kc);
               const int st = it % C::kStages;
               mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
               tc_fence_after();
-              DIINN_TR(t, (layer - 1) * 20 + h * 10 + 2 + 2 * kc);
+              if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 2 + 2 * kc);
               const uint32_t a0 = a_base + kc * kChunkBytes;
               const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
-                              (kc | k) != 0 ? 1u : 0u);
-              umma_commit<CG>(&sm.w_empty[st]);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
+                                (kc | k) != 0 ? 1u : 0u);
+                umma_commit<CG>(&sm.w_empty[st]);
+                if (kc == 3) umma_commit<CG>(&sm.tmem_full[h]);
+              }
+              __syncwarp();
             }
-            umma_commit<CG>(&sm.tmem_full[h]);
-            DIINN_TR(t, (layer - 1) * 20 + h * 10 + 9);
+            if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 9);
           }
           act_phase ^= 1u << bin;
           ++slot_uses;
@@ -346,34 +358,46 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   }
   } else {
     // ===================== epilogue warps =====================
+    // Two groups of 8 warps: group g owns TMEM half slot g of every layer (and K-chunks 2g, 2g+1 of layer 0), so the
+    // epilogue of one half overlaps the MMAs of the other and each group has a whole layer period per half slot.
+    // Inside a group the two warps of a TMEM lane quarter split every 64-feature chunk 32/32 and walk it in
+    // 16-feature steps, with the matching slice of P prefetched one step ahead.
     setmaxnreg_inc<kRegsEpi>();
     const int ew = warp - 4;
-    const int wg = ew >> 2;             // which 16-feature quarter of each 64-feature chunk
+    const int grp = ew >> 3;            // half slot owned by this warp
+    const int sub = (ew >> 2) & 1;      // which 32-feature half of every 64-feature chunk
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
-    const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t full_uses = 0;             // completed uses per TMEM slot (layer granularity)
+    const int h = grp;
+    const uint32_t tslot = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + h * 256;
+    const bool tracer = tracing && (warp == 4 + 8 * h) && lane == 0;
+    uint32_t full_uses = 0;             // completed uses of this group's TMEM slot
     int t = 0;
     int work = unit_id;
     RowCtx rc{};
+
+    // this group's two K-chunks of layer 0 for the tile described by rcx -> activation buffer `bufidx`
+    auto layer0_pair = [&](int bufidx, const RowCtx& rcx) {
+      const uint32_t buf = act0 + bufidx * kActBytes;
+      const float* pn = rcx.prow + sub * 32;
+      float4 ka[4], kb[4];
+      load16(pn + (2 * grp) * 64, ka);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int kc = 2 * grp + c;
+        load16(pn + kc * 64 + 16, kb);
+        layer0_step(buf, kc, sub * 2, r, rcx, sp, ka);
+        if (c == 0) load16(pn + (kc + 1) * 64, ka);
+        layer0_step(buf, kc, sub * 2 + 1, r, rcx, sp, kb);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc]);
+      }
+    };
+
     if (work < wk.n_work) {
       rc = make_row<CG>(src, out, P, wk, work, rank, r);
-      // layer 0 of the first tile -> buf 0
-      float4 ka[4], kb[4];
-      load16(rc.prow + wg * 16, ka);
-#pragma unroll 1
-      for (int kc = 0; kc < 4; kc += 2) {
-        load16(rc.prow + (kc + 1) * 64 + wg * 16, kb);
-        layer0_step(act0, kc, wg, r, rc, sp, ka);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) signal<CG>(&sm.act_ready[0][kc]);
-        if (kc + 2 < 4) load16(rc.prow + (kc + 2) * 64 + wg * 16, ka);
-        layer0_step(act0, kc + 1, wg, r, rc, sp, kb);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) signal<CG>(&sm.act_ready[0][kc + 1]);
-      }
+      layer0_pair(0, rc);  // first tile -> buffer 0
     }
     for (; work < wk.n_work; work += n_units, ++t) {
       const int X = t & 1;
@@ -385,77 +409,68 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       for (int layer = 1; layer <= 3; ++layer) {
         const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
         const uint32_t out_base = act0 + bout * kActBytes;
-        if (layer == 3 && has_next) rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
-        const float* pl = rc.prow + layer * kD + wg * 16;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          float4 ka[4], kb[4];
-          if (layer == 3 && has_next) {
-            // layer 0 of the next tile, two K-chunks ahead of each layer-3 half (buffer X^1 is free: layer 2's
-            // MMAs, its last readers, completed before tmem_full of layer 2 half 1 was observed)
-            const float* pn = rc_next.prow + wg * 16;
-            load16(pn + (2 * h) * 64, ka);
-            load16(pn + (2 * h + 1) * 64, kb);
-            layer0_step(act0 + (X ^ 1) * kActBytes, 2 * h, wg, r, rc_next, sp, ka);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) signal<CG>(&sm.act_ready[X ^ 1][2 * h]);
-            load16(pl + h * 128, ka);  // kx of this half's first chunk, in flight across the second layer-0 step
-            layer0_step(act0 + (X ^ 1) * kActBytes, 2 * h + 1, wg, r, rc_next, sp, kb);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) signal<CG>(&sm.act_ready[X ^ 1][2 * h + 1]);
-          } else {
-            load16(pl + h * 128, ka);  // in flight while waiting for the accumulators
-          }
-          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
-          mbar_wait(&sm.tmem_full[h], full_uses & 1);
-          tc_fence_after();
-          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
-          load16(pl + h * 128 + 64, kb);
-          const uint32_t tslot = tmem_base + lane_bits + h * 256;
-          if (layer < 3) {
-            long long* tr = (tracing && warp == 4 && lane == 0 && layer == 2 && t < 8) ? trace + t * 128 + 96 + h * 8 : nullptr;
-            epi_step<false>(tslot, out_base, layer, h, 0, wg, r, sp, ka, rgb, tr);
-            fence_proxy_async_smem();
-            if (tr) tr[3] = clock64();
-            __syncwarp();
-            if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h]);
-            if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
-            epi_step<false>(tslot, out_base, layer, h, 1, wg, r, sp, kb, rgb, tr ? tr + 4 : nullptr);
-            fence_proxy_async_smem();
-            if (tr) tr[7] = clock64();
-            __syncwarp();
-            if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + 1]);
-          } else {
-            epi_step<true>(tslot, out_base, layer, h, 0, wg, r, sp, ka, rgb);
-            epi_step<true>(tslot, out_base, layer, h, 1, wg, r, sp, kb, rgb);
-          }
-          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
-          if (warp == 4 && lane == 0) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
+        if (layer == 3 && has_next) {
+          // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs. Group 1 has consumed
+          // tmem_full[1] of layer 2 itself; group 0 observes the same phase before it overwrites the buffer.
+          rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
+          if (grp == 0) mbar_wait(&sm.tmem_full[1], (full_uses - 1) & 1);
+          layer0_pair(X ^ 1, rc_next);
         }
+        const float* pl = rc.prow + layer * kD + h * 128 + sub * 32;  // P slice of features 128h + 64c + 32sub + 16s
+        float4 ka[4], kb[4];
+        load16(pl, ka);  // in flight while waiting for the accumulators
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
+        mbar_wait(&sm.tmem_full[h], full_uses & 1);
+        tc_fence_after();
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
+        load16(pl + 16, kb);
+        if (layer < 3) {
+          long long* tr = (tracer && layer == 2 && t < 8) ? trace + t * 128 + 96 + h * 8 : nullptr;
+          epi_step<false>(tslot, out_base, layer, h, 0, sub * 2, r, sp, ka, rgb, tr);
+          load16(pl + 64, ka);
+          epi_step<false>(tslot, out_base, layer, h, 0, sub * 2 + 1, r, sp, kb, rgb);
+          fence_proxy_async_smem();
+          if (tr) tr[3] = clock64();
+          __syncwarp();
+          if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h]);
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
+          load16(pl + 64 + 16, kb);
+          epi_step<false>(tslot, out_base, layer, h, 1, sub * 2, r, sp, ka, rgb, tr ? tr + 4 : nullptr);
+          epi_step<false>(tslot, out_base, layer, h, 1, sub * 2 + 1, r, sp, kb, rgb);
+          fence_proxy_async_smem();
+          if (tr) tr[7] = clock64();
+          __syncwarp();
+          if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + 1]);
+        } else {
+          epi_step<true>(tslot, out_base, layer, h, 0, sub * 2, r, sp, ka, rgb);
+          load16(pl + 64, ka);
+          epi_step<true>(tslot, out_base, layer, h, 0, sub * 2 + 1, r, sp, kb, rgb);
+          load16(pl + 64 + 16, kb);
+          epi_step<true>(tslot, out_base, layer, h, 1, sub * 2, r, sp, ka, rgb);
+          epi_step<true>(tslot, out_base, layer, h, 1, sub * 2 + 1, r, sp, kb, rgb);
+        }
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
         ++full_uses;
       }
-      // Combine the four feature quarters of the RGB projection in a fixed order (bit-reproducible) and store.
-      // Scratch = the first bytes of activation buffer X: its last readers (layer 3's MMAs) have completed, and its
-      // next writers (layer 1 epilogue of the next tile) wait on named barrier 2 below.
-      float* scratch = reinterpret_cast<float*>(s_act + X * kActBytes);
-      if (wg != 0) {
-        float* p = scratch + ((wg - 1) * kTileM + r) * 3;
-        p[0] = rgb[0], p[1] = rgb[1], p[2] = rgb[2];
+      // Combine the four partial RGB projections of a row (2 groups x 2 subs) in a fixed order (bit-reproducible).
+      // The last warps to finish (group 1, sub 1) reduce and store; the others drop their partials in smem.
+      const int pidx = grp * 2 + sub;
+      if (pidx != 3) {
+        if (t > 0) named_bar_sync(2, kEpiThreads);  // the reducers have read the previous tile's partials
+        float* pp = &sm.partial[pidx][r][0];
+        pp[0] = rgb[0], pp[1] = rgb[1], pp[2] = rgb[2];
         named_bar_arrive(1, kEpiThreads);
-        if (has_next) named_bar_sync(2, kEpiThreads);
       } else {
         named_bar_sync(1, kEpiThreads);
         float o[3];
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch)
-          o[ch] = ((rgb[ch] + scratch[r * 3 + ch]) + scratch[(kTileM + r) * 3 + ch]) +
-                  scratch[(2 * kTileM + r) * 3 + ch] + sp.bl[ch];
-        if (has_next) named_bar_sync(2, kEpiThreads);
+          o[ch] = ((sm.partial[0][r][ch] + sm.partial[1][r][ch]) + sm.partial[2][r][ch]) + rgb[ch] + sp.bl[ch];
+        if (has_next) named_bar_arrive(2, kEpiThreads);
         if (rc.valid) {
           const int64_t cs = src.mode == 0 ? out.chan_stride : 1;
           if (out.io_dtype == DIINN_IO_F32) {

@@ -103,6 +103,149 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1) tmem_dealloc<CG>(tmem_base, 256);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-pipe pace probe: `iters` back-to-back UMMAs (M = 128 x CG, N = n_cols, K = 16) on resident smem operands, no
+// TMA, no epilogue. Reports clock64 cycles per MMA as seen by the issuing thread of every leader CTA. Used to separate
+// "the tensor pipe is this fast here" from pipeline stalls when reading the fused kernels' traces.
+// ---------------------------------------------------------------------------------------------------------
+template <int CG>
+__global__ void __launch_bounds__(640, 1) umma_pace_kernel(int n_cols, int iters, float* __restrict__ cyc_per_mma, int noise) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* sA = smem;              // 4 K-chunk tiles of [128 x 128 B]
+  uint8_t* sB = smem + 4 * 16384;  // 4 tiles of [256/CG x 128 B]
+  uint8_t* sN = sB + 4 * 32768;    // 16 KB scratch for the noise warps' stores
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sN + 16384);
+  uint64_t* ring = bar + 1;  // 6 barriers that only ever receive commits (noise bit 4: fused-kernel loop structure)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ring + 6);
+  volatile int* done = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool leader = CG == 1 || cluster_ctarank() == 0;
+  for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += blockDim.x) {
+    // noise bit 3: pseudo-random bf16 operands in [-2,2) instead of zeros (data-dependent power)
+    uint32_t x = (i + 1) * 2654435761u + blockIdx.x * 40503u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    const uint32_t lo = 0x3c00u | (x & 0x83ffu), hi = 0x3c00u | ((x >> 16) & 0x83ffu);
+    reinterpret_cast<uint32_t*>(smem)[i] = (noise & 8) ? (lo | (hi << 16)) : 0u;
+  }
+  if (threadIdx.x == 0) *done = 0;
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar, 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&ring[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<CG>(tmem_ptr, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 0 && lane == 0 && leader) {
+    const uint32_t idesc = umma_idesc_bf16(128 * CG, n_cols);
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int kc = (i >> 2) & 3, k = i & 3, slot = (i >> 4) & 1;
+      if ((noise & 16) && k == 0) {
+        // what the fused kernels do per K-chunk: a barrier wait that passes immediately, then the fence
+        mbar_wait(&ring[5], 1);
+        tc_fence_after();
+      }
+      umma_bf16<CG>(tmem_base + slot * 256, umma_desc_sw128(a0 + kc * 16384 + k * 32),
+                    umma_desc_sw128(b0 + kc * (32768 / CG) + k * 32), idesc, i ? 1u : 0u);
+      if ((noise & 16) && k == 3) umma_commit<CG>(&ring[(i >> 2) % 5]);
+    }
+    if constexpr (CG == 2) umma_commit_2sm_local(bar); else umma_commit<1>(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (!(noise & 32)) cyc_per_mma[blockIdx.x / CG] = static_cast<float>(t1 - t0) / iters;
+  }
+  if (warp == 0 && lane == 0) {  // follower CTAs learn about completion through the teardown barrier only
+    if (leader) *done = 1;
+  }
+  // noise warps 4..19 (the fused kernel's epilogue population): bit0 = tcgen05.ld of the idle TMEM half, bit1 = 128-bit
+  // shared stores, bit2 = MUFU, until the leader's MMAs are done (followers: fixed trip count)
+  if (warp >= 4 && (noise & 32)) {
+    // TMEM read bandwidth probe: (noise >> 8) warps per lane quarter stream tcgen05.ld.32x32b.x16 back to back
+    const int per_quarter = (noise >> 8) & 7;
+    if (((warp - 4) >> 2) < per_quarter) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+      uint32_t v[16], w[16];
+      float acc = 0.f;
+      const long long t0 = clock64();
+      if (noise & 64) {  // one x32 load instead of two x16 loads per step
+        uint32_t u[32];
+        for (int it = 0; it < 512; ++it) {
+          tmem_ld32(taddr + ((it * 32) & 255), u);
+          tmem_ld_wait();
+          acc += __uint_as_float(u[it & 31]);
+        }
+      } else {
+        for (int it = 0; it < 512; ++it) {
+          tmem_ld16(taddr + ((it * 32) & 255), v);
+          tmem_ld16(taddr + ((it * 32 + 16) & 255), w);
+          tmem_ld_wait();
+          acc += __uint_as_float(v[it & 15]) + __uint_as_float(w[it & 15]);
+        }
+      }
+      const long long t1 = clock64();
+      if (warp == 4 && lane == 0) cyc_per_mma[blockIdx.x / CG] = static_cast<float>(t1 - t0) / 1024.f;
+      if (acc == 12345.678f) cyc_per_mma[0] = acc;
+    }
+  } else if (warp >= 4 && (noise & 7)) {
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 256 + ((warp >> 2) & 3) * 16;
+    const uint32_t saddr = smem_u32(sN) + (warp - 4) * 1024 + lane * 16 + ((lane >> 3) & 1) * 0;
+    float acc = 0.f;
+    uint32_t v[16];
+    for (int it = 0; it < (leader ? (1 << 30) : iters / 2); ++it) {
+      if (noise & 1) {
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        acc += __uint_as_float(v[it & 15]);
+      }
+      if (noise & 2) st_shared_v4(saddr + ((it & 1) << 9), it, it, it, it);
+      if (noise & 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += __sinf(acc + j);
+      }
+      if (leader && *done) break;
+    }
+    if (acc == 12345.678f) cyc_per_mma[0] = acc;
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, 512);
+}
+
+int launch_umma_pace(Handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma, int noise,
+                     cudaStream_t s) {
+  const size_t smem = 4 * 16384 + 4 * 32768 + 16384 + 128 + 1024;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_ctas, 1, 1);
+  cfg.blockDim = dim3(640, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cta_group == 1) {
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(umma_pace_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_pace_kernel<1>, n_cols, iters, cyc_per_mma, noise));
+  } else {
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(umma_pace_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_pace_kernel<2>, n_cols, iters, cyc_per_mma, noise));
+  }
+  h->launches += 1;
+  return DIINN_OK;
+}
+
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
                          cudaStream_t s) {
   CUtensorMap tmA, tmB;

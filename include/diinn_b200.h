@@ -134,6 +134,12 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
 int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
                           int cta_group, void* stream);
 
+/* Tensor-pipe pace probe: `iters` back-to-back tcgen05.mma (M = 128*cta_group, N = n_cols, K = 16, bf16) on resident
+ * shared-memory operands in n_ctas CTAs; cyc_per_mma[n_ctas / cta_group] (device) receives clock64 cycles per MMA.
+ * noise: 16 extra warps per CTA hammer the idle TMEM half (bit 0), shared memory (bit 1) or the MUFU (bit 2) meanwhile. */
+int diinn_debug_umma_pace(diinn_handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma,
+                          int noise, void* stream);
+
 /* Per-kernel device timing of the tcgen05 path, measured with CUDA events recorded on the caller's stream around
  * the three kernels of every diinn_decode (layout pass, stage A, stage B) while enabled. diinn_get_kernel_times
  * synchronises on the recorded events, returns the summed milliseconds and the number of decodes, and resets.

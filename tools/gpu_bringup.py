@@ -206,6 +206,35 @@ def mma_rate():
     print(f"cuBLAS same shape: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s")
 
 
+@stage
+def mma_pace():
+    import ctypes as C
+    np, torch, diinn_b200, synth, orc = _setup()
+    from diinn_b200 import _lib
+    dec = diinn_b200.FusedImplicitDecoder(mode=3).cuda()
+    lib, h = dec._ensure_handle(torch.device("cuda:0"))
+    for per_q in (1, 2, 4):
+        for x32 in (0, 64):
+            mma_iters = 20000
+            buf = torch.zeros(74, device="cuda")
+            noise = 32 | 8 | (per_q << 8) | x32
+            for _ in range(2):
+                _lib.check(lib, h, lib.diinn_debug_umma_pace(h, 2, 256, mma_iters, 148, C.c_void_p(buf.data_ptr()), noise, None))
+            torch.cuda.synchronize()
+            v = buf.cpu().numpy()
+            print(f"ldtm_pace warps/quarter={per_q} x32={bool(x32)}: {v.mean():.1f} clk per 16 columns per warp "
+                  f"-> {per_q * 4 * 2048 / v.mean():.1f} B/clk/SM")
+    for cg in ():
+        for noise in (0, 8, 24):
+            n_cols, n_ctas = 256, 148
+            buf = torch.zeros(n_ctas // cg, device="cuda")
+            for _ in range(2):
+                _lib.check(lib, h, lib.diinn_debug_umma_pace(h, cg, n_cols, 65536, n_ctas, C.c_void_p(buf.data_ptr()), noise, None))
+            torch.cuda.synchronize()
+            v = buf.cpu().numpy()
+            print(f"mma_pace cg={cg} N={n_cols} ctas={n_ctas} noise={noise}: {v.mean():.1f} clk/MMA (min {v.min():.1f} max {v.max():.1f})")
+
+
 def main():
     names = sys.argv[1:] or list(STAGES)
     if len(names) == 1 and names[0].startswith("--run="):
