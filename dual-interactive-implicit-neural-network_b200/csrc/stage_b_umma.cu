@@ -413,7 +413,13 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs. Group 1 has consumed
           // tmem_full[1] of layer 2 itself; group 0 observes the same phase before it overwrites the buffer.
           rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
-          if (grp == 0) mbar_wait(&sm.tmem_full[1], (full_uses - 1) & 1);
+          // (tmem_full[1] is drained by group 1 and could in principle already be a whole phase further -- layer 3 half
+          // 1 -- which a parity wait cannot tell apart from "not yet"; but then layer 3 half 0, issued before it and
+          // waiting for THIS group, is complete too, so either observation proves layer 2 is done.)
+          if (grp == 0) {
+            while (!mbar_try_wait(&sm.tmem_full[1], (full_uses - 1) & 1) && !mbar_try_wait(&sm.tmem_full[0], full_uses & 1)) {
+            }
+          }
           layer0_pair(X ^ 1, rc_next);
         }
         const float* pl = rc.prow + layer * kD + h * 128 + sub * 32;  // P slice of features 128h + 64c + 32sub + 16s
