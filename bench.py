@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-extra", action="store_true", help="skip the c2/c4 extra measurements")
+    ap.add_argument("--assembly", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused = stage B stores every pixel into all ranks' image buffers over NVLink (peer / "
+                         "NVSwitch multicast stores, no collective); nccl = local tiles + NCCL all-gather")
     return ap.parse_args()
 
 
@@ -181,10 +184,13 @@ def main():
     parts = diinn_b200.row_partition(H_up, world)
     r0, r1 = parts[rank]
 
-    def step():
+    def step(assembly=args.assembly):
         if world == 1:
             return dec(feat, (H_up, W_up))
-        return diinn_b200.decode_sharded(dec, feat, (H_up, W_up))
+        if assembly == "fused":
+            # clone=False: the assembled image stays in the symmetric buffer (overwritten by the next step)
+            return diinn_b200.decode_sharded_fused(dec, feat, (H_up, W_up), clone=False)
+        return diinn_b200.decode_sharded(dec, feat, (H_up, W_up), bands=1)
 
     def barrier():
         if world > 1:
@@ -228,10 +234,24 @@ def main():
         ms_e2e = e2.elapsed_time(e3)
         checksum = float(out_host.double().sum())
 
-    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    ms_other = 0.0
+    if world > 1:  # the other assembly path, for the record
+        other = "nccl" if args.assembly == "fused" else "fused"
+        with torch.no_grad():
+            for _ in range(3):
+                step(other)
+            barrier()
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record()
+            for _ in range(20):
+                step(other)
+            o1.record()
+            barrier()
+            ms_other = o0.elapsed_time(o1) / 20
+    times = torch.tensor([ms_total, ms_e2e, ms_other], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = (float(v) for v in times.cpu())
+    ms_total, ms_e2e, ms_other = (float(v) for v in times.cpu())
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
@@ -272,7 +292,10 @@ def main():
             "workload": workload_desc(args.workload),
             "io_dtype": "fp32 feature map in, fp32 image out",
             "compute": "tcgen05 bf16 operands, fp32 TMEM accumulation" if args.precision == "bf16" else "fp32 CUDA cores",
-            "sharding": f"HR row tiles over {world} rank(s), NCCL all-gather assembles the image on every rank"
+            "sharding": (f"HR row tiles over {world} ranks, feature map and weights replicated, no data-path collective; "
+                         + (f"assembly fused into stage B ({diinn_b200.sharding.last_fused_mode} over NVLink, symmetric "
+                            "memory + 2 barriers)" if args.assembly == "fused" else
+                            "assembly by in-place NCCL all_gather_into_tensor per channel"))
                         if world > 1 else "single GPU, whole image",
             "l2": "no explicit flush: each step writes then re-reads the 708 MB fp32 LR pre-activation tensor P "
                   "(5.6x the 126 MB L2) plus 33 MB of output, so no step finds its working set in L2",
@@ -315,6 +338,9 @@ def main():
         cpu = time_cpu_port(args.workload, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": cpu["px_per_s"], "unit": "px/s", "cores": cpu["cores"], "kind": "port",
                                 "sample": cpu["sample"] + "; best of 3 after 1 warm-up", "host_cpus": cpu["host_cpus"]}
+    if world > 1:
+        line["other_assembly"] = {"mode": "nccl" if args.assembly == "fused" else "fused", "ms_per_step": ms_other,
+                                  "px_per_s": npx / ms_other * 1e3}
     if extra:
         line["extra_single_gpu_configs"] = extra
     print(json.dumps(line), flush=True)

@@ -23,7 +23,7 @@ STATUS_NAMES = {
 # every symbol include/diinn_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
     "diinn_create", "diinn_destroy", "diinn_last_error", "diinn_set_weights", "diinn_workspace_bytes",
-    "diinn_decode", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_debug_gather",
+    "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_debug_gather",
     "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace", "diinn_debug_umma_pace", "diinn_set_profiling", "diinn_get_kernel_times",
     "diinn_launch_count",
     "diinn_version",
@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     lib.diinn_workspace_bytes.restype = sz
     lib.diinn_decode.argtypes = [vp, vp, i, i, i, i, i, i, i, i, vp, i64, i64, i64, vp, sz, i, i, vp]
     lib.diinn_decode.restype = i
+    lib.diinn_decode_multi.argtypes = [vp, vp, i, i, i, i, i, i, i, i, C.POINTER(vp), i, vp, i64, i64, i64, vp, sz, i, i, vp]
+    lib.diinn_decode_multi.restype = i
     lib.diinn_decode_host.argtypes = [vp, vp, i, i, i, i, i, i, i, i, vp, i, i, vp]
     lib.diinn_decode_host.restype = i
     lib.diinn_query_workspace_bytes.argtypes = [vp, i, i, i, i, i]

@@ -219,9 +219,45 @@ size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_u
   return plan_decode(B, H, W, H_up, W_up, row0, row1, compute).total;
 }
 
+static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
+                       int row1, OutSpec o, void* workspace, size_t workspace_bytes, int compute, void* stream);
+
 int diinn_decode(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
                  int row1, void* out, int64_t out_batch_stride, int64_t out_chan_stride, int64_t out_row_stride,
                  void* workspace, size_t workspace_bytes, int io_dtype, int compute, void* stream) {
+  OutSpec o{};
+  o.ptr = out;
+  o.batch_stride = out_batch_stride, o.chan_stride = out_chan_stride, o.row_stride = out_row_stride;
+  o.io_dtype = io_dtype;
+  return decode_impl(h, feat, B, C, H, W, H_up, W_up, row0, row1, o, workspace, workspace_bytes, compute, stream);
+}
+
+int diinn_decode_multi(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
+                       int row1, void* const* out_peers, int n_peers, void* out_multicast, int64_t out_batch_stride,
+                       int64_t out_chan_stride, int64_t out_row_stride, void* workspace, size_t workspace_bytes,
+                       int io_dtype, int compute, void* stream) {
+  if (!h) return DIINN_ERR_BAD_ARG;
+  if (!out_peers || n_peers < 1 || n_peers > kMaxPeers) return fail(h, DIINN_ERR_BAD_ARG, "need 1..8 peer buffers");
+  if (out_multicast && io_dtype != DIINN_IO_F32)
+    return fail(h, DIINN_ERR_BAD_DTYPE, "multicast stores are implemented for fp32 images only");
+  OutSpec o{};
+  o.ptr = out_peers[0];
+  o.batch_stride = out_batch_stride, o.chan_stride = out_chan_stride, o.row_stride = out_row_stride;
+  o.io_dtype = io_dtype;
+  o.n_peers = n_peers;
+  o.mc = out_multicast;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!out_peers[i]) return fail(h, DIINN_ERR_BAD_ARG, "null peer buffer");
+    // every destination starts at the same row offset as a plain decode's `out` would
+    o.peers[i] = static_cast<char*>(out_peers[i]);
+  }
+  return decode_impl(h, feat, B, C, H, W, H_up, W_up, row0, row1, o, workspace, workspace_bytes, compute, stream);
+}
+
+static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
+                       int row1, OutSpec o, void* workspace, size_t workspace_bytes, int compute, void* stream) {
+  const int io_dtype = o.io_dtype;
+  void* out = o.ptr;
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
   if (!feat || !out) return fail(h, DIINN_ERR_BAD_ARG, "null feat/out");
@@ -245,7 +281,6 @@ int diinn_decode(diinn_handle* h, const void* feat, int B, int C, int H, int W, 
   src.ratio = static_cast<float>((static_cast<double>(H) * W) / (static_cast<double>(H_up) * W_up));
   src.B = B, src.H = H, src.W = W, src.H_up = H_up, src.W_up = W_up, src.row0 = row0, src.row1 = row1;
   src.lr_row0 = plan.lr_row0, src.lr_rows = plan.lr_rows;
-  OutSpec o{out, out_batch_stride, out_chan_stride, out_row_stride, io_dtype};
 
   if (compute == DIINN_COMPUTE_FP32) {
     if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, plan.lr_row0, plan.lr_rows, P, s))) return rc;
@@ -351,7 +386,9 @@ int diinn_query(diinn_handle* h, const void* feat, int B, int C, int H, int W, c
   float* P = reinterpret_cast<float*>(ws);
   size_t off = align_up(static_cast<size_t>(B) * H * W * kPCols * sizeof(float));
   const PixelSource src = make_query_source(B, H, W, coord, cell, Q);
-  OutSpec o{out, 0, 0, 0, io_dtype};
+  OutSpec o{};
+  o.ptr = out;
+  o.io_dtype = io_dtype;
   if (compute == DIINN_COMPUTE_FP32) {
     const int64_t total = static_cast<int64_t>(B) * Q;
     const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;

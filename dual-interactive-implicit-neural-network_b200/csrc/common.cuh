@@ -82,11 +82,34 @@ struct PixelSource {
   float hw_f;  // fp32(H*W)
 };
 
+constexpr int kMaxPeers = 8;
+
 struct OutSpec {
   void* ptr;
   int64_t batch_stride, chan_stride, row_stride;  // grid mode (elements); query mode: out[(b*Q+q)*3 + c]
   int io_dtype;
+  // Fused assembly across the GPUs of one NVLink domain (diinn_decode_multi): every pixel is stored into the same
+  // offset of n_peers peer-mapped image buffers (peers[] includes this GPU's own buffer), or once through an NVSwitch
+  // multicast address (mc != nullptr, fp32 only). n_peers == 0: plain local store to ptr.
+  void* peers[kMaxPeers];
+  int n_peers;
+  void* mc;
 };
+
+// store one fp32/bf16 value of the output image at element offset `off` of every destination
+__device__ __forceinline__ void store_out(const OutSpec& o, int64_t off, float v) {
+  if (o.mc != nullptr) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(static_cast<float*>(o.mc) + off), "f"(v) : "memory");
+  } else if (o.n_peers > 0) {
+    for (int i = 0; i < o.n_peers; ++i) {
+      if (o.io_dtype == DIINN_IO_F32) static_cast<float*>(o.peers[i])[off] = v;
+      else static_cast<__nv_bfloat16*>(o.peers[i])[off] = __float2bfloat16_rn(v);
+    }
+  } else {
+    if (o.io_dtype == DIINN_IO_F32) static_cast<float*>(o.ptr)[off] = v;
+    else static_cast<__nv_bfloat16*>(o.ptr)[off] = __float2bfloat16_rn(v);
+  }
+}
 
 // small fp32 parameters every path needs in registers/constant bank (passed by value as kernel params)
 struct SmallParams {

@@ -63,10 +63,7 @@ __device__ __forceinline__ void store_rgb(const OutSpec& o, const PixelSource& s
     off = pi.b * o.batch_stride + c * o.chan_stride + static_cast<int64_t>(pi.oh - s.row0) * o.row_stride + pi.ow;
   else
     off = g * 3 + c;
-  if (o.io_dtype == DIINN_IO_F32)
-    static_cast<float*>(o.ptr)[off] = v;
-  else
-    static_cast<__nv_bfloat16*>(o.ptr)[off] = __float2bfloat16_rn(v);
+  store_out(o, off, v);
 }
 
 // ---------------------------------------------------------------------------------------------------------

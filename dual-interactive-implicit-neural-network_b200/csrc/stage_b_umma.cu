@@ -479,13 +479,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         if (has_next) named_bar_arrive(2, kEpiThreads);
         if (rc.valid) {
           const int64_t cs = src.mode == 0 ? out.chan_stride : 1;
-          if (out.io_dtype == DIINN_IO_F32) {
-            float* op = static_cast<float*>(out.ptr) + rc.out_off;
-            op[0] = o[0], op[cs] = o[1], op[2 * cs] = o[2];
-          } else {
-            __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out.ptr) + rc.out_off;
-            op[0] = __float2bfloat16_rn(o[0]), op[cs] = __float2bfloat16_rn(o[1]), op[2 * cs] = __float2bfloat16_rn(o[2]);
-          }
+          store_out(out, rc.out_off, o[0]);
+          store_out(out, rc.out_off + cs, o[1]);
+          store_out(out, rc.out_off + 2 * cs, o[2]);
         }
       }
       rc = rc_next;

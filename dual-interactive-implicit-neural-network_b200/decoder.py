@@ -142,7 +142,8 @@ class FusedImplicitDecoder(nn.Module):
         H_up, W_up = int(size[0]), int(size[1])
         return self.forward_rows(x, (H_up, W_up), 0, H_up)
 
-    def forward_rows(self, x: torch.Tensor, size, row0: int, row1: int, out: Optional[torch.Tensor] = None):
+    def forward_rows(self, x: torch.Tensor, size, row0: int, row1: int, out: Optional[torch.Tensor] = None,
+                     peer_ptrs: Optional[Sequence[int]] = None, multicast_ptr: int = 0):
         """HR rows [row0,row1) only -> (B,3,row1-row0,W_up), or written in place into rows [row0,row1) of a full
         (B,3,H_up,W_up) ``out``. Row tiles are how the query grid shards across GPUs."""
         self._check_input(x)
@@ -158,13 +159,27 @@ class FusedImplicitDecoder(nn.Module):
         ws = self._get_workspace(nbytes, x.device)
         if out is None:
             res = torch.empty((B, 3, row1 - row0, W_up), dtype=x.dtype, device=x.device)
-            base, bs, cs, rs = res, 3 * (row1 - row0) * W_up, (row1 - row0) * W_up, W_up
+            bs, cs, rs = 3 * (row1 - row0) * W_up, (row1 - row0) * W_up, W_up
             ptr = res.data_ptr()
         else:
-            if out.shape != (B, 3, H_up, W_up) or out.dtype != x.dtype or not out.is_contiguous():
-                raise ValueError("out must be a contiguous (B,3,H_up,W_up) tensor of x.dtype")
-            res, bs, cs, rs = out, 3 * H_up * W_up, H_up * W_up, W_up
+            # a full-size image buffer, possibly with extra (padding) rows per channel: rows [row0,row1) are written in place
+            if (out.dim() != 4 or out.shape[0] != B or out.shape[1] != 3 or out.shape[2] < H_up or out.shape[3] != W_up
+                    or out.dtype != x.dtype or not out.is_contiguous() or out.device != x.device):
+                raise ValueError("out must be a contiguous (B,3,>=H_up,W_up) tensor of x.dtype on x.device")
+            H_alloc = out.shape[2]
+            res, bs, cs, rs = out, 3 * H_alloc * W_up, H_alloc * W_up, W_up
             ptr = out.data_ptr() + row0 * W_up * out.element_size()
+        if peer_ptrs is not None:
+            # fused assembly: `out` is this rank's symmetric image buffer, peer_ptrs the base addresses of every rank's
+            # buffer (same layout), multicast_ptr an optional NVSwitch multicast mapping of them
+            if out is None:
+                raise ValueError("peer stores need the local full-size `out` buffer")
+            off = row0 * W_up * out.element_size()
+            arr = (C.c_void_p * len(peer_ptrs))(*[int(p_) + off for p_ in peer_ptrs])
+            mc = C.c_void_p(int(multicast_ptr) + off) if multicast_ptr else C.c_void_p(0)
+            _lib.check(lib, h, lib.diinn_decode_multi(h, _ptr(x), B, Cc, H, W, H_up, W_up, row0, row1, arr, len(peer_ptrs),
+                                                      mc, bs, cs, rs, _ptr(ws), ws.numel(), io, comp, _stream(x.device)))
+            return res
         _lib.check(lib, h, lib.diinn_decode(h, _ptr(x), B, Cc, H, W, H_up, W_up, row0, row1, C.c_void_p(ptr), bs, cs,
                                             rs, _ptr(ws), ws.numel(), io, comp, _stream(x.device)))
         return res

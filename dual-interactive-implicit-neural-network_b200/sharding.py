@@ -25,30 +25,119 @@ def row_partition(n_rows: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessGroup] = None,
-                   gather: str = "all") -> torch.Tensor:
-    """Each rank decodes its row tile of the (B,3,H_up,W_up) output, then the tiles are assembled with NCCL
-    (gloo in the CPU tests, with a stand-in decoder).
+def band_partition(n_rows: int, world: int, bands: int) -> Tuple[int, List[List[Tuple[int, int]]]]:
+    """Block-cyclic row bands for pipelined assembly: the image is cut into `bands` super-bands of world*sub rows, and
+    inside super-band k rank r owns rows [(k*world + r)*sub, +sub) (clipped to n_rows). Returns (sub, per-rank lists).
+    With bands=1 this is the plain contiguous split with equal (padded) tiles."""
+    sub = -(-n_rows // (world * bands))
+    out = []
+    for r in range(world):
+        mine = []
+        for k in range(bands):
+            a = (k * world + r) * sub
+            mine.append((min(a, n_rows), min(a + sub, n_rows)))
+        out.append(mine)
+    return sub, out
 
-    gather="all": every rank returns the full image (all_gather of padded equal-size row tiles);
-    gather="none": returns only this rank's (B,3,rows,W_up) tile.
+
+_side_streams = {}
+_symm_images = {}
+last_fused_mode = None  # how the last decode_sharded_fused call reached the peers (for reports)
+
+
+def _symmetric_image(shape, dtype, device, group):
+    """A (B,3,H_up,W_up) image buffer allocated in symmetric memory and mapped into every rank of `group`
+    (torch.distributed._symmetric_memory): returns (local tensor, handle with .buffer_ptrs / .multicast_ptr / .barrier)."""
+    import torch.distributed._symmetric_memory as symm_mem
+    pg = group if group is not None else dist.group.WORLD
+    key = (tuple(shape), dtype, device.index, pg.group_name)
+    if key not in _symm_images:
+        buf = symm_mem.empty(*shape, dtype=dtype, device=device)
+        hdl = symm_mem.rendezvous(buf, pg.group_name)
+        _symm_images[key] = (buf, hdl)
+    return _symm_images[key]
+
+
+def decode_sharded_fused(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessGroup] = None,
+                         multicast: bool = True, clone: bool = True) -> torch.Tensor:
+    """Fused decode + assembly: the stage-B kernel of every rank stores each RGB value of its row tile straight into
+    the image buffers of ALL ranks over NVLink (one `multimem.st` through the NVSwitch multicast mapping when the
+    fabric offers it, else one peer store per rank), so the transfer rides under the math tile by tile and no
+    collective is launched; two symmetric-memory barriers order buffer reuse and completion.
+
+    Returns the assembled (B,3,H_up,W_up) image on every rank. clone=False returns the symmetric buffer itself, which
+    the next call with the same shape overwrites."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    H_up, W_up = int(size[0]), int(size[1])
+    B = x.shape[0]
+    buf, hdl = _symmetric_image((B, 3, H_up, W_up), x.dtype, x.device, group)
+    r0, r1 = row_partition(H_up, world)[rank]
+    mc = int(hdl.multicast_ptr) if (multicast and x.dtype == torch.float32) else 0  # 0 when the fabric has no multicast
+    global last_fused_mode
+    last_fused_mode = "nvswitch-multicast multimem.st" if mc else f"{world} peer stores per value"
+    hdl.barrier(channel=0)  # every rank is done reading the previous image held in these buffers
+    if r1 > r0:
+        decoder.forward_rows(x, (H_up, W_up), r0, r1, out=buf, peer_ptrs=list(hdl.buffer_ptrs), multicast_ptr=mc)
+    hdl.barrier(channel=1)  # every rank's stores have landed everywhere
+    return buf.clone() if clone else buf
+
+
+
+def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessGroup] = None, gather: str = "all",
+                   bands: Optional[int] = None) -> torch.Tensor:
+    """One rank per GPU: every rank decodes its HR row bands of the (B,3,H_up,W_up) image **in place** into a (row-
+    padded) full-size buffer, and NCCL all-gathers each band in place, channel by channel, on a side stream while the
+    next band is being decoded. No copy, no data-path collective; returns the assembled image on every rank (a view of
+    the padded buffer; rows are contiguous, the channel stride is H_pad*W_up).
+
+    gather="none": returns only this rank's first band tile (B,3,rows,W_up) (used by tests / e2e).
+    bands: number of bands per rank (pipelining depth); default 1 below ~1 Mpx per rank, else 4.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     H_up, W_up = int(size[0]), int(size[1])
-    parts = row_partition(H_up, world)
-    r0, r1 = parts[rank]
     B = x.shape[0]
-    max_rows = max(b - a for a, b in parts)
-    # padded tile so that all_gather_into_tensor sees equal shapes even when H_up % world != 0
-    tile = torch.zeros((B, 3, max_rows, W_up), dtype=x.dtype, device=x.device)
-    if r1 > r0:
-        tile[:, :, : r1 - r0] = decoder.forward_rows(x, (H_up, W_up), r0, r1)
-    if gather == "none" or world == 1:
-        return tile[:, :, : r1 - r0] if gather == "none" else tile[:, :, :H_up]
-    # output laid out as the dim-0 concatenation of the per-rank tiles (the form both NCCL and gloo accept)
-    flat = torch.empty((world * B, 3, max_rows, W_up), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(flat, tile, group=group)
-    gathered = flat.view(world, B, 3, max_rows, W_up)
-    # one concatenation kernel re-interleaves the rank-major tiles into NCHW and drops the padding rows
-    return torch.cat([gathered[r, :, :, : b - a] for r, (a, b) in enumerate(parts) if b > a], dim=2)
+    if gather == "none":
+        r0, r1 = row_partition(H_up, world)[rank]
+        if r1 > r0:
+            return decoder.forward_rows(x, (H_up, W_up), r0, r1)
+        return torch.empty((B, 3, 0, W_up), dtype=x.dtype, device=x.device)
+    if world == 1:
+        return decoder.forward_rows(x, (H_up, W_up), 0, H_up)
+    if bands is None:
+        bands = 4 if (H_up // world) * W_up * B >= (1 << 21) else 1
+    sub, parts = band_partition(H_up, world, bands)
+    H_pad = world * bands * sub
+    out = torch.empty((B, 3, H_pad, W_up), dtype=x.dtype, device=x.device)
+    on_gpu = x.is_cuda
+    in_place = dist.get_backend(group) == "nccl"
+    if on_gpu:
+        key = (x.device.index, id(group))
+        side = _side_streams.setdefault(key, torch.cuda.Stream(device=x.device))
+        main = torch.cuda.current_stream(x.device)
+        side.wait_stream(main)  # `out` was allocated on the main stream
+    for k, (a, b) in enumerate(parts[rank]):
+        if b > a:
+            decoder.forward_rows(x, (H_up, W_up), a, b, out=out)
+        base = k * world * sub
+        mine = (k * world + rank) * sub
+
+        def _gather():
+            for bi in range(B):
+                for c in range(3):
+                    dst = out[bi, c, base:base + world * sub]
+                    src = out[bi, c, mine:mine + sub]
+                    dist.all_gather_into_tensor(dst, src if in_place else src.clone(), group=group)
+
+        if on_gpu:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                _gather()
+        else:
+            _gather()
+    if on_gpu:
+        main.wait_stream(side)
+    return out[:, :, :H_up]

@@ -103,6 +103,17 @@ int diinn_decode(diinn_handle* h, const void* feat, int B, int C, int H, int W, 
                  int64_t out_row_stride, void* workspace, size_t workspace_bytes, int io_dtype, int compute,
                  void* stream);
 
+/* Fused decode + assembly across the GPUs of one NVLink/NVSwitch domain. Same as diinn_decode, but every pixel of rows
+ * [row0,row1) is stored into n_peers peer-mapped image buffers at once (out_peers[i] = the address a plain decode would
+ * get as `out` in rank i's buffer, i.e. already offset to row0; this GPU's own buffer is one of them), so when all ranks'
+ * kernels have finished every rank holds the whole image and no collective is needed. If out_multicast is non-NULL
+ * (an NVSwitch multicast mapping of the same buffers, fp32 only) one multimem.st per value replaces the n_peers stores.
+ * The caller synchronises the ranks afterwards (e.g. a symmetric-memory barrier). */
+int diinn_decode_multi(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
+                       int row1, void* const* out_peers, int n_peers, void* out_multicast, int64_t out_batch_stride,
+                       int64_t out_chan_stride, int64_t out_row_stride, void* workspace, size_t workspace_bytes,
+                       int io_dtype, int compute, void* stream);
+
 /* Same call with HOST buffers: copies feat H2D, decodes, copies the (B,3,row1-row0,W_up) band D2H into
  * out_host (contiguous), synchronises `stream`. Device scratch is owned and cached by the handle. This is the
  * call a CPU-side caller such as demo2.py:40 makes; bench.py's `e2e` times it. */

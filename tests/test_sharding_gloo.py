@@ -19,6 +19,9 @@ class StandInDecoder:
         B = x.shape[0]
         H_up, W_up = size
         full = self.full(B, H_up, W_up, x.dtype)
+        if out is not None:  # in-place into a (row-padded) full-size buffer, like FusedImplicitDecoder.forward_rows
+            out[:, :, r0:r1] = full[:, :, r0:r1]
+            return out
         return full[:, :, r0:r1].contiguous()
 
     @staticmethod
@@ -44,8 +47,9 @@ def _worker(rank, world, port, sizes, results):
         ok = True
         for (B, H_up, W_up) in sizes:
             x = torch.zeros(B, 64, 4, 4)
-            full = diinn_b200.decode_sharded(StandInDecoder(), x, (H_up, W_up))
-            ok &= bool(torch.equal(full, StandInDecoder.full(B, H_up, W_up, x.dtype)))
+            for bands in (None, 1, 3):
+                full = diinn_b200.decode_sharded(StandInDecoder(), x, (H_up, W_up), bands=bands)
+                ok &= bool(torch.equal(full, StandInDecoder.full(B, H_up, W_up, x.dtype)))
             tile = diinn_b200.decode_sharded(StandInDecoder(), x, (H_up, W_up), gather="none")
             r0, r1 = diinn_b200.row_partition(H_up, world)[rank]
             ok &= bool(torch.equal(tile, StandInDecoder.full(B, H_up, W_up, x.dtype)[:, :, r0:r1]))
@@ -62,6 +66,18 @@ def test_decode_sharded_world2_gloo():
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), sizes, results), nprocs=world, join=True)
     assert dict(results) == {0: True, 1: True}
+
+
+def test_band_partition_covers_every_row_once():
+    for n_rows, world, bands in [(1356, 8, 1), (4320, 8, 4), (7, 2, 3), (1, 2, 1), (100, 3, 5)]:
+        sub, parts = diinn_b200.band_partition(n_rows, world, bands)
+        seen = []
+        for r in range(world):
+            assert len(parts[r]) == bands
+            for k, (a, b) in enumerate(parts[r]):
+                assert b - a <= sub and (b == a or a == (k * world + r) * sub)
+                seen += list(range(a, b))
+        assert sorted(seen) == list(range(n_rows))
 
 
 def test_single_process_passthrough():

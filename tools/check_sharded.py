@@ -1,0 +1,48 @@
+"""torchrun --nproc-per-node N tools/check_sharded.py : decode_sharded over NCCL must be bit-identical to a single-GPU
+decode on every rank, for contiguous tiles (bands=1) and pipelined block-cyclic bands."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import diinn_b200  # noqa: E402
+from diinn_b200 import synth  # noqa: E402
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+rank, world = dist.get_rank(), dist.get_world_size()
+dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="bf16"), synth.make_weights(seed=0)).to(dev)
+ok = True
+for name, bands in (("c1", 1), ("c1", 3), ("c3", None), ("c3", 2), ("c5", 1)):
+    B, H, W, H_up, W_up = synth.CONFIGS[name]
+    x = torch.from_numpy(synth.make_feat(1, B, H, W)).to(dev)
+    with torch.no_grad():
+        full = dec(x, (H_up, W_up))
+        sh = diinn_b200.decode_sharded(dec, x, (H_up, W_up), bands=bands)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(full, sh))
+    ok &= same
+    print(f"rank {rank}/{world} {name} bands={bands}: bit-identical={same}", flush=True)
+for name, mc in (("c1", False), ("c3", False), ("c1", True), ("c3", True), ("c5", True)):
+    B, H, W, H_up, W_up = synth.CONFIGS[name]
+    x = torch.from_numpy(synth.make_feat(1, B, H, W)).to(dev)
+    with torch.no_grad():
+        full = dec(x, (H_up, W_up))
+        try:
+            sh = diinn_b200.decode_sharded_fused(dec, x, (H_up, W_up), multicast=mc)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(full, sh))
+        except Exception as e:  # report, do not hide
+            same = False
+            print(f"rank {rank} fused {name} multicast={mc}: EXCEPTION {type(e).__name__}: {e}", flush=True)
+    ok &= same
+    print(f"rank {rank}/{world} fused {name} multicast={mc}: bit-identical={same}", flush=True)
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("SHARDED_OK" if int(flag) else "SHARDED_MISMATCH", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if int(flag) else 1)
