@@ -189,6 +189,22 @@ def test_row_tiles_bit_identical(w0, precision, world):
     assert torch.equal(full, parts)
 
 
+def test_decode_multi_writes_every_peer_buffer(w0):
+    """diinn_decode_multi (fused multi-GPU assembly) on one GPU: two 'peer' image buffers both receive the row tile,
+    bit-identical to a plain decode; rows outside the tile stay untouched."""
+    x = torch.from_numpy(synth.make_feat(6, 1, 23, 31)).cuda()
+    size = (91, 125)
+    dec = _decoder(w0, "bf16")
+    with torch.no_grad():
+        full = dec(x, size)
+        a = torch.full_like(full, -7.0)
+        b = torch.full_like(full, -7.0)
+        dec.forward_rows(x, size, 20, 61, out=a, peer_ptrs=[a.data_ptr(), b.data_ptr()])
+    for buf in (a, b):
+        assert torch.equal(buf[:, :, 20:61], full[:, :, 20:61])
+        assert bool((buf[:, :, :20] == -7.0).all()) and bool((buf[:, :, 61:] == -7.0).all())
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the (feat, coord, cell) superset entry
 # ---------------------------------------------------------------------------------------------------------
