@@ -194,6 +194,14 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->host_feat_dev);
   cudaFree(h->host_out_dev);
   cudaFree(h->host_ws);
+  if (h->s_h2d) {
+    cudaStreamDestroy(h->s_h2d);
+    cudaStreamDestroy(h->s_d2h);
+    for (int i = 0; i < 8; ++i) {
+      cudaEventDestroy(h->ev_h2d[i]);
+      cudaEventDestroy(h->ev_dec[i]);
+    }
+  }
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   delete h;
 }
@@ -321,7 +329,19 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   const size_t feat_bytes = static_cast<size_t>(B) * C * H * W * esz;
   const int nrows = row1 - row0;
   const size_t out_bytes = static_cast<size_t>(B) * 3 * nrows * W_up * esz;
-  const size_t ws_bytes = diinn_workspace_bytes(h, B, H, W, H_up, W_up, row0, row1, compute);
+  // Row bands: while band k decodes, band k+1's LR rows go up and band k-1's HR rows come down on two copy streams, so
+  // a large image costs about max(PCIe, compute) instead of their sum. Small images take one band.
+  const int64_t px = static_cast<int64_t>(B) * nrows * W_up;
+  int bands = px >= (1 << 21) ? 4 : (px >= (1 << 19) ? 2 : 1);
+  if (bands > nrows) bands = nrows;
+  const int band_rows = (nrows + bands - 1) / bands;
+  size_t ws_bytes = 0;
+  for (int k = 0; k < bands; ++k) {
+    const int a = row0 + k * band_rows, b = (a + band_rows < row1) ? a + band_rows : row1;
+    if (a >= b) continue;
+    const size_t n = diinn_workspace_bytes(h, B, H, W, H_up, W_up, a, b, compute);
+    ws_bytes = n > ws_bytes ? n : ws_bytes;
+  }
   auto grow = [&](void** p, size_t* have, size_t need) -> cudaError_t {
     if (*have >= need) return cudaSuccess;
     if (*p) cudaFree(*p);
@@ -334,12 +354,53 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   DIINN_CUDA_OK(h, grow(&h->host_feat_dev, &h->host_feat_bytes, feat_bytes));
   DIINN_CUDA_OK(h, grow(&h->host_out_dev, &h->host_out_bytes, out_bytes));
   DIINN_CUDA_OK(h, grow(&h->host_ws, &h->host_ws_bytes, ws_bytes));
-  DIINN_CUDA_OK(h, cudaMemcpyAsync(h->host_feat_dev, feat_host, feat_bytes, cudaMemcpyHostToDevice, s));
-  rc = diinn_decode(h, h->host_feat_dev, B, C, H, W, H_up, W_up, row0, row1, h->host_out_dev,
-                    static_cast<int64_t>(3) * nrows * W_up, static_cast<int64_t>(nrows) * W_up, W_up, h->host_ws,
-                    h->host_ws_bytes, io_dtype, compute, s);
-  if (rc) return rc;
-  DIINN_CUDA_OK(h, cudaMemcpyAsync(out_host, h->host_out_dev, out_bytes, cudaMemcpyDeviceToHost, s));
+  if (!h->s_h2d) {
+    DIINN_CUDA_OK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    DIINN_CUDA_OK(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) {
+      DIINN_CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      DIINN_CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_dec[i], cudaEventDisableTiming));
+    }
+  }
+  // the copy streams start after whatever the caller queued on `s` before this call
+  DIINN_CUDA_OK(h, cudaEventRecord(h->ev_dec[7], s));
+  DIINN_CUDA_OK(h, cudaStreamWaitEvent(h->s_h2d, h->ev_dec[7], 0));
+  DIINN_CUDA_OK(h, cudaStreamWaitEvent(h->s_d2h, h->ev_dec[7], 0));
+
+  const AxisParams ah = make_axis(H, H_up);
+  const size_t plane = static_cast<size_t>(H) * W * esz;      // one (b, c) plane of feat
+  const size_t oplane = static_cast<size_t>(nrows) * W_up * esz;  // one (b, c) plane of the output band buffer
+  int uploaded = 0;                                           // LR rows [0, uploaded) are already on the device
+  for (int k = 0; k < bands; ++k) {
+    const int a = row0 + k * band_rows, b = (a + band_rows < row1) ? a + band_rows : row1;
+    if (a >= b) break;
+    // LR rows this band reads (nearest-exact rows of [a,b) plus the 3x3 halo), minus what is already up
+    int lr0 = host_axis_index(ah, a) - 1, lr1 = host_axis_index(ah, b - 1) + 2;
+    lr0 = lr0 < 0 ? 0 : lr0;
+    lr1 = lr1 > H ? H : lr1;
+    if (k == 0) uploaded = lr0;
+    const int c0 = lr0 > uploaded ? lr0 : uploaded;
+    if (lr1 > c0) {
+      const size_t off = static_cast<size_t>(c0) * W * esz;
+      DIINN_CUDA_OK(h, cudaMemcpy2DAsync(static_cast<char*>(h->host_feat_dev) + off, plane,
+                                         static_cast<const char*>(feat_host) + off, plane,
+                                         static_cast<size_t>(lr1 - c0) * W * esz, static_cast<size_t>(B) * C,
+                                         cudaMemcpyHostToDevice, h->s_h2d));
+      uploaded = lr1;
+    }
+    DIINN_CUDA_OK(h, cudaEventRecord(h->ev_h2d[k], h->s_h2d));
+    DIINN_CUDA_OK(h, cudaStreamWaitEvent(s, h->ev_h2d[k], 0));
+    char* oband = static_cast<char*>(h->host_out_dev) + static_cast<size_t>(a - row0) * W_up * esz;
+    rc = diinn_decode(h, h->host_feat_dev, B, C, H, W, H_up, W_up, a, b, oband, static_cast<int64_t>(3) * nrows * W_up,
+                      static_cast<int64_t>(nrows) * W_up, W_up, h->host_ws, h->host_ws_bytes, io_dtype, compute, s);
+    if (rc) return rc;
+    DIINN_CUDA_OK(h, cudaEventRecord(h->ev_dec[k], s));
+    DIINN_CUDA_OK(h, cudaStreamWaitEvent(h->s_d2h, h->ev_dec[k], 0));
+    DIINN_CUDA_OK(h, cudaMemcpy2DAsync(static_cast<char*>(out_host) + static_cast<size_t>(a - row0) * W_up * esz, oplane,
+                                       oband, oplane, static_cast<size_t>(b - a) * W_up * esz,
+                                       static_cast<size_t>(B) * 3, cudaMemcpyDeviceToHost, h->s_d2h));
+  }
+  DIINN_CUDA_OK(h, cudaStreamSynchronize(h->s_d2h));
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
   return DIINN_OK;
 }
@@ -489,9 +550,10 @@ int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n) {
 int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
                           int cta_group, void* stream) {
   if (!h || !A || !B || !D) return DIINN_ERR_BAD_ARG;
-  if (M < 128 || M % 128 || N < 256 || N % 256 || K < 64 || K % 64 || (cta_group != 1 && cta_group != 2))
-    return fail(h, DIINN_ERR_BAD_SHAPE, "need M%128==0, N%256==0, K%64==0, cta_group in {1,2}");
-  if (cta_group == 2 && M % 256) return fail(h, DIINN_ERR_BAD_SHAPE, "cta_group 2 needs M%256==0");
+  if (M < 128 || M % 128 || N < 256 || N % 256 || K < 64 || K % 64 ||
+      (cta_group != 1 && cta_group != 2 && cta_group != 11 && cta_group != 12))
+    return fail(h, DIINN_ERR_BAD_SHAPE, "need M%128==0, N%256==0, K%64==0, cta_group in {1,2,11,12}");
+  if (cta_group % 10 == 2 && M % 256) return fail(h, DIINN_ERR_BAD_SHAPE, "cta_group 2 needs M%256==0");
   cudaSetDevice(h->cfg.device);
   return launch_umma_selftest(h, A, B, D, M, N, K, cta_group, static_cast<cudaStream_t>(stream));
 }

@@ -42,6 +42,9 @@ struct Handle {
   size_t host_out_bytes = 0;
   void* host_ws = nullptr;
   size_t host_ws_bytes = 0;
+  // copy streams + events of the banded host pipeline (upload band k+1 / download band k-1 while band k decodes)
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[8] = {}, ev_dec[8] = {};
 };
 
 inline int fail(Handle* h, int code, const std::string& msg) {

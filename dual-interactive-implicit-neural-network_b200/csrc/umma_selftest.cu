@@ -4,6 +4,8 @@
 // allocation, tcgen05.commit -> mbarrier, tcgen05.ld 32x32b, and (cta_group 2) the CTA-pair variants: leader-CTA
 // barrier for both CTAs' TMA loads, multicast commit, M=256 split across the pair, B split by N halves.
 // One 128(x2) x 256 output tile per CTA (pair); 4-stage K pipeline of 64-element chunks.
+#include <cuda_fp16.h>
+
 #include "handle.h"
 #include "ptx.cuh"
 
@@ -13,7 +15,7 @@ using namespace ptx;
 template <int CG>
 __global__ void __launch_bounds__(192, 1)
 umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     float* __restrict__ D, int M, int N, int K) {
+                     float* __restrict__ D, int M, int N, int K, int f16acc) {
   constexpr int STAGES = 4;
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_ROWS = 256 / CG;
@@ -66,7 +68,7 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, 256);
+    const uint32_t idesc = f16acc ? umma_idesc_f16_acc16(128 * CG, 256) : umma_idesc_bf16(128 * CG, 256);
     for (int kb = 0; kb < nk; ++kb) {
       const int st = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
@@ -86,6 +88,22 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int q = warp & 3;
     const int row = row0 + q * 32 + lane;
     float* drow = D + static_cast<size_t>(row) * N + n0;
+    if (f16acc) {
+      // fp16 accumulators: one value per TMEM column, read two columns per register with .pack::16b
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t v[16];
+        tmem_ld32_pack16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __half2 hv = *reinterpret_cast<const __half2*>(&v[j]);
+            drow[c0 + 2 * j] = __low2float(hv);
+            drow[c0 + 2 * j + 1] = __high2float(hv);
+          }
+        }
+      }
+    } else
     for (int c0 = 0; c0 < 256; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
@@ -174,7 +192,14 @@ __global__ void __launch_bounds__(640, 1) umma_pace_kernel(int n_cols, int iters
       uint32_t v[16], w[16];
       float acc = 0.f;
       const long long t0 = clock64();
-      if (noise & 64) {  // one x32 load instead of two x16 loads per step
+      if (noise & 128) {  // x32 columns of 16-bit data packed into 16 registers, two per step (= 64 columns per step)
+        for (int it = 0; it < 512; ++it) {
+          tmem_ld32_pack16(taddr + ((it * 64) & 255), v);
+          tmem_ld32_pack16(taddr + ((it * 64 + 32) & 255), w);
+          tmem_ld_wait();
+          acc += __uint_as_float(v[it & 15]) + __uint_as_float(w[it & 15]);
+        }
+      } else if (noise & 64) {  // one x32 load instead of two x16 loads per step
         uint32_t u[32];
         for (int it = 0; it < 512; ++it) {
           tmem_ld32(taddr + ((it * 32) & 255), u);
@@ -248,6 +273,9 @@ int launch_umma_pace(Handle* h, int cta_group, int n_cols, int iters, int n_ctas
 
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
                          cudaStream_t s) {
+  // cta_group 1|2: bf16 operands, fp32 accumulators; 11|12: the same GEMM with fp16 operands and fp16 accumulators
+  const int f16acc = cta_group >= 10 ? 1 : 0;
+  cta_group = cta_group % 10;
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_2d_bf16(h, &tmA, A, K, M, 64, 128))) return rc;
@@ -268,11 +296,11 @@ int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int 
   if (cta_group == 1) {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(umma_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<1>, tmA, tmB, D, M, N, K));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<1>, tmA, tmB, D, M, N, K, f16acc));
   } else {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(umma_selftest_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<2>, tmA, tmB, D, M, N, K));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<2>, tmA, tmB, D, M, N, K, f16acc));
   }
   h->launches += 1;
   return DIINN_OK;

@@ -141,7 +141,8 @@ int diinn_debug_query_gather(diinn_handle* h, int B, int H, int W, const float* 
 int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, int W, float* P, void* workspace,
                         size_t workspace_bytes, int io_dtype, int compute, void* stream);
 /* tcgen05 self-test: D(M x N fp32) = A(M x K bf16, row-major) * B(N x K bf16, row-major)^T through the same
- * TMA / UMMA-descriptor / TMEM plumbing the fused kernels use. M%128==0, N%256==0, K%64==0. cta_group 1|2. */
+ * TMA / UMMA-descriptor / TMEM plumbing the fused kernels use. M%128==0, N%256==0, K%64==0. cta_group 1|2;
+ * 11|12 = the same with A, B holding fp16 and fp16 TMEM accumulators read back with tcgen05.ld.pack::16b. */
 int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
                           int cta_group, void* stream);
 

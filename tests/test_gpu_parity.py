@@ -368,6 +368,11 @@ def test_config_c3_div2k(w0):
         for r0, r1 in diinn_b200.row_partition(H_up, 8):
             dec16.forward_rows(x, (H_up, W_up), r0, r1, out=tiled)
     assert torch.equal(o16, tiled)
+    # host entry at full size: 4 pipelined row bands (upload / decode / download on three streams)
+    host = dec16.decode_host(torch.from_numpy(feat).pin_memory(), (H_up, W_up))
+    assert torch.equal(o16.cpu(), host)
+    band = dec16.decode_host(torch.from_numpy(feat).pin_memory(), (H_up, W_up), 170, 1187)
+    assert torch.equal(o16[:, :, 170:1187].cpu(), band)
     assert float((o16 - o32).abs().max()) <= TIGHT["bf16"]
     assert _psnr_delta(o16.cpu().numpy(), o32.cpu().numpy()) < 0.01
     bands = [(0, 1), (169, 171), (677, 679), (1355, 1356)]  # first/last rows and shard boundaries

@@ -46,6 +46,25 @@ def _selftest(cg):
 
 
 @stage
+def selftest_f16():
+    np, torch, diinn_b200, synth, orc = _setup()
+    dec = diinn_b200.FusedImplicitDecoder(mode=3).cuda()
+    for cg in (11, 12):
+        for (M, N, K) in [(256, 256, 64), (512, 512, 256)]:
+            g = torch.Generator(device="cpu").manual_seed(M + N + K)
+            A = (torch.randn(M, K, generator=g) * 0.25).to(torch.float16).cuda()
+            B = (torch.randn(N, K, generator=g) * 0.25).to(torch.float16).cuda()
+            D = dec.debug_umma_gemm(A.view(torch.bfloat16), B.view(torch.bfloat16), cta_group=cg)
+            torch.cuda.synchronize()
+            ref = A.float() @ B.float().t()
+            err = (D - ref).abs().max().item()
+            print(f"selftest fp16-acc cg={cg} M={M} N={N} K={K}: max err {err:.3e} (ref absmax {ref.abs().max().item():.2f})")
+            if err > 0.05:
+                bad = (D - ref).abs() > 0.05
+                print("  MISMATCH frac", bad.float().mean().item(), "D[0,:8]", D[0, :8].tolist(), "ref[0,:8]", ref[0, :8].tolist())
+
+
+@stage
 def selftest1():
     _selftest(1)
 
@@ -213,8 +232,8 @@ def mma_pace():
     from diinn_b200 import _lib
     dec = diinn_b200.FusedImplicitDecoder(mode=3).cuda()
     lib, h = dec._ensure_handle(torch.device("cuda:0"))
-    for per_q in (1, 2, 4):
-        for x32 in (0, 64):
+    for per_q in (2, 4):
+        for x32 in (0, 128):
             mma_iters = 20000
             buf = torch.zeros(74, device="cuda")
             noise = 32 | 8 | (per_q << 8) | x32
@@ -222,8 +241,8 @@ def mma_pace():
                 _lib.check(lib, h, lib.diinn_debug_umma_pace(h, 2, 256, mma_iters, 148, C.c_void_p(buf.data_ptr()), noise, None))
             torch.cuda.synchronize()
             v = buf.cpu().numpy()
-            print(f"ldtm_pace warps/quarter={per_q} x32={bool(x32)}: {v.mean():.1f} clk per 16 columns per warp "
-                  f"-> {per_q * 4 * 2048 / v.mean():.1f} B/clk/SM")
+            print(f"ldtm_pace warps/quarter={per_q} mode={x32}: {v.mean():.1f} clk per load instruction per warp "
+                  f"(mode 0: 16 columns per instruction, mode 128: 32 columns of 16-bit data packed)")
     for cg in ():
         for noise in (0, 8, 24):
             n_cols, n_ctas = 256, 148
