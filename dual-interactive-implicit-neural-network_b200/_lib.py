@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdiinn_b200.so")
 
 OK = 0
-COMPUTE_FP32, COMPUTE_BF16 = 0, 1
+COMPUTE_FP32, COMPUTE_BF16, COMPUTE_FP16ACC = 0, 1, 2
 IO_F32, IO_BF16 = 0, 1
 
 STATUS_NAMES = {

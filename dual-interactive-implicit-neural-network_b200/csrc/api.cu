@@ -63,8 +63,8 @@ int check_common(Handle* h, int B, int C, int H, int W, int io_dtype, int comput
   if (C != kC) return fail(h, DIINN_ERR_BAD_SHAPE, "feat must have 64 channels");
   if (B < 1 || H < 1 || W < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "empty feature map");
   if (io_dtype != DIINN_IO_F32 && io_dtype != DIINN_IO_BF16) return fail(h, DIINN_ERR_BAD_DTYPE, "io_dtype");
-  if (compute != DIINN_COMPUTE_FP32 && compute != DIINN_COMPUTE_BF16)
-    return fail(h, DIINN_ERR_BAD_DTYPE, "compute must be DIINN_COMPUTE_FP32 or DIINN_COMPUTE_BF16");
+  if (compute != DIINN_COMPUTE_FP32 && compute != DIINN_COMPUTE_BF16 && compute != DIINN_COMPUTE_FP16ACC)
+    return fail(h, DIINN_ERR_BAD_DTYPE, "compute must be DIINN_COMPUTE_FP32, _BF16 or _FP16ACC");
   return DIINN_OK;
 }
 
@@ -191,6 +191,7 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->WB32);
   cudaFree(h->WA16);
   cudaFree(h->WB16);
+  cudaFree(h->WB16h);
   cudaFree(h->host_feat_dev);
   cudaFree(h->host_out_dev);
   cudaFree(h->host_ws);
@@ -311,7 +312,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s)))
     return rc;
   mark();
-  rc = launch_stage_b_umma(h, src, o, P, 0, s);
+  rc = launch_stage_b_umma(h, src, o, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
   mark();
   return rc;
 }
@@ -461,7 +462,7 @@ int diinn_query(diinn_handle* h, const void* feat, int B, int C, int H, int W, c
   __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + off);
   if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
   if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s))) return rc;
-  return launch_stage_b_umma(h, src, o, P, 0, s);
+  return launch_stage_b_umma(h, src, o, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
 }
 
 int diinn_debug_gather(diinn_handle* h, int H, int W, int H_up, int W_up, int32_t* ih, int32_t* iw, float* rel_h,

@@ -1,6 +1,7 @@
 // diinn_handle: library-owned state (repacked weights, TMA descriptors, cached host-entry scratch).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <string>
 #include <vector>
@@ -33,6 +34,11 @@ struct Handle {
   CUtensorMap tmapWA_half{};
   CUtensorMap tmapWB{};           // 2-D (64, 6144 rows)
   CUtensorMap tmapWB_half{};
+  // fp16 twin of WB16 for the fp16-accumulator variant; inside every 256-row tile the K and Q rows are interleaved in
+  // 16-feature blocks (K f -> 32*(f/16) + f%16, Q f -> that + 16) so one packed TMEM load returns both branches
+  __half* WB16h = nullptr;
+  CUtensorMap tmapWBh{};
+  CUtensorMap tmapWBh_half{};
   SmallParams small{};            // host copy; passed by value to kernels
 
   // ---- cached device scratch for diinn_decode_host ----
@@ -76,7 +82,7 @@ int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, cons
 int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H, int W, int fr0, int frows,
                         int lr_row0, int lr_rows, float* P, cudaStream_t s);
 int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group,
-                        cudaStream_t s);
+                        bool f16acc, cudaStream_t s);
 // umma_selftest.cu
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
                          cudaStream_t s);

@@ -38,7 +38,8 @@ __global__ void pack_stage_a_kernel(RefPtrs r, float* __restrict__ WA32, float* 
   if (threadIdx.x == 0) bA[n] = r.kb[layer][row];
 }
 
-__global__ void pack_stage_b_kernel(RefPtrs r, float* __restrict__ WB32, __nv_bfloat16* __restrict__ WB16) {
+__global__ void pack_stage_b_kernel(RefPtrs r, float* __restrict__ WB32, __nv_bfloat16* __restrict__ WB16,
+                                    __half* __restrict__ WB16h) {
   const int n = blockIdx.x;   // 0..511
   const int li = blockIdx.y;  // 0..2 -> reference layer li+1
   const bool is_q = n >= kD;
@@ -47,11 +48,14 @@ __global__ void pack_stage_b_kernel(RefPtrs r, float* __restrict__ WB32, __nv_bf
                           : r.kw[li + 1] + static_cast<size_t>(row) * (kD + kUnfold);
   const int half = row >> 7;                              // which 128-feature half of the layer output
   const int tile_row = (is_q ? 128 : 0) + (row & 127);    // K-part rows [0,128), Q-part rows [128,256)
+  const int fh = row & 127;                               // fp16 twin: K/Q interleaved in 16-feature blocks
+  const int tile_row_h = 32 * (fh >> 4) + (is_q ? 16 : 0) + (fh & 15);
   for (int k = threadIdx.x; k < kD; k += blockDim.x) {
     const float v = src[k];
     WB32[(static_cast<size_t>(li) * 512 + n) * kD + k] = v;
     const int kc = k >> 6, e = k & 63;
     WB16[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row) * 64 + e] = __float2bfloat16_rn(v);
+    WB16h[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row_h) * 64 + e] = __float2half_rn(v);
   }
 }
 
@@ -97,9 +101,10 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     DIINN_CUDA_OK(h, cudaMalloc(&h->bq_dev, sizeof(float) * kLayers * kD));
     DIINN_CUDA_OK(h, cudaMalloc(&h->WA16, sizeof(__nv_bfloat16) * kPCols * kUnfold));
     DIINN_CUDA_OK(h, cudaMalloc(&h->WB16, sizeof(__nv_bfloat16) * 3 * 512 * kD));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WB16h, sizeof(__half) * 3 * 512 * kD));
   }
   pack_stage_a_kernel<<<kPCols, 192, 0, s>>>(r, h->WA32, h->bA, h->WA16);
-  pack_stage_b_kernel<<<dim3(512, 3), 128, 0, s>>>(r, h->WB32, h->WB16);
+  pack_stage_b_kernel<<<dim3(512, 3), 128, 0, s>>>(r, h->WB32, h->WB16, h->WB16h);
   h->launches += 2;
   DIINN_CUDA_OK(h, cudaGetLastError());
 
@@ -137,6 +142,9 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   if ((rc = make_tmap_2d_bf16(h, &h->tmapWA_half, h->WA16, 64, 4 * 9 * 256, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(h, &h->tmapWB, h->WB16, 64, 3 * 2 * 4 * 256, 64, 256))) return rc;
   if ((rc = make_tmap_2d_bf16(h, &h->tmapWB_half, h->WB16, 64, 3 * 2 * 4 * 256, 64, 128))) return rc;
+  // (same element size and no arithmetic in a TMA copy: the bf16 descriptor type moves fp16 bits unchanged)
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh, h->WB16h, 64, 3 * 2 * 4 * 256, 64, 256))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh_half, h->WB16h, 64, 3 * 2 * 4 * 256, 64, 128))) return rc;
   h->has_weights = true;
   return DIINN_OK;
 }

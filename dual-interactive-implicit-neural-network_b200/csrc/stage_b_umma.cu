@@ -160,6 +160,7 @@ __device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[
 }
 
 // layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
+template <bool F16>
 __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
                                             const SmallParams& sp, const float4 (&k0v)[4]) {
   const uint32_t chunk_base = act_base + kc * kChunkBytes;
@@ -177,34 +178,53 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
       t = fmaf(w.z, rc.ratio, t);
       q[e] = k0[j + e] * __sinf(t);
     }
-    pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+    pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
   }
   st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
   st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
 }
 
-// epilogue of 16 features [128h + 64c + 16wg, +16) of row r for reference layer `layer` (1..3); kx = the matching
-// slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
-template <bool kLast>
-__device__ __forceinline__ void epi_step(uint32_t tslot, uint32_t out_base, int layer, int h, int c, int wg, int r,
-                                         const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3],
-                                         long long* tr = nullptr) {
+// ---- epilogue of 16 features [128h + 64c + 16wg, +16) of one row, reference layer `layer` (1..3) ------------------
+// raw accumulator registers of one step: fp32 accumulators = 16 K + 16 Q columns (32 regs); fp16 accumulators (K and Q
+// rows interleaved in 16-feature blocks by pack.cu) = 32 columns packed two per register (16 regs)
+template <bool F16>
+struct Raw {
+  uint32_t v[F16 ? 16 : 32];
+};
+
+template <bool F16>
+__device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw<F16>& raw) {  // issue only; caller waits
+  if constexpr (F16) {
+    tmem_ld32_pack16(tslot + 2 * col, raw.v);
+  } else {
+    tmem_ld16(tslot + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[0]));
+    tmem_ld16(tslot + 128 + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[16]));
+  }
+}
+
+// kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
+template <bool kLast, bool F16>
+__device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
+                                         const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3]) {
   const int col = c * 64 + wg * 16;
   const int f0 = h * 128 + col;
   const float* kx = reinterpret_cast<const float*>(kxv);
-  uint32_t vk[16], vq[16];
-  tmem_ld16(tslot + col, vk);
-  tmem_ld16(tslot + 128 + col, vq);
-  tmem_ld_wait();
-  if (tr) tr[0] = clock64();
   uint32_t pk[8];
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
+    float ak[2], aq[2];
+    if constexpr (F16) {
+      unpack_f16x2(raw.v[j >> 1], ak[0], ak[1]);
+      unpack_f16x2(raw.v[8 + (j >> 1)], aq[0], aq[1]);
+    } else {
+      ak[0] = __uint_as_float(raw.v[j]), ak[1] = __uint_as_float(raw.v[j + 1]);
+      aq[0] = __uint_as_float(raw.v[16 + j]), aq[1] = __uint_as_float(raw.v[16 + j + 1]);
+    }
     float q[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float k = fmaxf(__uint_as_float(vk[j + e]) + kx[j + e], 0.f);
-      const float sn = __sinf(__uint_as_float(vq[j + e]) + sp.bq[layer][f0 + j + e]);
+      const float k = fmaxf(ak[e] + kx[j + e], 0.f);
+      const float sn = __sinf(aq[e] + sp.bq[layer][f0 + j + e]);
       q[e] = k * sn;
       if constexpr (kLast) {
         const float4 w = *reinterpret_cast<const float4*>(&sp.wl_t[f0 + j + e][0]);
@@ -213,21 +233,20 @@ __device__ __forceinline__ void epi_step(uint32_t tslot, uint32_t out_base, int 
         rgb[2] = fmaf(w.z, q[e], rgb[2]);
       }
     }
-    if constexpr (!kLast) pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+    if constexpr (!kLast) pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
   }
   if constexpr (!kLast) {
     const uint32_t chunk_base = out_base + (2 * h + c) * kChunkBytes;
-    if (tr) tr[1] = clock64();
     st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
     st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
-    if (tr) tr[2] = clock64();
   }
 }
 
-template <int CG>
+template <int CG, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SmallParams sp,
-                    const PixelSource src, const OutSpec out, const float* __restrict__ P, const Work wk,
+                    const __grid_constant__ PixelSource src, const __grid_constant__ OutSpec out,
+                    const float* __restrict__ P, const __grid_constant__ Work wk,
                     int* __restrict__ err_flag, long long* __restrict__ trace) {
   using C = Cfg<CG>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -303,7 +322,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // from a divergent single-lane region instead, each UTCHMMA costs an ELECT + 5x R2UR.BROADCAST waterfall
     // (~100 clk), which capped the tensor pipe at ~200 clk per MMA instead of 128.
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, 256);
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16_acc16(128 * CG, 256) : umma_idesc_bf16(128 * CG, 256);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0;            // weight stage counter
       uint32_t act_phase = 0;     // bit b: parity to wait for on act_ready[b][*]
@@ -386,9 +405,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       for (int c = 0; c < 2; ++c) {
         const int kc = 2 * grp + c;
         load16(pn + kc * 64 + 16, kb);
-        layer0_step(buf, kc, sub * 2, r, rcx, sp, ka);
+        layer0_step<F16>(buf, kc, sub * 2, r, rcx, sp, ka);
         if (c == 0) load16(pn + (kc + 1) * 64, ka);
-        layer0_step(buf, kc, sub * 2 + 1, r, rcx, sp, kb);
+        layer0_step<F16>(buf, kc, sub * 2 + 1, r, rcx, sp, kb);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc]);
@@ -429,37 +448,51 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         mbar_wait(&sm.tmem_full[h], full_uses & 1);
         tc_fence_after();
         if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
+        // four 16-feature steps (c = chunk of the half, s = which 16 of this warp's 32): kx slices ping-pong between
+        // ka / kb one step ahead; with fp16 accumulators the TMEM loads ping-pong too (16 regs each), so every step's
+        // math runs under the next step's tcgen05.ld. The slot is handed back to the MMA issuer as soon as the last
+        // load has landed, before the last step's math.
+        Raw<F16> ra, rb;
+        auto free_slot = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
+        };
+        auto chunk_done = [&](int c) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + c]);
+        };
+        const int w0 = sub * 2, w1 = sub * 2 + 1;
+        const bool last = layer == 3;
+        epi_load<F16>(tslot, w0 * 16, ra);
+        tmem_ld_wait();
+        if constexpr (F16) epi_load<F16>(tslot, w1 * 16, rb);
         load16(pl + 16, kb);
-        if (layer < 3) {
-          long long* tr = (tracer && layer == 2 && t < 8) ? trace + t * 128 + 96 + h * 8 : nullptr;
-          epi_step<false>(tslot, out_base, layer, h, 0, sub * 2, r, sp, ka, rgb, tr);
-          load16(pl + 64, ka);
-          epi_step<false>(tslot, out_base, layer, h, 0, sub * 2 + 1, r, sp, kb, rgb);
-          fence_proxy_async_smem();
-          if (tr) tr[3] = clock64();
-          __syncwarp();
-          if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h]);
-          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
-          load16(pl + 64 + 16, kb);
-          epi_step<false>(tslot, out_base, layer, h, 1, sub * 2, r, sp, ka, rgb, tr ? tr + 4 : nullptr);
-          epi_step<false>(tslot, out_base, layer, h, 1, sub * 2 + 1, r, sp, kb, rgb);
-          fence_proxy_async_smem();
-          if (tr) tr[7] = clock64();
-          __syncwarp();
-          if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + 1]);
-        } else {
-          epi_step<true>(tslot, out_base, layer, h, 0, sub * 2, r, sp, ka, rgb);
-          load16(pl + 64, ka);
-          epi_step<true>(tslot, out_base, layer, h, 0, sub * 2 + 1, r, sp, kb, rgb);
-          load16(pl + 64 + 16, kb);
-          epi_step<true>(tslot, out_base, layer, h, 1, sub * 2, r, sp, ka, rgb);
-          epi_step<true>(tslot, out_base, layer, h, 1, sub * 2 + 1, r, sp, kb, rgb);
-        }
+        if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, w0, r, sp, ka, rgb);
+        else epi_math<false, F16>(ra, out_base, layer, h, 0, w0, r, sp, ka, rgb);
+        if constexpr (!F16) epi_load<F16>(tslot, w1 * 16, rb);
+        tmem_ld_wait();
+        if constexpr (F16) epi_load<F16>(tslot, 64 + w0 * 16, ra);
+        load16(pl + 64, ka);
+        if (last) epi_math<true, F16>(rb, out_base, layer, h, 0, w1, r, sp, kb, rgb);
+        else epi_math<false, F16>(rb, out_base, layer, h, 0, w1, r, sp, kb, rgb);
+        if (!last) chunk_done(0);
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
+        if constexpr (!F16) epi_load<F16>(tslot, 64 + w0 * 16, ra);
+        tmem_ld_wait();
+        if constexpr (F16) epi_load<F16>(tslot, 64 + w1 * 16, rb);
+        load16(pl + 64 + 16, kb);
+        if (last) epi_math<true, F16>(ra, out_base, layer, h, 1, w0, r, sp, ka, rgb);
+        else epi_math<false, F16>(ra, out_base, layer, h, 1, w0, r, sp, ka, rgb);
+        if constexpr (!F16) epi_load<F16>(tslot, 64 + w1 * 16, rb);
+        tmem_ld_wait();
+        free_slot();
+        if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, w1, r, sp, kb, rgb);
+        else epi_math<false, F16>(rb, out_base, layer, h, 1, w1, r, sp, kb, rgb);
+        if (!last) chunk_done(1);
         if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
-        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
         ++full_uses;
       }
       // Combine the four partial RGB projections of a row (2 groups x 2 subs) in a fixed order (bit-reproducible).
@@ -494,8 +527,18 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
 }  // namespace sb
 
+template <int CG, bool F16>
+static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const PixelSource& src,
+                          const OutSpec& out, const float* P, const sb::Work& wk, int* err_flag, long long* trace) {
+  using namespace sb;
+  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kSmemBytes)));
+  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, F16>, tm, h->small, src, out, P, wk, err_flag, trace));
+  return DIINN_OK;
+}
+
 int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group,
-                        cudaStream_t s) {
+                        bool f16acc, cudaStream_t s) {
   using namespace sb;
   if (cta_group == 0) {
     static int env_cg = -1;
@@ -546,16 +589,14 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cta_group == 1) {
-    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(kSmemBytes)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_b_umma_kernel<1>, h->tmapWB, h->small, src, out, P, wk, err_flag, trace));
-  } else {
-    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(kSmemBytes)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_b_umma_kernel<2>, h->tmapWB_half, h->small, src, out, P, wk,
-                                        err_flag, trace));
-  }
+  int rc;
+  if (cta_group == 1)
+    rc = f16acc ? launch_variant<1, true>(h, &cfg, h->tmapWBh, src, out, P, wk, err_flag, trace)
+                : launch_variant<1, false>(h, &cfg, h->tmapWB, src, out, P, wk, err_flag, trace);
+  else
+    rc = f16acc ? launch_variant<2, true>(h, &cfg, h->tmapWBh_half, src, out, P, wk, err_flag, trace)
+                : launch_variant<2, false>(h, &cfg, h->tmapWB_half, src, out, P, wk, err_flag, trace);
+  if (rc) return rc;
   h->launches += 1;
   return DIINN_OK;
 }

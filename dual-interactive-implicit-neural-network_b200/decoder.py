@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import _lib
 
-_PRECISIONS = {"fp32": _lib.COMPUTE_FP32, "bf16": _lib.COMPUTE_BF16}
+_PRECISIONS = {"fp32": _lib.COMPUTE_FP32, "bf16": _lib.COMPUTE_BF16, "fp16acc": _lib.COMPUTE_FP16ACC}
 
 
 class SineAct(nn.Module):
@@ -38,7 +38,8 @@ def _stream(device) -> C.c_void_p:
 class FusedImplicitDecoder(nn.Module):
     """B200-native DIINN query decoder (mode=3, init_q=False).
 
-    precision: "bf16" -> tcgen05 tensor cores, bf16 operands / fp32 accumulation (throughput path);
+    precision: "bf16" -> tcgen05 tensor cores, bf16 operands / fp32 accumulation (default throughput path);
+               "fp16acc" -> stage B with fp16 operands and fp16 TMEM accumulators (faster epilogue, opt-in);
                "fp32" -> fp32 FMA on CUDA cores end to end (exact-fp32 parity path).
     The I/O dtype follows ``x.dtype`` (float32 or bfloat16), as in the reference where out.dtype == x.dtype.
     """

@@ -46,7 +46,10 @@ typedef enum diinn_status {
 /* arithmetic path */
 typedef enum diinn_compute {
   DIINN_COMPUTE_FP32 = 0, /* fp32 FMA on CUDA cores end to end (exact-fp32 path; slow, used for fp32 parity)   */
-  DIINN_COMPUTE_BF16 = 1  /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation, fp32 bias/sin/relu     */
+  DIINN_COMPUTE_BF16 = 1, /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation, fp32 bias/sin/relu     */
+  DIINN_COMPUTE_FP16ACC = 2 /* stage B with fp16 operands AND fp16 TMEM accumulators (read back two per register, which
+                               halves the TMEM->register traffic that bounds the fp32-accumulator kernel); stage A, P,
+                               biases, sin, relu stay as in _BF16. Opt-in: ~1e-3 relative error on pre-activations. */
 } diinn_compute;
 
 /* element type of the feat / out buffers */

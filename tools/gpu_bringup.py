@@ -159,6 +159,37 @@ def _bf16(cg):
 
 
 @stage
+def fp16acc():
+    np, torch, diinn_b200, synth, orc = _setup()
+    for name in ["x1_batch", "c1", "odd2", "frac", "stress"]:
+        weights, feat, size, ref = _case(name)
+        dec = _decoder(weights, "fp16acc")
+        with torch.no_grad():
+            out = dec(torch.from_numpy(feat).cuda(), size)
+        torch.cuda.synchronize()
+        e = np.abs(out.cpu().numpy() - ref)
+        print(f"fp16acc {name}: max-abs err {e.max():.3e} mean {e.mean():.3e} (|ref| max {np.abs(ref).max():.3f})")
+    weights = synth.make_weights(seed=0)
+    for prec in ("fp16acc", "bf16"):
+        for name in ["c2x2", "c2x4", "c3", "c4"]:
+            B, H, W, H_up, W_up = synth.CONFIGS[name]
+            x = torch.from_numpy(synth.make_feat(1, B, H, W)).cuda()
+            dec = _decoder(weights, prec)
+            with torch.no_grad():
+                for _ in range(3):
+                    dec(x, (H_up, W_up))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    dec(x, (H_up, W_up))
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            print(f"timing {prec} {name}: {ms:.3f} ms  {B * H_up * W_up / ms / 1e3:.1f} Mpx/s")
+
+
+@stage
 def bf16_cg1():
     _bf16(1)
 
