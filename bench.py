@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16acc", "fp32"])
     ap.add_argument("--no-extra", action="store_true", help="skip the c2/c4 extra measurements")
     ap.add_argument("--assembly", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused = stage B stores every pixel into all ranks' image buffers over NVLink (peer / "
@@ -201,7 +201,7 @@ def main():
         for _ in range(max(3, args.warmup)):
             out = step()
         barrier()
-        dec.set_profiling(args.precision == "bf16", dev)
+        dec.set_profiling(args.precision != "fp32", dev)
         launches0 = dec.launch_count()
         sampler = ClockSampler(local)
         if rank == 0:
@@ -216,7 +216,7 @@ def main():
         ms_total = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
         launches = dec.launch_count() - launches0
-        kt = dec.kernel_times() if args.precision == "bf16" else None
+        kt = dec.kernel_times() if args.precision != "fp32" else None
         dec.set_profiling(False, dev)
 
         # ---- e2e: host buffers through the C-ABI host entry (H2D feat + decode of this rank's tile + D2H tile)
@@ -291,7 +291,8 @@ def main():
         "config": {
             "workload": workload_desc(args.workload),
             "io_dtype": "fp32 feature map in, fp32 image out",
-            "compute": "tcgen05 bf16 operands, fp32 TMEM accumulation" if args.precision == "bf16" else "fp32 CUDA cores",
+            "compute": {"bf16": "tcgen05 bf16 operands, fp32 TMEM accumulation", "fp16acc": "tcgen05; stage B fp16 operands, fp16 TMEM "
+                        "accumulation", "fp32": "fp32 CUDA cores"}[args.precision],
             "sharding": (f"HR row tiles over {world} ranks, feature map and weights replicated, no data-path collective; "
                          + (f"assembly fused into stage B ({diinn_b200.sharding.last_fused_mode} over NVLink, symmetric "
                             "memory + 2 barriers)" if args.assembly == "fused" else
@@ -320,7 +321,7 @@ def main():
             with open(pj) as f:
                 prof = json.load(f)
         line["roofline"] = {
-            "bound": "tensor", "kernel": "stage_b_umma_kernel<2>", "achieved": ach, "peak": peaks["bf16_sustained"],
+            "bound": "tensor", "kernel": "stage_b_umma_kernel<2, %s>" % ("true" if args.precision == "fp16acc" else "false"), "achieved": ach, "peak": peaks["bf16_sustained"],
             "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
             "traffic": prof.get("dram_bytes_per_launch_c3") if args.workload == "c3" and world == 1 else None,
             "peak_source": peaks["source"] + "; sustained cuBLAS bf16 figure because the kernel is timed inside the step",

@@ -23,7 +23,7 @@ STATUS_NAMES = {
 # every symbol include/diinn_b200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
     "diinn_create", "diinn_destroy", "diinn_last_error", "diinn_set_weights", "diinn_workspace_bytes",
-    "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_debug_gather",
+    "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_query_ensemble", "diinn_debug_gather",
     "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace", "diinn_debug_umma_pace", "diinn_set_profiling", "diinn_get_kernel_times",
     "diinn_launch_count",
     "diinn_version",
@@ -74,6 +74,8 @@ def load() -> C.CDLL:
     lib.diinn_query_workspace_bytes.restype = sz
     lib.diinn_query.argtypes = [vp, vp, i, i, i, i, vp, vp, i, vp, vp, sz, i, i, vp]
     lib.diinn_query.restype = i
+    lib.diinn_query_ensemble.argtypes = [vp, vp, i, i, i, i, vp, vp, i, vp, vp, sz, i, i, vp]
+    lib.diinn_query_ensemble.restype = i
     lib.diinn_debug_gather.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp]
     lib.diinn_debug_gather.restype = i
     lib.diinn_debug_query_gather.argtypes = [vp, i, i, i, vp, vp, i, vp, vp, vp, vp]

@@ -421,8 +421,18 @@ size_t diinn_query_workspace_bytes(const diinn_handle* h, int B, int H, int W, i
   return off;
 }
 
-static PixelSource make_query_source(int B, int H, int W, const float* coord, const float* cell, int Q) {
+static PixelSource make_query_source(int B, int H, int W, const float* coord, const float* cell, int Q,
+                                     int ensemble = 0) {
   PixelSource src{};
+  src.ensemble = ensemble;
+  // python-double scalars of liif.py:79-80,92-94 rounded to fp32 when they meet the fp32 coordinate tensor
+  for (int i = 0; i < 2; ++i) {
+    const double v = i ? 1.0 : -1.0;
+    src.sh_h[i] = static_cast<float>(v * (2.0 / H / 2.0) + 1e-6);
+    src.sh_w[i] = static_cast<float>(v * (2.0 / W / 2.0) + 1e-6);
+  }
+  src.clamp_lo = static_cast<float>(-1 + 1e-6);
+  src.clamp_hi = static_cast<float>(1 - 1e-6);
   src.mode = 1;
   src.ax_h = make_axis(H, H);
   src.ax_w = make_axis(W, W);
@@ -433,13 +443,31 @@ static PixelSource make_query_source(int B, int H, int W, const float* coord, co
   return src;
 }
 
+static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, const float* coord,
+                      const float* cell, int Q, int ensemble, void* out, void* workspace, size_t workspace_bytes,
+                      int io_dtype, int compute, void* stream);
+
 int diinn_query(diinn_handle* h, const void* feat, int B, int C, int H, int W, const float* coord, const float* cell,
                 int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype, int compute, void* stream) {
+  return query_impl(h, feat, B, C, H, W, coord, cell, Q, 0, out, workspace, workspace_bytes, io_dtype, compute, stream);
+}
+
+int diinn_query_ensemble(diinn_handle* h, const void* feat, int B, int C, int H, int W, const float* coord,
+                         const float* cell, int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype,
+                         int compute, void* stream) {
+  return query_impl(h, feat, B, C, H, W, coord, cell, Q, 1, out, workspace, workspace_bytes, io_dtype, compute, stream);
+}
+
+static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, const float* coord,
+                      const float* cell, int Q, int ensemble, void* out, void* workspace, size_t workspace_bytes,
+                      int io_dtype, int compute, void* stream) {
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
   if (!feat || !out || !coord || !cell) return fail(h, DIINN_ERR_BAD_ARG, "null pointer");
   if (Q < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "Q must be positive");
-  const size_t need = diinn_query_workspace_bytes(h, B, H, W, Q, compute);
+  const int E = ensemble ? 4 : 1;
+  if (static_cast<int64_t>(Q) * E >= (1ll << 31) / 8) return fail(h, DIINN_ERR_BAD_SHAPE, "too many queries per call");
+  const size_t need = diinn_query_workspace_bytes(h, B, H, W, Q * E, compute);
   if (!workspace || workspace_bytes < need)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL, "workspace too small: need " + std::to_string(need) + " bytes");
   cudaSetDevice(h->cfg.device);
@@ -447,12 +475,12 @@ int diinn_query(diinn_handle* h, const void* feat, int B, int C, int H, int W, c
   char* ws = static_cast<char*>(workspace);
   float* P = reinterpret_cast<float*>(ws);
   size_t off = align_up(static_cast<size_t>(B) * H * W * kPCols * sizeof(float));
-  const PixelSource src = make_query_source(B, H, W, coord, cell, Q);
+  const PixelSource src = make_query_source(B, H, W, coord, cell, Q, ensemble);
   OutSpec o{};
   o.ptr = out;
   o.io_dtype = io_dtype;
   if (compute == DIINN_COMPUTE_FP32) {
-    const int64_t total = static_cast<int64_t>(B) * Q;
+    const int64_t total = static_cast<int64_t>(B) * Q * E;
     const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;
     float* q0 = reinterpret_cast<float*>(ws + off);
     float* q1 = reinterpret_cast<float*>(ws + off + align_up(static_cast<size_t>(chunk) * kD * sizeof(float)));

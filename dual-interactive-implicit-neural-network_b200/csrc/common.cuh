@@ -64,6 +64,14 @@ __device__ __forceinline__ float query_rel(const AxisParams& p, float c, int i) 
   return __fmul_rn(__fsub_rn(c, axis_centre_in(p, i)), p.n_in_f);
 }
 
+// local-ensemble lookup (LIIF.query_rgb, liif.py:88-104): shifted + clamped coordinate -> grid_sample(nearest,
+// align_corners=False) index = nearbyint(((c_ + 1) * n - 1) / 2), every step rounded in fp32
+__device__ __forceinline__ int ensemble_index(const AxisParams& p, float c, float shift, float lo, float hi) {
+  const float cs = fminf(fmaxf(__fadd_rn(c, shift), lo), hi);
+  const float t = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(cs, 1.0f), p.n_in_f), 1.0f), 0.5f);
+  return max(0, min(__float2int_rn(t), p.n_in - 1));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // How the fused kernels enumerate "HR query pixels". Two sources: the regular grid of forward(x, size) and the
 // explicit (coord, cell) list of query().
@@ -80,6 +88,11 @@ struct PixelSource {
   const float* cell;   // (B,Q,2)
   int Q;
   float hw_f;  // fp32(H*W)
+  // query list with LIIF's 4-neighbour local ensemble (diinn_query_ensemble): row g = 4*query + v, v = 2*(vx>0) + (vy>0);
+  // the four rows of a query are blended by area in the last epilogue (liif.py:117-127)
+  int ensemble;
+  float sh_h[2], sh_w[2];  // fp32(v/n + 1e-6) for v = -1, +1
+  float clamp_lo, clamp_hi;
 };
 
 constexpr int kMaxPeers = 8;

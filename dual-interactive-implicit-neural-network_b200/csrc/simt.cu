@@ -17,6 +17,7 @@ namespace diinn {
 struct PixInfo {
   int p_idx;  // row of P
   float rel_h, rel_w, ratio;
+  float area;  // ensemble rows only: |rel_h * rel_w| + 1e-9
   int b, oh, ow;  // grid: batch / HR row / HR col; query: b, q, unused
 };
 
@@ -38,22 +39,32 @@ __device__ __forceinline__ PixInfo pixel_info(const PixelSource& s, int64_t g) {
     pi.oh = oh;
     pi.ow = ow;
   } else {
-    const int b = static_cast<int>(g / s.Q);
-    const float ch = s.coord[g * 2], cw = s.coord[g * 2 + 1];
-    const int ih = query_index(s.ax_h, ch), iw = query_index(s.ax_w, cw);
+    const int64_t q = s.ensemble ? (g >> 2) : g;  // query index in (B*Q)
+    const int v = static_cast<int>(g & 3);
+    const int b = static_cast<int>(q / s.Q);
+    const float ch = s.coord[q * 2], cw = s.coord[q * 2 + 1];
+    int ih, iw;
+    if (s.ensemble) {
+      ih = ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi);
+      iw = ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi);
+    } else {
+      ih = query_index(s.ax_h, ch), iw = query_index(s.ax_w, cw);
+    }
     pi.p_idx = (b * s.H + ih) * s.W + iw;
     pi.rel_h = query_rel(s.ax_h, ch, ih);
     pi.rel_w = query_rel(s.ax_w, cw, iw);
-    pi.ratio = __fmul_rn(__fmul_rn(__fmul_rn(s.cell[g * 2], s.cell[g * 2 + 1]), s.hw_f), 0.25f);
+    pi.ratio = __fmul_rn(__fmul_rn(__fmul_rn(s.cell[q * 2], s.cell[q * 2 + 1]), s.hw_f), 0.25f);
+    pi.area = __fadd_rn(fabsf(__fmul_rn(pi.rel_h, pi.rel_w)), 1e-9f);
     pi.b = b;
-    pi.oh = static_cast<int>(g - static_cast<int64_t>(b) * s.Q);
+    pi.oh = static_cast<int>(q - static_cast<int64_t>(b) * s.Q);
     pi.ow = 0;
   }
   return pi;
 }
 
 __device__ __forceinline__ int64_t total_pixels(const PixelSource& s) {
-  return s.mode == 0 ? static_cast<int64_t>(s.B) * (s.row1 - s.row0) * s.W_up : static_cast<int64_t>(s.B) * s.Q;
+  return s.mode == 0 ? static_cast<int64_t>(s.B) * (s.row1 - s.row0) * s.W_up
+                     : static_cast<int64_t>(s.B) * s.Q * (s.ensemble ? 4 : 1);
 }
 
 __device__ __forceinline__ void store_rgb(const OutSpec& o, const PixelSource& s, const PixInfo& pi, int64_t g,
@@ -62,7 +73,7 @@ __device__ __forceinline__ void store_rgb(const OutSpec& o, const PixelSource& s
   if (s.mode == 0)
     off = pi.b * o.batch_stride + c * o.chan_stride + static_cast<int64_t>(pi.oh - s.row0) * o.row_stride + pi.ow;
   else
-    off = g * 3 + c;
+    off = (s.ensemble ? (g >> 2) : g) * 3 + c;
   store_out(o, off, v);
 }
 
@@ -316,8 +327,10 @@ __global__ void __launch_bounds__(256) last_fp32_kernel(PixelSource src, OutSpec
                                                         const __grid_constant__ SmallParams sp,
                                                         const float* __restrict__ q, int64_t g0, int64_t g1) {
   const int lane = threadIdx.x & 31;
-  const int64_t g = g0 + static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (g >= g1) return;
+  const int64_t g_raw = g0 + static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const bool ens = src.mode == 1 && src.ensemble;
+  if (g_raw >= g1 && !ens) return;
+  const int64_t g = g_raw < g1 ? g_raw : g1 - 1;  // ensemble blocks keep all warps alive for the block barrier
   const float* row = q + static_cast<size_t>(g - g0) * kD;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -334,6 +347,29 @@ __global__ void __launch_bounds__(256) last_fp32_kernel(PixelSource src, OutSpec
     a1 += __shfl_xor_sync(0xffffffffu, a1, o);
     a2 += __shfl_xor_sync(0xffffffffu, a2, o);
   }
+  if (src.mode == 1 && src.ensemble) {
+    // the block's 8 warps hold the 4 variants of 2 queries (g0 and every chunk are multiples of 8): blend by area with
+    // the diagonal swap, accumulating in the reference's order (liif.py:117-127)
+    __shared__ float s_v[8][4];
+    if (lane == 0) {
+      s_v[threadIdx.x >> 5][0] = a0 + sp.bl[0];
+      s_v[threadIdx.x >> 5][1] = a1 + sp.bl[1];
+      s_v[threadIdx.x >> 5][2] = a2 + sp.bl[2];
+      s_v[threadIdx.x >> 5][3] = pixel_info(src, g).area;
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5;
+    if (lane == 0 && (w & 3) == 0 && g_raw < g1) {
+      const float tot = ((s_v[w][3] + s_v[w + 1][3]) + s_v[w + 2][3]) + s_v[w + 3][3];
+      const PixInfo pi = pixel_info(src, g);
+      for (int c = 0; c < 3; ++c) {
+        float acc = 0.f;
+        for (int v = 0; v < 4; ++v) acc += s_v[w + v][c] * (s_v[w + 3 - v][3] / tot);
+        store_rgb(out, src, pi, g, c, acc);
+      }
+    }
+    return;
+  }
   if (lane == 0) {
     const PixInfo pi = pixel_info(src, g);
     store_rgb(out, src, pi, g, 0, a0 + sp.bl[0]);
@@ -345,7 +381,7 @@ __global__ void __launch_bounds__(256) last_fp32_kernel(PixelSource src, OutSpec
 int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,
                      float* qbuf1, int64_t chunk, cudaStream_t s) {
   const int64_t total = src.mode == 0 ? static_cast<int64_t>(src.B) * (src.row1 - src.row0) * src.W_up
-                                      : static_cast<int64_t>(src.B) * src.Q;
+                                      : static_cast<int64_t>(src.B) * src.Q * (src.ensemble ? 4 : 1);
   const float* bq_dev = h->bq_dev;
   for (int64_t g0 = 0; g0 < total; g0 += chunk) {
     const int64_t g1 = g0 + chunk < total ? g0 + chunk : total;

@@ -68,6 +68,7 @@ struct Work {
 struct RowCtx {
   const float* prow;  // P row of this pixel's LR cell
   float rel_h, rel_w, ratio;
+  float area;  // ensemble rows: |rel_h * rel_w| + 1e-9
   int64_t out_off;  // offset of channel 0
   bool valid;
 };
@@ -92,18 +93,28 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
     rc.ratio = s.ratio;
     rc.out_off = b * o.batch_stride + static_cast<int64_t>(ohc - s.row0) * o.row_stride + owc;
   } else {
-    const int64_t total = static_cast<int64_t>(s.B) * s.Q;
+    const int64_t total = static_cast<int64_t>(s.B) * s.Q * (s.ensemble ? 4 : 1);
     const int64_t g = (static_cast<int64_t>(work) * CG + rank) * kTileM + r;
     rc.valid = g < total;
     const int64_t gc = rc.valid ? g : total - 1;
-    const int b = static_cast<int>(gc / s.Q);
-    const float ch = __ldg(s.coord + gc * 2), cw = __ldg(s.coord + gc * 2 + 1);
-    const int ih = query_index(s.ax_h, ch), iw = query_index(s.ax_w, cw);
+    const int64_t qi = s.ensemble ? (gc >> 2) : gc;  // query index; ensemble rows 4q..4q+3 are its four neighbours
+    const int v = static_cast<int>(gc & 3);
+    const int b = static_cast<int>(qi / s.Q);
+    const float ch = __ldg(s.coord + qi * 2), cw = __ldg(s.coord + qi * 2 + 1);
+    int ih, iw;
+    if (s.ensemble) {
+      ih = ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi);
+      iw = ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi);
+    } else {
+      ih = query_index(s.ax_h, ch), iw = query_index(s.ax_w, cw);
+    }
     rc.prow = P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kPCols;
     rc.rel_h = query_rel(s.ax_h, ch, ih);
     rc.rel_w = query_rel(s.ax_w, cw, iw);
-    rc.ratio = __fmul_rn(__fmul_rn(__fmul_rn(__ldg(s.cell + gc * 2), __ldg(s.cell + gc * 2 + 1)), s.hw_f), 0.25f);
-    rc.out_off = gc * 3;
+    rc.ratio = __fmul_rn(__fmul_rn(__fmul_rn(__ldg(s.cell + qi * 2), __ldg(s.cell + qi * 2 + 1)), s.hw_f), 0.25f);
+    rc.area = __fadd_rn(fabsf(__fmul_rn(rc.rel_h, rc.rel_w)), 1e-9f);
+    if (s.ensemble) rc.valid = rc.valid && v == 0;  // lane 4j stores the blended query
+    rc.out_off = qi * 3;
   }
   return rc;
 }
@@ -133,12 +144,16 @@ __device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const f
                        static_cast<uint32_t>(nc) * kPCols * 4u);
     }
   } else {
-    const int64_t total = static_cast<int64_t>(s.B) * s.Q;
+    const int64_t total = static_cast<int64_t>(s.B) * s.Q * (s.ensemble ? 4 : 1);
     for (int rr = lane; rr < kTileM; rr += 32) {
       const int64_t g = (static_cast<int64_t>(work) * CG + rank) * kTileM + rr;
       if (g >= total) break;
-      const int b = static_cast<int>(g / s.Q);
-      const int ih = query_index(s.ax_h, __ldg(s.coord + g * 2)), iw = query_index(s.ax_w, __ldg(s.coord + g * 2 + 1));
+      const int64_t qi = s.ensemble ? (g >> 2) : g;
+      const int v = static_cast<int>(g & 3);
+      const int b = static_cast<int>(qi / s.Q);
+      const float ch = __ldg(s.coord + qi * 2), cw = __ldg(s.coord + qi * 2 + 1);
+      const int ih = s.ensemble ? ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi) : query_index(s.ax_h, ch);
+      const int iw = s.ensemble ? ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi) : query_index(s.ax_w, cw);
       prefetch_l2_bulk(P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kPCols, kPCols * 4u);
     }
   }
@@ -510,6 +525,21 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         for (int ch = 0; ch < 3; ++ch)
           o[ch] = ((sm.partial[0][r][ch] + sm.partial[1][r][ch]) + sm.partial[2][r][ch]) + rgb[ch] + sp.bl[ch];
         if (has_next) named_bar_arrive(2, kEpiThreads);
+        if (src.mode == 1 && src.ensemble) {
+          // lanes 4j..4j+3 hold the four neighbours of one query: out = sum_v pred_v * area_{3-v} / sum(area)
+          // (liif.py:117-127; butterfly sums, every lane of the warp participates)
+          const float a_sw = __shfl_xor_sync(0xffffffffu, rc.area, 3);
+          float tot = rc.area + __shfl_xor_sync(0xffffffffu, rc.area, 1);
+          tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+          const float wgt = a_sw / tot;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float t2 = o[ch] * wgt;
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 2);
+            o[ch] = t2;
+          }
+        }
         if (rc.valid) {
           const int64_t cs = src.mode == 0 ? out.chan_stride : 1;
           store_out(out, rc.out_off, o[0]);
@@ -572,7 +602,7 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
     wk.n_txp = (tiles_x + cta_group - 1) / cta_group;
     wk.n_work = src.B * wk.tiles_y * wk.n_txp;
   } else {
-    const int64_t total = static_cast<int64_t>(src.B) * src.Q;
+    const int64_t total = static_cast<int64_t>(src.B) * src.Q * (src.ensemble ? 4 : 1);
     wk.n_work = static_cast<int>((total + kTileM * cta_group - 1) / (kTileM * cta_group));
   }
   int units = h->sm_count / cta_group;

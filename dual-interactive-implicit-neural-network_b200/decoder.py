@@ -185,9 +185,10 @@ class FusedImplicitDecoder(nn.Module):
                                             rs, _ptr(ws), ws.numel(), io, comp, _stream(x.device)))
         return res
 
-    def query(self, feat: torch.Tensor, coord: torch.Tensor, cell: torch.Tensor) -> torch.Tensor:
+    def query(self, feat: torch.Tensor, coord: torch.Tensor, cell: torch.Tensor, local_ensemble: bool = False) -> torch.Tensor:
         """(feat, coord, cell) superset entry named by north_star (signature of LIIF.query_rgb, liif.py:59):
-        coord (B,Q,2) as (h,w) in [-1,1], cell (B,Q,2) -> (B,Q,3), DIINN semantics."""
+        coord (B,Q,2) as (h,w) in [-1,1], cell (B,Q,2) -> (B,Q,3), DIINN semantics.
+        local_ensemble=True adds LIIF's 4-neighbour ensemble + area blend (liif.py:71-127) around the DIINN step."""
         self._check_input(feat)
         lib, h = self._ensure_handle(feat.device)
         feat = feat.contiguous()
@@ -199,11 +200,12 @@ class FusedImplicitDecoder(nn.Module):
             raise ValueError("coord and cell must be (B,Q,2)")
         io = self._io_dtype(feat)
         comp = _PRECISIONS[self.precision]
-        nbytes = lib.diinn_query_workspace_bytes(h, B, H, W, Q, comp)
+        nbytes = lib.diinn_query_workspace_bytes(h, B, H, W, Q * (4 if local_ensemble else 1), comp)
         ws = self._get_workspace(nbytes, feat.device)
         out = torch.empty((B, Q, 3), dtype=feat.dtype, device=feat.device)
-        _lib.check(lib, h, lib.diinn_query(h, _ptr(feat), B, Cc, H, W, _ptr(coord), _ptr(cell), Q, _ptr(out), _ptr(ws),
-                                           ws.numel(), io, comp, _stream(feat.device)))
+        fn = lib.diinn_query_ensemble if local_ensemble else lib.diinn_query
+        _lib.check(lib, h, fn(h, _ptr(feat), B, Cc, H, W, _ptr(coord), _ptr(cell), Q, _ptr(out), _ptr(ws),
+                              ws.numel(), io, comp, _stream(feat.device)))
         return out
 
     def decode_host(self, feat_host: torch.Tensor, size, row0: int = 0, row1: Optional[int] = None,

@@ -132,6 +132,14 @@ int diinn_query(diinn_handle* h, const void* feat, int B, int C, int H, int W, c
                 const float* cell, int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype,
                 int compute, void* stream);
 
+/* "Next" row 1 of SURVEY.md section 8(f): the same query with LIIF's 4-neighbour local ensemble (LIIF.query_rgb,
+ * liif.py:71-127): every query is decoded at its four shifted nearest LR cells (shift +-1/n + 1e-6, clamp, nearest
+ * lookup) and the four RGB predictions are blended by the diagonally swapped areas |rel_h*rel_w| + 1e-9 inside the
+ * last epilogue. Workspace: diinn_query_workspace_bytes(h, B, H, W, 4*Q, compute). */
+int diinn_query_ensemble(diinn_handle* h, const void* feat, int B, int C, int H, int W, const float* coord,
+                         const float* cell, int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype,
+                         int compute, void* stream);
+
 /* ---- debug taps for the bit-exact tests -------------------------------------------------------------- */
 /* Per-axis nearest-exact source index and scaled relative coordinate, exactly the values
  * _make_pos_encoding (diinn.py:94-110) produces: ih[H_up], iw[W_up] int32; rel_h[H_up], rel_w[W_up] fp32. */

@@ -195,6 +195,52 @@ def query(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.ndarray, 
     return out
 
 
+# --------------------------------------------------------------------------------------------------
+# "next" row 1: LIIF-style 4-neighbour local ensemble + area blend around the DIINN step.
+# Restates LIIF.query_rgb, /root/reference/src/models/components/liif.py:59-127, with the imnet replaced by
+# ImplicitDecoder.step (diinn.py:132-139) fed (rel_h, rel_w, ratio) instead of the concatenated 580-vector.
+# --------------------------------------------------------------------------------------------------
+def ensemble_index_rel(coord_axis: np.ndarray, n: int, v: int):
+    """One axis, one shift direction v in {-1,+1} (liif.py:88-104):
+      c_  = clamp(fl(c + fp32(v/n + 1e-6)), fp32(-1+1e-6), fp32(1-1e-6))           shifted lookup coordinate
+      idx = nearbyint(fl(fl(fl(c_ + 1) * n) - 1) / 2)                               grid_sample(nearest, align_corners=False)
+      rel = fl(fl(c - centre[idx]) * n)                                             relative to the ORIGINAL coordinate"""
+    c = coord_axis.astype(F32)
+    shift = F32(v * (2.0 / n / 2.0) + 1e-6)
+    c_ = np.clip((c + shift).astype(F32), F32(-1 + 1e-6), F32(1 - 1e-6)).astype(F32)
+    t = ((((c_ + F32(1.0)).astype(F32) * F32(n)).astype(F32) - F32(1.0)).astype(F32) * F32(0.5)).astype(F32)
+    idx = np.clip(np.rint(t).astype(np.int64), 0, n - 1)
+    rel = ((c - axis_centres(n)[idx]).astype(F32) * F32(n)).astype(F32)
+    return idx, rel
+
+
+def query_ensemble(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.ndarray, fp64: bool = False):
+    """feat (B,64,H,W), coord/cell (B,Q,2) -> (B,Q,3): sum_v pred_v * area_{3-v} / sum(area), v = (vx,vy) in
+    [(-1,-1), (-1,1), (1,-1), (1,1)], area_v = |rel_h * rel_w| + 1e-9 (liif.py:117-127)."""
+    B, C, H, W = feat.shape
+    u = np.ascontiguousarray(unfold3x3(feat).transpose(0, 2, 3, 1))
+    dt = np.float64 if fp64 else F32
+    out = np.zeros(coord.shape[:2] + (3,), dtype=dt)
+    for b in range(B):
+        ce = cell[b].astype(F32)
+        ratio = (((ce[:, 0] * ce[:, 1]).astype(F32) * F32(H * W)).astype(F32) * F32(0.25)).astype(F32)
+        preds, areas = [], []
+        for vx in (-1, 1):
+            for vy in (-1, 1):
+                ih, rh = ensemble_index_rel(coord[b, :, 0], H, vx)
+                iw, rw = ensemble_index_rel(coord[b, :, 1], W, vy)
+                syn = np.stack([rh, rw, ratio], axis=1).astype(F32)
+                preds.append(step_mode3(weights, u[b][ih, iw], syn, fp64=fp64))
+                areas.append((np.abs((rh * rw).astype(F32)) + F32(1e-9)).astype(F32))
+        tot = ((areas[0] + areas[1]).astype(F32) + areas[2]).astype(F32) + areas[3]
+        areas = [areas[3], areas[2], areas[1], areas[0]]
+        acc = np.zeros_like(preds[0])
+        for p_, a_ in zip(preds, areas):
+            acc = acc + p_ * (a_ / tot).astype(dt)[:, None]
+        out[b] = acc
+    return out
+
+
 def grid_coords(H_up: int, W_up: int):
     """Cell-centre coords of the HR grid, as the reference builds them (diinn.py:101-102)."""
     return axis_centres(H_up), axis_centres(W_up)

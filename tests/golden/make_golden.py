@@ -103,6 +103,42 @@ def main():
     out["taps.out"] = dec.last_layer(q).numpy()
     out["taps.rows"] = np.array([93, 95, 0, 64], dtype=np.int64)
 
+    # ---- 4. "next" row: LIIF's local-ensemble query machinery (liif.py:59-127, unmodified) around the reference DIINN
+    #         step: LIIF.imnet is replaced by an adapter that feeds ImplicitDecoder.step -----------------------------
+    from src.models.components.liif import LIIF
+
+    class ImnetAdapter(torch.nn.Module):
+        def __init__(self, dec):
+            super().__init__()
+            self.dec = dec
+
+        def forward(self, inp):  # (N, 580) = [q_feat 576 | rel_coord 2 | rel_cell 2]  (liif.py:105-111)
+            n = inp.shape[0]
+            x = inp[:, :576].t().reshape(1, 576, n, 1)
+            ratio = inp[:, 578] * inp[:, 579] * 0.25
+            syn = torch.stack([inp[:, 576], inp[:, 577], ratio], 0).reshape(1, 3, n, 1)
+            return self.dec.step(x, syn)[0, :, :, 0].t()
+
+    for name, (wkw, fseed, B, H, W, Q, cellhw) in {
+        "ens": (dict(seed=0), 12, 2, 24, 20, 3000, (2.0 / 53, 2.0 / 47)),
+        "ens_stress": (dict(seed=5, k_gain=3.0, q_gain=10.0), 13, 1, 16, 16, 2000, (2.0 / 64, 2.0 / 64)),
+    }.items():
+        weights = synth.make_weights(**wkw)
+        feat = synth.make_feat(fseed, B, H, W)
+        coord, cell = synth.make_query(fseed + 1, B, Q, cellhw)
+        # include exact grid centres and the image border among the queries
+        coord[:, :50, 0] = np.linspace(-1, 1, 50, dtype=np.float32)
+        coord[:, 50:100, 1] = np.linspace(-1, 1, 50, dtype=np.float32)
+        liif = LIIF().eval()
+        liif.imnet = ImnetAdapter(ref_decoder(weights))
+        y = liif.query_rgb(torch.from_numpy(feat), torch.from_numpy(coord), torch.from_numpy(cell)).numpy()
+        out[f"{name}.out"] = y.astype(np.float32)
+        out[f"{name}.meta"] = np.array([wkw.get("seed", 0), fseed, B, H, W, Q], dtype=np.int64)
+        out[f"{name}.gains"] = np.array([wkw.get("k_gain", 1.0), wkw.get("q_gain", 1.0)], dtype=np.float64)
+        out[f"{name}.cell"] = np.array(cellhw, dtype=np.float64)
+        out[f"{name}.coord"] = coord
+        print(name, y.shape, float(np.abs(y).max()))
+
     np.savez_compressed(os.path.join(HERE, "decoder.npz"), **out)
     np.savez(os.path.join(HERE, "provenance.npz"),
              torch_version=np.array(torch.__version__), numpy_version=np.array(np.__version__))

@@ -14,9 +14,9 @@ from oracle import diinn_oracle as orc
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a GPU")]
 
-TOL = {"fp32": 1e-4, "bf16": 1e-2}
+TOL = {"fp32": 1e-4, "bf16": 1e-2, "fp16acc": 1e-2}
 # regression guards well inside the contract (measured: fp32 ~5e-8, bf16 ~3e-5 on the default-init weight set)
-TIGHT = {"fp32": 2e-6, "bf16": 2e-4}
+TIGHT = {"fp32": 2e-6, "bf16": 2e-4, "fp16acc": 2e-4}
 POS_CASES = ["c1", "c2x2", "c2x3", "c2x4", "c3", "c4", "c5", "odd1", "odd2", "odd3", "down"]
 GOLDEN_CASES = ["c1", "c1_bsize", "odd2", "x1_batch", "frac"]
 
@@ -120,7 +120,7 @@ def test_stage_a_matches_oracle(w0, precision, tol):
     assert float(np.abs(P - ref).max()) <= tol
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16acc"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_decode_matches_reference_golden(golden_decoder, precision, name):
     weights, feat, size, ref, bsize = _case(golden_decoder, name)
@@ -135,7 +135,7 @@ def test_decode_matches_reference_golden(golden_decoder, precision, name):
     assert _psnr_delta(out, ref) < 0.01
 
 
-@pytest.mark.parametrize("precision,rel_tol", [("fp32", 2e-5), ("bf16", 5e-2)])
+@pytest.mark.parametrize("precision,rel_tol", [("fp32", 2e-5), ("bf16", 5e-2), ("fp16acc", 5e-2)])
 def test_decode_stress_weights(golden_decoder, precision, rel_tol):
     """Gain-scaled weights (activations O(0.3) instead of being dominated by last_layer.bias):
     report the error relative to the output range; fp32 path must still meet the absolute 1e-4."""
@@ -171,7 +171,7 @@ def test_bsize_is_pure_scheduling(w0, precision):
 # ---------------------------------------------------------------------------------------------------------
 # sharding: row tiles are bit-identical to the full decode
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16acc"])
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_row_tiles_bit_identical(w0, precision, world):
     x = torch.from_numpy(synth.make_feat(6, 2, 23, 31)).cuda()
@@ -239,6 +239,29 @@ def test_query_on_grid_equals_forward(w0, precision):
     q = q.reshape(B, H_up, W_up, 3).permute(0, 3, 1, 2)
     # same indices and relative coordinates; only `ratio` is formed differently (one fp32 rounding)
     assert float((grid - q).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["ens", "ens_stress"])
+def test_local_ensemble_query(golden_decoder, precision, name):
+    """4-neighbour local ensemble + area blend fused into the last epilogue, against the
+    reference's own LIIF.query_rgb machinery (golden) wrapped around the DIINN step."""
+    seed, fseed, B, H, W, Q = (int(v) for v in golden_decoder[f"{name}.meta"])
+    kg, qg = (float(v) for v in golden_decoder[f"{name}.gains"])
+    weights = synth.make_weights(seed=seed, k_gain=kg, q_gain=qg)
+    feat = synth.make_feat(fseed, B, H, W)
+    coord = golden_decoder[f"{name}.coord"]
+    cell = np.empty_like(coord)
+    cell[..., 0], cell[..., 1] = (np.float32(v) for v in golden_decoder[f"{name}.cell"])
+    ref = golden_decoder[f"{name}.out"]
+    with torch.no_grad():
+        out = _decoder(weights, precision).query(torch.from_numpy(feat).cuda(), torch.from_numpy(coord).cuda(),
+                                                 torch.from_numpy(cell).cuda(), local_ensemble=True).cpu().numpy()
+    err = float(np.abs(out - ref).max())
+    if name == "ens":
+        assert err <= TIGHT[precision], err
+    else:
+        assert err <= (1e-4 if precision == "fp32" else 5e-2 * float(np.abs(ref).max())), err
 
 
 def test_c5_grid_form(w0):

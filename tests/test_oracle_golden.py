@@ -91,6 +91,26 @@ def test_query_on_regular_grid_equals_forward(golden_decoder):
         assert float(np.abs(out - ref).max()) <= 5e-6
 
 
+def _ens_case(golden_decoder, name):
+    seed, fseed, B, H, W, Q = (int(v) for v in golden_decoder[f"{name}.meta"])
+    kg, qg = (float(v) for v in golden_decoder[f"{name}.gains"])
+    weights = synth.make_weights(seed=seed, k_gain=kg, q_gain=qg)
+    feat = synth.make_feat(fseed, B, H, W)
+    coord = golden_decoder[f"{name}.coord"]
+    cell = np.empty_like(coord)
+    cell[..., 0], cell[..., 1] = (np.float32(v) for v in golden_decoder[f"{name}.cell"])
+    return weights, feat, coord, cell, golden_decoder[f"{name}.out"]
+
+
+@pytest.mark.parametrize("name,tol", [("ens", 2e-6), ("ens_stress", 2e-5)])
+def test_local_ensemble_matches_reference_liif_machinery(golden_decoder, name, tol):
+    """'next' row 1: LIIF.query_rgb's 4-neighbour lookup + area blend (run unmodified in make_golden.py with the DIINN
+    step as its imnet) vs the oracle's restatement."""
+    weights, feat, coord, cell, ref = _ens_case(golden_decoder, name)
+    out = orc.query_ensemble(weights, feat, coord, cell)
+    assert float(np.abs(out - ref).max()) <= tol
+
+
 def test_torch_cpu_port_matches(golden_decoder):
     weights, feat, size, ref = _case(golden_decoder, "frac")
     out = orc.decoder_forward_torch_cpu(weights, feat, size)
