@@ -568,7 +568,7 @@ int diinn_get_kernel_times(diinn_handle* h, double* ms_layout, double* ms_stage_
 }
 
 int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n) {
-  if (!h || !host_out || n < 1 || n > 2048) return DIINN_ERR_BAD_ARG;
+  if (!h || !host_out || n < 1 || n > 1024) return DIINN_ERR_BAD_ARG;
   if (!h->trace_dev) return fail(h, DIINN_ERR_BAD_ARG, "no trace: run a bf16 decode with DIINN_TRACE=1 first");
   cudaSetDevice(h->cfg.device);
   DIINN_CUDA_OK(h, cudaDeviceSynchronize());

@@ -29,12 +29,12 @@ struct Handle {
   float* WB32 = nullptr;  // (3, 512, 256): layer i=1..3: rows [0,256) K.i[:, :256], rows [256,512) Q.i
   // ---- tcgen05 path (bf16) ----
   __nv_bfloat16* WA16 = nullptr;  // (4 n-blocks, 9 taps, 256 rows, 64 ch): K index permuted to tap*64 + c
-  __nv_bfloat16* WB16 = nullptr;  // (3 layers, 4 quarters, 4 k-chunks, 128 rows, 64): rows [0,64) K-part, [64,128) Q-part
+  __nv_bfloat16* WB16 = nullptr;  // (3 layers, 2 halves, 4 k-chunks, 256 rows, 64): rows [0,128) K-part, [128,256) Q-part
   CUtensorMap tmapWA{};           // 2-D (64, 9216 rows), box (64, 256|128), 128B swizzle
   CUtensorMap tmapWA_half{};
   CUtensorMap tmapWB{};           // 2-D (64, 6144 rows)
   CUtensorMap tmapWB_half{};
-  // fp16 twin of WB16 for the fp16-accumulator variant; inside every 128-row tile the K and Q rows are interleaved in
+  // fp16 twin of WB16 for the fp16-accumulator variant; inside every 256-row tile the K and Q rows are interleaved in
   // 16-feature blocks (K f -> 32*(f/16) + f%16, Q f -> that + 16) so one packed TMEM load returns both branches
   __half* WB16h = nullptr;
   CUtensorMap tmapWBh{};

@@ -46,16 +46,16 @@ __global__ void pack_stage_b_kernel(RefPtrs r, float* __restrict__ WB32, __nv_bf
   const int row = is_q ? n - kD : n;
   const float* src = is_q ? r.qw[li + 1] + static_cast<size_t>(row) * kD
                           : r.kw[li + 1] + static_cast<size_t>(row) * (kD + kUnfold);
-  const int quarter = row >> 6;                           // which 64-feature quarter of the layer output (= TMEM slot)
-  const int tile_row = (is_q ? 64 : 0) + (row & 63);      // K-part rows [0,64), Q-part rows [64,128)
-  const int fh = row & 63;                                // fp16 twin: K/Q interleaved in 16-feature blocks
+  const int half = row >> 7;                              // which 128-feature half of the layer output
+  const int tile_row = (is_q ? 128 : 0) + (row & 127);    // K-part rows [0,128), Q-part rows [128,256)
+  const int fh = row & 127;                               // fp16 twin: K/Q interleaved in 16-feature blocks
   const int tile_row_h = 32 * (fh >> 4) + (is_q ? 16 : 0) + (fh & 15);
   for (int k = threadIdx.x; k < kD; k += blockDim.x) {
     const float v = src[k];
     WB32[(static_cast<size_t>(li) * 512 + n) * kD + k] = v;
     const int kc = k >> 6, e = k & 63;
-    WB16[((((static_cast<size_t>(li) * 4 + quarter) * 4 + kc) * 128) + tile_row) * 64 + e] = __float2bfloat16_rn(v);
-    WB16h[((((static_cast<size_t>(li) * 4 + quarter) * 4 + kc) * 128) + tile_row_h) * 64 + e] = __float2half_rn(v);
+    WB16[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row) * 64 + e] = __float2bfloat16_rn(v);
+    WB16h[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row_h) * 64 + e] = __float2half_rn(v);
   }
 }
 
@@ -140,11 +140,11 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   int rc;
   if ((rc = make_tmap_2d_bf16(h, &h->tmapWA, h->WA16, 64, 4 * 9 * 256, 64, 256))) return rc;
   if ((rc = make_tmap_2d_bf16(h, &h->tmapWA_half, h->WA16, 64, 4 * 9 * 256, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB, h->WB16, 64, 3 * 4 * 4 * 128, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB_half, h->WB16, 64, 3 * 4 * 4 * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB, h->WB16, 64, 3 * 2 * 4 * 256, 64, 256))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB_half, h->WB16, 64, 3 * 2 * 4 * 256, 64, 128))) return rc;
   // (same element size and no arithmetic in a TMA copy: the bf16 descriptor type moves fp16 bits unchanged)
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh, h->WB16h, 64, 3 * 4 * 4 * 128, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh_half, h->WB16h, 64, 3 * 4 * 4 * 128, 64, 64))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh, h->WB16h, 64, 3 * 2 * 4 * 256, 64, 256))) return rc;
+  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh_half, h->WB16h, 64, 3 * 2 * 4 * 256, 64, 128))) return rc;
   h->has_weights = true;
   return DIINN_OK;
 }

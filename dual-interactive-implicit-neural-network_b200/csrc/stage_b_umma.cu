@@ -10,16 +10,15 @@
 // HBM except the 12 B/px output: activations live in two 64 KB shared-memory A-operand buffers (bf16, K-major,
 // 128B swizzle) and the fp32 accumulators in TMEM.
 //
-// Per layer the [128 x 512] pre-activation is produced as four "quarter slots" of N = 128: TMEM columns
-// [128q, 128q+64) = K-branch and [128q+64, 128q+128) = Q-branch of output features [64q, 64q+64). The epilogue of
-// quarter q writes exactly K-chunk q (64 features = one 128-byte swizzle row) of the next A operand and signals it, so
-// the next layer's MMAs run on chunks 0..2 while the last quarter's epilogue is still in flight, and layer 0 of the
-// NEXT tile is interleaved into the epilogue warps during layer 3. With four slots, the MMA -> epilogue -> MMA cycle
-// of one slot is hidden behind the other three (the two-slot version spent ~6500 clk per layer for 4096 clk of MMA).
+// Per layer the [128 x 512] pre-activation is produced as two "half slots" of N = 256: TMEM columns
+// [256h, 256h+128) = K-branch and [256h+128, 256h+256) = Q-branch of output features [128h, 128h+128). The
+// epilogue of half h writes exactly K-chunks 2h, 2h+1 (64 features = one 128-byte swizzle row) of the next A
+// operand and signals each chunk separately, so the next layer's MMAs start while the previous epilogue is still
+// running, and layer 0 of the NEXT tile is interleaved into the epilogue warps during layer 3.
 //
-// Warp roles (640 threads): warp 0 = TMA producer (streams the 3 x 4 x 4 weight stages of [128 x 64] bf16 from L2),
-// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps in four groups of 4:
-// group q drains TMEM slot q of every layer (one warp per TMEM lane quarter, four 16-feature steps each). The control
+// Warp roles (640 threads): warp 0 = TMA producer (streams the 3 x 2 x 4 weight stages of [256 x 64] bf16 from L2),
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps in two groups of 8:
+// group g drains TMEM half slot g of every layer, so one half's epilogue runs under the other half's MMAs. The control
 // warpgroup gives its registers away (setmaxnreg) so each epilogue thread can hold a prefetched slice of P next to
 // its accumulators.
 #include <cstdlib>
@@ -41,26 +40,19 @@ constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kRegsCtrl = 40, kRegsEpi = 104;
 
-constexpr int kSlots = 4;                        // TMEM slots of 128 columns: [64 K-branch | 64 Q-branch]
-constexpr int kSlotN = 128;
-constexpr int kGroupWarps = kEpiWarps / kSlots;  // 4 epilogue warps (one per TMEM lane quarter) per slot
-
 template <int CG>
 struct Cfg {
-  static constexpr int kBoxRows = kSlotN / CG;             // B rows this CTA holds of a [128 x 64] weight tile
-  static constexpr int kBoxBytes = kBoxRows * 128;         // one K-chunk
-  static constexpr int kStageBytes = 2 * kBoxBytes;        // a weight stage = two K-chunks (8 UMMAs per barrier round trip:
-                                                           // with one chunk per stage the issuing warp's own loop latency,
-                                                           // ~400 clk, exceeded the 296 clk of N=128 MMAs it fed)
-  static constexpr int kStages = kWBytesTotal / kStageBytes;  // 2 (CG=1) or 5 (CG=2)
+  static constexpr int kStageRows = 256 / CG;
+  static constexpr int kStageBytes = kStageRows * 128;
+  static constexpr int kStages = kWBytesTotal / kStageBytes;  // 3 (CG=1) or 6 (CG=2)
 };
 
 struct Smem {  // after the big buffers
-  uint64_t w_full[10];
-  uint64_t w_empty[10];
+  uint64_t w_full[6];
+  uint64_t w_empty[6];
   uint64_t act_ready[2][4];
-  uint64_t tmem_full[kSlots];
-  uint64_t tmem_empty[kSlots];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
   uint32_t tmem_ptr;
   uint32_t pad[3];
   float partial[3][kTileM][3];  // RGB partial sums of the three non-reducing warp sets
@@ -216,21 +208,21 @@ struct Raw {
 };
 
 template <bool F16>
-__device__ __forceinline__ void epi_load(uint32_t tslot, int step, Raw<F16>& raw) {  // issue only; caller waits
+__device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw<F16>& raw) {  // issue only; caller waits
   if constexpr (F16) {
-    tmem_ld32_pack16(tslot + 32 * step, raw.v);
+    tmem_ld32_pack16(tslot + 2 * col, raw.v);
   } else {
-    tmem_ld16(tslot + 16 * step, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[0]));
-    tmem_ld16(tslot + 64 + 16 * step, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[16]));
+    tmem_ld16(tslot + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[0]));
+    tmem_ld16(tslot + 128 + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[16]));
   }
 }
 
-// features [64*slot + 16*step, +16) of one row. kx = the matching slice of P (prefetched). kLast: accumulate the RGB
-// projection instead of writing the next A operand (K-chunk `slot` of activation buffer out_base).
+// kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
 template <bool kLast, bool F16>
-__device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base, int layer, int slot, int step, int r,
+__device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
                                          const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3]) {
-  const int f0 = slot * 64 + step * 16;
+  const int col = c * 64 + wg * 16;
+  const int f0 = h * 128 + col;
   const float* kx = reinterpret_cast<const float*>(kxv);
   uint32_t pk[8];
 #pragma unroll
@@ -259,9 +251,9 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
     if constexpr (!kLast) pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
   }
   if constexpr (!kLast) {
-    const uint32_t chunk_base = out_base + slot * kChunkBytes;
-    st_shared_v4(swz(chunk_base, r, step * 2), pk[0], pk[1], pk[2], pk[3]);
-    st_shared_v4(swz(chunk_base, r, step * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
+    const uint32_t chunk_base = out_base + (2 * h + c) * kChunkBytes;
+    st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
@@ -287,7 +279,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const int n_units = gridDim.x / CG;
   // optional timeline capture (DIINN_TRACE=1): leader CTA of unit 0, first 8 tiles, clock64 at pipeline events
   const bool tracing = trace != nullptr && blockIdx.x == 0;
-#define DIINN_TR(tile, idx) do { if (tracing && (tile) < 8) trace[(tile) * 256 + (idx)] = clock64(); } while (0)
+#define DIINN_TR(tile, idx) do { if (tracing && (tile) < 8) trace[(tile) * 128 + (idx)] = clock64(); } while (0)
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) atomicExch(err_flag, 1);
 
@@ -297,10 +289,10 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_init(&sm.w_full[i], 1);
       mbar_init(&sm.w_empty[i], 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&sm.act_ready[0][0] + i, kGroupWarps * CG);  // one group writes a chunk
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < 8; ++i) mbar_init(&sm.act_ready[0][0] + i, (kEpiWarps / 2) * CG);  // one group per chunk
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.tmem_full[i], 1);
-      mbar_init(&sm.tmem_empty[i], kGroupWarps * CG);
+      mbar_init(&sm.tmem_empty[i], (kEpiWarps / 2) * CG);
     }
     fence_barrier_init();
   }
@@ -315,28 +307,26 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   setmaxnreg_dec<kRegsCtrl>();
   if (warp == 0) {
     // ===================== weight producer (+ L2 prefetch of upcoming tiles' P rows) =====================
-    int st = 0;
-    uint32_t ph = 0;
+    uint32_t it = 0;
     if (unit_id + n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, unit_id + n_units, rank, lane);
     for (int work = unit_id; work < wk.n_work; work += n_units) {
       if (work + 2 * n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, work + 2 * n_units, rank, lane);
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
       // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues
-      for (int s24 = 0; s24 < 24; ++s24) {  // (layer-1, slot, kc pair) in MMA consumption order
+      for (int s24 = 0; s24 < 24; ++s24, ++it) {  // (layer-1, half, kc) in MMA consumption order
+        const int st = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
         mbar_wait(&sm.w_empty[st], ph ^ 1);
         if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
-          uint8_t* dst = s_w + st * C::kStageBytes;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int row = (s24 * 2 + j) * kSlotN + rank * C::kBoxRows;
-            if constexpr (CG == 1) tma_load_2d(dst + j * C::kBoxBytes, &tmW, &sm.w_full[st], 0, row);
-            else tma_load_2d_2sm(dst + j * C::kBoxBytes, &tmW, &sm.w_full[st], 0, row);
-          }
+          void* dst = s_w + st * C::kStageBytes;
+          if constexpr (CG == 1)
+            tma_load_2d(dst, &tmW, &sm.w_full[st], 0, s24 * 256);
+          else
+            tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s24 * 256 + rank * 128);
         }
         __syncwarp();
-        if (++st == C::kStages) st = 0, ph ^= 1;
       }
     }
     __syncwarp();
@@ -347,12 +337,11 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // from a divergent single-lane region instead, each UTCHMMA costs an ELECT + 5x R2UR.BROADCAST waterfall
     // (~100 clk), which capped the tensor pipe at ~200 clk per MMA instead of 128.
     if (leader) {
-      constexpr uint32_t idesc = F16 ? umma_idesc_f16_acc16(128 * CG, kSlotN) : umma_idesc_bf16(128 * CG, kSlotN);
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16_acc16(128 * CG, 256) : umma_idesc_bf16(128 * CG, 256);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      int st = 0;                 // weight stage ring position
-      uint32_t wph = 0;
+      uint32_t it = 0;            // weight stage counter
       uint32_t act_phase = 0;     // bit b: parity to wait for on act_ready[b][*]
-      uint32_t slot_uses = 0;     // completed uses per TMEM slot (every layer uses every slot once)
+      uint32_t slot_uses = 0;     // completed uses per TMEM slot (same for both slots at layer granularity)
       int t = 0;
       for (int work = unit_id; work < wk.n_work; work += n_units, ++t) {
         const int X = t & 1;
@@ -361,44 +350,38 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           const int bin = (layer == 2) ? (X ^ 1) : X;  // L1: buf X, L2: buf X^1, L3: buf X
           const uint32_t a_base = act0 + bin * kActBytes;
           const uint32_t aph = (act_phase >> bin) & 1;
-          uint32_t seen = 0;  // K-chunks of this layer's input already observed ready
 #pragma unroll 1
-          for (int q = 0; q < kSlots; ++q) {
-            // slot q must have been drained by the epilogue of its previous use
-            if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[q], (slot_uses & 1) ^ 1);
-            else mbar_wait(&sm.tmem_empty[q], (slot_uses & 1) ^ 1);
-            if (lane == 0) DIINN_TR(t, (layer - 1) * 32 + q * 8);
-            const uint32_t d_tmem = tmem_u + q * kSlotN;
+          for (int h = 0; h < 2; ++h) {
+            // slot h must have been drained by the epilogue of its previous use
+            if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
+            else mbar_wait(&sm.tmem_empty[h], (slot_uses & 1) ^ 1);
+            tc_fence_after();
+            if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10);
+            const uint32_t d_tmem = tmem_u + h * 256;
 #pragma unroll 1
-            for (int kp = 0; kp < 2; ++kp) {  // K-chunk pairs = weight stages
-              if (!((seen >> kp) & 1)) {
-                if constexpr (CG == 2) {
-                  mbar_wait_cluster(&sm.act_ready[bin][2 * kp], aph);
-                  mbar_wait_cluster(&sm.act_ready[bin][2 * kp + 1], aph);
-                } else {
-                  mbar_wait(&sm.act_ready[bin][2 * kp], aph);
-                  mbar_wait(&sm.act_ready[bin][2 * kp + 1], aph);
-                }
-                seen |= 1u << kp;
+            for (int kc = 0; kc < 4; ++kc, ++it) {
+              if (h == 0) {  // half 1 re-reads chunks whose readiness half 0 already observed
+                if constexpr (CG == 2) mbar_wait_cluster(&sm.act_ready[bin][kc], aph);
+                else mbar_wait(&sm.act_ready[bin][kc], aph);
               }
-              mbar_wait(&sm.w_full[st], wph);
+              if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 1 + 2 * kc);
+              const int st = it % C::kStages;
+              mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
               tc_fence_after();
-              if (lane == 0) DIINN_TR(t, (layer - 1) * 32 + q * 8 + 1 + kp);
-              const uint32_t a0 = a_base + 2 * kp * kChunkBytes;
+              if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 2 + 2 * kc);
+              const uint32_t a0 = a_base + kc * kChunkBytes;
               const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
               if (elect_one()) {
 #pragma unroll
-                for (int m = 0; m < 8; ++m)
-                  umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + (m >> 2) * kChunkBytes + (m & 3) * 32),
-                                umma_desc_sw128(b0 + (m >> 2) * C::kBoxBytes + (m & 3) * 32), idesc,
-                                (kp | m) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
+                                (kc | k) != 0 ? 1u : 0u);
                 umma_commit<CG>(&sm.w_empty[st]);
-                if (kp == 1) umma_commit<CG>(&sm.tmem_full[q]);
+                if (kc == 3) umma_commit<CG>(&sm.tmem_full[h]);
               }
               __syncwarp();
-              if (++st == C::kStages) st = 0, wph ^= 1;
             }
-            if (lane == 0) DIINN_TR(t, (layer - 1) * 32 + q * 8 + 5);
+            if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 9);
           }
           act_phase ^= 1u << bin;
           ++slot_uses;
@@ -409,42 +392,46 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   }
   } else {
     // ===================== epilogue warps =====================
-    // Four groups of 4 warps: group q owns TMEM slot q of every layer (and K-chunk q of layer 0), one warp per TMEM
-    // lane quarter. A warp walks its 32 rows x 64 features in four 16-feature steps, with the matching slice of P
-    // prefetched one step ahead.
+    // Two groups of 8 warps: group g owns TMEM half slot g of every layer (and K-chunks 2g, 2g+1 of layer 0), so the
+    // epilogue of one half overlaps the MMAs of the other and each group has a whole layer period per half slot.
+    // Inside a group the two warps of a TMEM lane quarter split every 64-feature chunk 32/32 and walk it in
+    // 16-feature steps, with the matching slice of P prefetched one step ahead.
     setmaxnreg_inc<kRegsEpi>();
     const int ew = warp - 4;
-    const int q = ew >> 2;              // slot / K-chunk owned by this warp's group
+    const int grp = ew >> 3;            // half slot owned by this warp
+    const int sub = (ew >> 2) & 1;      // which 32-feature half of every 64-feature chunk
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
-    const uint32_t tslot = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + q * kSlotN;
-    const bool tracer = tracing && quarter == 0 && lane == 0;
+    const int h = grp;
+    const uint32_t tslot = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + h * 256;
+    const bool tracer = tracing && (warp == 4 + 8 * h) && lane == 0;
     uint32_t full_uses = 0;             // completed uses of this group's TMEM slot
     int t = 0;
     int work = unit_id;
     RowCtx rc{};
 
-    // this group's K-chunk of layer 0 for the tile described by rcx -> activation buffer `bufidx`
-    auto layer0_chunk = [&](int bufidx, const RowCtx& rcx) {
+    // this group's two K-chunks of layer 0 for the tile described by rcx -> activation buffer `bufidx`
+    auto layer0_pair = [&](int bufidx, const RowCtx& rcx) {
       const uint32_t buf = act0 + bufidx * kActBytes;
-      const float* pn = rcx.prow + q * 64;
+      const float* pn = rcx.prow + sub * 32;
       float4 ka[4], kb[4];
-      load16(pn, ka);
-      load16(pn + 16, kb);
-      layer0_step<F16>(buf, q, 0, r, rcx, sp, ka);
-      load16(pn + 32, ka);
-      layer0_step<F16>(buf, q, 1, r, rcx, sp, kb);
-      load16(pn + 48, kb);
-      layer0_step<F16>(buf, q, 2, r, rcx, sp, ka);
-      layer0_step<F16>(buf, q, 3, r, rcx, sp, kb);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) signal<CG>(&sm.act_ready[bufidx][q]);
+      load16(pn + (2 * grp) * 64, ka);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int kc = 2 * grp + c;
+        load16(pn + kc * 64 + 16, kb);
+        layer0_step<F16>(buf, kc, sub * 2, r, rcx, sp, ka);
+        if (c == 0) load16(pn + (kc + 1) * 64, ka);
+        layer0_step<F16>(buf, kc, sub * 2 + 1, r, rcx, sp, kb);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc]);
+      }
     };
 
     if (work < wk.n_work) {
       rc = make_row<CG>(src, out, P, wk, work, rank, r);
-      layer0_chunk(0, rc);  // first tile -> buffer 0
+      layer0_pair(0, rc);  // first tile -> buffer 0
     }
     for (; work < wk.n_work; work += n_units, ++t) {
       const int X = t & 1;
@@ -457,70 +444,78 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
         const uint32_t out_base = act0 + bout * kActBytes;
         if (layer == 3 && has_next) {
-          // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs. They are all complete
-          // once the LAST slot of layer 2 is accumulated; group 3 has consumed that phase itself, the other groups
-          // observe it. (tmem_full[3] is drained by group 3 and could already be a whole phase further -- layer 3 --
-          // which a parity wait cannot tell apart from "not yet"; but then this group's own layer-3 slot, issued
-          // before it and waiting for THIS group, is complete too, so either observation proves layer 2 is done.)
+          // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs. Group 1 has consumed
+          // tmem_full[1] of layer 2 itself; group 0 observes the same phase before it overwrites the buffer.
           rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
-          if (q != kSlots - 1) {
-            while (!mbar_try_wait(&sm.tmem_full[kSlots - 1], (full_uses - 1) & 1) &&
-                   !mbar_try_wait(&sm.tmem_full[q], full_uses & 1)) {
+          // (tmem_full[1] is drained by group 1 and could in principle already be a whole phase further -- layer 3 half
+          // 1 -- which a parity wait cannot tell apart from "not yet"; but then layer 3 half 0, issued before it and
+          // waiting for THIS group, is complete too, so either observation proves layer 2 is done.)
+          if (grp == 0) {
+            while (!mbar_try_wait(&sm.tmem_full[1], (full_uses - 1) & 1) && !mbar_try_wait(&sm.tmem_full[0], full_uses & 1)) {
             }
           }
-          layer0_chunk(X ^ 1, rc_next);
+          layer0_pair(X ^ 1, rc_next);
         }
-        const float* pl = rc.prow + layer * kD + q * 64;  // P slice of features 64q + 16 step
+        const float* pl = rc.prow + layer * kD + h * 128 + sub * 32;  // P slice of features 128h + 64c + 32sub + 16s
         float4 ka[4], kb[4];
         load16(pl, ka);  // in flight while waiting for the accumulators
-        if (tracer) DIINN_TR(t, 128 + (layer - 1) * 32 + q * 8);
-        mbar_wait(&sm.tmem_full[q], full_uses & 1);
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
+        mbar_wait(&sm.tmem_full[h], full_uses & 1);
         tc_fence_after();
-        if (tracer) DIINN_TR(t, 128 + (layer - 1) * 32 + q * 8 + 1);
-        // four 16-feature steps: kx slices ping-pong between ka / kb one step ahead; with fp16 accumulators the TMEM
-        // loads ping-pong too (16 regs each). The slot is handed back to the MMA issuer as soon as the last load has
-        // landed, before the last step's math.
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
+        // four 16-feature steps (c = chunk of the half, s = which 16 of this warp's 32): kx slices ping-pong between
+        // ka / kb one step ahead; with fp16 accumulators the TMEM loads ping-pong too (16 regs each), so every step's
+        // math runs under the next step's tcgen05.ld. The slot is handed back to the MMA issuer as soon as the last
+        // load has landed, before the last step's math.
         Raw<F16> ra, rb;
-        const bool last = layer == 3;
-        epi_load<F16>(tslot, 0, ra);
-        tmem_ld_wait();
-        if constexpr (F16) epi_load<F16>(tslot, 1, rb);
-        load16(pl + 16, kb);
-        if (last) epi_math<true, F16>(ra, out_base, layer, q, 0, r, sp, ka, rgb);
-        else epi_math<false, F16>(ra, out_base, layer, q, 0, r, sp, ka, rgb);
-        if constexpr (!F16) epi_load<F16>(tslot, 1, rb);
-        tmem_ld_wait();
-        if constexpr (F16) epi_load<F16>(tslot, 2, ra);
-        load16(pl + 32, ka);
-        if (last) epi_math<true, F16>(rb, out_base, layer, q, 1, r, sp, kb, rgb);
-        else epi_math<false, F16>(rb, out_base, layer, q, 1, r, sp, kb, rgb);
-        if constexpr (!F16) epi_load<F16>(tslot, 2, ra);
-        tmem_ld_wait();
-        if constexpr (F16) epi_load<F16>(tslot, 3, rb);
-        load16(pl + 48, kb);
-        if (last) epi_math<true, F16>(ra, out_base, layer, q, 2, r, sp, ka, rgb);
-        else epi_math<false, F16>(ra, out_base, layer, q, 2, r, sp, ka, rgb);
-        if constexpr (!F16) epi_load<F16>(tslot, 3, rb);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) signal<CG>(&sm.tmem_empty[q]);
-        if (tracer) DIINN_TR(t, 128 + (layer - 1) * 32 + q * 8 + 2);
-        if (last) epi_math<true, F16>(rb, out_base, layer, q, 3, r, sp, kb, rgb);
-        else epi_math<false, F16>(rb, out_base, layer, q, 3, r, sp, kb, rgb);
-        if (!last) {
+        auto free_slot = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
+        };
+        auto chunk_done = [&](int c) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) signal<CG>(&sm.act_ready[bout][q]);
-        }
-        if (tracer) DIINN_TR(t, 128 + (layer - 1) * 32 + q * 8 + 3);
+          if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + c]);
+        };
+        const int w0 = sub * 2, w1 = sub * 2 + 1;
+        const bool last = layer == 3;
+        epi_load<F16>(tslot, w0 * 16, ra);
+        tmem_ld_wait();
+        if constexpr (F16) epi_load<F16>(tslot, w1 * 16, rb);
+        load16(pl + 16, kb);
+        if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, w0, r, sp, ka, rgb);
+        else epi_math<false, F16>(ra, out_base, layer, h, 0, w0, r, sp, ka, rgb);
+        if constexpr (!F16) epi_load<F16>(tslot, w1 * 16, rb);
+        tmem_ld_wait();
+        if constexpr (F16) epi_load<F16>(tslot, 64 + w0 * 16, ra);
+        load16(pl + 64, ka);
+        if (last) epi_math<true, F16>(rb, out_base, layer, h, 0, w1, r, sp, kb, rgb);
+        else epi_math<false, F16>(rb, out_base, layer, h, 0, w1, r, sp, kb, rgb);
+        if (!last) chunk_done(0);
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
+        if constexpr (!F16) epi_load<F16>(tslot, 64 + w0 * 16, ra);
+        tmem_ld_wait();
+        if constexpr (F16) epi_load<F16>(tslot, 64 + w1 * 16, rb);
+        load16(pl + 64 + 16, kb);
+        if (last) epi_math<true, F16>(ra, out_base, layer, h, 1, w0, r, sp, ka, rgb);
+        else epi_math<false, F16>(ra, out_base, layer, h, 1, w0, r, sp, ka, rgb);
+        if constexpr (!F16) epi_load<F16>(tslot, 64 + w1 * 16, rb);
+        tmem_ld_wait();
+        free_slot();
+        if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, w1, r, sp, kb, rgb);
+        else epi_math<false, F16>(rb, out_base, layer, h, 1, w1, r, sp, kb, rgb);
+        if (!last) chunk_done(1);
+        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
         ++full_uses;
       }
-      // Combine the four partial RGB projections of a row (one per group) in a fixed order (bit-reproducible). The
-      // last group to finish (slot 3) reduces and stores; the others drop their partials in smem.
-      if (q != kSlots - 1) {
+      // Combine the four partial RGB projections of a row (2 groups x 2 subs) in a fixed order (bit-reproducible).
+      // The last warps to finish (group 1, sub 1) reduce and store; the others drop their partials in smem.
+      const int pidx = grp * 2 + sub;
+      if (pidx != 3) {
         if (t > 0) named_bar_sync(2, kEpiThreads);  // the reducers have read the previous tile's partials
-        float* pp = &sm.partial[q][r][0];
+        float* pp = &sm.partial[pidx][r][0];
         pp[0] = rgb[0], pp[1] = rgb[1], pp[2] = rgb[2];
         named_bar_arrive(1, kEpiThreads);
       } else {
@@ -594,8 +589,8 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
     const char* e = getenv("DIINN_TRACE");
     want_trace = (e && e[0] == '1') ? 1 : 0;
     if (want_trace) {
-      DIINN_CUDA_OK(h, cudaMalloc(&trace, 2048 * sizeof(long long)));
-      DIINN_CUDA_OK(h, cudaMemset(trace, 0, 2048 * sizeof(long long)));
+      DIINN_CUDA_OK(h, cudaMalloc(&trace, 1024 * sizeof(long long)));
+      DIINN_CUDA_OK(h, cudaMemset(trace, 0, 1024 * sizeof(long long)));
     }
   }
   h->trace_dev = trace;

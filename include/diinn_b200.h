@@ -172,7 +172,7 @@ int diinn_get_kernel_times(diinn_handle* h, double* ms_layout, double* ms_stage_
                            int64_t* n_decodes);
 
 /* DIINN_TRACE=1 in the environment makes the fused stage-B kernel record clock64() at its pipeline events (leader
- * CTA of the first CTA pair, first 8 tiles); this copies the first n (<=2048) samples to host_out. */
+ * CTA of the first CTA pair, first 8 tiles); this copies the first n (<=1024) samples to host_out. */
 int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n);
 
 /* Number of kernels this library launched on the handle since creation (bench.py's gpu_launches). */

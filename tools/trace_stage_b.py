@@ -19,16 +19,20 @@ with torch.no_grad():
     dec(x, (H_up, W_up))
     dec(x, (H_up, W_up))
 torch.cuda.synchronize()
-buf = np.zeros(2048, dtype=np.int64)
+buf = np.zeros(1024, dtype=np.int64)
 lib = _lib.load()
-_lib.check(lib, dec._handle, lib.diinn_debug_read_trace(dec._handle, buf.ctypes.data_as(C.c_void_p), 2048))
-tr = buf.reshape(8, 256)
+_lib.check(lib, dec._handle, lib.diinn_debug_read_trace(dec._handle, buf.ctypes.data_as(C.c_void_p), 1024))
+tr = buf.reshape(8, 128)
 t0 = tr[tr > 0].min()
 for t in range(1, 5):
     print(f"--- tile {t} (clk relative to first event {t0})")
     for layer in range(3):
-        for q in range(4):
-            m = tr[t, layer * 32 + q * 8: layer * 32 + q * 8 + 6] - t0
-            e = tr[t, 128 + layer * 32 + q * 8: 128 + layer * 32 + q * 8 + 4] - t0
-            print(f" L{layer + 1}.q{q} MMA slot_free {m[0]:7d} | kc-pair ready {m[1]:7d} {m[2]:7d} issued {m[5]:7d} "
-                  f"|| EPI wait {e[0]:7d} full {e[1]:7d} slot_freed {e[2]:7d} done {e[3]:7d}")
+        for h in range(2):
+            m = tr[t, layer * 20 + h * 10: layer * 20 + h * 10 + 10] - t0
+            e = tr[t, 64 + layer * 10 + h * 5: 64 + layer * 10 + h * 5 + 5] - t0
+            print(f" L{layer + 1}.h{h} MMA slot_free {m[0]:7d} | act/w ready kc0 {m[1]:7d}/{m[2]:7d} kc1 {m[3]:7d}/{m[4]:7d} "
+                  f"kc2 {m[5]:7d}/{m[6]:7d} kc3 {m[7]:7d}/{m[8]:7d} issued {m[9]:7d} || EPI wait {e[0]:7d} full {e[1]:7d} "
+                  f"c0 {e[2]:7d} c1 {e[3]:7d} freed {e[4]:7d}")
+    for h in range(2):
+        f = tr[t, 96 + h * 8: 96 + h * 8 + 8] - t0
+        print(f" L2.h{h} epi detail: c0 ld_done {f[0]} math_done {f[1]} sts_done {f[2]} fence_done {f[3]} | c1 ld_done {f[4]} math_done {f[5]} sts_done {f[6]} fence_done {f[7]}")
