@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdiinn_b200.so")
+LIB_PATH = os.environ.get("DIINN_B200_LIB") or os.path.join(HERE, "libdiinn_b200.so")  # override: ablation builds
 
 OK = 0
 COMPUTE_FP32, COMPUTE_BF16, COMPUTE_FP16ACC = 0, 1, 2

@@ -88,6 +88,9 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
     const int ohc = min(oh, s.row1 - 1), owc = min(ow, s.W_up - 1);
     const int ih = axis_index(s.ax_h, ohc), iw = axis_index(s.ax_w, owc);
     rc.prow = P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw) * kPCols;
+#if DIINN_ABL & 1
+    rc.prow = P;
+#endif
     rc.rel_h = axis_rel(s.ax_h, ohc, ih);
     rc.rel_w = axis_rel(s.ax_w, owc, iw);
     rc.ratio = s.ratio;
@@ -169,9 +172,32 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
   if constexpr (CG == 2) mbar_arrive_cluster(bar, 0); else mbar_arrive(bar);
 }
 
+// Timing ablations (tools/ablate_stage_b.py builds side libraries with -DDIINN_ABL=<mask>; results are WRONG by
+// construction, only the run time is meaningful). bit 0: P slices read from one fixed row; bit 1: bq as an immediate;
+// bit 2: sine replaced by one FMUL; bit 3: no activation stores; bit 4: no TMEM loads.
+#ifndef DIINN_ABL
+#define DIINN_ABL 0
+#endif
+// packed fp32x2 (FADD2 / FMUL2 / FFMA2) in: 1 = layer 1..3 K/Q math, 2 = layer 0, 4 = RGB projection
+// per-step epilogue timestamps for tools/trace_stage_b.py: the extra basic-block boundaries cost ~10 % (measured), so off
+#ifndef DIINN_FINE_TRACE
+#define DIINN_FINE_TRACE 0
+#endif
+#ifndef DIINN_PK
+#define DIINN_PK 7
+#endif
+
 __device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p) + j);
+}
+
+__device__ __forceinline__ float act_sin(float x) {
+#if DIINN_ABL & 4
+  return x * 0.5f;
+#else
+  return __sinf(x);
+#endif
 }
 
 // layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
@@ -182,6 +208,19 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
   const int f0 = kc * 64 + wg * 16;
   const float* k0 = reinterpret_cast<const float*>(k0v);
   uint32_t pk[8];
+#if DIINN_PK & 2
+  const float2 rh = make_float2(rc.rel_h, rc.rel_h), rw = make_float2(rc.rel_w, rc.rel_w), ra = make_float2(rc.ratio, rc.ratio);
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    // packed fp32x2 (two features per instruction; per feature the same three fused multiply-adds as the scalar form)
+    const float2* w = &sp.wq0_p[(f0 + j) >> 1][0];
+    float2 t = __ffma2_rn(w[0], rh, w[3]);
+    t = __ffma2_rn(w[1], rw, t);
+    t = __ffma2_rn(w[2], ra, t);
+    const float2 q = __fmul2_rn(make_float2(k0[j], k0[j + 1]), make_float2(act_sin(t.x), act_sin(t.y)));
+    pk[j >> 1] = F16 ? pack_f16x2(q.x, q.y) : pack_bf16x2(q.x, q.y);
+  }
+#else
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
     float q[2];
@@ -191,10 +230,11 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
       float t = fmaf(w.x, rc.rel_h, w.w);
       t = fmaf(w.y, rc.rel_w, t);
       t = fmaf(w.z, rc.ratio, t);
-      q[e] = k0[j + e] * __sinf(t);
+      q[e] = k0[j + e] * act_sin(t);
     }
     pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
   }
+#endif
   st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
   st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
 }
@@ -209,6 +249,11 @@ struct Raw {
 
 template <bool F16>
 __device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw<F16>& raw) {  // issue only; caller waits
+#if DIINN_ABL & 16
+#pragma unroll
+  for (int i = 0; i < (F16 ? 16 : 32); ++i) raw.v[i] = tslot + col + i;
+  return;
+#endif
   if constexpr (F16) {
     tmem_ld32_pack16(tslot + 2 * col, raw.v);
   } else {
@@ -220,7 +265,7 @@ __device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw<F16>& raw)
 // kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
 template <bool kLast, bool F16>
 __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
-                                         const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3]) {
+                                         const SmallParams& sp, const float4 (&kxv)[4], float2 (&rgb2)[3]) {
   const int col = c * 64 + wg * 16;
   const int f0 = h * 128 + col;
   const float* kx = reinterpret_cast<const float*>(kxv);
@@ -235,25 +280,51 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
       ak[0] = __uint_as_float(raw.v[j]), ak[1] = __uint_as_float(raw.v[j + 1]);
       aq[0] = __uint_as_float(raw.v[16 + j]), aq[1] = __uint_as_float(raw.v[16 + j + 1]);
     }
-    float q[2];
+#if DIINN_PK & 1
+    // packed fp32x2 adds / multiplies (Blackwell FADD2 / FMUL2)
+    float2 k2 = __fadd2_rn(make_float2(ak[0], ak[1]), make_float2(kx[j], kx[j + 1]));
+    k2.x = fmaxf(k2.x, 0.f), k2.y = fmaxf(k2.y, 0.f);
+    const float2 t2 = __fadd2_rn(make_float2(aq[0], aq[1]), *reinterpret_cast<const float2*>(&sp.bq[layer][f0 + j]));
+    const float2 q2 = __fmul2_rn(k2, make_float2(act_sin(t2.x), act_sin(t2.y)));
+#else
+    float2 q2;
+    {
+      const float ka0 = fmaxf(ak[0] + kx[j], 0.f), ka1 = fmaxf(ak[1] + kx[j + 1], 0.f);
+#if DIINN_ABL & 2
+      const float s0 = act_sin(aq[0] + 0.1f), s1 = act_sin(aq[1] + 0.1f);
+#else
+      const float s0 = act_sin(aq[0] + sp.bq[layer][f0 + j]), s1 = act_sin(aq[1] + sp.bq[layer][f0 + j + 1]);
+#endif
+      q2 = make_float2(ka0 * s0, ka1 * s1);
+    }
+#endif
+    const float q[2] = {q2.x, q2.y};
+    if constexpr (kLast) {
+#if DIINN_PK & 4
+      const float2* w = &sp.wl_p[(f0 + j) >> 1][0];
+      rgb2[0] = __ffma2_rn(w[0], q2, rgb2[0]);
+      rgb2[1] = __ffma2_rn(w[1], q2, rgb2[1]);
+      rgb2[2] = __ffma2_rn(w[2], q2, rgb2[2]);
+#else
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float k = fmaxf(ak[e] + kx[j + e], 0.f);
-      const float sn = __sinf(aq[e] + sp.bq[layer][f0 + j + e]);
-      q[e] = k * sn;
-      if constexpr (kLast) {
+      for (int e = 0; e < 2; ++e) {
         const float4 w = *reinterpret_cast<const float4*>(&sp.wl_t[f0 + j + e][0]);
-        rgb[0] = fmaf(w.x, q[e], rgb[0]);
-        rgb[1] = fmaf(w.y, q[e], rgb[1]);
-        rgb[2] = fmaf(w.z, q[e], rgb[2]);
+        rgb2[0].x = fmaf(w.x, q[e], rgb2[0].x);
+        rgb2[1].x = fmaf(w.y, q[e], rgb2[1].x);
+        rgb2[2].x = fmaf(w.z, q[e], rgb2[2].x);
       }
+#endif
     }
     if constexpr (!kLast) pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
   }
   if constexpr (!kLast) {
     const uint32_t chunk_base = out_base + (2 * h + c) * kChunkBytes;
+#if DIINN_ABL & 8
+    if (pk[0] == 0x12345678u) st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1] ^ pk[2] ^ pk[3] ^ pk[4], pk[5] ^ pk[6], pk[7]);
+#else
     st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
     st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
+#endif
   }
 }
 
@@ -289,10 +360,10 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_init(&sm.w_full[i], 1);
       mbar_init(&sm.w_empty[i], 1);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&sm.act_ready[0][0] + i, (kEpiWarps / 2) * CG);  // one group per chunk
+    for (int i = 0; i < 8; ++i) mbar_init(&sm.act_ready[0][0] + i, kEpiWarps * CG);  // every epilogue warp writes part of a chunk
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.tmem_full[i], 1);
-      mbar_init(&sm.tmem_empty[i], (kEpiWarps / 2) * CG);
+      mbar_init(&sm.tmem_empty[i], kEpiWarps * CG);
     }
     fence_barrier_init();
   }
@@ -392,127 +463,125 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   }
   } else {
     // ===================== epilogue warps =====================
-    // Two groups of 8 warps: group g owns TMEM half slot g of every layer (and K-chunks 2g, 2g+1 of layer 0), so the
-    // epilogue of one half overlaps the MMAs of the other and each group has a whole layer period per half slot.
-    // Inside a group the two warps of a TMEM lane quarter split every 64-feature chunk 32/32 and walk it in
-    // 16-feature steps, with the matching slice of P prefetched one step ahead.
+    // All 16 warps drain half slot 0, then half slot 1, of every layer. A warp owns one TMEM lane quarter (32 tile
+    // rows) and one 16-feature group fg of every 64-feature K-chunk, so a half slot is two steps per warp and EVERY STEP
+    // COMPLETES ONE K-CHUNK of the next layer's A operand: the chunk published last -- which gates the next layer's
+    // first half slot -- is one step (not a whole half-slot epilogue) behind the layer's last MMA.
     setmaxnreg_inc<kRegsEpi>();
     const int ew = warp - 4;
-    const int grp = ew >> 3;            // half slot owned by this warp
-    const int sub = (ew >> 2) & 1;      // which 32-feature half of every 64-feature chunk
+    const int fg = ew >> 2;             // 16-feature group inside every 64-feature chunk
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;  // tile row == TMEM lane
-    const int h = grp;
-    const uint32_t tslot = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + h * 256;
-    const bool tracer = tracing && (warp == 4 + 8 * h) && lane == 0;
-    uint32_t full_uses = 0;             // completed uses of this group's TMEM slot
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const bool tracer = tracing && warp == 4 && lane == 0;
+    uint32_t full_uses = 0;             // completed layers (each half slot is used once per layer)
     int t = 0;
     int work = unit_id;
     RowCtx rc{};
 
-    // this group's two K-chunks of layer 0 for the tile described by rcx -> activation buffer `bufidx`
-    auto layer0_pair = [&](int bufidx, const RowCtx& rcx) {
+    // P slices of this warp's next two steps. Software pipeline over the whole step sequence of the kernel (layer 0
+    // chunk pairs and half slots alike): the step that consumes ka / kb re-issues the load for the same step of the
+    // NEXT unit, so every slice has at least one full step (>= 700 clk) plus the barrier wait to arrive from L2.
+    float4 ka[4], kb[4];
+
+    // this warp's share of K-chunks [kc0, kc0 + 2) of layer 0 for the tile described by rcx -> activation buffer
+    // `bufidx`; nb = P slice base of the next unit (nullptr: none)
+    auto layer0_unit = [&](int bufidx, int kc0, const RowCtx& rcx, const float* nb) {
       const uint32_t buf = act0 + bufidx * kActBytes;
-      const float* pn = rcx.prow + sub * 32;
-      float4 ka[4], kb[4];
-      load16(pn + (2 * grp) * 64, ka);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        const int kc = 2 * grp + c;
-        load16(pn + kc * 64 + 16, kb);
-        layer0_step<F16>(buf, kc, sub * 2, r, rcx, sp, ka);
-        if (c == 0) load16(pn + (kc + 1) * 64, ka);
-        layer0_step<F16>(buf, kc, sub * 2 + 1, r, rcx, sp, kb);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc]);
-      }
+      layer0_step<F16>(buf, kc0, fg, r, rcx, sp, ka);
+      if (nb) load16(nb, ka);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
+      layer0_step<F16>(buf, kc0 + 1, fg, r, rcx, sp, kb);
+      if (nb) load16(nb + 64, kb);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
     };
 
     if (work < wk.n_work) {
       rc = make_row<CG>(src, out, P, wk, work, rank, r);
-      layer0_pair(0, rc);  // first tile -> buffer 0
+      const float* p0 = rc.prow + fg * 16;
+      load16(p0, ka);
+      load16(p0 + 64, kb);
+      layer0_unit(0, 0, rc, p0 + 128);  // first tile -> buffer 0
+      layer0_unit(0, 2, rc, p0 + kD);
     }
     for (; work < wk.n_work; work += n_units, ++t) {
       const int X = t & 1;
       const int next_work = work + n_units;
       const bool has_next = next_work < wk.n_work;
       RowCtx rc_next{};
-      float rgb[3] = {0.f, 0.f, 0.f};
+      const float* const pw = rc.prow + fg * 16;  // this warp's column of the tile row's P entry
+      const float* pn = nullptr;                  // same for the next tile
+      float2 rgb2[3] = {};  // RGB projection, even / odd features accumulated separately (packed FFMA2)
 #pragma unroll 1
       for (int layer = 1; layer <= 3; ++layer) {
         const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
         const uint32_t out_base = act0 + bout * kActBytes;
-        if (layer == 3 && has_next) {
-          // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs. Group 1 has consumed
-          // tmem_full[1] of layer 2 itself; group 0 observes the same phase before it overwrites the buffer.
-          rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
-          // (tmem_full[1] is drained by group 1 and could in principle already be a whole phase further -- layer 3 half
-          // 1 -- which a parity wait cannot tell apart from "not yet"; but then layer 3 half 0, issued before it and
-          // waiting for THIS group, is complete too, so either observation proves layer 2 is done.)
-          if (grp == 0) {
-            while (!mbar_try_wait(&sm.tmem_full[1], (full_uses - 1) & 1) && !mbar_try_wait(&sm.tmem_full[0], full_uses & 1)) {
-            }
-          }
-          layer0_pair(X ^ 1, rc_next);
-        }
-        const float* pl = rc.prow + layer * kD + h * 128 + sub * 32;  // P slice of features 128h + 64c + 32sub + 16s
-        float4 ka[4], kb[4];
-        load16(pl, ka);  // in flight while waiting for the accumulators
-        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
-        mbar_wait(&sm.tmem_full[h], full_uses & 1);
-        tc_fence_after();
-        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
-        // four 16-feature steps (c = chunk of the half, s = which 16 of this warp's 32): kx slices ping-pong between
-        // ka / kb one step ahead; with fp16 accumulators the TMEM loads ping-pong too (16 regs each), so every step's
-        // math runs under the next step's tcgen05.ld. The slot is handed back to the MMA issuer as soon as the last
-        // load has landed, before the last step's math.
-        Raw<F16> ra, rb;
-        auto free_slot = [&]() {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
-          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
-        };
-        auto chunk_done = [&](int c) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + c]);
-        };
-        const int w0 = sub * 2, w1 = sub * 2 + 1;
         const bool last = layer == 3;
-        epi_load<F16>(tslot, w0 * 16, ra);
-        tmem_ld_wait();
-        if constexpr (F16) epi_load<F16>(tslot, w1 * 16, rb);
-        load16(pl + 16, kb);
-        if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, w0, r, sp, ka, rgb);
-        else epi_math<false, F16>(ra, out_base, layer, h, 0, w0, r, sp, ka, rgb);
-        if constexpr (!F16) epi_load<F16>(tslot, w1 * 16, rb);
-        tmem_ld_wait();
-        if constexpr (F16) epi_load<F16>(tslot, 64 + w0 * 16, ra);
-        load16(pl + 64, ka);
-        if (last) epi_math<true, F16>(rb, out_base, layer, h, 0, w1, r, sp, kb, rgb);
-        else epi_math<false, F16>(rb, out_base, layer, h, 0, w1, r, sp, kb, rgb);
-        if (!last) chunk_done(0);
-        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
-        if constexpr (!F16) epi_load<F16>(tslot, 64 + w0 * 16, ra);
-        tmem_ld_wait();
-        if constexpr (F16) epi_load<F16>(tslot, 64 + w1 * 16, rb);
-        load16(pl + 64 + 16, kb);
-        if (last) epi_math<true, F16>(ra, out_base, layer, h, 1, w0, r, sp, ka, rgb);
-        else epi_math<false, F16>(ra, out_base, layer, h, 1, w0, r, sp, ka, rgb);
-        if constexpr (!F16) epi_load<F16>(tslot, 64 + w1 * 16, rb);
-        tmem_ld_wait();
-        free_slot();
-        if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, w1, r, sp, kb, rgb);
-        else epi_math<false, F16>(rb, out_base, layer, h, 1, w1, r, sp, kb, rgb);
-        if (!last) chunk_done(1);
-        if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
+        if (layer == 2 && has_next) {
+          rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
+          pn = rc_next.prow + fg * 16;
+        }
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs: complete, because
+          // this warp has itself consumed tmem_full[1] of layer 2. Its four chunks are interleaved with layer 3's halves.
+          if (last && has_next) layer0_unit(X ^ 1, 2 * h, rc_next, pw + 3 * kD + h * 128);
+          // unit after this one: the other half / the next layer / layer 0 of the next tile / the next tile's layer 1
+          const float* nb;
+          if (!last) nb = (h == 0) ? pw + layer * kD + 128 : (layer == 1 || !has_next) ? pw + (layer + 1) * kD : pn;
+          else nb = has_next ? (h == 0 ? pn + 128 : pn + kD) : (h == 0 ? pw + 3 * kD + 128 : nullptr);
+          const uint32_t tslot = tlane + h * 256;
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
+          mbar_wait(&sm.tmem_full[h], full_uses & 1);
+          tc_fence_after();
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
+          Raw<F16> ra, rb;
+          epi_load<F16>(tslot, fg * 16, ra);
+          if constexpr (F16) epi_load<F16>(tslot, 64 + fg * 16, rb);
+          tmem_ld_wait();
+          if constexpr (F16) {  // both loads have landed: hand the slot back before any math
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+            if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
+          }
+          if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb2);
+          else epi_math<false, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb2);
+          if constexpr (!F16) epi_load<F16>(tslot, 64 + fg * 16, rb);
+          if (nb) load16(nb, ka);
+          if (!last) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h]);
+          }
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
+          if constexpr (!F16) {
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+            if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
+          }
+          if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb2);
+          else epi_math<false, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb2);
+          if (nb) load16(nb + 64, kb);
+          if (!last) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + 1]);
+          }
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
+        }
         ++full_uses;
       }
       // Combine the four partial RGB projections of a row (2 groups x 2 subs) in a fixed order (bit-reproducible).
-      // The last warps to finish (group 1, sub 1) reduce and store; the others drop their partials in smem.
-      const int pidx = grp * 2 + sub;
+      // The warps of feature group 3 reduce and store; the others drop their partials in smem.
+      const float rgb[3] = {rgb2[0].x + rgb2[0].y, rgb2[1].x + rgb2[1].y, rgb2[2].x + rgb2[2].y};
+      const int pidx = fg;
       if (pidx != 3) {
         if (t > 0) named_bar_sync(2, kEpiThreads);  // the reducers have read the previous tile's partials
         float* pp = &sm.partial[pidx][r][0];

@@ -12,7 +12,7 @@ from diinn_b200 import synth, _lib  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 B, H, W, H_up, W_up = synth.CONFIGS[name]
-dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="bf16"),
+dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision=(sys.argv[2] if len(sys.argv) > 2 else "bf16")),
                                     synth.make_weights(seed=0)).cuda()
 x = torch.from_numpy(synth.make_feat(1, B, H, W)).cuda()
 with torch.no_grad():
@@ -35,4 +35,4 @@ for t in range(1, 5):
                   f"c0 {e[2]:7d} c1 {e[3]:7d} freed {e[4]:7d}")
     for h in range(2):
         f = tr[t, 96 + h * 8: 96 + h * 8 + 8] - t0
-        print(f" L2.h{h} epi detail: c0 ld_done {f[0]} math_done {f[1]} sts_done {f[2]} fence_done {f[3]} | c1 ld_done {f[4]} math_done {f[5]} sts_done {f[6]} fence_done {f[7]}")
+        print(f" L2.h{h} epi steps (ld landed / math done): " + "  ".join(f"{f[2 * i]}/{f[2 * i + 1]}" for i in range(4)))
