@@ -543,6 +543,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           epi_load<F16>(tslot, fg * 16, ra);
           if constexpr (F16) epi_load<F16>(tslot, 64 + fg * 16, rb);
           tmem_ld_wait();
+#if DIINN_TOUCH_KA
+          { float tch = ka[0].x + ka[1].y + ka[2].z + ka[3].w; asm volatile("" ::"f"(tch) : "memory"); }
+#endif
+#if DIINN_FINE_TRACE
+          if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 0);
+#endif
           if constexpr (F16) {  // both loads have landed: hand the slot back before any math
             tc_fence_before();
             __syncwarp();
@@ -551,6 +557,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           }
           if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb2);
           else epi_math<false, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb2);
+#if DIINN_FINE_TRACE
+          if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
+#endif
           if constexpr (!F16) epi_load<F16>(tslot, 64 + fg * 16, rb);
           if (nb) load16(nb, ka);
           if (!last) {
@@ -561,6 +570,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
           if constexpr (!F16) {
             tmem_ld_wait();
+#if DIINN_FINE_TRACE
+            if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 2);
+#endif
             tc_fence_before();
             __syncwarp();
             if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
@@ -568,6 +580,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           }
           if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb2);
           else epi_math<false, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb2);
+#if DIINN_FINE_TRACE
+          if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
+#endif
           if (nb) load16(nb + 64, kb);
           if (!last) {
             fence_proxy_async_smem();

@@ -35,4 +35,4 @@ for t in range(1, 5):
                   f"c0 {e[2]:7d} c1 {e[3]:7d} freed {e[4]:7d}")
     for h in range(2):
         f = tr[t, 96 + h * 8: 96 + h * 8 + 8] - t0
-        print(f" L2.h{h} epi steps (ld landed / math done): " + "  ".join(f"{f[2 * i]}/{f[2 * i + 1]}" for i in range(4)))
+        print(f" L2.h{h} fine (needs -DDIINN_FINE_TRACE=1): ld0 landed {f[0]} math0 done {f[1]} ld1 landed {f[2]} math1 done {f[3]}")
