@@ -26,13 +26,18 @@ SYMBOLS = [
     "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_query_ensemble", "diinn_debug_gather",
     "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace", "diinn_debug_umma_pace", "diinn_set_profiling", "diinn_get_kernel_times",
     "diinn_launch_count",
-    "diinn_version",
+    "diinn_version", "diinn_set_output_transform", "diinn_psnr",
 ]
 
 
 class Config(C.Structure):
     _fields_ = [("in_channels", C.c_int), ("hidden", C.c_int), ("n_layers", C.c_int), ("mode", C.c_int),
                 ("init_q", C.c_int), ("device", C.c_int)]
+
+
+class OutputTransform(C.Structure):
+    _fields_ = [("affine", C.c_int), ("scale", C.c_float), ("bias", C.c_float), ("clamp", C.c_int), ("lo", C.c_float),
+                ("hi", C.c_float), ("quantize_u8", C.c_int)]
 
 
 class WeightsF32(C.Structure):
@@ -95,6 +100,10 @@ def load() -> C.CDLL:
     lib.diinn_get_kernel_times.restype = i
     lib.diinn_launch_count.argtypes = [vp]
     lib.diinn_launch_count.restype = i64
+    lib.diinn_set_output_transform.argtypes = [vp, C.POINTER(OutputTransform)]
+    lib.diinn_set_output_transform.restype = i
+    lib.diinn_psnr.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, C.c_float, C.POINTER(C.c_double), vp]
+    lib.diinn_psnr.restype = i
     lib.diinn_version.argtypes = []
     lib.diinn_version.restype = C.c_char_p
     _lib = lib

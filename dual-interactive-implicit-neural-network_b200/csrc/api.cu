@@ -192,6 +192,7 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->WA16);
   cudaFree(h->WB16);
   cudaFree(h->WB16h);
+  cudaFree(h->psnr_acc);
   cudaFree(h->host_feat_dev);
   cudaFree(h->host_out_dev);
   cudaFree(h->host_ws);
@@ -231,6 +232,22 @@ size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_u
 static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
                        int row1, OutSpec o, void* workspace, size_t workspace_bytes, int compute, void* stream);
 
+int diinn_set_output_transform(diinn_handle* h, const diinn_output_transform* t) {
+  if (!h) return DIINN_ERR_BAD_ARG;
+  if (t && t->clamp && !(t->lo <= t->hi)) return fail(h, DIINN_ERR_BAD_ARG, "output transform: lo > hi");
+  h->out_tf = t ? *t : diinn_output_transform{};
+  return DIINN_OK;
+}
+
+// copy the handle's eval glue into the OutSpec of one call
+static int apply_output_transform(Handle* h, OutSpec* o) {
+  const diinn_output_transform& t = h->out_tf;
+  o->t_flags = (t.affine ? 1 : 0) | (t.clamp ? 2 : 0) | (t.quantize_u8 ? 4 : 0);
+  o->t_scale = t.scale, o->t_bias = t.bias, o->t_lo = t.lo, o->t_hi = t.hi;
+  if (t.quantize_u8 && o->mc) return fail(h, DIINN_ERR_BAD_DTYPE, "multicast stores are fp32-only; uint8 output needs peer stores");
+  return DIINN_OK;
+}
+
 int diinn_decode(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
                  int row1, void* out, int64_t out_batch_stride, int64_t out_chan_stride, int64_t out_row_stride,
                  void* workspace, size_t workspace_bytes, int io_dtype, int compute, void* stream) {
@@ -269,6 +286,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   void* out = o.ptr;
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
+  if ((rc = apply_output_transform(h, &o))) return rc;
   if (!feat || !out) return fail(h, DIINN_ERR_BAD_ARG, "null feat/out");
   if (H_up < 1 || W_up < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "size must be positive");
   if (row0 < 0 || row1 > H_up || row0 >= row1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad row range");
@@ -327,9 +345,10 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   cudaSetDevice(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t esz = io_dtype == DIINN_IO_F32 ? 4 : 2;
+  const size_t osz = h->out_tf.quantize_u8 ? 1 : esz;  // output element size (uint8 with the quantising eval glue)
   const size_t feat_bytes = static_cast<size_t>(B) * C * H * W * esz;
   const int nrows = row1 - row0;
-  const size_t out_bytes = static_cast<size_t>(B) * 3 * nrows * W_up * esz;
+  const size_t out_bytes = static_cast<size_t>(B) * 3 * nrows * W_up * osz;
   // Row bands: while band k decodes, band k+1's LR rows go up and band k-1's HR rows come down on two copy streams, so
   // a large image costs about max(PCIe, compute) instead of their sum. Small images take one band.
   const int64_t px = static_cast<int64_t>(B) * nrows * W_up;
@@ -370,7 +389,7 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
 
   const AxisParams ah = make_axis(H, H_up);
   const size_t plane = static_cast<size_t>(H) * W * esz;      // one (b, c) plane of feat
-  const size_t oplane = static_cast<size_t>(nrows) * W_up * esz;  // one (b, c) plane of the output band buffer
+  const size_t oplane = static_cast<size_t>(nrows) * W_up * osz;  // one (b, c) plane of the output band buffer
   int uploaded = 0;                                           // LR rows [0, uploaded) are already on the device
   for (int k = 0; k < bands; ++k) {
     const int a = row0 + k * band_rows, b = (a + band_rows < row1) ? a + band_rows : row1;
@@ -391,14 +410,14 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
     }
     DIINN_CUDA_OK(h, cudaEventRecord(h->ev_h2d[k], h->s_h2d));
     DIINN_CUDA_OK(h, cudaStreamWaitEvent(s, h->ev_h2d[k], 0));
-    char* oband = static_cast<char*>(h->host_out_dev) + static_cast<size_t>(a - row0) * W_up * esz;
+    char* oband = static_cast<char*>(h->host_out_dev) + static_cast<size_t>(a - row0) * W_up * osz;
     rc = diinn_decode(h, h->host_feat_dev, B, C, H, W, H_up, W_up, a, b, oband, static_cast<int64_t>(3) * nrows * W_up,
                       static_cast<int64_t>(nrows) * W_up, W_up, h->host_ws, h->host_ws_bytes, io_dtype, compute, s);
     if (rc) return rc;
     DIINN_CUDA_OK(h, cudaEventRecord(h->ev_dec[k], s));
     DIINN_CUDA_OK(h, cudaStreamWaitEvent(h->s_d2h, h->ev_dec[k], 0));
-    DIINN_CUDA_OK(h, cudaMemcpy2DAsync(static_cast<char*>(out_host) + static_cast<size_t>(a - row0) * W_up * esz, oplane,
-                                       oband, oplane, static_cast<size_t>(b - a) * W_up * esz,
+    DIINN_CUDA_OK(h, cudaMemcpy2DAsync(static_cast<char*>(out_host) + static_cast<size_t>(a - row0) * W_up * osz, oplane,
+                                       oband, oplane, static_cast<size_t>(b - a) * W_up * osz,
                                        static_cast<size_t>(B) * 3, cudaMemcpyDeviceToHost, h->s_d2h));
   }
   DIINN_CUDA_OK(h, cudaStreamSynchronize(h->s_d2h));
@@ -479,6 +498,7 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   OutSpec o{};
   o.ptr = out;
   o.io_dtype = io_dtype;
+  if ((rc = apply_output_transform(h, &o))) return rc;
   if (compute == DIINN_COMPUTE_FP32) {
     const int64_t total = static_cast<int64_t>(B) * Q * E;
     const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;

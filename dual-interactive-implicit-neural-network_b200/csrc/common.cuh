@@ -107,20 +107,32 @@ struct OutSpec {
   void* peers[kMaxPeers];
   int n_peers;
   void* mc;
+  // eval glue fused into the store (diinn_set_output_transform): bit 0 affine, bit 1 clamp, bit 2 uint8 quantisation
+  int t_flags;
+  float t_scale, t_bias, t_lo, t_hi;
 };
 
-// store one fp32/bf16 value of the output image at element offset `off` of every destination
+__device__ __forceinline__ void store_elem(const OutSpec& o, void* base, int64_t off, float v) {
+  if (o.t_flags & 4) {
+    const float q = fminf(fmaxf(__fadd_rn(__fmul_rn(v, 255.f), 0.5f), 0.f), 255.f);
+    static_cast<uint8_t*>(base)[off] = static_cast<uint8_t>(q);
+  } else if (o.io_dtype == DIINN_IO_F32) {
+    static_cast<float*>(base)[off] = v;
+  } else {
+    static_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
+  }
+}
+
+// store one value of the output image at element offset `off` of every destination (after the optional eval glue)
 __device__ __forceinline__ void store_out(const OutSpec& o, int64_t off, float v) {
+  if (o.t_flags & 1) v = __fadd_rn(__fmul_rn(v, o.t_scale), o.t_bias);  // two rounded ops, as the reference's `x * div + sub`
+  if (o.t_flags & 2) v = fminf(fmaxf(v, o.t_lo), o.t_hi);
   if (o.mc != nullptr) {
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(static_cast<float*>(o.mc) + off), "f"(v) : "memory");
   } else if (o.n_peers > 0) {
-    for (int i = 0; i < o.n_peers; ++i) {
-      if (o.io_dtype == DIINN_IO_F32) static_cast<float*>(o.peers[i])[off] = v;
-      else static_cast<__nv_bfloat16*>(o.peers[i])[off] = __float2bfloat16_rn(v);
-    }
+    for (int i = 0; i < o.n_peers; ++i) store_elem(o, o.peers[i], off, v);
   } else {
-    if (o.io_dtype == DIINN_IO_F32) static_cast<float*>(o.ptr)[off] = v;
-    else static_cast<__nv_bfloat16*>(o.ptr)[off] = __float2bfloat16_rn(v);
+    store_elem(o, o.ptr, off, v);
   }
 }
 

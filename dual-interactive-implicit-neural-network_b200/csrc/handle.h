@@ -40,6 +40,8 @@ struct Handle {
   CUtensorMap tmapWBh{};
   CUtensorMap tmapWBh_half{};
   SmallParams small{};            // host copy; passed by value to kernels
+  diinn_output_transform out_tf{};  // eval glue fused into the output store (all zero = identity)
+  double* psnr_acc = nullptr;       // device accumulator of diinn_psnr
 
   // ---- cached device scratch for diinn_decode_host ----
   void* host_feat_dev = nullptr;

@@ -89,6 +89,9 @@ class FusedImplicitDecoder(nn.Module):
             h = C.c_void_p()
             _lib.check(lib, None, lib.diinn_create(C.byref(h), C.byref(cfg)))
             self._handle, self._handle_device, self._packed_versions = h, idx, None
+            tf = getattr(self, "_out_tf", None)
+            if tf is not None:  # the eval glue belongs to the module, not to one device's handle
+                _lib.check(lib, h, lib.diinn_set_output_transform(h, C.byref(tf)))
         tensors = self._ref_tensors()
         versions = tuple((t.data_ptr(), t._version) for t in tensors)
         if versions != self._packed_versions:
@@ -137,6 +140,28 @@ class FusedImplicitDecoder(nn.Module):
             raise ValueError(f"expected a (B,64,H,W) feature map, got {tuple(x.shape)}")
 
     # ------------------------------------------------------------------ reference interface
+    # ------------------------------------------------------------------ eval glue fused into the output store
+    def set_output_transform(self, sub: Optional[float] = None, div: Optional[float] = None, clamp=None,
+                             uint8: bool = False, device=None):
+        """Fuse the step AFTER the decoder into its store:
+        ``out = pred * div + sub`` (sr_module.py:123), ``.clamp_(lo, hi)`` (clamp=(0, 1)), and with ``uint8=True``
+        torchvision save_image's ``mul(255).add_(0.5).clamp_(0, 255).to(uint8)`` (demo2.py:41), so the image leaves the
+        GPU at a quarter of the bytes. ``set_output_transform()`` with no arguments restores the identity."""
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        lib, h = self._ensure_handle(device)
+        t = _lib.OutputTransform()
+        t.affine = int(sub is not None or div is not None)
+        t.scale = 1.0 if div is None else float(div)
+        t.bias = 0.0 if sub is None else float(sub)
+        t.clamp = int(clamp is not None)
+        t.lo, t.hi = (0.0, 0.0) if clamp is None else (float(clamp[0]), float(clamp[1]))
+        t.quantize_u8 = int(bool(uint8))
+        _lib.check(lib, h, lib.diinn_set_output_transform(h, C.byref(t)))
+        self._out_tf, self._out_u8 = t, bool(uint8)
+
+    def _out_dtype(self, x: torch.Tensor) -> torch.dtype:
+        return torch.uint8 if getattr(self, "_out_u8", False) else x.dtype
+
     def forward(self, x: torch.Tensor, size, bsize: Optional[int] = None) -> torch.Tensor:
         """(B,64,H,W), size=(H_up,W_up) -> (B,3,H_up,W_up). ``bsize`` (the reference's query-chunk size,
         diinn.py:149-160) is accepted and ignored: no per-pixel intermediate is ever materialised."""
@@ -159,14 +184,15 @@ class FusedImplicitDecoder(nn.Module):
             raise _lib.DiinnError(-2, f"bad shape/rows: feat {tuple(x.shape)}, size {(H_up, W_up)}, rows {(row0, row1)}")
         ws = self._get_workspace(nbytes, x.device)
         if out is None:
-            res = torch.empty((B, 3, row1 - row0, W_up), dtype=x.dtype, device=x.device)
+            res = torch.empty((B, 3, row1 - row0, W_up), dtype=self._out_dtype(x), device=x.device)
             bs, cs, rs = 3 * (row1 - row0) * W_up, (row1 - row0) * W_up, W_up
             ptr = res.data_ptr()
         else:
             # a full-size image buffer, possibly with extra (padding) rows per channel: rows [row0,row1) are written in place
             if (out.dim() != 4 or out.shape[0] != B or out.shape[1] != 3 or out.shape[2] < H_up or out.shape[3] != W_up
-                    or out.dtype != x.dtype or not out.is_contiguous() or out.device != x.device):
-                raise ValueError("out must be a contiguous (B,3,>=H_up,W_up) tensor of x.dtype on x.device")
+                    or out.dtype != self._out_dtype(x) or not out.is_contiguous() or out.device != x.device):
+                raise ValueError("out must be a contiguous (B,3,>=H_up,W_up) tensor of x.dtype (uint8 with the "
+                                 "quantising output transform) on x.device")
             H_alloc = out.shape[2]
             res, bs, cs, rs = out, 3 * H_alloc * W_up, H_alloc * W_up, W_up
             ptr = out.data_ptr() + row0 * W_up * out.element_size()
@@ -202,7 +228,7 @@ class FusedImplicitDecoder(nn.Module):
         comp = _PRECISIONS[self.precision]
         nbytes = lib.diinn_query_workspace_bytes(h, B, H, W, Q * (4 if local_ensemble else 1), comp)
         ws = self._get_workspace(nbytes, feat.device)
-        out = torch.empty((B, Q, 3), dtype=feat.dtype, device=feat.device)
+        out = torch.empty((B, Q, 3), dtype=self._out_dtype(feat), device=feat.device)
         fn = lib.diinn_query_ensemble if local_ensemble else lib.diinn_query
         _lib.check(lib, h, fn(h, _ptr(feat), B, Cc, H, W, _ptr(coord), _ptr(cell), Q, _ptr(out), _ptr(ws),
                               ws.numel(), io, comp, _stream(feat.device)))
@@ -221,7 +247,7 @@ class FusedImplicitDecoder(nn.Module):
         H_up, W_up = int(size[0]), int(size[1])
         row1 = H_up if row1 is None else row1
         if out_host is None:
-            out_host = torch.empty((B, 3, row1 - row0, W_up), dtype=feat_host.dtype).pin_memory()
+            out_host = torch.empty((B, 3, row1 - row0, W_up), dtype=self._out_dtype(feat_host)).pin_memory()
         io = self._io_dtype(feat_host)
         comp = _PRECISIONS[self.precision]
         _lib.check(lib, h, lib.diinn_decode_host(h, _ptr(feat_host), B, Cc, H, W, H_up, W_up, row0, row1,
@@ -287,6 +313,22 @@ class FusedImplicitDecoder(nn.Module):
         _lib.check(lib, self._handle, lib.diinn_get_kernel_times(self._handle, C.byref(a), C.byref(b), C.byref(c),
                                                                  C.byref(n)))
         return dict(layout_ms=a.value, stage_a_ms=b.value, stage_b_ms=c.value, decodes=n.value)
+
+    def calc_psnr(self, sr: torch.Tensor, hr: torch.Tensor, dataset: Optional[str] = None, scale: int = 1,
+                  rgb_range: float = 1.0) -> float:
+        """The reference's ``calc_psnr`` (sr_module.py:21-38) on the device: one pass over sr and hr."""
+        if sr.shape != hr.shape or sr.dim() != 4 or sr.dtype != hr.dtype or sr.device != hr.device:
+            raise ValueError("sr and hr must be (B,C,H,W) tensors of one dtype on one device")
+        if dataset not in (None, "benchmark", "div2k"):
+            raise NotImplementedError(dataset)
+        lib, h = self._ensure_handle(sr.device)
+        sr, hr = sr.contiguous(), hr.contiguous()
+        B, Cc, H, W = sr.shape
+        out = C.c_double()
+        _lib.check(lib, h, lib.diinn_psnr(h, _ptr(sr), _ptr(hr), self._io_dtype(sr), B, Cc, H, W,
+                                          {None: 0, "benchmark": 1, "div2k": 2}[dataset], int(scale), float(rgb_range),
+                                          C.byref(out), _stream(sr.device)))
+        return out.value
 
     def launch_count(self) -> int:
         return int(_lib.load().diinn_launch_count(self._handle)) if self._handle is not None else 0

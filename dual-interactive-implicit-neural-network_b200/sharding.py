@@ -45,6 +45,11 @@ _symm_images = {}
 last_fused_mode = None  # how the last decode_sharded_fused call reached the peers (for reports)
 
 
+def _out_dtype(decoder, x: torch.Tensor) -> torch.dtype:
+    fn = getattr(decoder, "_out_dtype", None)   # FusedImplicitDecoder: uint8 with the quantising output transform
+    return fn(x) if fn is not None else x.dtype
+
+
 def _symmetric_image(shape, dtype, device, group):
     """A (B,3,H_up,W_up) image buffer allocated in symmetric memory and mapped into every rank of `group`
     (torch.distributed._symmetric_memory): returns (local tensor, handle with .buffer_ptrs / .multicast_ptr / .barrier)."""
@@ -71,9 +76,10 @@ def decode_sharded_fused(decoder, x: torch.Tensor, size, group: Optional[dist.Pr
     rank = dist.get_rank(group)
     H_up, W_up = int(size[0]), int(size[1])
     B = x.shape[0]
-    buf, hdl = _symmetric_image((B, 3, H_up, W_up), x.dtype, x.device, group)
+    odt = _out_dtype(decoder, x)   # uint8 when the decoder's eval glue quantises: a quarter of the bytes over NVLink
+    buf, hdl = _symmetric_image((B, 3, H_up, W_up), odt, x.device, group)
     r0, r1 = row_partition(H_up, world)[rank]
-    mc = int(hdl.multicast_ptr) if (multicast and x.dtype == torch.float32) else 0  # 0 when the fabric has no multicast
+    mc = int(hdl.multicast_ptr) if (multicast and odt == torch.float32) else 0  # 0 when the fabric has no multicast
     global last_fused_mode
     last_fused_mode = "nvswitch-multicast multimem.st" if mc else f"{world} peer stores per value"
     hdl.barrier(channel=0)  # every rank is done reading the previous image held in these buffers
@@ -102,14 +108,14 @@ def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessG
         r0, r1 = row_partition(H_up, world)[rank]
         if r1 > r0:
             return decoder.forward_rows(x, (H_up, W_up), r0, r1)
-        return torch.empty((B, 3, 0, W_up), dtype=x.dtype, device=x.device)
+        return torch.empty((B, 3, 0, W_up), dtype=_out_dtype(decoder, x), device=x.device)
     if world == 1:
         return decoder.forward_rows(x, (H_up, W_up), 0, H_up)
     if bands is None:
         bands = 4 if (H_up // world) * W_up * B >= (1 << 21) else 1
     sub, parts = band_partition(H_up, world, bands)
     H_pad = world * bands * sub
-    out = torch.empty((B, 3, H_pad, W_up), dtype=x.dtype, device=x.device)
+    out = torch.empty((B, 3, H_pad, W_up), dtype=_out_dtype(decoder, x), device=x.device)
     on_gpu = x.is_cuda
     in_place = dist.get_backend(group) == "nccl"
     if on_gpu:

@@ -123,6 +123,30 @@ int diinn_decode_multi(diinn_handle* h, const void* feat, int B, int C, int H, i
 int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int H, int W, int H_up, int W_up,
                       int row0, int row1, void* out_host, int io_dtype, int compute, void* stream);
 
+/* Eval glue either side of the decode, fused into the store of the last epilogue:
+ *   v = pred * scale + bias          (sr_module.py:123  `pred_hr * self.div + self.sub`, two rounded fp32 ops)
+ *   v = clamp(v, lo, hi)             (sr_module.py:123  `.clamp_(0, 1)`)
+ *   u8 = (uint8) clamp(v*255 + 0.5, 0, 255)   (torchvision save_image's quantisation, demo2.py:41)
+ * With quantize_u8 the `out` buffers of decode / decode_multi / decode_host / query hold uint8 elements (strides stay in
+ * elements), whatever io_dtype says about feat: 4x fewer bytes to assemble across GPUs or to copy back to the host.
+ * Multicast stores (diinn_decode_multi with out_multicast) stay fp32-only. NULL restores the identity. */
+typedef struct diinn_output_transform {
+  int affine;       /* apply scale/bias */
+  float scale, bias;
+  int clamp;        /* apply lo/hi */
+  float lo, hi;
+  int quantize_u8;
+} diinn_output_transform;
+int diinn_set_output_transform(diinn_handle* h, const diinn_output_transform* t);
+
+/* PSNR as the reference evaluates it (calc_psnr, sr_module.py:21-38), computed on the device:
+ *   dataset 0 = None (all pixels, all channels), 1 = 'benchmark' (shave = scale, Y conversion with
+ *   (65.738, 129.057, 25.064)/256 when C > 1), 2 = 'div2k' (shave = scale + 6).
+ * sr, hr: (B,C,H,W) contiguous device tensors of `dtype` (DIINN_IO_F32 / _BF16). Synchronises `stream`;
+ * *psnr_host = -10 log10(mean(valid^2)). */
+int diinn_psnr(diinn_handle* h, const void* sr, const void* hr, int dtype, int B, int C, int H, int W, int dataset,
+               int scale, float rgb_range, double* psnr_host, void* stream);
+
 /* Superset entry with the (feat, coord, cell) signature north_star names (LIIF.query_rgb's, liif.py:59):
  *   coord (B,Q,2) fp32 (h,w) in [-1,1], cell (B,Q,2) fp32, out (B,Q,3) io_dtype.
  * DIINN semantics per axis: idx = clamp(floor((c+1)*n/2)), rel = (c - centre[idx])*n,

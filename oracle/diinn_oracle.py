@@ -246,11 +246,41 @@ def grid_coords(H_up: int, W_up: int):
     return axis_centres(H_up), axis_centres(W_up)
 
 
-def calc_psnr(sr: np.ndarray, hr: np.ndarray, rgb_range: float = 1.0) -> float:
-    """PSNR as in sr_module.py:21-38 with dataset=None (no shave, no gray conversion)."""
-    diff = (sr.astype(np.float64) - hr.astype(np.float64)) / rgb_range
-    mse = float(np.mean(diff ** 2))
+def calc_psnr(sr: np.ndarray, hr: np.ndarray, rgb_range: float = 1.0, dataset=None, scale: int = 1) -> float:
+    """PSNR as in sr_module.py:21-38: dataset None = every pixel and channel; 'benchmark' = shave `scale` pixels and,
+    for C > 1, convert the difference to luma with (65.738, 129.057, 25.064)/256 in fp32; 'div2k' = shave scale + 6.
+    (`[shave:-shave]` with shave == 0 is an empty slice there -> nan, mirrored.) Mean in fp64."""
+    diff = ((sr.astype(F32) - hr.astype(F32)) / F32(rgb_range)).astype(F32)
+    if dataset is not None:
+        if dataset == "benchmark":
+            shave = int(scale)
+            if diff.shape[1] > 1:
+                conv = (np.array([65.738, 129.057, 25.064], dtype=F32) / F32(256)).reshape(1, 3, 1, 1)
+                prod = (diff * conv).astype(F32)
+                diff = ((prod[:, 0] + prod[:, 1]).astype(F32) + prod[:, 2]).astype(F32)
+        elif dataset == "div2k":
+            shave = int(scale) + 6
+        else:
+            raise NotImplementedError(dataset)
+        if shave == 0:
+            return float("nan")
+        diff = diff[..., shave:-shave, shave:-shave]
+    mse = float(np.mean(diff.astype(np.float64) ** 2))
     return float(-10.0 * np.log10(mse))
+
+
+def denorm_clamp(pred: np.ndarray, sub: float = 0.5, div: float = 0.5, lo: float = 0.0, hi: float = 1.0) -> np.ndarray:
+    """`(pred_hr * self.div + self.sub).clamp_(0, 1)` (sr_module.py:123): two rounded fp32 ops, then the clamp."""
+    v = (pred.astype(F32) * F32(div)).astype(F32)
+    v = (v + F32(sub)).astype(F32)
+    return np.clip(v, F32(lo), F32(hi)).astype(F32)
+
+
+def quantize_u8(img: np.ndarray) -> np.ndarray:
+    """torchvision.utils.save_image's quantisation (reached from demo2.py:41): mul(255).add_(0.5).clamp_(0,255).to(uint8)."""
+    v = (img.astype(F32) * F32(255)).astype(F32)
+    v = (v + F32(0.5)).astype(F32)
+    return np.clip(v, F32(0), F32(255)).astype(np.uint8)
 
 
 # --------------------------------------------------------------------------------------------------

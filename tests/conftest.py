@@ -23,3 +23,8 @@ def golden_posenc():
 @pytest.fixture(scope="session")
 def golden_decoder():
     return np.load(os.path.join(GOLDEN, "decoder.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_eval():
+    return np.load(os.path.join(GOLDEN, "eval.npz"))

@@ -127,3 +127,21 @@ def test_synth_is_stable():
     chk = float(np.float64(f.astype(np.float64).sum()))
     assert abs(float(f.std()) - 0.34) < 0.05
     assert chk == pytest.approx(float(synth.make_feat(1, 1, 4, 4).astype(np.float64).sum()), abs=0)
+
+
+# ---- eval glue: fixtures produced by the reference's own calc_psnr / torchvision.save_image
+def test_calc_psnr_matches_reference(golden_eval):
+    g = golden_eval
+    name = {0: None, 1: "benchmark", 2: "div2k"}
+    for ds, sc, rr, want in zip(g["psnr.dataset"], g["psnr.scale"], g["psnr.rgb_range"], g["psnr.value"]):
+        got = orc.calc_psnr(g["sr"], g["hr"], rgb_range=float(rr), dataset=name[int(ds)], scale=int(sc))
+        assert abs(got - float(want)) <= 2e-4, (ds, sc, rr, got, want)   # reference sums in fp32, oracle in fp64
+    got = orc.calc_psnr(g["sr"][:, :1], g["hr"][:, :1], dataset="benchmark", scale=3)
+    assert abs(got - float(g["psnr.gray1"])) <= 2e-4
+
+
+def test_denorm_clamp_and_u8_bit_exact(golden_eval):
+    g = golden_eval
+    den = orc.denorm_clamp(g["pred"], 0.5, 0.5)
+    assert np.array_equal(den, g["denorm"])
+    assert np.array_equal(orc.quantize_u8(den), g["u8"])
