@@ -25,13 +25,13 @@ inline int host_axis_index(const AxisParams& p, int j) {
 struct DecodePlan {
   int lr_row0 = 0, lr_rows = 0;  // LR rows P must hold
   int fr0 = 0, frows = 0;        // LR rows (with +-1 halo, clipped) of the NHWC bf16 copy
-  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, total = 0;
+  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, off_chain = 0, total = 0;
   int64_t chunk = 0;
 };
 
 constexpr int64_t kFp32Chunk = 1 << 17;  // HR pixels per activation ping-pong pass of the fp32 path
 
-DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int row1, int compute) {
+DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int row1, int compute, int mode) {
   DecodePlan p;
   const AxisParams ah = make_axis(H, H_up);
   p.lr_row0 = host_axis_index(ah, row0);
@@ -52,6 +52,10 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
   } else {
     p.off_nhwc = off;
     off += align_up(static_cast<size_t>(B) * p.frows * W * kC * sizeof(__nv_bfloat16));
+    if (mode != 3) {  // modes 1 / 2: scratch of the LR-resolution K chain
+      p.off_chain = off;
+      off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * p.lr_rows * W));
+    }
   }
   p.total = off;
   return p;
@@ -143,10 +147,10 @@ int diinn_create(diinn_handle** out, const diinn_config* cfg) {
     return DIINN_ERR_BAD_ARG;
   }
   *out = nullptr;
-  if (cfg->mode != 3 || cfg->init_q != 0 || cfg->in_channels != kC || cfg->hidden != kD ||
+  if (cfg->mode < 1 || cfg->mode > 3 || cfg->init_q != 0 || cfg->in_channels != kC || cfg->hidden != kD ||
       cfg->n_layers != kLayers) {
     g_create_error =
-        "only mode=3, init_q=False, in_channels=64, hidden_dims=[256]*4 is implemented (diinn.py:73-80)";
+        "only mode in {1,2,3}, init_q=False, in_channels=64, hidden_dims=[256]*4 is implemented (diinn.py:57-80)";
     return DIINN_ERR_UNSUPPORTED_MODE;
   }
   int ndev = 0;
@@ -192,6 +196,8 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->WA16);
   cudaFree(h->WB16);
   cudaFree(h->WB16h);
+  cudaFree(h->WH32);
+  cudaFree(h->WH16);
   cudaFree(h->psnr_acc);
   cudaFree(h->host_feat_dev);
   cudaFree(h->host_out_dev);
@@ -224,9 +230,8 @@ int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream)
 
 size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_up, int W_up, int row0, int row1,
                              int compute) {
-  (void)h;
   if (B < 1 || H < 1 || W < 1 || H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1) return 0;
-  return plan_decode(B, H, W, H_up, W_up, row0, row1, compute).total;
+  return plan_decode(B, H, W, H_up, W_up, row0, row1, compute, h ? h->cfg.mode : 3).total;
 }
 
 static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
@@ -292,7 +297,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   if (row0 < 0 || row1 > H_up || row0 >= row1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad row range");
   if (static_cast<int64_t>(B) * H * W >= (1ll << 31) / kPCols * 512)
     return fail(h, DIINN_ERR_BAD_SHAPE, "feature map too large");
-  const DecodePlan plan = plan_decode(B, H, W, H_up, W_up, row0, row1, compute);
+  const DecodePlan plan = plan_decode(B, H, W, H_up, W_up, row0, row1, compute, h->cfg.mode);
   if (!workspace || workspace_bytes < plan.total)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL,
                 "workspace too small: need " + std::to_string(plan.total) + " bytes");
@@ -311,6 +316,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
 
   if (compute == DIINN_COMPUTE_FP32) {
     if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, plan.lr_row0, plan.lr_rows, P, s))) return rc;
+    if (h->cfg.mode != 3 && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, s))) return rc;
     return run_stage_b_fp32(h, src, o, P, reinterpret_cast<float*>(ws + plan.off_q0),
                             reinterpret_cast<float*>(ws + plan.off_q1), plan.chunk, s);
   }
@@ -328,6 +334,9 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
     return rc;
   mark();
   if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s)))
+    return rc;
+  if (h->cfg.mode != 3 &&
+      (rc = run_lr_chain_umma(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, ws + plan.off_chain, s)))
     return rc;
   mark();
   rc = launch_stage_b_umma(h, src, o, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
@@ -350,14 +359,47 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   const int nrows = row1 - row0;
   const size_t out_bytes = static_cast<size_t>(B) * 3 * nrows * W_up * osz;
   // Row bands: while band k decodes, band k+1's LR rows go up and band k-1's HR rows come down on two copy streams, so
-  // a large image costs about max(PCIe, compute) instead of their sum. Small images take one band.
+  // a large image costs about max(PCIe, compute) instead of their sum. What stays exposed is the FIRST band's upload
+  // and the LAST band's download, so large images get a thin first and last band (2/16 and 1/16 of the rows) around three
+  // thick ones. Small images take one band. DIINN_HOST_BANDS="a,b,c,..." (relative weights) overrides the split.
   const int64_t px = static_cast<int64_t>(B) * nrows * W_up;
-  int bands = px >= (1 << 21) ? 4 : (px >= (1 << 19) ? 2 : 1);
-  if (bands > nrows) bands = nrows;
-  const int band_rows = (nrows + bands - 1) / bands;
+  int weights[7] = {1, 0, 0, 0, 0, 0, 0};
+  int bands = 1;
+  if (px >= (1 << 21)) {
+    const int w5[5] = {2, 5, 5, 3, 1};
+    bands = 5;
+    for (int k = 0; k < 5; ++k) weights[k] = w5[k];
+  } else if (px >= (1 << 19)) {
+    bands = 2;
+    weights[0] = weights[1] = 1;
+  }
+  if (const char* e = getenv("DIINN_HOST_BANDS")) {
+    int n = 0;
+    for (const char* p = e; *p && n < 7;) {
+      const int v = atoi(p);
+      if (v > 0) weights[n++] = v;
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+    if (n > 0) bands = n;
+  }
+  if (bands > nrows) {
+    bands = 1;
+    weights[0] = 1;
+  }
+  int wsum = 0;
+  for (int k = 0; k < bands; ++k) wsum += weights[k];
+  int edge[8];  // band k = HR rows [edge[k], edge[k+1])
+  edge[0] = row0;
+  for (int k = 0, acc = 0; k < bands; ++k) {
+    acc += weights[k];
+    edge[k + 1] = k + 1 == bands ? row1 : row0 + static_cast<int>(static_cast<int64_t>(nrows) * acc / wsum);
+    if (edge[k + 1] <= edge[k]) edge[k + 1] = edge[k] + 1 <= row1 ? edge[k] + 1 : row1;
+  }
+  edge[bands] = row1;
   size_t ws_bytes = 0;
   for (int k = 0; k < bands; ++k) {
-    const int a = row0 + k * band_rows, b = (a + band_rows < row1) ? a + band_rows : row1;
+    const int a = edge[k], b = edge[k + 1];
     if (a >= b) continue;
     const size_t n = diinn_workspace_bytes(h, B, H, W, H_up, W_up, a, b, compute);
     ws_bytes = n > ws_bytes ? n : ws_bytes;
@@ -391,14 +433,15 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   const size_t plane = static_cast<size_t>(H) * W * esz;      // one (b, c) plane of feat
   const size_t oplane = static_cast<size_t>(nrows) * W_up * osz;  // one (b, c) plane of the output band buffer
   int uploaded = 0;                                           // LR rows [0, uploaded) are already on the device
+  bool started = false;
   for (int k = 0; k < bands; ++k) {
-    const int a = row0 + k * band_rows, b = (a + band_rows < row1) ? a + band_rows : row1;
-    if (a >= b) break;
+    const int a = edge[k], b = edge[k + 1];
+    if (a >= b) continue;
     // LR rows this band reads (nearest-exact rows of [a,b) plus the 3x3 halo), minus what is already up
     int lr0 = host_axis_index(ah, a) - 1, lr1 = host_axis_index(ah, b - 1) + 2;
     lr0 = lr0 < 0 ? 0 : lr0;
     lr1 = lr1 > H ? H : lr1;
-    if (k == 0) uploaded = lr0;
+    if (!started) uploaded = lr0, started = true;
     const int c0 = lr0 > uploaded ? lr0 : uploaded;
     if (lr1 > c0) {
       const size_t off = static_cast<size_t>(c0) * W * esz;
@@ -426,7 +469,6 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
 }
 
 size_t diinn_query_workspace_bytes(const diinn_handle* h, int B, int H, int W, int Q, int compute) {
-  (void)h;
   if (B < 1 || H < 1 || W < 1 || Q < 1) return 0;
   // same carving as a full-image decode whose "grid" has B*Q pixels
   size_t off = align_up(static_cast<size_t>(B) * H * W * kPCols * sizeof(float));
@@ -436,6 +478,7 @@ size_t diinn_query_workspace_bytes(const diinn_handle* h, int B, int H, int W, i
     off += 2 * align_up(static_cast<size_t>(chunk) * kD * sizeof(float));
   } else {
     off += align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+    if (h && h->cfg.mode != 3) off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * H * W));
   }
   return off;
 }
@@ -505,11 +548,16 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
     float* q0 = reinterpret_cast<float*>(ws + off);
     float* q1 = reinterpret_cast<float*>(ws + off + align_up(static_cast<size_t>(chunk) * kD * sizeof(float)));
     if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, 0, H, P, s))) return rc;
+    if (h->cfg.mode != 3 && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * H * W, s))) return rc;
     return run_stage_b_fp32(h, src, o, P, q0, q1, chunk, s);
   }
   __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + off);
   if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
   if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s))) return rc;
+  if (h->cfg.mode != 3) {
+    char* chain = ws + off + align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+    if ((rc = run_lr_chain_umma(h, P, static_cast<int64_t>(B) * H * W, chain, s))) return rc;
+  }
   return launch_stage_b_umma(h, src, o, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
 }
 

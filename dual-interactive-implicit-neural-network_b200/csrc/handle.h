@@ -39,6 +39,9 @@ struct Handle {
   __half* WB16h = nullptr;
   CUtensorMap tmapWBh{};
   CUtensorMap tmapWBh_half{};
+  // modes 1 / 2 (K chain entirely at LR resolution): the k-facing 256x256 blocks of K.1..3, row-major [n][k]
+  float* WH32 = nullptr;          // (3, 256, 256)
+  __nv_bfloat16* WH16 = nullptr;  // (3, 256, 256)
   SmallParams small{};            // host copy; passed by value to kernels
   diinn_output_transform out_tf{};  // eval glue fused into the output store (all zero = identity)
   double* psnr_acc = nullptr;       // device accumulator of diinn_psnr
@@ -78,6 +81,10 @@ int launch_axis_tables(Handle* h, const AxisParams& ah, const AxisParams& aw, in
 int launch_query_gather(Handle* h, const PixelSource& src, int32_t* idx, float* rel, float* ratio, cudaStream_t s);
 int launch_stage_a_fp32(Handle* h, const void* feat, int io_dtype, int B, int H, int W, int lr_row0, int lr_rows,
                         float* P, cudaStream_t s);
+// LR-resolution K chain of modes 1 / 2: P[:, 256 i ..] += WH[i-1] . relu(P[:, 256 (i-1) ..]) for i = 1..3, M rows of P
+int run_lr_chain_fp32(Handle* h, float* P, int64_t M, cudaStream_t s);
+int run_lr_chain_umma(Handle* h, float* P, int64_t M, void* scratch, cudaStream_t s);
+size_t lr_chain_scratch_bytes(int64_t M);
 int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,
                      float* qbuf1, int64_t chunk, cudaStream_t s);
 // stage_a_umma.cu / stage_b_umma.cu

@@ -4,6 +4,10 @@
 //   K.0 (256,576)   K.i (256,832) with input channels [0,256) <- q and [256,832) <- x   (torch.cat([q,x]), diinn.py:136)
 //   Q.0 (256,3)     Q.i (256,256)      last (3,256)
 //   x channel c*9 + kh*3 + kw = feat[c, h+kh-1, w+kw-1]                                   (F.unfold, diinn.py:168)
+// Mode 2 (diinn.py:65-72,124-131) has the same shapes with K.i's first 256 input channels fed by k instead of q; mode 1
+// (diinn.py:57-64,116-123) has K.i (256,256) fed by k alone. In both the K chain never sees a per-HR-pixel quantity, so
+// it is evaluated per LR pixel: stage A's matrix keeps the x-facing blocks (zero for mode 1), the k-facing 256x256 blocks
+// go to WH for the LR chain (run_lr_chain_*), and stage B's K rows are ZERO so that its relu(0 + P[l]) returns k_i.
 //
 // Because every term multiplying x depends only on the LR pixel, the four x-facing blocks are stacked into one
 // (1024 x 576) matrix evaluated once per LR pixel ("stage A"); the per-HR-pixel work ("stage B") keeps only the
@@ -21,15 +25,16 @@ struct RefPtrs {
   const float* lb;
 };
 
-__global__ void pack_stage_a_kernel(RefPtrs r, float* __restrict__ WA32, float* __restrict__ bA,
+__global__ void pack_stage_a_kernel(RefPtrs r, int mode, float* __restrict__ WA32, float* __restrict__ bA,
                                     __nv_bfloat16* __restrict__ WA16) {
   const int n = blockIdx.x;  // 0..1023
   const int layer = n >> 8, row = n & 255;
   const int stride = layer == 0 ? kUnfold : kD + kUnfold;
   const int off = layer == 0 ? 0 : kD;
+  const bool has_x = layer == 0 || mode != 1;  // mode 1: K.1..3 take k only
   const float* src = r.kw[layer] + static_cast<size_t>(row) * stride + off;
   for (int k = threadIdx.x; k < kUnfold; k += blockDim.x) {
-    const float v = src[k];
+    const float v = has_x ? src[k] : 0.f;
     WA32[static_cast<size_t>(n) * kUnfold + k] = v;
     const int c = k / 9, tap = k % 9;
     // (n-block, tap, row, c)
@@ -38,20 +43,27 @@ __global__ void pack_stage_a_kernel(RefPtrs r, float* __restrict__ WA32, float* 
   if (threadIdx.x == 0) bA[n] = r.kb[layer][row];
 }
 
-__global__ void pack_stage_b_kernel(RefPtrs r, float* __restrict__ WB32, __nv_bfloat16* __restrict__ WB16,
-                                    __half* __restrict__ WB16h) {
+__global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB32, __nv_bfloat16* __restrict__ WB16,
+                                    __half* __restrict__ WB16h, float* __restrict__ WH32,
+                                    __nv_bfloat16* __restrict__ WH16) {
   const int n = blockIdx.x;   // 0..511
   const int li = blockIdx.y;  // 0..2 -> reference layer li+1
   const bool is_q = n >= kD;
   const int row = is_q ? n - kD : n;
   const float* src = is_q ? r.qw[li + 1] + static_cast<size_t>(row) * kD
-                          : r.kw[li + 1] + static_cast<size_t>(row) * (kD + kUnfold);
+                          : r.kw[li + 1] + static_cast<size_t>(row) * (mode == 1 ? kD : kD + kUnfold);
+  const bool to_chain = !is_q && mode != 3;  // k-facing block: LR chain instead of stage B
   const int half = row >> 7;                              // which 128-feature half of the layer output
   const int tile_row = (is_q ? 128 : 0) + (row & 127);    // K-part rows [0,128), Q-part rows [128,256)
   const int fh = row & 127;                               // fp16 twin: K/Q interleaved in 16-feature blocks
   const int tile_row_h = 32 * (fh >> 4) + (is_q ? 16 : 0) + (fh & 15);
   for (int k = threadIdx.x; k < kD; k += blockDim.x) {
-    const float v = src[k];
+    float v = src[k];
+    if (to_chain) {
+      WH32[(static_cast<size_t>(li) * kD + row) * kD + k] = v;
+      WH16[(static_cast<size_t>(li) * kD + row) * kD + k] = __float2bfloat16_rn(v);
+      v = 0.f;
+    }
     WB32[(static_cast<size_t>(li) * 512 + n) * kD + k] = v;
     const int kc = k >> 6, e = k & 63;
     WB16[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row) * 64 + e] = __float2bfloat16_rn(v);
@@ -62,7 +74,9 @@ __global__ void pack_stage_b_kernel(RefPtrs r, float* __restrict__ WB32, __nv_bf
 int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   RefPtrs r{};
   float* staging = nullptr;
-  const size_t sizes_kw[4] = {256 * 576, 256 * 832, 256 * 832, 256 * 832};
+  const int mode = h->cfg.mode;
+  const size_t kw_i = mode == 1 ? 256 * 256 : 256 * 832;
+  const size_t sizes_kw[4] = {256 * 576, kw_i, kw_i, kw_i};
   const size_t sizes_qw[4] = {256 * 3, 256 * 256, 256 * 256, 256 * 256};
   size_t total = 0;
   for (int i = 0; i < 4; ++i) total += sizes_kw[i] + sizes_qw[i] + 512;
@@ -102,9 +116,11 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     DIINN_CUDA_OK(h, cudaMalloc(&h->WA16, sizeof(__nv_bfloat16) * kPCols * kUnfold));
     DIINN_CUDA_OK(h, cudaMalloc(&h->WB16, sizeof(__nv_bfloat16) * 3 * 512 * kD));
     DIINN_CUDA_OK(h, cudaMalloc(&h->WB16h, sizeof(__half) * 3 * 512 * kD));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WH32, sizeof(float) * 3 * kD * kD));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WH16, sizeof(__nv_bfloat16) * 3 * kD * kD));
   }
-  pack_stage_a_kernel<<<kPCols, 192, 0, s>>>(r, h->WA32, h->bA, h->WA16);
-  pack_stage_b_kernel<<<dim3(512, 3), 128, 0, s>>>(r, h->WB32, h->WB16, h->WB16h);
+  pack_stage_a_kernel<<<kPCols, 192, 0, s>>>(r, mode, h->WA32, h->bA, h->WA16);
+  pack_stage_b_kernel<<<dim3(512, 3), 128, 0, s>>>(r, mode, h->WB32, h->WB16, h->WB16h, h->WH32, h->WH16);
   h->launches += 2;
   DIINN_CUDA_OK(h, cudaGetLastError());
 

@@ -48,10 +48,11 @@ class FusedImplicitDecoder(nn.Module):
                  init_q: bool = False, precision: str = "bf16"):
         super().__init__()
         hidden_dims = list(hidden_dims)
-        if mode != 3 or init_q:
+        if mode not in (1, 2, 3) or init_q:
             raise NotImplementedError(
-                "FusedImplicitDecoder implements the paper's final model only: mode=3, init_q=False "
-                "(diinn.py:73-80); other wirings are SURVEY.md section 8(f) 'next' rows")
+                "FusedImplicitDecoder implements mode=3 (the paper's final model, diinn.py:73-80) and the k-fed wirings "
+                "mode=1 / mode=2 (diinn.py:57-72), all with init_q=False; mode 4 and init_q=True are SURVEY.md section "
+                "8(f) 'next' rows")
         if in_channels != 64 or hidden_dims != [256] * 4:
             raise NotImplementedError("only in_channels=64, hidden_dims=[256]*4 is implemented")
         if precision not in _PRECISIONS:
@@ -64,7 +65,7 @@ class FusedImplicitDecoder(nn.Module):
         for hd in hidden_dims:
             self.K.append(nn.Sequential(nn.Conv2d(last_k, hd, 1), nn.ReLU()))
             self.Q.append(nn.Sequential(nn.Conv2d(last_q, hd, 1), SineAct()))
-            last_k, last_q = hd + in_channels * 9, hd
+            last_k, last_q = (hd if mode == 1 else hd + in_channels * 9), hd
         self.last_layer = nn.Conv2d(hidden_dims[-1], 3, 1)
         self._handle = None
         self._handle_device = None
@@ -85,7 +86,7 @@ class FusedImplicitDecoder(nn.Module):
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if self._handle is None or self._handle_device != idx:
             self.release()
-            cfg = _lib.Config(64, 256, 4, 3, 0, idx)
+            cfg = _lib.Config(64, 256, 4, self.mode, 0, idx)
             h = C.c_void_p()
             _lib.check(lib, None, lib.diinn_create(C.byref(h), C.byref(cfg)))
             self._handle, self._handle_device, self._packed_versions = h, idx, None

@@ -64,12 +64,12 @@ def weight_names(n_layers: int = N_LAYERS):
     return names
 
 
-def weight_shapes(in_channels: int = IN_CHANNELS, hidden: int = HIDDEN, n_layers: int = N_LAYERS):
-    """name -> shape, identical to the reference state_dict."""
+def weight_shapes(in_channels: int = IN_CHANNELS, hidden: int = HIDDEN, n_layers: int = N_LAYERS, mode: int = 3):
+    """name -> shape, identical to the reference state_dict (mode 1: K.i takes k only, diinn.py:57-64)."""
     unfold = in_channels * 9
     shapes = {}
     for i in range(n_layers):
-        kin = unfold if i == 0 else hidden + unfold
+        kin = unfold if i == 0 else (hidden if mode == 1 else hidden + unfold)
         qin = 3 if i == 0 else hidden
         shapes[f"K.{i}.0.weight"] = (hidden, kin, 1, 1)
         shapes[f"K.{i}.0.bias"] = (hidden,)
@@ -80,14 +80,15 @@ def weight_shapes(in_channels: int = IN_CHANNELS, hidden: int = HIDDEN, n_layers
     return shapes
 
 
-def make_weights(seed: int = 0, k_gain: float = 1.0, q_gain: float = 1.0, last_gain: float = 1.0):
+def make_weights(seed: int = 0, k_gain: float = 1.0, q_gain: float = 1.0, last_gain: float = 1.0, mode: int = 3):
     """Reference-layout decoder weights as a dict of float32 numpy arrays.
 
     k_gain/q_gain > 1 give the "stress" set of SURVEY.md §4 item 8 (activations O(1) instead of being
     dominated by last_layer.bias)."""
     out = {}
-    for s, (name, shape) in enumerate(weight_shapes().items()):
-        fan_in = shape[1] if len(shape) == 4 else weight_shapes()[name.replace("bias", "weight")][1]
+    shapes = weight_shapes(mode=mode)
+    for s, (name, shape) in enumerate(shapes.items()):
+        fan_in = shape[1] if len(shape) == 4 else shapes[name.replace("bias", "weight")][1]
         bound = 1.0 / np.sqrt(float(fan_in))
         gain = k_gain if name.startswith("K.") else q_gain if name.startswith("Q.") else last_gain
         out[name] = uniform(seed, 100 + s, shape, -bound * gain, bound * gain)

@@ -108,11 +108,13 @@ def _w2d(w: np.ndarray) -> np.ndarray:
     return w.reshape(w.shape[0], w.shape[1])
 
 
-def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False, taps: dict | None = None):
+def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False, taps: dict | None = None,
+               mode: int = 3):
     """x: (N,576) gathered unfolded features, syn: (N,3) -> (N,3) RGB.
 
     k = relu(K0 x); q = k * sin(Q0 syn); for i in 1..3: k = relu(K_i [q,x]); q = k * sin(Q_i q);
-    out = last(q).  1x1 Conv2d == per-pixel affine map."""
+    out = last(q).  1x1 Conv2d == per-pixel affine map.
+    mode 2 (diinn.py:124-131): K_i takes [k,x] instead of [q,x]; mode 1 (diinn.py:116-123): K_i takes k alone."""
     dt = np.float64 if fp64 else F32
     x = x.astype(dt)
     syn = syn.astype(dt)
@@ -123,7 +125,7 @@ def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False
     if taps is not None:
         taps["k0"], taps["q0"] = k, q
     for i in range(1, n_layers):
-        qx = np.concatenate([q, x], axis=1)
+        qx = k if mode == 1 else np.concatenate([k if mode == 2 else q, x], axis=1)
         k = np.maximum(qx @ _w2d(W[f"K.{i}.0.weight"]).T + W[f"K.{i}.0.bias"], 0)
         q = k * np.sin(q @ _w2d(W[f"Q.{i}.0.weight"]).T + W[f"Q.{i}.0.bias"])
         if taps is not None:
@@ -136,7 +138,7 @@ def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False
 # forward (diinn.py:163-173) and the row-band form used for sharding / large configs
 # --------------------------------------------------------------------------------------------------
 def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool = False,
-                    chunk: int = 1 << 16) -> np.ndarray:
+                    chunk: int = 1 << 16, mode: int = 3) -> np.ndarray:
     """(B,64,H,W), size=(H_up,W_up) -> (B,3,rows,W_up); rows=(r0,r1) restricts to an HR row band."""
     B, C, H, W = feat.shape
     H_up, W_up = int(size[0]), int(size[1])
@@ -157,7 +159,7 @@ def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool
             syn[..., 0] = rh[a:e, None]
             syn[..., 1] = rw[None, :]
             syn[..., 2] = ratio
-            y = step_mode3(weights, x, syn.reshape(-1, 3), fp64=fp64)
+            y = step_mode3(weights, x, syn.reshape(-1, 3), fp64=fp64, mode=mode)
             out[b, :, a - r0:e - r0] = y.reshape(e - a, W_up, 3).transpose(2, 0, 1)
     return out
 
@@ -177,7 +179,8 @@ def query_index_rel(coord_axis: np.ndarray, n: int):
     return idx, rel
 
 
-def query(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.ndarray, fp64: bool = False) -> np.ndarray:
+def query(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.ndarray, fp64: bool = False,
+          mode: int = 3) -> np.ndarray:
     """feat (B,64,H,W), coord (B,Q,2) as (h,w) in [-1,1], cell (B,Q,2) -> (B,Q,3).
 
     ratio = fl(fl(fl(cell_h * cell_w) * fl(H*W)) * 0.25) -- for a regular grid cell=(2/H_up, 2/W_up)
@@ -191,7 +194,7 @@ def query(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.ndarray, 
         ce = cell[b].astype(F32)
         ratio = (((ce[:, 0] * ce[:, 1]).astype(F32) * F32(H * W)).astype(F32) * F32(0.25)).astype(F32)
         syn = np.stack([rh, rw, ratio], axis=1).astype(F32)
-        out[b] = step_mode3(weights, u[b][ih, iw], syn, fp64=fp64)
+        out[b] = step_mode3(weights, u[b][ih, iw], syn, fp64=fp64, mode=mode)
     return out
 
 

@@ -28,3 +28,8 @@ def golden_decoder():
 @pytest.fixture(scope="session")
 def golden_eval():
     return np.load(os.path.join(GOLDEN, "eval.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_modes():
+    return np.load(os.path.join(GOLDEN, "modes.npz"))

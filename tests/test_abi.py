@@ -36,9 +36,9 @@ def test_version_and_create_errors_without_gpu():
     lib = _lib.load()
     assert b"sm_100a" in lib.diinn_version()
     h = ctypes.c_void_p()
-    bad = _lib.Config(64, 256, 4, 1, 0, 0)  # mode 1 is not implemented
-    assert lib.diinn_create(ctypes.byref(h), ctypes.byref(bad)) == -4
-    assert b"mode=3" in lib.diinn_last_error(None)
+    for bad in (_lib.Config(64, 256, 4, 4, 0, 0), _lib.Config(64, 256, 4, 3, 1, 0)):  # mode 4 / init_q: not implemented
+        assert lib.diinn_create(ctypes.byref(h), ctypes.byref(bad)) == -4
+        assert b"mode in {1,2,3}" in lib.diinn_last_error(None)
     if not torch.cuda.is_available():
         ok = _lib.Config(64, 256, 4, 3, 0, 0)
         assert lib.diinn_create(ctypes.byref(h), ctypes.byref(ok)) == -8  # no CPU fallback
@@ -73,7 +73,7 @@ def test_same_default_init_as_reference_layout():
 
 
 def test_unsupported_wirings_raise():
-    for kw in (dict(mode=1), dict(mode=2), dict(mode=4), dict(mode=3, init_q=True),
+    for kw in (dict(mode=4), dict(mode=3, init_q=True), dict(mode=1, init_q=True),
                dict(mode=3, in_channels=32), dict(mode=3, hidden_dims=[128] * 4)):
         with pytest.raises(NotImplementedError):
             diinn_b200.FusedImplicitDecoder(**kw)

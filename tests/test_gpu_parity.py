@@ -482,3 +482,66 @@ def test_psnr_full_size_c3():
     for ds in (None, "div2k"):
         got = dec.calc_psnr(torch.from_numpy(sr).cuda(), torch.from_numpy(hr).cuda(), dataset=ds, scale=4)
         assert abs(got - orc.calc_psnr(sr, hr, dataset=ds, scale=4)) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------
+# decoder modes 1 / 2: K chain evaluated per LR pixel, stage B with zero K rows
+# ---------------------------------------------------------------------------------------------------------
+MODE_CASES = [f"m{m}.{n}" for m in (1, 2) for n in ("small", "c1", "batch_bsize", "stress")]
+
+
+def _mode_case(golden_modes, key):
+    mode, fseed, B, H, W, H_up, W_up, bsize = (int(v) for v in golden_modes[f"{key}.meta"])
+    kg, qg = (float(v) for v in golden_modes[f"{key}.gains"])
+    w = synth.make_weights(seed=mode, mode=mode, k_gain=kg, q_gain=qg)
+    dec = lambda precision: diinn_b200.load_numpy_weights(  # noqa: E731
+        diinn_b200.FusedImplicitDecoder(mode=mode, init_q=False, precision=precision), w).cuda()
+    return mode, w, dec, synth.make_feat(fseed, B, H, W), (H_up, W_up), golden_modes[f"{key}.out"], (None if bsize < 0 else bsize)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("key", MODE_CASES)
+def test_modes_1_2_match_reference(golden_modes, key, precision):
+    mode, w, dec, feat, size, want, bsize = _mode_case(golden_modes, key)
+    got = dec(precision)(torch.from_numpy(feat).cuda(), size, bsize).cpu().numpy()
+    err = float(np.abs(got - want).max())
+    stress = key.endswith("stress")
+    assert err <= TOL[precision], (key, precision, err)
+    if not stress:
+        assert err <= TIGHT[precision], (key, precision, err)
+        assert _psnr_delta(got, want) < 0.01
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_modes_1_2_row_tiles_and_query(golden_modes, mode):
+    """row tiles bit-identical to the full decode, host entry == device entry, query on the grid == forward"""
+    _, w, dec, feat, size, want, _ = _mode_case(golden_modes, f"m{mode}.small")
+    d = dec("bf16")
+    x = torch.from_numpy(feat).cuda()
+    full = d(x, size)
+    tiles = torch.cat([d.forward_rows(x, size, a, b) for a, b in ((0, 19), (19, 50), (50, size[0]))], dim=2)
+    assert torch.equal(tiles, full)
+    assert torch.equal(d.decode_host(x.cpu().pin_memory(), size), full.cpu())
+    # (feat, coord, cell) entry on the regular grid
+    H_up, W_up = size
+    ch = torch.from_numpy(orc.axis_centres(H_up)).cuda()
+    cw = torch.from_numpy(orc.axis_centres(W_up)).cuda()
+    coord = torch.stack(torch.meshgrid(ch, cw, indexing="ij"), dim=-1).reshape(1, -1, 2)
+    cell = torch.tensor([2.0 / H_up, 2.0 / W_up], device="cuda").expand(1, coord.shape[1], 2)
+    q = d.query(x, coord, cell).reshape(1, H_up, W_up, 3).permute(0, 3, 1, 2)
+    assert float((q - full).abs().max()) <= 1e-6
+    # fp32 path against the fp64 oracle
+    got32 = dec("fp32")(x, size).cpu().numpy()
+    ref64 = orc.decoder_forward(w, feat, size, fp64=True, mode=mode)
+    assert float(np.abs(got32 - ref64).max()) <= 2e-6
+
+
+def test_mode_swap_decoder_keeps_mode():
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.decoder = diinn_b200.FusedImplicitDecoder(mode=1, precision="fp32")
+    m = diinn_b200.swap_decoder(Net().cuda(), precision="bf16")
+    assert m.decoder.mode == 1 and m.decoder.K[1][0].weight.shape[1] == 256
+    x = torch.from_numpy(synth.make_feat(3, 1, 16, 16)).cuda()
+    assert m.decoder(x, (32, 32)).shape == (1, 3, 32, 32)

@@ -145,3 +145,18 @@ def test_denorm_clamp_and_u8_bit_exact(golden_eval):
     den = orc.denorm_clamp(g["pred"], 0.5, 0.5)
     assert np.array_equal(den, g["denorm"])
     assert np.array_equal(orc.quantize_u8(den), g["u8"])
+
+
+# ---- decoder modes 1 / 2: fixtures produced by the reference ImplicitDecoder(mode=1|2)
+MODE_CASES = [f"m{m}.{n}" for m in (1, 2) for n in ("small", "c1", "batch_bsize", "stress")]
+
+
+@pytest.mark.parametrize("key", MODE_CASES)
+def test_modes_1_2_match_reference(golden_modes, key):
+    mode, fseed, B, H, W, H_up, W_up, _ = (int(v) for v in golden_modes[f"{key}.meta"])
+    kg, qg = (float(v) for v in golden_modes[f"{key}.gains"])
+    w = synth.make_weights(seed=mode, mode=mode, k_gain=kg, q_gain=qg)
+    got = orc.decoder_forward(w, synth.make_feat(fseed, B, H, W), (H_up, W_up), mode=mode)
+    want = golden_modes[f"{key}.out"]
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) <= (2e-6 if kg == 1.0 else 2e-5)
