@@ -182,6 +182,20 @@ int diinn_create(diinn_handle** out, const diinn_config* cfg) {
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
   cudaSetDevice(cfg->device);
+  // per-handle device scratch lives here so that decode / query never allocate (CUDA-graph capturable, one handle per
+  // device or thread with no shared state)
+  bool ok = cudaMalloc(&h->err_flag, sizeof(int)) == cudaSuccess && cudaMemset(h->err_flag, 0, sizeof(int)) == cudaSuccess;
+  const char* tr = getenv("DIINN_TRACE");
+  if (ok && tr && tr[0] == '1')
+    ok = cudaMalloc(&h->trace_dev, 1024 * sizeof(long long)) == cudaSuccess &&
+         cudaMemset(h->trace_dev, 0, 1024 * sizeof(long long)) == cudaSuccess;
+  if (!ok) {
+    g_create_error = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    cudaFree(h->err_flag);
+    cudaFree(h->trace_dev);
+    delete h;
+    return DIINN_ERR_CUDA;
+  }
   *out = h;
   return DIINN_OK;
 }
@@ -196,6 +210,8 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->WA16);
   cudaFree(h->WB16);
   cudaFree(h->WB16h);
+  cudaFree(h->err_flag);
+  cudaFree(h->trace_dev);
   cudaFree(h->WH32);
   cudaFree(h->WH16);
   cudaFree(h->psnr_acc);

@@ -20,6 +20,7 @@ struct Handle {
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
   long long* trace_dev = nullptr;  // DIINN_TRACE=1: 1024 clock64 samples of the last stage-B launch
+  int* err_flag = nullptr;         // device word the tcgen05 kernels raise on an internal consistency failure
 
   // ---- fp32 CUDA-core path ----
   float* WA32 = nullptr;  // (1024, 576): rows [0,256) K.0; rows 256*i.. K.i[:,256:832]; reference k order c*9+tap

@@ -248,11 +248,7 @@ int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H,
     env_cg = (e && e[0] == '1') ? 1 : 2;
   }
   const int cta_group = env_cg;
-  static int* err_flag = nullptr;
-  if (!err_flag) {
-    DIINN_CUDA_OK(h, cudaMalloc(&err_flag, sizeof(int)));
-    DIINN_CUDA_OK(h, cudaMemset(err_flag, 0, sizeof(int)));
-  }
+  int* err_flag = h->err_flag;
   CUtensorMap tmF;
   const uint64_t dims[4] = {static_cast<uint64_t>(kC), static_cast<uint64_t>(W), static_cast<uint64_t>(frows),
                             static_cast<uint64_t>(B)};

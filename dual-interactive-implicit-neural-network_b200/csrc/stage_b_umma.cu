@@ -662,22 +662,8 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
     }
     cta_group = env_cg;
   }
-  static int* err_flag = nullptr;
-  if (!err_flag) {
-    DIINN_CUDA_OK(h, cudaMalloc(&err_flag, sizeof(int)));
-    DIINN_CUDA_OK(h, cudaMemset(err_flag, 0, sizeof(int)));
-  }
-  static long long* trace = nullptr;
-  static int want_trace = -1;
-  if (want_trace < 0) {
-    const char* e = getenv("DIINN_TRACE");
-    want_trace = (e && e[0] == '1') ? 1 : 0;
-    if (want_trace) {
-      DIINN_CUDA_OK(h, cudaMalloc(&trace, 1024 * sizeof(long long)));
-      DIINN_CUDA_OK(h, cudaMemset(trace, 0, 1024 * sizeof(long long)));
-    }
-  }
-  h->trace_dev = trace;
+  int* err_flag = h->err_flag;   // per-handle device scratch, allocated by diinn_create (no allocation in decode)
+  long long* trace = h->trace_dev;
 
   Work wk{};
   if (src.mode == 0) {

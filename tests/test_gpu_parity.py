@@ -545,3 +545,44 @@ def test_mode_swap_decoder_keeps_mode():
     assert m.decoder.mode == 1 and m.decoder.K[1][0].weight.shape[1] == 256
     x = torch.from_numpy(synth.make_feat(3, 1, 16, 16)).cuda()
     assert m.decoder(x, (32, 32)).shape == (1, 3, 32, 32)
+
+
+def test_decode_is_cuda_graph_capturable(w0):
+    """the C ABI promises no allocation / no sync inside decode: capture one decode, replay it on new feature values"""
+    dec = _decoder(w0, "bf16")
+    B, H, W, size = 1, 40, 36, (97, 120)
+    x = torch.from_numpy(synth.make_feat(21, B, H, W)).cuda()
+    out = torch.empty((B, 3, size[0], size[1]), device="cuda")
+    dec.forward_rows(x, size, 0, size[0], out=out)          # warm-up: packs weights, sizes the cached workspace
+    want_a = out.clone()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            dec.forward_rows(x, size, 0, size[0], out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want_a)
+    x.copy_(torch.from_numpy(synth.make_feat(22, B, H, W)))  # same buffers, new values
+    g.replay()
+    torch.cuda.synchronize()
+    want_b = dec(x, size)
+    assert torch.equal(out, want_b) and not torch.equal(want_a, want_b)
+
+
+def test_two_handles_on_one_device_are_independent(w0):
+    """no shared global state between handles: interleaved decodes of two decoders with different weights"""
+    a, b = _decoder(w0, "bf16"), _decoder(synth.make_weights(seed=5), "bf16")
+    x = torch.from_numpy(synth.make_feat(23, 1, 24, 24)).cuda()
+    ya, yb = a(x, (48, 48)), b(x, (48, 48))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        ya2 = a(x, (48, 48))
+    with torch.cuda.stream(s2):
+        yb2 = b(x, (48, 48))
+    torch.cuda.synchronize()
+    assert torch.equal(ya, ya2) and torch.equal(yb, yb2) and not torch.equal(ya, yb)
