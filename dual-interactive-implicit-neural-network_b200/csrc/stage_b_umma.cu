@@ -23,6 +23,9 @@
 // its accumulators.
 #include <cstdlib>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "handle.h"
 #include "ptx.cuh"
 
@@ -182,6 +185,9 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
 // per-step epilogue timestamps for tools/trace_stage_b.py: the extra basic-block boundaries cost ~10 % (measured), so off
 #ifndef DIINN_FINE_TRACE
 #define DIINN_FINE_TRACE 0
+#endif
+#ifndef DIINN_TRACE_BUILD
+#define DIINN_TRACE_BUILD DIINN_FINE_TRACE
 #endif
 #ifndef DIINN_PK
 #define DIINN_PK 7
@@ -350,7 +356,13 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   const int n_units = gridDim.x / CG;
   // optional timeline capture (DIINN_TRACE=1): leader CTA of unit 0, first 8 tiles, clock64 at pipeline events
   const bool tracing = trace != nullptr && blockIdx.x == 0;
+  // The timeline points are compiled in only with -DDIINN_TRACE_BUILD=1 (tools/trace_stage_b.py builds that side library):
+  // even never-taken `if (tracer) clock64()` sites split the epilogue into more basic blocks and cost issue slots.
+#if DIINN_TRACE_BUILD
 #define DIINN_TR(tile, idx) do { if (tracing && (tile) < 8) trace[(tile) * 128 + (idx)] = clock64(); } while (0)
+#else
+#define DIINN_TR(tile, idx) do { } while (0)
+#endif
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) atomicExch(err_flag, 1);
 
@@ -647,6 +659,12 @@ static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap&
   using namespace sb;
   DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kSmemBytes)));
+  if (getenv("DIINN_DEBUG_OCC")) {
+    int nc = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, F16>, cfg);
+    fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
+            cudaGetErrorString(e));
+  }
   DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, F16>, tm, h->small, src, out, P, wk, err_flag, trace));
   return DIINN_OK;
 }

@@ -4,6 +4,12 @@ import os
 import sys
 
 os.environ["DIINN_TRACE"] = "1"
+# the timeline points are compiled out of the product library: build (here, no GPU needed) a side library first with
+#   ABL_DEFS="-DDIINN_TRACE_BUILD=1" python tools/ablate_stage_b.py build 60      [add -DDIINN_FINE_TRACE=1 for per-step points]
+_side = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dual-interactive-implicit-neural-network_b200",
+                     "build", "libdiinn_b200_abl60.so")
+if "DIINN_B200_LIB" not in os.environ and os.path.exists(_side):
+    os.environ["DIINN_B200_LIB"] = _side
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
