@@ -500,16 +500,19 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // `bufidx`; nb = P slice base of the next unit (nullptr: none)
     auto layer0_unit = [&](int bufidx, int kc0, const RowCtx& rcx, const float* nb) {
       const uint32_t buf = act0 + bufidx * kActBytes;
+      // (the P prefetch is issued AFTER the proxy fence: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
+      // which waits for every outstanding global load of the thread -- a prefetch issued just before it exposes its
+      // whole L2 latency in every step; measured)
       layer0_step<F16>(buf, kc0, fg, r, rcx, sp, ka);
-      if (nb) load16(nb, ka);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
+      if (nb) load16(nb, ka);
       layer0_step<F16>(buf, kc0 + 1, fg, r, rcx, sp, kb);
-      if (nb) load16(nb + 64, kb);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
+      if (nb) load16(nb + 64, kb);
     };
 
     if (work < wk.n_work) {
@@ -573,12 +576,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
 #endif
           if constexpr (!F16) epi_load<F16>(tslot, 64 + fg * 16, rb);
-          if (nb) load16(nb, ka);
           if (!last) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h]);
           }
+          if (nb) load16(nb, ka);  // after the fence (see layer0_unit)
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
           if constexpr (!F16) {
             tmem_ld_wait();
@@ -595,12 +598,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
 #endif
-          if (nb) load16(nb + 64, kb);
           if (!last) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + 1]);
           }
+          if (nb) load16(nb + 64, kb);
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
         }
         ++full_uses;
