@@ -113,6 +113,33 @@ def cpu_reference_band(workload, rows_px_target=200_000):
     return (0, nrows), B * nrows * W_up
 
 
+def time_eager_gpu_port(workload, steps=5, warmup=2, bsize=30000 * 16):
+    """Informative only ("the real same-box bar"): the reference's eager op sequence -- unfold, 576-channel
+    nearest-exact gather, 9 convs, cat / relu / sin / mul kernels, query strips as in batched_step (diinn.py:149-160) --
+    run by PyTorch on THIS GPU through the oracle's torch port (the reference itself is not on the GPU box)."""
+    import torch
+    from diinn_b200 import synth
+    from oracle import diinn_oracle as orc
+    B, H, W, H_up, W_up = synth.CONFIGS[workload]
+    weights = synth.make_weights(seed=0)
+    feat = synth.make_feat(1, B, H, W)
+    run = lambda: orc.decoder_forward_torch_cpu(weights, feat, (H_up, W_up), bsize=bsize, device="cuda",  # noqa: E731
+                                                return_tensor=True)
+    for _ in range(warmup):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "px_per_s": B * H_up * W_up / ms * 1e3,
+            "what": f"oracle torch port on cuda:0, fp32 (cudnn TF32 convs at PyTorch's default), bsize={bsize}, includes the "
+                    "per-call H2D of the 44 MB feature map and weights; not the product path, not a parity reference"}
+
+
 def time_cpu_port(workload, steps, warmup):
     import torch
     from diinn_b200 import synth
@@ -339,6 +366,10 @@ def main():
         cpu = time_cpu_port(args.workload, steps=3, warmup=1)
         line["cpu_baseline"] = {"value": cpu["px_per_s"], "unit": "px/s", "cores": cpu["cores"], "kind": "port",
                                 "sample": cpu["sample"] + "; best of 3 after 1 warm-up", "host_cpus": cpu["host_cpus"]}
+        try:
+            line["eager_gpu_reference"] = time_eager_gpu_port(args.workload)
+        except Exception as e:  # informative leg only (e.g. out of memory on a busy box)
+            line["eager_gpu_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if world > 1:
         line["other_assembly"] = {"mode": "nccl" if args.assembly == "fused" else "fused", "ms_per_step": ms_other,
                                   "px_per_s": npx / ms_other * 1e3}

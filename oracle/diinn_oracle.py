@@ -291,14 +291,16 @@ def quantize_u8(img: np.ndarray) -> np.ndarray:
 # diinn.py:168 does) on PyTorch CPU kernels with all host threads -- used ONLY as bench.py's cpu_baseline
 # / --impl reference arm, because /root/reference does not exist on the GPU box.
 # --------------------------------------------------------------------------------------------------
-def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None, rows=None):
+def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None, rows=None, device="cpu", return_tensor=False):
     """rows=(r0,r1) restricts the work to an HR row band (the bounded sample bench.py times); everything else is the
-    reference's algorithm at full arithmetic cost per pixel (1.97 MFLOP/px, nothing hoisted)."""
+    reference's algorithm at full arithmetic cost per pixel (1.97 MFLOP/px, nothing hoisted).
+    device="cuda" runs the SAME eager op sequence on the GPU (bench.py's informative `eager_gpu_reference`: what the
+    reference's own PyTorch path costs on the box, SURVEY.md section 8(d) "the real same-box bar")."""
     import torch
     import torch.nn.functional as TF
 
     with torch.no_grad():
-        x = torch.as_tensor(feat, dtype=torch.float32)
+        x = torch.as_tensor(feat, dtype=torch.float32).to(device)
         B, C, H, W = x.shape
         H_up, W_up = int(size[0]), int(size[1])
         r0, r1 = (0, H_up) if rows is None else (int(rows[0]), int(rows[1]))
@@ -308,12 +310,13 @@ def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None, rows=None):
         syn_np[0] = rh[r0:r1, None]
         syn_np[1] = rw[None, :]
         syn_np[2] = ratio_value(H, W, H_up, W_up)
-        syn = torch.from_numpy(syn_np).unsqueeze(0).expand(B, -1, -1, -1)
-        ih = torch.from_numpy(nearest_exact_index(H, H_up)[r0:r1])
-        iw = torch.from_numpy(nearest_exact_index(W, W_up))
+        syn = torch.from_numpy(syn_np).to(device).unsqueeze(0).expand(B, -1, -1, -1)
+        ih = torch.from_numpy(nearest_exact_index(H, H_up)[r0:r1]).to(device)
+        iw = torch.from_numpy(nearest_exact_index(W, W_up)).to(device)
         u = TF.unfold(x, 3, padding=1).view(B, C * 9, H, W)
         xu = u[:, :, ih][:, :, :, iw]                      # nearest-exact gather -> (B,576,H_up,W_up)
-        Wt = {k: torch.as_tensor(v) for k, v in weights.items()}
+        Wt = {k: torch.as_tensor(v).to(device) for k, v in weights.items()}
+        fin = (lambda t: t) if return_tensor else (lambda t: t.cpu().numpy())
 
         def step(xs, ss):
             k = torch.relu(TF.conv2d(xs, Wt["K.0.0.weight"], Wt["K.0.0.bias"]))
@@ -324,7 +327,7 @@ def decoder_forward_torch_cpu(weights: dict, feat, size, bsize=None, rows=None):
             return TF.conv2d(q, Wt["last_layer.weight"], Wt["last_layer.bias"])
 
         if bsize is None:
-            return step(xu, syn).numpy()
+            return fin(step(xu, syn))
         strip = max(1, bsize // (r1 - r0))
         outs = [step(xu[..., a:a + strip], syn[..., a:a + strip]) for a in range(0, W_up, strip)]
-        return torch.cat(outs, -1).numpy()
+        return fin(torch.cat(outs, -1))
