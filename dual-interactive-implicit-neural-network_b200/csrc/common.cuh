@@ -142,9 +142,8 @@ struct SmallParams {
   float wq0[kD][4];        // per feature: Q.0 weight row + bias = (w_relh, w_relw, w_ratio, bq0)  -> one LDC.128
   float wl_t[kD][4];       // per feature: last_layer.weight column = (wl[0][f], wl[1][f], wl[2][f], 0)
   float bl[4];             // last_layer.bias (+pad)
-  // the same two tables for feature PAIRS (f, f+1), component-major, for the packed fp32x2 math of the tensor path:
+  // wq0 again for feature PAIRS (f, f+1), component-major, for the packed fp32x2 (FFMA2) layer 0 of the tensor path:
   float2 wq0_p[kD / 2][4]; // (w_relh, w_relw, w_ratio, bq0) x (f, f+1)
-  float2 wl_p[kD / 2][4];  // (wl[0], wl[1], wl[2], 0) x (f, f+1)
 };
 
 struct Handle;  // defined in handle.h

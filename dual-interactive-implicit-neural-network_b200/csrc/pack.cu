@@ -149,10 +149,7 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     sp.wl_t[f][3] = 0.f;
   }
   for (int f = 0; f < kD; f += 2)
-    for (int c = 0; c < 4; ++c) {
-      sp.wq0_p[f >> 1][c] = make_float2(sp.wq0[f][c], sp.wq0[f + 1][c]);
-      sp.wl_p[f >> 1][c] = make_float2(sp.wl_t[f][c], sp.wl_t[f + 1][c]);
-    }
+    for (int c = 0; c < 4; ++c) sp.wq0_p[f >> 1][c] = make_float2(sp.wq0[f][c], sp.wq0[f + 1][c]);
   DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bq_dev, sp.bq, sizeof(float) * kLayers * kD, cudaMemcpyHostToDevice, s));
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
   if (staging) cudaFree(staging);

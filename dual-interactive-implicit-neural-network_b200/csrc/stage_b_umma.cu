@@ -176,7 +176,7 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
 }
 
 // Timing ablations (tools/ablate_stage_b.py builds side libraries with -DDIINN_ABL=<mask>; results are WRONG by
-// construction, only the run time is meaningful). bit 0: P slices read from one fixed row; bit 1: bq as an immediate;
+// construction, only the run time is meaningful). bit 0: P slices read from one fixed row;
 // bit 2: sine replaced by one FMUL; bit 3: no activation stores; bit 4: no TMEM loads.
 #ifndef DIINN_ABL
 #define DIINN_ABL 0
@@ -188,9 +188,6 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
 #endif
 #ifndef DIINN_TRACE_BUILD
 #define DIINN_TRACE_BUILD DIINN_FINE_TRACE
-#endif
-#ifndef DIINN_PK
-#define DIINN_PK 7
 #endif
 
 __device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[4]) {
@@ -214,7 +211,6 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
   const int f0 = kc * 64 + wg * 16;
   const float* k0 = reinterpret_cast<const float*>(k0v);
   uint32_t pk[8];
-#if DIINN_PK & 2
   const float2 rh = make_float2(rc.rel_h, rc.rel_h), rw = make_float2(rc.rel_w, rc.rel_w), ra = make_float2(rc.ratio, rc.ratio);
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
@@ -226,21 +222,6 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
     const float2 q = __fmul2_rn(make_float2(k0[j], k0[j + 1]), make_float2(act_sin(t.x), act_sin(t.y)));
     pk[j >> 1] = F16 ? pack_f16x2(q.x, q.y) : pack_bf16x2(q.x, q.y);
   }
-#else
-#pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    float q[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float4 w = *reinterpret_cast<const float4*>(&sp.wq0[f0 + j + e][0]);
-      float t = fmaf(w.x, rc.rel_h, w.w);
-      t = fmaf(w.y, rc.rel_w, t);
-      t = fmaf(w.z, rc.ratio, t);
-      q[e] = k0[j + e] * act_sin(t);
-    }
-    pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
-  }
-#endif
   st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
   st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
 }
@@ -271,7 +252,7 @@ __device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw<F16>& raw)
 // kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
 template <bool kLast, bool F16>
 __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
-                                         const SmallParams& sp, const float4 (&kxv)[4], float2 (&rgb2)[3]) {
+                                         const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3]) {
   const int col = c * 64 + wg * 16;
   const int f0 = h * 128 + col;
   const float* kx = reinterpret_cast<const float*>(kxv);
@@ -286,40 +267,20 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
       ak[0] = __uint_as_float(raw.v[j]), ak[1] = __uint_as_float(raw.v[j + 1]);
       aq[0] = __uint_as_float(raw.v[16 + j]), aq[1] = __uint_as_float(raw.v[16 + j + 1]);
     }
-#if DIINN_PK & 1
     // packed fp32x2 adds / multiplies (Blackwell FADD2 / FMUL2)
     float2 k2 = __fadd2_rn(make_float2(ak[0], ak[1]), make_float2(kx[j], kx[j + 1]));
     k2.x = fmaxf(k2.x, 0.f), k2.y = fmaxf(k2.y, 0.f);
     const float2 t2 = __fadd2_rn(make_float2(aq[0], aq[1]), *reinterpret_cast<const float2*>(&sp.bq[layer][f0 + j]));
     const float2 q2 = __fmul2_rn(k2, make_float2(act_sin(t2.x), act_sin(t2.y)));
-#else
-    float2 q2;
-    {
-      const float ka0 = fmaxf(ak[0] + kx[j], 0.f), ka1 = fmaxf(ak[1] + kx[j + 1], 0.f);
-#if DIINN_ABL & 2
-      const float s0 = act_sin(aq[0] + 0.1f), s1 = act_sin(aq[1] + 0.1f);
-#else
-      const float s0 = act_sin(aq[0] + sp.bq[layer][f0 + j]), s1 = act_sin(aq[1] + sp.bq[layer][f0 + j + 1]);
-#endif
-      q2 = make_float2(ka0 * s0, ka1 * s1);
-    }
-#endif
     const float q[2] = {q2.x, q2.y};
     if constexpr (kLast) {
-#if DIINN_PK & 4
-      const float2* w = &sp.wl_p[(f0 + j) >> 1][0];
-      rgb2[0] = __ffma2_rn(w[0], q2, rgb2[0]);
-      rgb2[1] = __ffma2_rn(w[1], q2, rgb2[1]);
-      rgb2[2] = __ffma2_rn(w[2], q2, rgb2[2]);
-#else
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const float4 w = *reinterpret_cast<const float4*>(&sp.wl_t[f0 + j + e][0]);
-        rgb2[0].x = fmaf(w.x, q[e], rgb2[0].x);
-        rgb2[1].x = fmaf(w.y, q[e], rgb2[1].x);
-        rgb2[2].x = fmaf(w.z, q[e], rgb2[2].x);
+        rgb[0] = fmaf(w.x, q[e], rgb[0]);
+        rgb[1] = fmaf(w.y, q[e], rgb[1]);
+        rgb[2] = fmaf(w.z, q[e], rgb[2]);
       }
-#endif
     }
     if constexpr (!kLast) pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
   }
@@ -530,7 +491,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       RowCtx rc_next{};
       const float* const pw = rc.prow + fg * 16;  // this warp's column of the tile row's P entry
       const float* pn = nullptr;                  // same for the next tile
-      float2 rgb2[3] = {};  // RGB projection, even / odd features accumulated separately (packed FFMA2)
+      float rgb[3] = {0.f, 0.f, 0.f};  // this warp's share of the RGB projection (scalar FFMA: measured faster than FFMA2 here)
 #pragma unroll 1
       for (int layer = 1; layer <= 3; ++layer) {
         const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
@@ -570,8 +531,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
             if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
           }
-          if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb2);
-          else epi_math<false, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb2);
+          if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
+          else epi_math<false, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
 #endif
@@ -593,8 +554,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
             if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
           }
-          if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb2);
-          else epi_math<false, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb2);
+          if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
+          else epi_math<false, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
 #endif
@@ -610,7 +571,6 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       }
       // Combine the four partial RGB projections of a row (2 groups x 2 subs) in a fixed order (bit-reproducible).
       // The warps of feature group 3 reduce and store; the others drop their partials in smem.
-      const float rgb[3] = {rgb2[0].x + rgb2[0].y, rgb2[1].x + rgb2[1].y, rgb2[2].x + rgb2[2].y};
       const int pidx = fg;
       if (pidx != 3) {
         if (t > 0) named_bar_sync(2, kEpiThreads);  // the reducers have read the previous tile's partials
