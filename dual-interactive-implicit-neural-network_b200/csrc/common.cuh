@@ -146,6 +146,16 @@ struct SmallParams {
   float2 wq0_p[kD / 2][4]; // (w_relh, w_relw, w_ratio, bq0) x (f, f+1)
 };
 
+// Optional fused epilogue of the library GEMM (umma_selftest.cu) for the LR-resolution K chain of modes 1 / 2
+// (lr_chain.cu): instead of D = A.B^T it does  P[m0 + r][256 layer + n] += acc  and hands the next layer its A operand,
+// A_next[r][n] = bf16(relu(that)).
+struct ChainEpilogue {
+  float* P;                 // nullptr: plain GEMM, D is written
+  __nv_bfloat16* A_next;    // nullptr for the last layer
+  long long m0, rows;       // first P row of this chunk / valid rows in it
+  int layer;
+};
+
 struct Handle;  // defined in handle.h
 
 }  // namespace diinn

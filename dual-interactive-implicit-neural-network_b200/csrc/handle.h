@@ -95,7 +95,7 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
                         bool f16acc, cudaStream_t s);
 // umma_selftest.cu
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
-                         cudaStream_t s);
+                         cudaStream_t s, const ChainEpilogue* chain = nullptr);
 int launch_umma_pace(Handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma, int noise,
                      cudaStream_t s);
 // tensor maps (api.cu)

@@ -9,9 +9,9 @@
 // unchanged with ZERO K rows: relu(0 + P_i) = k_i, q_i = k_i * sin(Q_i q_{i-1} + bq_i).
 //
 // fp32 path: a plain tiled SGEMM on CUDA cores (exact fp32 FMA). Tensor path: per chunk of <= 32768 LR pixels,
-// relu + bf16 conversion -> the library's tcgen05 GEMM (umma_selftest.cu, 128x256 tiles, fp32 accumulation) -> add.
-// The conversion and the add are two extra HBM passes per layer; fusing them into the GEMM is a listed next step --
-// modes 1 / 2 are outside the benchmarked configuration.
+// one relu + bf16 conversion of block 0, then per layer the library's tcgen05 GEMM (umma_selftest.cu, 128x256 tiles,
+// fp32 accumulation) with a fused epilogue: P_i += acc, and the next layer's A operand bf16(relu(P_i)) written
+// alongside (ChainEpilogue). Modes 1 / 2 are outside the benchmarked configuration.
 #include "handle.h"
 
 namespace diinn {
@@ -88,22 +88,6 @@ __global__ void __launch_bounds__(256) lr_chain_prep_kernel(const float* __restr
   }
 }
 
-// P[m0 + r][256 layer + n] += D[r][n]
-__global__ void __launch_bounds__(256) lr_chain_add_kernel(float* __restrict__ P, const float* __restrict__ D, int64_t m0,
-                                                           int64_t rows, int layer) {
-  const int64_t total = rows * (kD / 4);
-  for (int64_t g = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; g < total;
-       g += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = g / (kD / 4);
-    const int n = static_cast<int>(g % (kD / 4)) * 4;
-    float4* dst = reinterpret_cast<float4*>(P + (m0 + r) * kPCols + layer * kD + n);
-    const float4 d = *reinterpret_cast<const float4*>(D + r * kD + n);
-    float4 v = *dst;
-    v.x += d.x, v.y += d.y, v.z += d.z, v.w += d.w;
-    *dst = v;
-  }
-}
-
 static int64_t chain_rows_pad(int64_t M) {
   const int64_t c = M < kChainChunk ? M : kChainChunk;
   return (c + 255) / 256 * 256;
@@ -111,26 +95,26 @@ static int64_t chain_rows_pad(int64_t M) {
 
 size_t lr_chain_scratch_bytes(int64_t M) {
   const int64_t rp = chain_rows_pad(M);
-  return static_cast<size_t>(rp) * kD * (sizeof(__nv_bfloat16) + sizeof(float));
+  return 2 * static_cast<size_t>(rp) * kD * sizeof(__nv_bfloat16);  // A operand ping-pong
 }
 
 int run_lr_chain_umma(Handle* h, float* P, int64_t M, void* scratch, cudaStream_t s) {
   const int64_t rp_max = chain_rows_pad(M);
-  __nv_bfloat16* A16 = static_cast<__nv_bfloat16*>(scratch);
-  float* D = reinterpret_cast<float*>(static_cast<char*>(scratch) + static_cast<size_t>(rp_max) * kD * sizeof(__nv_bfloat16));
+  __nv_bfloat16* A16[2] = {static_cast<__nv_bfloat16*>(scratch), static_cast<__nv_bfloat16*>(scratch) + rp_max * kD};
   const int blocks_cap = (h->sm_count > 0 ? h->sm_count : 148) * 8;
   for (int64_t m0 = 0; m0 < M; m0 += kChainChunk) {
     const int64_t rows = (M - m0 < kChainChunk) ? M - m0 : kChainChunk;
     const int64_t rp = (rows + 255) / 256 * 256;
+    // layer 1's A operand from stage A's block 0; the GEMM epilogue of layer i then produces layer i+1's
+    const int64_t nb = (rp * (kD / 4) + 255) / 256;
+    lr_chain_prep_kernel<<<static_cast<unsigned>(nb < blocks_cap ? nb : blocks_cap), 256, 0, s>>>(P, A16[0], m0, rows, rp, 1);
+    h->launches += 1;
     for (int layer = 1; layer <= 3; ++layer) {
-      int64_t nb = (rp * (kD / 4) + 255) / 256;
-      lr_chain_prep_kernel<<<static_cast<unsigned>(nb < blocks_cap ? nb : blocks_cap), 256, 0, s>>>(P, A16, m0, rows, rp, layer);
-      int rc = launch_umma_selftest(h, A16, h->WH16 + static_cast<size_t>(layer - 1) * kD * kD, D, static_cast<int>(rp), kD,
-                                    kD, 2, s);
+      ChainEpilogue ce{};
+      ce.P = P, ce.A_next = layer < 3 ? A16[layer & 1] : nullptr, ce.m0 = m0, ce.rows = rows, ce.layer = layer;
+      int rc = launch_umma_selftest(h, A16[(layer - 1) & 1], h->WH16 + static_cast<size_t>(layer - 1) * kD * kD, nullptr,
+                                    static_cast<int>(rp), kD, kD, 2, s, &ce);
       if (rc) return rc;
-      nb = (rows * (kD / 4) + 255) / 256;
-      lr_chain_add_kernel<<<static_cast<unsigned>(nb < blocks_cap ? nb : blocks_cap), 256, 0, s>>>(P, D, m0, rows, layer);
-      h->launches += 2;
     }
   }
   DIINN_CUDA_OK(h, cudaGetLastError());

@@ -12,11 +12,15 @@
 namespace diinn {
 using namespace ptx;
 
+// two operand stages (2 x 32 KB with CTA pairs): with 256 TMEM columns per CTA two CTAs share an SM, so one tile's
+// epilogue runs under the other's loads and MMAs (the LR chain of modes 1 / 2 is epilogue / HBM bound)
+constexpr int kGemmStages = 2;
+
 template <int CG>
 __global__ void __launch_bounds__(192, 1)
 umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     float* __restrict__ D, int M, int N, int K, int f16acc) {
-  constexpr int STAGES = 4;
+                     float* __restrict__ D, int M, int N, int K, int f16acc, const ChainEpilogue ce) {
+  constexpr int STAGES = kGemmStages;
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_ROWS = 256 / CG;
   constexpr int B_BYTES = B_ROWS * 128;
@@ -101,6 +105,41 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             drow[c0 + 2 * j] = __low2float(hv);
             drow[c0 + 2 * j + 1] = __high2float(hv);
           }
+        }
+      }
+    } else if (ce.P != nullptr) {
+      // LR chain: P_layer += acc, next layer's A operand = bf16(relu(P_layer)); a thread owns one row (64 B per step)
+      const bool valid = row < ce.rows;
+      float* prow = ce.P + (ce.m0 + row) * kPCols + ce.layer * kD + n0;
+      __nv_bfloat16* arow = ce.A_next ? ce.A_next + static_cast<size_t>(row) * kD + n0 : nullptr;
+      // 64 columns per pass: all 16 P loads of a pass are issued before the accumulators are read, so their latency
+      // overlaps (a thread's 64 B pieces are 4 KB apart: nothing to coalesce, only latency to hide)
+      for (int c0 = 0; c0 < 256; c0 += 64) {
+        float4 pv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          pv[j] = valid ? *reinterpret_cast<const float4*>(prow + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t v[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0 + 16 * g, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * g]));
+        tmem_ld_wait();
+        uint32_t pk[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float4 o = pv[j];
+          if (valid) {
+            o.x += __uint_as_float(v[4 * j]), o.y += __uint_as_float(v[4 * j + 1]);
+            o.z += __uint_as_float(v[4 * j + 2]), o.w += __uint_as_float(v[4 * j + 3]);
+            *reinterpret_cast<float4*>(prow + c0 + 4 * j) = o;
+          }
+          pk[2 * j] = pack_bf16x2(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f));          // padding rows of A_next stay zero
+          pk[2 * j + 1] = pack_bf16x2(fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+        }
+        if (arow && row < M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(arow + c0 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
     } else
@@ -272,7 +311,8 @@ int launch_umma_pace(Handle* h, int cta_group, int n_cols, int iters, int n_ctas
 }
 
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
-                         cudaStream_t s) {
+                         cudaStream_t s, const ChainEpilogue* chain) {
+  const ChainEpilogue ce = chain ? *chain : ChainEpilogue{};
   // cta_group 1|2: bf16 operands, fp32 accumulators; 11|12: the same GEMM with fp16 operands and fp16 accumulators
   const int f16acc = cta_group >= 10 ? 1 : 0;
   cta_group = cta_group % 10;
@@ -280,7 +320,7 @@ int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int 
   int rc;
   if ((rc = make_tmap_2d_bf16(h, &tmA, A, K, M, 64, 128))) return rc;
   if ((rc = make_tmap_2d_bf16(h, &tmB, B, K, N, 64, 256 / cta_group))) return rc;
-  const size_t smem = 4 * (128 * 128 + 256 / cta_group * 128) + 128 + 1024;
+  const size_t smem = kGemmStages * (128 * 128 + 256 / cta_group * 128) + 128 + 1024;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(M / 128, N / 256, 1);
   cfg.blockDim = dim3(192, 1, 1);
@@ -296,11 +336,11 @@ int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int 
   if (cta_group == 1) {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(umma_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<1>, tmA, tmB, D, M, N, K, f16acc));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<1>, tmA, tmB, D, M, N, K, f16acc, ce));
   } else {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(umma_selftest_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<2>, tmA, tmB, D, M, N, K, f16acc));
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, umma_selftest_kernel<2>, tmA, tmB, D, M, N, K, f16acc, ce));
   }
   h->launches += 1;
   return DIINN_OK;
