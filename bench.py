@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16acc", "fp32"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the c2/c4 extra measurements")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra measurements of the other BASELINE configs")
     ap.add_argument("--assembly", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused = stage B stores every pixel into all ranks' image buffers over NVLink (peer / "
                          "NVSwitch multicast stores, no collective); nccl = local tiles + NCCL all-gather")
@@ -284,7 +284,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_extra:
         # other BASELINE configs on one GPU (not the headline; parity for them lives in tests/)
         with torch.no_grad():
-            for name in ("c2x2", "c2x3", "c2x4", "c4"):
+            for name in ("c1", "c2x2", "c2x3", "c2x4", "c4", "c5"):
                 b, h, w, hu, wu = synth.CONFIGS[name]
                 x = torch.from_numpy(synth.make_feat(1, b, h, w)).to(dev)
                 for _ in range(2):
@@ -299,6 +299,18 @@ def main():
                 torch.cuda.synchronize()
                 ms = a0.elapsed_time(a1) / n_it
                 extra[name] = {"ms": round(ms, 4), "px_per_s": b * hu * wu / ms * 1e3}
+                if name == "c5":   # the sampled form: 16 patches x 2304 random query coordinates through query()
+                    coord, cell = (torch.from_numpy(v).to(dev) for v in synth.make_query(3, b, 2304))
+                    for _ in range(2):
+                        dec.query(x, coord, cell)
+                    torch.cuda.synchronize()
+                    a0.record()
+                    for _ in range(n_it):
+                        dec.query(x, coord, cell)
+                    a1.record()
+                    torch.cuda.synchronize()
+                    ms = a0.elapsed_time(a1) / n_it
+                    extra["c5_sampled_query"] = {"ms": round(ms, 4), "px_per_s": b * 2304 / ms * 1e3}
                 del x
         dec._workspace = None
         torch.cuda.empty_cache()
