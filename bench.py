@@ -105,6 +105,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def h2d_bytes_all_ranks(H, W, H_up, world, B, C=64):
+    """Bytes diinn_decode_host uploads per step, summed over ranks: the LR rows each rank's HR row tile reads
+    (nearest-exact rows of the tile +-1 for the 3x3 unfold), fp32."""
+    import diinn_b200
+    total = 0
+    for r0, r1 in diinn_b200.row_partition(H_up, world):
+        lo = max(min(int((r0 + 0.5) * H / H_up), H - 1) - 1, 0)
+        hi = min(min(int((r1 - 0.5) * H / H_up), H - 1) + 2, H)
+        total += B * C * (hi - lo) * W * 4
+    return int(total)
+
+
 def cpu_reference_band(workload, rows_px_target=200_000):
     """Bounded sample of `workload` for the CPU arm: the first HR rows of the image, ~200k pixels."""
     from diinn_b200 import synth
@@ -342,10 +354,10 @@ def main():
         },
         "ms_per_div2k_x4_image": ms_step if args.workload == "c3" else None,
         "e2e": {"value": npx / (ms_e2e / args.steps) * 1e3, "unit": "px/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(feat_host.numel() * 4 * world),
+                "h2d_bytes_per_step": h2d_bytes_all_ranks(H, W, H_up, world, B),
                 "d2h_bytes_per_step": int(npx * 3 * 4),
-                "api": "diinn_decode_host (C ABI, pinned host buffers; every rank uploads the replicated feature map and "
-                       "downloads its own row tile)", "checksum": checksum},
+                "api": "diinn_decode_host (C ABI, pinned host buffers; every rank uploads the LR rows its row tile reads "
+                       "(tile + 3x3 halo) of the replicated feature map and downloads its own row tile)", "checksum": checksum},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
