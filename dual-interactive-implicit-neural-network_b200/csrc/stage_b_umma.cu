@@ -17,12 +17,14 @@
 // running, and layer 0 of the NEXT tile is interleaved into the epilogue warps during layer 3.
 //
 // Warp roles (640 threads): warp 0 = TMA producer (streams the 3 x 2 x 4 weight stages of [256 x 64] bf16 from L2),
-// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps in two groups of 8:
-// group g drains TMEM half slot g of every layer, so one half's epilogue runs under the other half's MMAs. The control
-// warpgroup gives its registers away (setmaxnreg) so each epilogue thread can hold a prefetched slice of P next to
-// its accumulators.
-#include <cstdlib>
-
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps. ALL of them drain
+// half slot 0, then half slot 1, of every layer: a warp owns one TMEM lane quarter and one 16-feature group of every
+// 64-feature chunk, so a half slot is two steps per warp and every step completes one K-chunk of the next layer's A
+// operand (the chunk that gates the next layer is one step behind the layer's last MMA). The control warpgroup gives
+// its registers away (setmaxnreg) so each epilogue thread can hold two prefetched slices of P next to its accumulators.
+//
+// Measured alternatives that did NOT pay: two 8-warp groups (one per half slot), four 128-column
+// slots with per-slot groups, three slots (256|128|128), fp16 accumulators, packed FFMA2 for the RGB projection.
 #include <cstdio>
 #include <cstdlib>
 
