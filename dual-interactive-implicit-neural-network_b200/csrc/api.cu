@@ -185,6 +185,7 @@ int diinn_create(diinn_handle** out, const diinn_config* cfg) {
   // per-handle device scratch lives here so that decode / query never allocate (CUDA-graph capturable, one handle per
   // device or thread with no shared state)
   bool ok = cudaMalloc(&h->err_flag, sizeof(int)) == cudaSuccess && cudaMemset(h->err_flag, 0, sizeof(int)) == cudaSuccess;
+  if (const char* np = getenv("DIINN_NO_PDL")) h->pdl = !(np[0] == '1');
   const char* tr = getenv("DIINN_TRACE");
   if (ok && tr && tr[0] == '1')
     ok = cudaMalloc(&h->trace_dev, 1024 * sizeof(long long)) == cudaSuccess &&

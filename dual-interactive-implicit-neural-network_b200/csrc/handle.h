@@ -18,6 +18,7 @@ struct Handle {
   int64_t launches = 0;
   // optional per-kernel timing of the tcgen05 path (diinn_set_profiling): 4 events per decode
   bool profiling = false;
+  bool pdl = true;  // programmatic dependent launch of stage A / stage B (DIINN_NO_PDL=1 at diinn_create turns it off)
   std::vector<cudaEvent_t> prof_events;
   long long* trace_dev = nullptr;  // DIINN_TRACE=1: 1024 clock64 samples of the last stage-B launch
   int* err_flag = nullptr;         // device word the tcgen05 kernels raise on an internal consistency failure

@@ -175,6 +175,7 @@ template <typename T>
 __global__ void feat_to_nhwc_bf16_kernel(const T* __restrict__ feat, __nv_bfloat16* __restrict__ dst, int H, int W,
                                          int r0, int rows) {
   __shared__ float tile[kC][33];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // stage A may be scheduled while we drain (PDL)
   const int w0 = blockIdx.x * 32;
   const int row = blockIdx.y;  // relative to r0
   const int b = blockIdx.z;

@@ -86,6 +86,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// Programmatic dependent launch (PDL). A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor in the stream is still draining;
+// it must execute grid_dep_wait() before touching anything the predecessor writes. grid_dep_launch() in the predecessor
+// allows the dependent grid to be scheduled as soon as SM resources free up (our CTAs are persistent and fill the SM, so
+// that is when they retire). Both are no-ops for a kernel launched without the attribute / without dependents.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

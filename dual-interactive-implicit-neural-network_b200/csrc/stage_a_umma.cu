@@ -100,6 +100,8 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_ptr;
   const int per_img = g.tiles_y * g.n_txp;
+  grid_dep_launch();  // stage B's CTAs may be scheduled as ours retire ...
+  grid_dep_wait();    // ... and we read feat_nhwc only once the layout kernel has completed (PDL, see ptx.cuh)
 
   if (warp == 0) {
     {  // whole warp walks the loops (uniform registers); one elected lane issues the TMA / expect_tx instructions
@@ -279,13 +281,15 @@ int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H,
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cta_group;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = h->pdl ? 2 : 1;
   if (cta_group == 1) {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(kSmemBytes)));

@@ -348,6 +348,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_ptr;
   const uint32_t act0 = smem_u32(s_act);
+  grid_dep_launch();  // the next decode's first kernel is a normal launch, so this only matters inside CUDA graphs
+  grid_dep_wait();    // P is complete once stage A (or the LR chain of modes 1 / 2) has finished (PDL, see ptx.cuh)
 
   if (warp < 4) {
   setmaxnreg_dec<kRegsCtrl>();
@@ -665,13 +667,15 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cta_group;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = h->pdl ? 2 : 1;
   int rc;
   if (cta_group == 1)
     rc = f16acc ? launch_variant<1, true>(h, &cfg, h->tmapWBh, src, out, P, wk, err_flag, trace)
