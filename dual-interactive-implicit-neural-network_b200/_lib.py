@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("DIINN_B200_LIB") or os.path.join(HERE, "libdiinn_b200
 
 OK = 0
 COMPUTE_FP32, COMPUTE_BF16, COMPUTE_FP16ACC = 0, 1, 2
-IO_F32, IO_BF16 = 0, 1
+IO_F32, IO_BF16, IO_BF16_NHWC = 0, 1, 2
 
 STATUS_NAMES = {
     0: "DIINN_OK", -1: "DIINN_ERR_BAD_ARG", -2: "DIINN_ERR_BAD_SHAPE", -3: "DIINN_ERR_BAD_DTYPE",

@@ -66,7 +66,10 @@ int check_common(Handle* h, int B, int C, int H, int W, int io_dtype, int comput
   if (!h->has_weights) return fail(h, DIINN_ERR_NO_WEIGHTS, "diinn_set_weights has not been called");
   if (C != kC) return fail(h, DIINN_ERR_BAD_SHAPE, "feat must have 64 channels");
   if (B < 1 || H < 1 || W < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "empty feature map");
-  if (io_dtype != DIINN_IO_F32 && io_dtype != DIINN_IO_BF16) return fail(h, DIINN_ERR_BAD_DTYPE, "io_dtype");
+  if (io_dtype != DIINN_IO_F32 && io_dtype != DIINN_IO_BF16 && io_dtype != DIINN_IO_BF16_NHWC)
+    return fail(h, DIINN_ERR_BAD_DTYPE, "io_dtype");
+  if (io_dtype == DIINN_IO_BF16_NHWC && compute == DIINN_COMPUTE_FP32)
+    return fail(h, DIINN_ERR_BAD_DTYPE, "channels-last bf16 feature maps are taken by the tensor paths only");
   if (compute != DIINN_COMPUTE_FP32 && compute != DIINN_COMPUTE_BF16 && compute != DIINN_COMPUTE_FP16ACC)
     return fail(h, DIINN_ERR_BAD_DTYPE, "compute must be DIINN_COMPUTE_FP32, _BF16 or _FP16ACC");
   return DIINN_OK;
@@ -308,6 +311,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   void* out = o.ptr;
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
+  if (io_dtype == DIINN_IO_BF16_NHWC) o.io_dtype = DIINN_IO_BF16;  // the image is bf16 NCHW either way
   if ((rc = apply_output_transform(h, &o))) return rc;
   if (!feat || !out) return fail(h, DIINN_ERR_BAD_ARG, "null feat/out");
   if (H_up < 1 || W_up < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "size must be positive");
@@ -347,11 +351,17 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
     }
   };
   mark();
-  if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, s)))
-    return rc;
-  mark();
-  if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s)))
-    return rc;
+  if (io_dtype == DIINN_IO_BF16_NHWC) {
+    // encoder hand-off: the caller's tensor already is (B,H,W,64) bf16 -- stage A's TMA boxes read it in place
+    mark();
+    rc = launch_stage_a_umma(h, static_cast<const __nv_bfloat16*>(feat), B, H, W, 0, H, plan.lr_row0, plan.lr_rows, P, s);
+  } else {
+    if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, s)))
+      return rc;
+    mark();
+    rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s);
+  }
+  if (rc) return rc;
   if (h->cfg.mode != 3 &&
       (rc = run_lr_chain_umma(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, ws + plan.off_chain, s)))
     return rc;
@@ -366,6 +376,8 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
   if (!feat_host || !out_host) return fail(h, DIINN_ERR_BAD_ARG, "null feat/out");
+  if (io_dtype == DIINN_IO_BF16_NHWC)
+    return fail(h, DIINN_ERR_BAD_DTYPE, "the host entry takes NCHW feature maps (its row bands upload channel planes)");
   if (H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1)
     return fail(h, DIINN_ERR_BAD_SHAPE, "bad size / row range");
   cudaSetDevice(h->cfg.device);
@@ -557,7 +569,7 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   const PixelSource src = make_query_source(B, H, W, coord, cell, Q, ensemble);
   OutSpec o{};
   o.ptr = out;
-  o.io_dtype = io_dtype;
+  o.io_dtype = io_dtype == DIINN_IO_BF16_NHWC ? DIINN_IO_BF16 : io_dtype;
   if ((rc = apply_output_transform(h, &o))) return rc;
   if (compute == DIINN_COMPUTE_FP32) {
     const int64_t total = static_cast<int64_t>(B) * Q * E;
@@ -568,8 +580,12 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
     if (h->cfg.mode != 3 && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * H * W, s))) return rc;
     return run_stage_b_fp32(h, src, o, P, q0, q1, chunk, s);
   }
-  __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + off);
-  if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
+  const __nv_bfloat16* nhwc = static_cast<const __nv_bfloat16*>(feat);  // channels-last bf16: read in place
+  if (io_dtype != DIINN_IO_BF16_NHWC) {
+    __nv_bfloat16* conv = reinterpret_cast<__nv_bfloat16*>(ws + off);
+    if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, conv, s))) return rc;
+    nhwc = conv;
+  }
   if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s))) return rc;
   if (h->cfg.mode != 3) {
     char* chain = ws + off + align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
@@ -607,6 +623,8 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
   const size_t need = align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
   if (!workspace || workspace_bytes < need)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL, "workspace too small: need " + std::to_string(need) + " bytes");
+  if (io_dtype == DIINN_IO_BF16_NHWC)
+    return launch_stage_a_umma(h, static_cast<const __nv_bfloat16*>(feat), B, H, W, 0, H, 0, H, P, s);
   __nv_bfloat16* nhwc = static_cast<__nv_bfloat16*>(workspace);
   if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
   return launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s);

@@ -126,7 +126,16 @@ class FusedImplicitDecoder(nn.Module):
         return self._workspace
 
     @staticmethod
+    def _is_nhwc_bf16(x: torch.Tensor) -> bool:
+        """bf16 in channels-last memory order = stage A's TMA layout: read in place, no layout pass (the encoder hand-off,
+        SURVEY.md 8(f) row 2: `encoder(...).to(torch.bfloat16, memory_format=torch.channels_last)`)"""
+        return (x.dtype == torch.bfloat16 and x.dim() == 4 and not x.is_contiguous()
+                and x.is_contiguous(memory_format=torch.channels_last))
+
+    @staticmethod
     def _io_dtype(x: torch.Tensor) -> int:
+        if FusedImplicitDecoder._is_nhwc_bf16(x):
+            return _lib.IO_BF16_NHWC
         if x.dtype == torch.float32:
             return _lib.IO_F32
         if x.dtype == torch.bfloat16:
@@ -175,7 +184,8 @@ class FusedImplicitDecoder(nn.Module):
         (B,3,H_up,W_up) ``out``. Row tiles are how the query grid shards across GPUs."""
         self._check_input(x)
         lib, h = self._ensure_handle(x.device)
-        x = x.contiguous()
+        if not (self._is_nhwc_bf16(x) and self.precision != "fp32"):
+            x = x.contiguous()
         B, Cc, H, W = x.shape
         H_up, W_up = int(size[0]), int(size[1])
         io = self._io_dtype(x)
@@ -218,7 +228,8 @@ class FusedImplicitDecoder(nn.Module):
         local_ensemble=True adds LIIF's 4-neighbour ensemble + area blend (liif.py:71-127) around the DIINN step."""
         self._check_input(feat)
         lib, h = self._ensure_handle(feat.device)
-        feat = feat.contiguous()
+        if not (self._is_nhwc_bf16(feat) and self.precision != "fp32"):
+            feat = feat.contiguous()
         B, Cc, H, W = feat.shape
         Q = coord.shape[1]
         coord = coord.to(torch.float32).contiguous()

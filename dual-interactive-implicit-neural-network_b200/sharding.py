@@ -50,6 +50,18 @@ def _out_dtype(decoder, x: torch.Tensor) -> torch.dtype:
     return fn(x) if fn is not None else x.dtype
 
 
+def broadcast_features(x: torch.Tensor, src: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Encoder hand-off for the multi-GPU decode: run the encoder on ONE rank and broadcast its
+    feature map over NVLink instead of running it on all of them; every rank passes a tensor of the right shape / dtype /
+    memory format (contents ignored except on `src`). Channels-last tensors are sent through their dense NHWC view."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dense = x if x.is_contiguous() else x.permute(0, 2, 3, 1)
+        if not dense.is_contiguous():
+            raise ValueError("broadcast_features needs a contiguous or channels-last feature map")
+        dist.broadcast(dense, src=src, group=group)
+    return x
+
+
 def _symmetric_image(shape, dtype, device, group):
     """A (B,3,H_up,W_up) image buffer allocated in symmetric memory and mapped into every rank of `group`
     (torch.distributed._symmetric_memory): returns (local tensor, handle with .buffer_ptrs / .multicast_ptr / .barrier)."""
@@ -64,14 +76,16 @@ def _symmetric_image(shape, dtype, device, group):
 
 
 def decode_sharded_fused(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessGroup] = None,
-                         multicast: bool = True, clone: bool = True) -> torch.Tensor:
+                         multicast: bool = True, clone: bool = True, feat_src: Optional[int] = None) -> torch.Tensor:
     """Fused decode + assembly: the stage-B kernel of every rank stores each RGB value of its row tile straight into
     the image buffers of ALL ranks over NVLink (one `multimem.st` through the NVSwitch multicast mapping when the
     fabric offers it, else one peer store per rank), so the transfer rides under the math tile by tile and no
     collective is launched; two symmetric-memory barriers order buffer reuse and completion.
 
     Returns the assembled (B,3,H_up,W_up) image on every rank. clone=False returns the symmetric buffer itself, which
-    the next call with the same shape overwrites."""
+    the next call with the same shape overwrites. feat_src: see decode_sharded."""
+    if feat_src is not None:
+        broadcast_features(x, feat_src, group)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     H_up, W_up = int(size[0]), int(size[1])
@@ -91,7 +105,7 @@ def decode_sharded_fused(decoder, x: torch.Tensor, size, group: Optional[dist.Pr
 
 
 def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessGroup] = None, gather: str = "all",
-                   bands: Optional[int] = None) -> torch.Tensor:
+                   bands: Optional[int] = None, feat_src: Optional[int] = None) -> torch.Tensor:
     """One rank per GPU: every rank decodes its HR row bands of the (B,3,H_up,W_up) image **in place** into a (row-
     padded) full-size buffer, and NCCL all-gathers each band in place, channel by channel, on a side stream while the
     next band is being decoded. No copy, no data-path collective; returns the assembled image on every rank (a view of
@@ -99,7 +113,10 @@ def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessG
 
     gather="none": returns only this rank's first band tile (B,3,rows,W_up) (used by tests / e2e).
     bands: number of bands per rank (pipelining depth); default 1 below ~1 Mpx per rank, else 4.
+    feat_src: rank whose `x` is the real feature map (broadcast first, see broadcast_features); None = already replicated.
     """
+    if feat_src is not None:
+        broadcast_features(x, feat_src, group)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     H_up, W_up = int(size[0]), int(size[1])

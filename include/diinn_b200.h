@@ -52,8 +52,10 @@ typedef enum diinn_compute {
                                biases, sin, relu stay as in _BF16. Opt-in: ~1e-3 relative error on pre-activations. */
 } diinn_compute;
 
-/* element type of the feat / out buffers */
-typedef enum diinn_io_dtype { DIINN_IO_F32 = 0, DIINN_IO_BF16 = 1 } diinn_io_dtype;
+/* element type of the feat / out buffers. DIINN_IO_BF16_NHWC (the encoder hand-off): feat is bf16 in
+ * channels-last memory order (B,H,W,64) -- what `x.to(torch.bfloat16, memory_format=torch.channels_last)` holds -- which IS
+ * stage A's TMA layout, so the layout pass is skipped; out is bf16 NCHW as with DIINN_IO_BF16. Tensor paths only. */
+typedef enum diinn_io_dtype { DIINN_IO_F32 = 0, DIINN_IO_BF16 = 1, DIINN_IO_BF16_NHWC = 2 } diinn_io_dtype;
 
 /* Constructor arguments of the reference ImplicitDecoder (diinn.py:40). */
 typedef struct diinn_config {

@@ -586,3 +586,27 @@ def test_two_handles_on_one_device_are_independent(w0):
         yb2 = b(x, (48, 48))
     torch.cuda.synchronize()
     assert torch.equal(ya, ya2) and torch.equal(yb, yb2) and not torch.equal(ya, yb)
+
+
+def test_channels_last_bf16_features_are_read_in_place(w0):
+    """encoder hand-off: a bf16 channels-last feature map IS stage A's TMA layout -- no layout
+    pass, results bit-identical to the same values handed over as NCHW bf16"""
+    dec = _decoder(w0, "bf16")
+    x = torch.from_numpy(synth.make_feat(31, 2, 37, 45)).cuda().bfloat16()
+    xcl = x.contiguous(memory_format=torch.channels_last)
+    assert not xcl.is_contiguous() and dec._io_dtype(xcl) == 2 and dec._io_dtype(x) == 1
+    size = (101, 150)
+    dec(x, size)                               # first call also packs the weights
+    n0 = dec.launch_count()
+    want = dec(x, size)
+    n1 = dec.launch_count()
+    got = dec(xcl, size)
+    n2 = dec.launch_count()
+    assert got.dtype == torch.bfloat16 and torch.equal(got, want)
+    assert (n2 - n1) == (n1 - n0) - 1          # one kernel fewer: the NCHW -> NHWC pass
+    assert torch.equal(dec.forward_rows(xcl, size, 33, 77), want[:, :, 33:77])
+    coord, cell = (torch.from_numpy(v).cuda() for v in synth.make_query(3, 2, 500))
+    assert torch.equal(dec.query(xcl, coord, cell), dec.query(x, coord, cell))
+    # the fp32 CUDA-core path takes the tensor too (through a plain .contiguous())
+    d32 = _decoder(w0, "fp32")
+    assert torch.equal(d32(xcl, size), d32(x, size))

@@ -50,6 +50,12 @@ def _worker(rank, world, port, sizes, results):
             for bands in (None, 1, 3):
                 full = diinn_b200.decode_sharded(StandInDecoder(), x, (H_up, W_up), bands=bands)
                 ok &= bool(torch.equal(full, StandInDecoder.full(B, H_up, W_up, x.dtype)))
+            # encoder hand-off: only rank 0 holds the real feature map; channels-last goes through its dense NHWC view
+            for fmt in (torch.contiguous_format, torch.channels_last):
+                real = torch.arange(B * 64 * 16, dtype=torch.float32).view(B, 64, 4, 4).contiguous(memory_format=fmt)
+                xb = real.clone() if rank == 0 else torch.zeros_like(real)
+                full = diinn_b200.decode_sharded(StandInDecoder(), xb, (H_up, W_up), feat_src=0)
+                ok &= bool(torch.equal(xb, real)) and bool(torch.equal(full, StandInDecoder.full(B, H_up, W_up, x.dtype)))
             tile = diinn_b200.decode_sharded(StandInDecoder(), x, (H_up, W_up), gather="none")
             r0, r1 = diinn_b200.row_partition(H_up, world)[rank]
             ok &= bool(torch.equal(tile, StandInDecoder.full(B, H_up, W_up, x.dtype)[:, :, r0:r1]))
