@@ -573,7 +573,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         }
         ++full_uses;
       }
-      // Combine the four partial RGB projections of a row (2 groups x 2 subs) in a fixed order (bit-reproducible).
+      // Combine the four partial RGB projections of a row (one per 16-feature group) in a fixed order (bit-reproducible).
       // The warps of feature group 3 reduce and store; the others drop their partials in smem.
       const int pidx = fg;
       if (pidx != 3) {
