@@ -258,6 +258,17 @@ def main():
         kt = dec.kernel_times() if args.precision != "fp32" else None
         dec.set_profiling(False, dev)
 
+        # ---- per-step distribution ("report best and median"), outside the timed region above
+        n_dist = min(args.steps, 30)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_dist + 1)]
+        barrier()
+        evs[0].record()
+        for i in range(n_dist):
+            out = step()
+            evs[i + 1].record()
+        barrier()
+        per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(n_dist))
+
         # ---- e2e: host buffers through the C-ABI host entry (H2D feat + decode of this rank's tile + D2H tile)
         out_host = torch.empty((B, 3, r1 - r0, W_up), dtype=torch.float32).pin_memory()
         for _ in range(3):
@@ -353,6 +364,7 @@ def main():
                   "(5.6x the 126 MB L2) plus 33 MB of output, so no step finds its working set in L2",
         },
         "ms_per_div2k_x4_image": ms_step if args.workload == "c3" else None,
+        "ms_per_step_best": per_step[0], "ms_per_step_median": per_step[len(per_step) // 2],
         "e2e": {"value": npx / (ms_e2e / args.steps) * 1e3, "unit": "px/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d_bytes_all_ranks(H, W, H_up, world, B),
                 "d2h_bytes_per_step": int(npx * 3 * 4),

@@ -610,3 +610,17 @@ def test_channels_last_bf16_features_are_read_in_place(w0):
     # the fp32 CUDA-core path takes the tensor too (through a plain .contiguous())
     d32 = _decoder(w0, "fp32")
     assert torch.equal(d32(xcl, size), d32(x, size))
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1, 1), (1, 1, 1, 7, 5), (2, 2, 3, 1, 1), (1, 3, 2, 200, 3), (1, 17, 1, 3, 250),
+                                   (3, 5, 5, 5, 5)])
+def test_degenerate_shapes(w0, shape):
+    """single-pixel feature maps / outputs, extreme aspect ratios, down-scaling: partial tiles everywhere"""
+    B, H, W, H_up, W_up = shape
+    feat = synth.make_feat(40 + H + W, B, H, W)
+    want = orc.decoder_forward(w0, feat, (H_up, W_up))
+    x = torch.from_numpy(feat).cuda()
+    for precision in ("fp32", "bf16"):
+        got = _decoder(w0, precision)(x, torch.Size((H_up, W_up))).cpu().numpy()
+        assert got.shape == (B, 3, H_up, W_up)
+        assert float(np.abs(got - want).max()) <= TIGHT[precision], (shape, precision)
