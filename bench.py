@@ -160,6 +160,11 @@ def time_cpu_port(workload, steps, warmup):
     weights = synth.make_weights(seed=0)
     feat = synth.make_feat(1, B, H, W)
     rows, npx = cpu_reference_band(workload)
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     for _ in range(warmup):
         orc.decoder_forward_torch_cpu(weights, feat, (H_up, W_up), rows=rows)
     ts = []
