@@ -7,7 +7,10 @@
 // A operand: feat as NHWC bf16; for tap (kh,kw) the K-chunk of LR pixel (h,w) is the 128-byte channel vector of pixel
 // (h+kh-1, w+kw-1), fetched as one TMA 4-D box (64 ch x 16 w x 8 h x 1 b) per tap whose out-of-bounds zero fill IS the
 // unfold's zero padding. B operand: the stacked weight matrix, K re-ordered to tap*64 + c (pack.cu), streamed from L2
-// in [256 x 64] bf16 stages. D: two 256-column TMEM slots, one N-block each, drained by 4 epilogue warps that add the
+// in [256 x 64] bf16 stages. Both operands travel through ONE ring of (A tap | W tap) stages: the tap tiles of a pixel
+// tile are re-fetched for each of the four N-blocks (4x the L2->smem traffic, 31 B/clk per SM) so that no tile-sized A
+// buffer has to be filled before a tile's first MMA -- the ring runs ahead across N-blocks and tiles alike. (The first
+// version kept the whole 144 KB A tile resident and serialised its load against the MMAs.) D: two 256-column TMEM slots, one N-block each, drained by 4 epilogue warps that add the
 // bias, apply ReLU to N-block 0, stage 32x32 fp32 blocks in 128B-swizzled shared memory and hand them to TMA stores
 // (4-D box over P = (1024 cols, W, LR rows, B): the store clips rows/columns outside the image by itself).
 //
@@ -23,17 +26,17 @@ using namespace ptx;
 
 namespace sa {
 constexpr int kPatchH = 8, kPatchW = 16;
-constexpr int kTapBytes = 128 * 128;            // 16 KB per tap
-constexpr int kABytes = 9 * kTapBytes;          // 144 KB: the whole K extent of one 128-pixel tile
-constexpr int kWBytesTotal = 64 * 1024;
+constexpr int kTapBytes = 128 * 128;            // 16 KB: one tap of a 128-pixel tile (128 rows x 64 ch bf16)
+constexpr int kRingBytes = 192 * 1024;
 constexpr int kThreads = 256;
 constexpr int kStoreBytes = 32 * 128;            // per epilogue warp: 32 rows x 32 fp32, 128B swizzle
 
 template <int CG>
 struct Cfg {
-  static constexpr int kStageRows = 256 / CG;
-  static constexpr int kStageBytes = kStageRows * 128;
-  static constexpr int kStages = kWBytesTotal / kStageBytes;  // 2 (CG=1) or 4 (CG=2)
+  static constexpr int kWRows = 256 / CG;                       // this CTA's share of an N-block's weight rows
+  static constexpr int kWBytes = kWRows * 128;
+  static constexpr int kStageBytes = kTapBytes + kWBytes;       // [A tap | W tap]: 32 KB (CG=2) or 48 KB (CG=1)
+  static constexpr int kStages = kRingBytes / kStageBytes;      // 6 (CG=2) or 4 (CG=1)
 };
 
 struct BiasParams {
@@ -41,16 +44,14 @@ struct BiasParams {
 };
 
 struct Smem {
-  uint8_t store[4][kStoreBytes];  // must stay first: 1024-byte aligned (kABytes + kWBytesTotal is a multiple of 1024)
-  uint64_t w_full[4];
-  uint64_t w_empty[4];
-  uint64_t a_full;
-  uint64_t a_empty;
+  uint8_t store[4][kStoreBytes];  // must stay first: 1024-byte aligned (kRingBytes is a multiple of 1024)
+  uint64_t w_full[6];
+  uint64_t w_empty[6];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_ptr;
 };
-constexpr size_t kSmemBytes = kABytes + kWBytesTotal + sizeof(Smem);
+constexpr size_t kSmemBytes = kRingBytes + sizeof(Smem);
 static_assert(kSmemBytes <= 232448, "exceeds 227 KB of dynamic shared memory");
 
 struct Geo {
@@ -67,9 +68,8 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
                     int* __restrict__ err_flag) {
   using C = Cfg<CG>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_a = smem;
-  uint8_t* s_w = smem + kABytes;
-  Smem& sm = *reinterpret_cast<Smem*>(smem + kABytes + kWBytesTotal);
+  uint8_t* s_ring = smem;
+  Smem& sm = *reinterpret_cast<Smem*>(smem + kRingBytes);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -86,8 +86,6 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
       mbar_init(&sm.w_full[i], 1);
       mbar_init(&sm.w_empty[i], 1);
     }
-    mbar_init(&sm.a_full, 1);
-    mbar_init(&sm.a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.tmem_full[i], 1);
       mbar_init(&sm.tmem_empty[i], 4 * CG);
@@ -113,26 +111,22 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
         const int ty = rem / g.n_txp, txp = rem - ty * g.n_txp;
         const int h0 = g.lr_row0 + ty * kPatchH;
         const int w0 = (txp * CG + rank) * kPatchW;
-        mbar_wait(&sm.a_empty, (t & 1) ^ 1);
-        if (elect_one()) {
-          if (leader) mbar_arrive_expect_tx(&sm.a_full, kABytes * CG);
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
-            if constexpr (CG == 1) tma_load_4d(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
-            else tma_load_4d_2sm(s_a + tap * kTapBytes, &tmF, &sm.a_full, 0, c1, c2, b);
-          }
-        }
-        __syncwarp();
-#pragma unroll 1
-        for (int s36 = 0; s36 < 36; ++s36, ++it) {  // (n-block, tap)
+        for (int s36 = 0; s36 < 36; ++s36, ++it) {  // (n-block, tap): the A tap tile is re-fetched per n-block (L2 hits)
+          const int tap = s36 % 9;
           const int st = it % C::kStages;
           mbar_wait(&sm.w_empty[st], ((it / C::kStages) & 1) ^ 1);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
-            void* dst = s_w + st * C::kStageBytes;
-            if constexpr (CG == 1) tma_load_2d(dst, &tmW, &sm.w_full[st], 0, s36 * 256);
-            else tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s36 * 256 + rank * 128);
+            uint8_t* dst = s_ring + st * C::kStageBytes;
+            const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
+            if constexpr (CG == 1) {
+              tma_load_4d(dst, &tmF, &sm.w_full[st], 0, c1, c2, b);
+              tma_load_2d(dst + kTapBytes, &tmW, &sm.w_full[st], 0, s36 * 256);
+            } else {
+              tma_load_4d_2sm(dst, &tmF, &sm.w_full[st], 0, c1, c2, b);
+              tma_load_2d_2sm(dst + kTapBytes, &tmW, &sm.w_full[st], 0, s36 * 256 + rank * 128);
+            }
           }
           __syncwarp();
         }
@@ -146,7 +140,6 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
       uint32_t it = 0, slot_use = 0;
       int t = 0;
       for (int work = unit_id; work < g.n_work; work += n_units, ++t) {
-        mbar_wait(&sm.a_full, t & 1);
 #pragma unroll 1
         for (int nb = 0; nb < 4; ++nb, ++slot_use) {
           const int slot = nb & 1;
@@ -160,18 +153,15 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
             const int st = it % C::kStages;
             mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
             tc_fence_after();
-            const uint32_t a0 = smem_u32(s_a + tap * kTapBytes);
-            const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
+            const uint32_t a0 = smem_u32(s_ring + st * C::kStageBytes);
+            const uint32_t b0 = a0 + kTapBytes;
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
                               (tap | k) != 0 ? 1u : 0u);
               umma_commit<CG>(&sm.w_empty[st]);
-              if (tap == 8) {
-                umma_commit<CG>(&sm.tmem_full[slot]);
-                if (nb == 3) umma_commit<CG>(&sm.a_empty);  // every MMA reading this tile's A has completed when this fires
-              }
+              if (tap == 8) umma_commit<CG>(&sm.tmem_full[slot]);
             }
             __syncwarp();
           }
