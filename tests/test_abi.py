@@ -126,3 +126,20 @@ def test_row_partition():
     assert all(parts[i][1] == parts[i + 1][0] for i in range(7))
     assert diinn_b200.row_partition(4320, 8) == [(540 * i, 540 * (i + 1)) for i in range(8)]
     assert diinn_b200.row_partition(3, 8)[3:] == [(3, 3)] * 5
+
+
+@pytest.mark.skipif(not __import__("shutil").which("gcc"), reason="needs gcc")
+def test_header_is_c99_and_links_from_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/diinn_b200.h must compile as C99 (-pedantic) and link against the .so"""
+    import subprocess
+    _ensure_built()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "abi_smoke")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-ldiinn_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr      # DIINN_OK with a B200, DIINN_ERR_UNSUPPORTED_DEVICE (-8) without
+    assert "sm_100a" in r.stdout
