@@ -26,7 +26,7 @@ SYMBOLS = [
     "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_query_ensemble", "diinn_debug_gather",
     "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace", "diinn_debug_umma_pace", "diinn_set_profiling", "diinn_get_kernel_times",
     "diinn_launch_count",
-    "diinn_version", "diinn_set_output_transform", "diinn_psnr",
+    "diinn_version", "diinn_set_output_transform", "diinn_psnr", "diinn_set_bsize",
 ]
 
 
@@ -102,6 +102,8 @@ def load() -> C.CDLL:
     lib.diinn_launch_count.restype = i64
     lib.diinn_set_output_transform.argtypes = [vp, C.POINTER(OutputTransform)]
     lib.diinn_set_output_transform.restype = i
+    lib.diinn_set_bsize.argtypes = [vp, i64]
+    lib.diinn_set_bsize.restype = i
     lib.diinn_psnr.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, C.c_float, C.POINTER(C.c_double), vp]
     lib.diinn_psnr.restype = i
     lib.diinn_version.argtypes = []

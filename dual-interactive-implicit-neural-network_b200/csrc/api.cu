@@ -25,7 +25,8 @@ inline int host_axis_index(const AxisParams& p, int j) {
 struct DecodePlan {
   int lr_row0 = 0, lr_rows = 0;  // LR rows P must hold
   int fr0 = 0, frows = 0;        // LR rows (with +-1 halo, clipped) of the NHWC bf16 copy
-  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, off_chain = 0, total = 0;
+  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, off_chain = 0, off_q3 = 0, total = 0;
+  int qr0 = 0, qr1 = 0;          // mode 4: HR rows whose q_3 is dumped (the band +- 1 halo row, clipped to the image)
   int64_t chunk = 0;
 };
 
@@ -34,6 +35,12 @@ constexpr int64_t kFp32Chunk = 1 << 17;  // HR pixels per activation ping-pong p
 DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int row1, int compute, int mode) {
   DecodePlan p;
   const AxisParams ah = make_axis(H, H_up);
+  p.qr0 = row0, p.qr1 = row1;
+  if (mode == 4) {  // stage A / stage B run over the band plus the rows its 3x3 reflect-padded last conv reads
+    p.qr0 = row0 > 0 ? row0 - 1 : 0;
+    p.qr1 = row1 < H_up ? row1 + 1 : H_up;
+    row0 = p.qr0, row1 = p.qr1;
+  }
   p.lr_row0 = host_axis_index(ah, row0);
   p.lr_rows = host_axis_index(ah, row1 - 1) - p.lr_row0 + 1;
   p.fr0 = p.lr_row0 > 0 ? p.lr_row0 - 1 : 0;
@@ -52,14 +59,21 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
   } else {
     p.off_nhwc = off;
     off += align_up(static_cast<size_t>(B) * p.frows * W * kC * sizeof(__nv_bfloat16));
-    if (mode != 3) {  // modes 1 / 2: scratch of the LR-resolution K chain
+    if (mode == 1 || mode == 2) {  // scratch of the LR-resolution K chain
       p.off_chain = off;
       off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * p.lr_rows * W));
     }
   }
+  if (mode == 4) {
+    p.off_q3 = off;
+    off += align_up(static_cast<size_t>(B) * (p.qr1 - p.qr0) * W_up * kD *
+                    (compute == DIINN_COMPUTE_FP32 ? sizeof(float) : sizeof(__nv_bfloat16)));
+  }
   p.total = off;
   return p;
 }
+
+inline bool chain_mode(const Handle* h) { return h->cfg.mode == 1 || h->cfg.mode == 2; }  // K chain at LR resolution
 
 int check_common(Handle* h, int B, int C, int H, int W, int io_dtype, int compute) {
   if (!h) return DIINN_ERR_BAD_ARG;
@@ -150,10 +164,10 @@ int diinn_create(diinn_handle** out, const diinn_config* cfg) {
     return DIINN_ERR_BAD_ARG;
   }
   *out = nullptr;
-  if (cfg->mode < 1 || cfg->mode > 3 || cfg->init_q != 0 || cfg->in_channels != kC || cfg->hidden != kD ||
+  if (cfg->mode < 1 || cfg->mode > 4 || cfg->init_q != 0 || cfg->in_channels != kC || cfg->hidden != kD ||
       cfg->n_layers != kLayers) {
     g_create_error =
-        "only mode in {1,2,3}, init_q=False, in_channels=64, hidden_dims=[256]*4 is implemented (diinn.py:57-80)";
+        "only mode in {1,2,3,4}, init_q=False, in_channels=64, hidden_dims=[256]*4 is implemented (diinn.py:57-90)";
     return DIINN_ERR_UNSUPPORTED_MODE;
   }
   int ndev = 0;
@@ -217,6 +231,7 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->err_flag);
   cudaFree(h->trace_dev);
   cudaFree(h->WH32);
+  cudaFree(h->WL4);
   cudaFree(h->WH16);
   cudaFree(h->psnr_acc);
   cudaFree(h->host_feat_dev);
@@ -261,6 +276,13 @@ int diinn_set_output_transform(diinn_handle* h, const diinn_output_transform* t)
   if (!h) return DIINN_ERR_BAD_ARG;
   if (t && t->clamp && !(t->lo <= t->hi)) return fail(h, DIINN_ERR_BAD_ARG, "output transform: lo > hi");
   h->out_tf = t ? *t : diinn_output_transform{};
+  return DIINN_OK;
+}
+
+int diinn_set_bsize(diinn_handle* h, int64_t bsize) {
+  if (!h) return DIINN_ERR_BAD_ARG;
+  if (bsize < 0) return fail(h, DIINN_ERR_BAD_ARG, "bsize must be >= 0 (0 = None)");
+  h->bsize = bsize;
   return DIINN_OK;
 }
 
@@ -335,12 +357,42 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   src.B = B, src.H = H, src.W = W, src.H_up = H_up, src.W_up = W_up, src.row0 = row0, src.row1 = row1;
   src.lr_row0 = plan.lr_row0, src.lr_rows = plan.lr_rows;
 
+  // Mode 4: stage B runs over the band plus its halo rows and dumps q_3 there instead of projecting to RGB; the 3x3
+  // reflect-padded last conv (csrc/mode4.cu) then writes the caller's band through the usual OutSpec.
+  const bool mode4 = h->cfg.mode == 4;
+  OutSpec ob = o;  // what stage B writes
+  if (mode4) {
+    if (H_up < 2 || W_up < 2) return fail(h, DIINN_ERR_BAD_SHAPE, "mode 4 (reflect padding) needs an output of at least 2x2");
+    src.row0 = plan.qr0, src.row1 = plan.qr1;
+    ob = OutSpec{};
+    ob.io_dtype = o.io_dtype;
+    ob.batch_stride = static_cast<int64_t>(plan.qr1 - plan.qr0) * W_up;  // pixel units: the dump is (B, rows, W_up, 256)
+    ob.row_stride = W_up;
+  }
+  // batched_step (diinn.py:149-160) convolves column strips of bsize // H_up columns one by one, each with its own
+  // reflect padding; a strip of width 1 cannot be reflect-padded (torch raises), a width of 0 never terminates there
+  int strip = W_up;
+  if (mode4 && h->bsize > 0) {
+    const int64_t sw = h->bsize / H_up;
+    if (sw < 1) return fail(h, DIINN_ERR_BAD_ARG, "bsize < H_up: the reference's batched_step makes no progress (diinn.py:155)");
+    strip = sw < W_up ? static_cast<int>(sw) : W_up;
+    if (strip == 1 || W_up % strip == 1)
+      return fail(h, DIINN_ERR_BAD_SHAPE, "bsize leaves a column strip of width 1, which reflect padding rejects");
+  }
+  auto last_conv = [&](const void* q3, bool is_f32) {
+    return launch_last_conv3x3(h, q3, is_f32, B, H_up, W_up, strip, plan.qr0, plan.qr1 - plan.qr0, row0, row1, o, s);
+  };
+
   if (compute == DIINN_COMPUTE_FP32) {
     if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, plan.lr_row0, plan.lr_rows, P, s))) return rc;
-    if (h->cfg.mode != 3 && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, s))) return rc;
-    return run_stage_b_fp32(h, src, o, P, reinterpret_cast<float*>(ws + plan.off_q0),
-                            reinterpret_cast<float*>(ws + plan.off_q1), plan.chunk, s);
+    if (chain_mode(h) && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, s))) return rc;
+    float* q3f = mode4 ? reinterpret_cast<float*>(ws + plan.off_q3) : nullptr;
+    if ((rc = run_stage_b_fp32(h, src, ob, P, reinterpret_cast<float*>(ws + plan.off_q0),
+                               reinterpret_cast<float*>(ws + plan.off_q1), plan.chunk, s, q3f)))
+      return rc;
+    return mode4 ? last_conv(q3f, true) : DIINN_OK;
   }
+  if (mode4) ob.q3 = reinterpret_cast<__nv_bfloat16*>(ws + plan.off_q3);
   __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + plan.off_nhwc);
   auto mark = [&]() {
     if (!h->profiling) return;
@@ -362,11 +414,12 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
     rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s);
   }
   if (rc) return rc;
-  if (h->cfg.mode != 3 &&
+  if (chain_mode(h) &&
       (rc = run_lr_chain_umma(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, ws + plan.off_chain, s)))
     return rc;
   mark();
-  rc = launch_stage_b_umma(h, src, o, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
+  rc = launch_stage_b_umma(h, src, ob, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
+  if (!rc && mode4) rc = last_conv(ob.q3, false);
   mark();
   return rc;
 }
@@ -507,7 +560,7 @@ size_t diinn_query_workspace_bytes(const diinn_handle* h, int B, int H, int W, i
     off += 2 * align_up(static_cast<size_t>(chunk) * kD * sizeof(float));
   } else {
     off += align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
-    if (h && h->cfg.mode != 3) off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * H * W));
+    if (h && (h->cfg.mode == 1 || h->cfg.mode == 2)) off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * H * W));
   }
   return off;
 }
@@ -555,6 +608,8 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
   if (!feat || !out || !coord || !cell) return fail(h, DIINN_ERR_BAD_ARG, "null pointer");
+  if (h->cfg.mode == 4)
+    return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "mode 4's 3x3 last conv is defined on the HR grid only: use diinn_decode");
   if (Q < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "Q must be positive");
   const int E = ensemble ? 4 : 1;
   if (static_cast<int64_t>(Q) * E >= (1ll << 31) / 8) return fail(h, DIINN_ERR_BAD_SHAPE, "too many queries per call");
@@ -577,7 +632,7 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
     float* q0 = reinterpret_cast<float*>(ws + off);
     float* q1 = reinterpret_cast<float*>(ws + off + align_up(static_cast<size_t>(chunk) * kD * sizeof(float)));
     if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, 0, H, P, s))) return rc;
-    if (h->cfg.mode != 3 && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * H * W, s))) return rc;
+    if (chain_mode(h) && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * H * W, s))) return rc;
     return run_stage_b_fp32(h, src, o, P, q0, q1, chunk, s);
   }
   const __nv_bfloat16* nhwc = static_cast<const __nv_bfloat16*>(feat);  // channels-last bf16: read in place
@@ -587,7 +642,7 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
     nhwc = conv;
   }
   if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s))) return rc;
-  if (h->cfg.mode != 3) {
+  if (chain_mode(h)) {
     char* chain = ws + off + align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
     if ((rc = run_lr_chain_umma(h, P, static_cast<int64_t>(B) * H * W, chain, s))) return rc;
   }

@@ -107,6 +107,10 @@ struct OutSpec {
   void* peers[kMaxPeers];
   int n_peers;
   void* mc;
+  // mode 4 (3x3 reflect-padded last conv over HR pixels, diinn.py:90): stage B does not project to RGB but dumps q_3 as
+  // bf16, pixel-major (pixel offset = the channel-0 offset computed from batch_stride / row_stride, x 256); csrc/mode4.cu
+  // then runs the convolution. nullptr everywhere else.
+  __nv_bfloat16* q3;
   // eval glue fused into the store (diinn_set_output_transform): bit 0 affine, bit 1 clamp, bit 2 uint8 quantisation
   int t_flags;
   float t_scale, t_bias, t_lo, t_hi;

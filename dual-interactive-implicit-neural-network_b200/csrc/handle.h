@@ -44,8 +44,10 @@ struct Handle {
   // modes 1 / 2 (K chain entirely at LR resolution): the k-facing 256x256 blocks of K.1..3, row-major [n][k]
   float* WH32 = nullptr;          // (3, 256, 256)
   __nv_bfloat16* WH16 = nullptr;  // (3, 256, 256)
+  float* WL4 = nullptr;           // mode 4: last_layer.weight as (9 taps, 256, 4) fp32 = (Wl[0], Wl[1], Wl[2], 0) per (tap, f)
   SmallParams small{};            // host copy; passed by value to kernels
   diinn_output_transform out_tf{};  // eval glue fused into the output store (all zero = identity)
+  int64_t bsize = 0;                // diinn_set_bsize: the reference's query-chunk size (0 = None); only mode 4 reads it
   double* psnr_acc = nullptr;       // device accumulator of diinn_psnr
 
   // ---- cached device scratch for diinn_decode_host ----
@@ -87,8 +89,11 @@ int launch_stage_a_fp32(Handle* h, const void* feat, int io_dtype, int B, int H,
 int run_lr_chain_fp32(Handle* h, float* P, int64_t M, cudaStream_t s);
 int run_lr_chain_umma(Handle* h, float* P, int64_t M, void* scratch, cudaStream_t s);
 size_t lr_chain_scratch_bytes(int64_t M);
+// mode 4: 3x3 reflect-padded last conv over the dumped q_3 (csrc/mode4.cu)
+int launch_last_conv3x3(Handle* h, const void* q3, bool q3_is_f32, int B, int H_up, int W_up, int strip, int qr0, int qrows,
+                        int row0, int row1, const OutSpec& out, cudaStream_t s);
 int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,
-                     float* qbuf1, int64_t chunk, cudaStream_t s);
+                     float* qbuf1, int64_t chunk, cudaStream_t s, float* q3_dump = nullptr);
 // stage_a_umma.cu / stage_b_umma.cu
 int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H, int W, int fr0, int frows,
                         int lr_row0, int lr_rows, float* P, cudaStream_t s);

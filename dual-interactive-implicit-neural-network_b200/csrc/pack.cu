@@ -52,7 +52,7 @@ __global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB3
   const int row = is_q ? n - kD : n;
   const float* src = is_q ? r.qw[li + 1] + static_cast<size_t>(row) * kD
                           : r.kw[li + 1] + static_cast<size_t>(row) * (mode == 1 ? kD : kD + kUnfold);
-  const bool to_chain = !is_q && mode != 3;  // k-facing block: LR chain instead of stage B
+  const bool to_chain = !is_q && (mode == 1 || mode == 2);  // k-facing block: LR chain instead of stage B
   const int half = row >> 7;                              // which 128-feature half of the layer output
   const int tile_row = (is_q ? 128 : 0) + (row & 127);    // K-part rows [0,128), Q-part rows [128,256)
   const int fh = row & 127;                               // fp16 twin: K/Q interleaved in 16-feature blocks
@@ -80,7 +80,7 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   const size_t sizes_qw[4] = {256 * 3, 256 * 256, 256 * 256, 256 * 256};
   size_t total = 0;
   for (int i = 0; i < 4; ++i) total += sizes_kw[i] + sizes_qw[i] + 512;
-  total += 3 * 256 + 4;
+  total += 9 * 3 * 256 + 4;
   if (!w->on_device) {
     DIINN_CUDA_OK(h, cudaMalloc(&staging, total * sizeof(float)));
     float* p = staging;
@@ -96,7 +96,7 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
       r.qw[i] = up(w->q_weight[i], sizes_qw[i]);
       r.qb[i] = up(w->q_bias[i], 256);
     }
-    r.lw = up(w->last_weight, 768);
+    r.lw = up(w->last_weight, mode == 4 ? 768 * 9 : 768);
     r.lb = up(w->last_bias, 3);
   } else {
     for (int i = 0; i < 4; ++i) {
@@ -131,8 +131,8 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     DIINN_CUDA_OK(h, cudaMemcpyAsync(sp.bq[i], w->q_bias[i], sizeof(float) * kD, kind, s));
   static thread_local float tmp_q0[kD * 3];
   DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_q0, w->q_weight[0], sizeof(float) * kD * 3, kind, s));
-  static thread_local float tmp_wl[3 * kD];
-  DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_wl, w->last_weight, sizeof(float) * 3 * kD, kind, s));
+  static thread_local float tmp_wl[9 * 3 * kD];
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_wl, w->last_weight, sizeof(float) * 3 * kD * (mode == 4 ? 9 : 1), kind, s));
   DIINN_CUDA_OK(h, cudaMemcpyAsync(sp.bl, w->last_bias, sizeof(float) * 3, kind, s));
   for (int i = 0; i < 4; ++i)
     DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bA_host + i * kD, w->k_bias[i], sizeof(float) * kD, kind, s));
@@ -143,13 +143,25 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     sp.wq0[f][1] = tmp_q0[f * 3 + 1];
     sp.wq0[f][2] = tmp_q0[f * 3 + 2];
     sp.wq0[f][3] = sp.bq[0][f];
-    sp.wl_t[f][0] = tmp_wl[f];
-    sp.wl_t[f][1] = tmp_wl[kD + f];
-    sp.wl_t[f][2] = tmp_wl[2 * kD + f];
+    // (mode 4's 3x3 last layer does not use wl_t: its (3,256,3,3) weight goes to WL4 below)
+    sp.wl_t[f][0] = mode == 4 ? 0.f : tmp_wl[f];
+    sp.wl_t[f][1] = mode == 4 ? 0.f : tmp_wl[kD + f];
+    sp.wl_t[f][2] = mode == 4 ? 0.f : tmp_wl[2 * kD + f];
     sp.wl_t[f][3] = 0.f;
   }
   for (int f = 0; f < kD; f += 2)
     for (int c = 0; c < 4; ++c) sp.wq0_p[f >> 1][c] = make_float2(sp.wq0[f][c], sp.wq0[f + 1][c]);
+  if (mode == 4) {
+    // (c, f, ky, kx) -> (tap = ky*3 + kx, f, c) padded to float4
+    static thread_local float wl4[9 * kD * 4];
+    for (int tap = 0; tap < 9; ++tap)
+      for (int f = 0; f < kD; ++f) {
+        for (int c = 0; c < 3; ++c) wl4[(tap * kD + f) * 4 + c] = tmp_wl[(c * kD + f) * 9 + tap];
+        wl4[(tap * kD + f) * 4 + 3] = 0.f;
+      }
+    if (!h->WL4) DIINN_CUDA_OK(h, cudaMalloc(&h->WL4, sizeof(wl4)));
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WL4, wl4, sizeof(wl4), cudaMemcpyHostToDevice, s));
+  }
   DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bq_dev, sp.bq, sizeof(float) * kLayers * kD, cudaMemcpyHostToDevice, s));
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
   if (staging) cudaFree(staging);

@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) last_fp32_kernel(PixelSource src, OutSpec
 }
 
 int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,
-                     float* qbuf1, int64_t chunk, cudaStream_t s) {
+                     float* qbuf1, int64_t chunk, cudaStream_t s, float* q3_dump) {
   const int64_t total = src.mode == 0 ? static_cast<int64_t>(src.B) * (src.row1 - src.row0) * src.W_up
                                       : static_cast<int64_t>(src.B) * src.Q * (src.ensemble ? 4 : 1);
   const float* bq_dev = h->bq_dev;
@@ -390,14 +390,18 @@ int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, cons
     float* qi = qbuf0;
     float* qo = qbuf1;
     for (int li = 1; li < kLayers; ++li) {
+      // mode 4: the last layer writes q_3 of the chunk's pixels straight into the dump (grid order = its pixel-major
+      // order); the 3x3 conv (csrc/mode4.cu) replaces last_fp32_kernel once every chunk is done
+      float* dst = (q3_dump != nullptr && li == kLayers - 1) ? q3_dump + static_cast<size_t>(g0) * kD : qo;
       layer_fp32_kernel<<<dim3(nblk, kD / 32), 256, 0, s>>>(src, qi, h->WB32 + static_cast<size_t>(li - 1) * 512 * kD,
-                                                            bq_dev + li * kD, P, li * kD, qo, g0, g1);
+                                                            bq_dev + li * kD, P, li * kD, dst, g0, g1);
       float* t = qi;
       qi = qo;
       qo = t;
     }
-    last_fp32_kernel<<<static_cast<unsigned>((g1 - g0 + 7) / 8), 256, 0, s>>>(src, out, h->small, qi, g0, g1);
-    h->launches += 5;
+    if (q3_dump == nullptr)
+      last_fp32_kernel<<<static_cast<unsigned>((g1 - g0 + 7) / 8), 256, 0, s>>>(src, out, h->small, qi, g0, g1);
+    h->launches += q3_dump == nullptr ? 5 : 4;
   }
   DIINN_CUDA_OK(h, cudaGetLastError());
   return DIINN_OK;

@@ -252,9 +252,10 @@ __device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw<F16>& raw)
 }
 
 // kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
-template <bool kLast, bool F16>
+template <bool kLast, bool F16, bool kDump = false>
 __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
-                                         const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3]) {
+                                         const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3],
+                                         __nv_bfloat16* q3row = nullptr) {
   const int col = c * 64 + wg * 16;
   const int f0 = h * 128 + col;
   const float* kx = reinterpret_cast<const float*>(kxv);
@@ -275,7 +276,9 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
     const float2 t2 = __fadd2_rn(make_float2(aq[0], aq[1]), *reinterpret_cast<const float2*>(&sp.bq[layer][f0 + j]));
     const float2 q2 = __fmul2_rn(k2, make_float2(act_sin(t2.x), act_sin(t2.y)));
     const float q[2] = {q2.x, q2.y};
-    if constexpr (kLast) {
+    if constexpr (kLast && kDump) {  // mode 4: q_3 goes to HBM as bf16 for the 3x3 last conv
+      pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+    } else if constexpr (kLast) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const float4 w = *reinterpret_cast<const float4*>(&sp.wl_t[f0 + j + e][0]);
@@ -285,6 +288,13 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
       }
     }
     if constexpr (!kLast) pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
+  }
+  if constexpr (kLast && kDump) {
+    if (q3row != nullptr) {  // rows outside the image / band have no store target
+      uint4* dst = reinterpret_cast<uint4*>(q3row + f0);
+      dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
   }
   if constexpr (!kLast) {
     const uint32_t chunk_base = out_base + (2 * h + c) * kChunkBytes;
@@ -297,7 +307,8 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
   }
 }
 
-template <int CG, bool F16>
+// kDump (mode 4): a separate instantiation, so the q_3 dump costs the RGB-projecting kernels neither a register nor a branch.
+template <int CG, bool F16, bool kDump>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SmallParams sp,
                     const __grid_constant__ PixelSource src, const __grid_constant__ OutSpec out,
@@ -496,6 +507,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       const float* const pw = rc.prow + fg * 16;  // this warp's column of the tile row's P entry
       const float* pn = nullptr;                  // same for the next tile
       float rgb[3] = {0.f, 0.f, 0.f};  // this warp's share of the RGB projection (scalar FFMA: measured faster than FFMA2 here)
+      // mode 4: this row's q_3 vector in the dump buffer (rows outside the image / band get no store target)
+      __nv_bfloat16* q3row = nullptr;
+      if constexpr (kDump) q3row = rc.valid ? out.q3 + rc.out_off * kD : nullptr;
 #pragma unroll 1
       for (int layer = 1; layer <= 3; ++layer) {
         const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
@@ -535,7 +549,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
             if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
           }
-          if (last) epi_math<true, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
+          if (last) epi_math<true, F16, kDump>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row);
           else epi_math<false, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
@@ -558,7 +572,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
             if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
           }
-          if (last) epi_math<true, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
+          if (last) epi_math<true, F16, kDump>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row);
           else epi_math<false, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
@@ -576,7 +590,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       // Combine the four partial RGB projections of a row (one per 16-feature group) in a fixed order (bit-reproducible).
       // The warps of feature group 3 reduce and store; the others drop their partials in smem.
       const int pidx = fg;
-      if (pidx != 3) {
+      if constexpr (kDump) {
+        // mode 4: nothing to reduce or store here, csrc/mode4.cu projects q_3 through the 3x3 conv afterwards
+      } else if (pidx != 3) {
         if (t > 0) named_bar_sync(2, kEpiThreads);  // the reducers have read the previous tile's partials
         float* pp = &sm.partial[pidx][r][0];
         pp[0] = rgb[0], pp[1] = rgb[1], pp[2] = rgb[2];
@@ -620,19 +636,19 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
 }  // namespace sb
 
-template <int CG, bool F16>
+template <int CG, bool F16, bool kDump = false>
 static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const PixelSource& src,
                           const OutSpec& out, const float* P, const sb::Work& wk, int* err_flag, long long* trace) {
   using namespace sb;
-  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, F16, kDump>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kSmemBytes)));
   if (getenv("DIINN_DEBUG_OCC")) {
     int nc = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, F16>, cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, F16, kDump>, cfg);
     fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
             cudaGetErrorString(e));
   }
-  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, F16>, tm, h->small, src, out, P, wk, err_flag, trace));
+  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, F16, kDump>, tm, h->small, src, out, P, wk, err_flag, trace));
   return DIINN_OK;
 }
 
@@ -677,7 +693,14 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   cfg.attrs = attr;
   cfg.numAttrs = h->pdl ? 2 : 1;
   int rc;
-  if (cta_group == 1)
+  if (out.q3 != nullptr) {  // mode 4: the q_3-dumping instantiations
+    if (cta_group == 1)
+      rc = f16acc ? launch_variant<1, true, true>(h, &cfg, h->tmapWBh, src, out, P, wk, err_flag, trace)
+                  : launch_variant<1, false, true>(h, &cfg, h->tmapWB, src, out, P, wk, err_flag, trace);
+    else
+      rc = f16acc ? launch_variant<2, true, true>(h, &cfg, h->tmapWBh_half, src, out, P, wk, err_flag, trace)
+                  : launch_variant<2, false, true>(h, &cfg, h->tmapWB_half, src, out, P, wk, err_flag, trace);
+  } else if (cta_group == 1)
     rc = f16acc ? launch_variant<1, true>(h, &cfg, h->tmapWBh, src, out, P, wk, err_flag, trace)
                 : launch_variant<1, false>(h, &cfg, h->tmapWB, src, out, P, wk, err_flag, trace);
   else

@@ -36,7 +36,7 @@ def _stream(device) -> C.c_void_p:
 
 
 class FusedImplicitDecoder(nn.Module):
-    """B200-native DIINN query decoder (mode=3, init_q=False).
+    """B200-native DIINN query decoder (modes 1-4, init_q=False; mode 3 is the paper's / the benchmarked wiring).
 
     precision: "bf16" -> tcgen05 tensor cores, bf16 operands / fp32 accumulation (default throughput path);
                "fp16acc" -> stage B with fp16 operands and fp16 TMEM accumulators (faster epilogue, opt-in);
@@ -48,11 +48,11 @@ class FusedImplicitDecoder(nn.Module):
                  init_q: bool = False, precision: str = "bf16"):
         super().__init__()
         hidden_dims = list(hidden_dims)
-        if mode not in (1, 2, 3) or init_q:
+        if mode not in (1, 2, 3, 4) or init_q:
             raise NotImplementedError(
-                "FusedImplicitDecoder implements mode=3 (the paper's final model, diinn.py:73-80) and the k-fed wirings "
-                "mode=1 / mode=2 (diinn.py:57-72), all with init_q=False; mode 4 and init_q=True are SURVEY.md section "
-                "8(f) 'next' rows")
+                "FusedImplicitDecoder implements mode=3 (the paper's final model, diinn.py:73-80), the k-fed wirings "
+                "mode=1 / mode=2 (diinn.py:57-72) and mode=4 (mode 3 with a 3x3 reflect-padded last conv, diinn.py:81-90), "
+                "all with init_q=False; init_q=True is a SURVEY.md section 8(f) 'next' row")
         if in_channels != 64 or hidden_dims != [256] * 4:
             raise NotImplementedError("only in_channels=64, hidden_dims=[256]*4 is implemented")
         if precision not in _PRECISIONS:
@@ -66,7 +66,8 @@ class FusedImplicitDecoder(nn.Module):
             self.K.append(nn.Sequential(nn.Conv2d(last_k, hd, 1), nn.ReLU()))
             self.Q.append(nn.Sequential(nn.Conv2d(last_q, hd, 1), SineAct()))
             last_k, last_q = (hd if mode == 1 else hd + in_channels * 9), hd
-        self.last_layer = nn.Conv2d(hidden_dims[-1], 3, 1)
+        self.last_layer = (nn.Conv2d(hidden_dims[-1], 3, 3, padding=1, padding_mode="reflect") if mode == 4
+                           else nn.Conv2d(hidden_dims[-1], 3, 1))
         self._handle = None
         self._handle_device = None
         self._packed_versions = None
@@ -174,16 +175,20 @@ class FusedImplicitDecoder(nn.Module):
 
     def forward(self, x: torch.Tensor, size, bsize: Optional[int] = None) -> torch.Tensor:
         """(B,64,H,W), size=(H_up,W_up) -> (B,3,H_up,W_up). ``bsize`` (the reference's query-chunk size,
-        diinn.py:149-160) is accepted and ignored: no per-pixel intermediate is ever materialised."""
+        diinn.py:149-160) is accepted and, for modes 1-3, ignored: no per-pixel intermediate is ever materialised.
+        In mode 4 it changes the reference's result (the 3x3 last conv reflect-pads every column strip of
+        ``bsize // H_up`` columns on its own) and is reproduced."""
         H_up, W_up = int(size[0]), int(size[1])
-        return self.forward_rows(x, (H_up, W_up), 0, H_up)
+        return self.forward_rows(x, (H_up, W_up), 0, H_up, bsize=bsize)
 
     def forward_rows(self, x: torch.Tensor, size, row0: int, row1: int, out: Optional[torch.Tensor] = None,
-                     peer_ptrs: Optional[Sequence[int]] = None, multicast_ptr: int = 0):
+                     peer_ptrs: Optional[Sequence[int]] = None, multicast_ptr: int = 0, bsize: Optional[int] = None):
         """HR rows [row0,row1) only -> (B,3,row1-row0,W_up), or written in place into rows [row0,row1) of a full
         (B,3,H_up,W_up) ``out``. Row tiles are how the query grid shards across GPUs."""
         self._check_input(x)
         lib, h = self._ensure_handle(x.device)
+        if self.mode == 4:
+            _lib.check(lib, h, lib.diinn_set_bsize(h, 0 if bsize is None else int(bsize)))
         if not (self._is_nhwc_bf16(x) and self.precision != "fp32"):
             x = x.contiguous()
         B, Cc, H, W = x.shape
@@ -227,6 +232,8 @@ class FusedImplicitDecoder(nn.Module):
         coord (B,Q,2) as (h,w) in [-1,1], cell (B,Q,2) -> (B,Q,3), DIINN semantics.
         local_ensemble=True adds LIIF's 4-neighbour ensemble + area blend (liif.py:71-127) around the DIINN step."""
         self._check_input(feat)
+        if self.mode == 4:
+            raise NotImplementedError("mode 4's 3x3 last conv is defined on the HR grid only: use forward()")
         lib, h = self._ensure_handle(feat.device)
         if not (self._is_nhwc_bf16(feat) and self.precision != "fp32"):
             feat = feat.contiguous()
@@ -247,13 +254,15 @@ class FusedImplicitDecoder(nn.Module):
         return out
 
     def decode_host(self, feat_host: torch.Tensor, size, row0: int = 0, row1: Optional[int] = None,
-                    out_host: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+                    out_host: Optional[torch.Tensor] = None, device=None, bsize: Optional[int] = None) -> torch.Tensor:
         """End-to-end call on HOST tensors (what a CPU-side caller such as demo2.py:40 does): H2D copy of the feature
         map, decode, D2H copy of the result, stream-synchronised. Use pinned tensors for full PCIe bandwidth."""
         if feat_host.device.type != "cpu":
             raise ValueError("decode_host takes CPU tensors")
         device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         lib, h = self._ensure_handle(device)
+        if self.mode == 4:
+            _lib.check(lib, h, lib.diinn_set_bsize(h, 0 if bsize is None else int(bsize)))
         feat_host = feat_host.contiguous()
         B, Cc, H, W = feat_host.shape
         H_up, W_up = int(size[0]), int(size[1])

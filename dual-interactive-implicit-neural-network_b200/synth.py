@@ -75,7 +75,7 @@ def weight_shapes(in_channels: int = IN_CHANNELS, hidden: int = HIDDEN, n_layers
         shapes[f"K.{i}.0.bias"] = (hidden,)
         shapes[f"Q.{i}.0.weight"] = (hidden, qin, 1, 1)
         shapes[f"Q.{i}.0.bias"] = (hidden,)
-    shapes["last_layer.weight"] = (3, hidden, 1, 1)
+    shapes["last_layer.weight"] = (3, hidden, 3, 3) if mode == 4 else (3, hidden, 1, 1)   # diinn.py:89-92
     shapes["last_layer.bias"] = (3,)
     return shapes
 
@@ -88,7 +88,8 @@ def make_weights(seed: int = 0, k_gain: float = 1.0, q_gain: float = 1.0, last_g
     out = {}
     shapes = weight_shapes(mode=mode)
     for s, (name, shape) in enumerate(shapes.items()):
-        fan_in = shape[1] if len(shape) == 4 else shapes[name.replace("bias", "weight")][1]
+        wshape = shape if len(shape) == 4 else shapes[name.replace("bias", "weight")]
+        fan_in = wshape[1] * wshape[2] * wshape[3]
         bound = 1.0 / np.sqrt(float(fan_in))
         gain = k_gain if name.startswith("K.") else q_gain if name.startswith("Q.") else last_gain
         out[name] = uniform(seed, 100 + s, shape, -bound * gain, bound * gain)

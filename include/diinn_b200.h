@@ -2,9 +2,9 @@
  * diinn_b200.h -- C ABI of the B200-native (sm_100a) DIINN query decoder.
  *
  * One shared library (libdiinn_b200.so) replaces the hot path of the reference:
- *   ImplicitDecoder.forward / _make_pos_encoding / step (mode 3 -- the benchmarked wiring -- and modes 1, 2; init_q=False),
- *   /root/reference/src/models/components/diinn.py:94-110 (coordinates), :163-173 (forward),
- *   :132-139 (dual-interactive K/Q MLP), reached from DIINN.forward (diinn.py:18),
+ *   ImplicitDecoder.forward / _make_pos_encoding / step (mode 3 -- the benchmarked wiring -- and modes 1, 2, 4;
+ *   init_q=False), /root/reference/src/models/components/diinn.py:94-110 (coordinates), :163-173 (forward),
+ *   :132-139 (dual-interactive K/Q MLP), :116-131,140-147 (the other wirings), reached from DIINN.forward (diinn.py:18),
  *   SRLitModule.forward (src/models/sr_module.py:104-105) and demo2.py:40.
  *
  * Conventions
@@ -36,7 +36,7 @@ typedef enum diinn_status {
   DIINN_ERR_BAD_ARG = -1,
   DIINN_ERR_BAD_SHAPE = -2,
   DIINN_ERR_BAD_DTYPE = -3,
-  DIINN_ERR_UNSUPPORTED_MODE = -4,   /* anything but mode in {1,2,3}, init_q=False, 64 channels, 4x256 hidden */
+  DIINN_ERR_UNSUPPORTED_MODE = -4,   /* anything but mode in {1,2,3,4}, init_q=False, 64 channels, 4x256 hidden */
   DIINN_ERR_WORKSPACE_TOO_SMALL = -5,
   DIINN_ERR_CUDA = -6,
   DIINN_ERR_NO_WEIGHTS = -7,
@@ -62,14 +62,15 @@ typedef struct diinn_config {
   int in_channels; /* 64 */
   int hidden;      /* 256 (hidden_dims = [256]*n_layers) */
   int n_layers;    /* 4 */
-  int mode;        /* 3 (paper / benchmark wiring), or 1 / 2: K chain fed by k instead of q (diinn.py:57-72,116-131) */
+  int mode;        /* 3 (paper / benchmark wiring); 1 / 2: K chain fed by k instead of q (diinn.py:57-72,116-131);
+                      4: mode 3 with a 3x3 reflect-padded last conv over the HR grid (diinn.py:73-90,140-147) */
   int init_q;      /* 0 */
   int device;      /* CUDA device ordinal the handle lives on */
 } diinn_config;
 
 /* The 18 tensors of the reference state_dict, fp32, contiguous, reference layout:
  *   k_weight[0] (256,576)  k_weight[1..3] (256,832) [mode 1: (256,256)]  q_weight[0] (256,3)  q_weight[1..3] (256,256)
- *   *_bias (256)           last_weight (3,256)       last_bias (3)
+ *   *_bias (256)           last_weight (3,256) [mode 4: (3,256,3,3)]       last_bias (3)
  * on_device != 0: pointers are device pointers on the handle's device; otherwise host pointers. */
 typedef struct diinn_weights_f32 {
   const float* k_weight[4];
@@ -140,6 +141,13 @@ typedef struct diinn_output_transform {
   int quantize_u8;
 } diinn_output_transform;
 int diinn_set_output_transform(diinn_handle* h, const diinn_output_transform* t);
+
+/* The reference's `bsize` argument (ImplicitDecoder.forward(x, size, bsize), diinn.py:163; 0 = None). For modes 1-3 it is
+ * pure scheduling and ignored. In mode 4 it is part of the RESULT: batched_step (diinn.py:149-160) runs `step`, and with it
+ * the 3x3 reflect-padded last conv, on column strips of bsize // H_up columns one at a time, so columns reflect at the
+ * borders of their strip. diinn_decode reproduces that; like the reference it rejects a bsize that leaves a strip one
+ * column wide (DIINN_ERR_BAD_SHAPE) and one below H_up (DIINN_ERR_BAD_ARG: the reference loops forever there). */
+int diinn_set_bsize(diinn_handle* h, int64_t bsize);
 
 /* PSNR as the reference evaluates it (calc_psnr, sr_module.py:21-38), computed on the device:
  *   dataset 0 = None (all pixels, all channels), 1 = 'benchmark' (shave = scale, Y conversion with

@@ -13,7 +13,9 @@ PyTorch/ATen (not vendored in the reference tree; the reference pins no torch ve
 * ``axis_centres`` / ``rel_axis`` / ``make_pos_encoding``  <- diinn.py:94-110.
 * ``syn_input``            <- diinn.py:165-167.
 * ``unfold3x3``            <- F.unfold(x, 3, padding=1).view(B, C*9, H, W), diinn.py:168.
-* ``step_mode3``           <- diinn.py:132-139 with K/Q/last_layer built at diinn.py:73-80,92.
+* ``step_mode3``           <- diinn.py:132-139 with K/Q/last_layer built at diinn.py:73-80,92 (and the mode 1 / 2 / 4
+                              wirings, diinn.py:116-131,140-147).
+* ``last_conv3x3_reflect`` <- mode 4's last_layer, Conv2d(256, 3, 3, padding=1, padding_mode='reflect'), diinn.py:89-90.
 * ``decoder_forward``      <- diinn.py:163-173 (bsize chunking, diinn.py:149-160, is pure scheduling).
 * ``query``                <- the (feat, coord, cell) superset entry of SURVEY.md section 8(b); on a regular
                               grid it reproduces ``decoder_forward`` (tested).
@@ -130,19 +132,45 @@ def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False
         q = k * np.sin(q @ _w2d(W[f"Q.{i}.0.weight"]).T + W[f"Q.{i}.0.bias"])
         if taps is not None:
             taps[f"k{i}"], taps[f"q{i}"] = k, q
+    if mode == 4:   # the 3x3 last conv couples HR pixels: the caller (decoder_forward) applies it on the assembled q_3
+        return q.astype(dt)
     out = q @ _w2d(W["last_layer.weight"]).T + W["last_layer.bias"]
     return out.astype(dt)
+
+
+def last_conv3x3_reflect(weights: dict, q3: np.ndarray, fp64: bool = False) -> np.ndarray:
+    """mode 4 (diinn.py:89-90,146): q3 (B,H_up,W_up,256) -> (B,3,H_up,W_up) through Conv2d(256,3,3,padding=1,
+    padding_mode='reflect'): out[c,y,x] = b[c] + sum_{ky,kx,f} W[c,f,ky,kx] q3[refl(y+ky-1), refl(x+kx-1), f]."""
+    dt = np.float64 if fp64 else F32
+    Wl = weights["last_layer.weight"].astype(dt)          # (3,256,3,3)
+    B, H, Wd, _ = q3.shape
+    qp = np.pad(q3.astype(dt), ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect")
+    out = np.zeros((B, 3, H, Wd), dtype=dt)
+    for ky in range(3):
+        for kx in range(3):
+            out += np.einsum("bhwf,cf->bchw", qp[:, ky:ky + H, kx:kx + Wd], Wl[:, :, ky, kx]).astype(dt)
+    return (out + weights["last_layer.bias"].astype(dt).reshape(1, 3, 1, 1)).astype(dt)
 
 
 # --------------------------------------------------------------------------------------------------
 # forward (diinn.py:163-173) and the row-band form used for sharding / large configs
 # --------------------------------------------------------------------------------------------------
 def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool = False,
-                    chunk: int = 1 << 16, mode: int = 3) -> np.ndarray:
-    """(B,64,H,W), size=(H_up,W_up) -> (B,3,rows,W_up); rows=(r0,r1) restricts to an HR row band."""
+                    chunk: int = 1 << 16, mode: int = 3, bsize=None) -> np.ndarray:
+    """(B,64,H,W), size=(H_up,W_up) -> (B,3,rows,W_up); rows=(r0,r1) restricts to an HR row band.
+
+    bsize matters in mode 4 only: batched_step (diinn.py:149-160) applies `step`, hence the reflect-padded 3x3 last
+    conv, to column strips of bsize // H_up columns one at a time."""
     B, C, H, W = feat.shape
     H_up, W_up = int(size[0]), int(size[1])
     r0, r1 = (0, H_up) if rows is None else (int(rows[0]), int(rows[1]))
+    if mode == 4:
+        q3 = _q3_grid(weights, feat, (H_up, W_up), fp64, chunk)            # (B,H_up,W_up,256)
+        strip = W_up if bsize is None else int(bsize) // H_up
+        if strip < 1:
+            raise ValueError("bsize < H_up: batched_step makes no progress (diinn.py:155)")
+        outs = [last_conv3x3_reflect(weights, q3[:, :, a:a + strip], fp64=fp64) for a in range(0, W_up, strip)]
+        return np.concatenate(outs, axis=-1)[:, :, r0:r1]
     ih, rh = rel_axis(H, H_up)
     iw, rw = rel_axis(W, W_up)
     ratio = ratio_value(H, W, H_up, W_up)
@@ -162,6 +190,29 @@ def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool
             y = step_mode3(weights, x, syn.reshape(-1, 3), fp64=fp64, mode=mode)
             out[b, :, a - r0:e - r0] = y.reshape(e - a, W_up, 3).transpose(2, 0, 1)
     return out
+
+
+def _q3_grid(weights: dict, feat: np.ndarray, size, fp64: bool, chunk: int) -> np.ndarray:
+    """mode 4: q_3 of every HR pixel, (B,H_up,W_up,256) -- the input of the 3x3 last conv (diinn.py:141-146)."""
+    B, C, H, W = feat.shape
+    H_up, W_up = size
+    ih, rh = rel_axis(H, H_up)
+    iw, rw = rel_axis(W, W_up)
+    ratio = ratio_value(H, W, H_up, W_up)
+    u = np.ascontiguousarray(unfold3x3(feat).transpose(0, 2, 3, 1))
+    n_hidden = weights["Q.3.0.weight"].shape[0]
+    q3 = np.empty((B, H_up, W_up, n_hidden), dtype=np.float64 if fp64 else F32)
+    rows_per_chunk = max(1, chunk // W_up)
+    for b in range(B):
+        for a in range(0, H_up, rows_per_chunk):
+            e = min(a + rows_per_chunk, H_up)
+            syn = np.empty((e - a, W_up, 3), dtype=F32)
+            syn[..., 0] = rh[a:e, None]
+            syn[..., 1] = rw[None, :]
+            syn[..., 2] = ratio
+            x = u[b][ih[a:e]][:, iw].reshape(-1, C * 9)
+            q3[b, a:e] = step_mode3(weights, x, syn.reshape(-1, 3), fp64=fp64, mode=4).reshape(e - a, W_up, -1)
+    return q3
 
 
 # --------------------------------------------------------------------------------------------------

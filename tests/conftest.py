@@ -33,3 +33,8 @@ def golden_eval():
 @pytest.fixture(scope="session")
 def golden_modes():
     return np.load(os.path.join(GOLDEN, "modes.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_mode4():
+    return np.load(os.path.join(GOLDEN, "mode4.npz"))

@@ -624,3 +624,79 @@ def test_degenerate_shapes(w0, shape):
         got = _decoder(w0, precision)(x, torch.Size((H_up, W_up))).cpu().numpy()
         assert got.shape == (B, 3, H_up, W_up)
         assert float(np.abs(got - want).max()) <= TIGHT[precision], (shape, precision)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# decoder mode 4: mode-3 stack, 3x3 reflect-padded last conv over HR pixels (csrc/mode4.cu)
+# ---------------------------------------------------------------------------------------------------------
+MODE4_CASES = ["small", "c1", "batch_bsize", "strips_uneven", "tiny", "stress"]
+
+
+def _mode4_case(g, name):
+    mode, fseed, B, H, W, H_up, W_up, bsize = (int(v) for v in g[f"m4.{name}.meta"])
+    kg, qg, lg = (float(v) for v in g[f"m4.{name}.gains"])
+    w = synth.make_weights(seed=mode, mode=mode, k_gain=kg, q_gain=qg, last_gain=lg)
+    dec = lambda precision: diinn_b200.load_numpy_weights(  # noqa: E731
+        diinn_b200.FusedImplicitDecoder(mode=4, init_q=False, precision=precision), w).cuda()
+    return w, dec, synth.make_feat(fseed, B, H, W), (H_up, W_up), (None if bsize < 0 else bsize), g[f"m4.{name}.out"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16acc"])
+@pytest.mark.parametrize("name", MODE4_CASES)
+def test_mode4_matches_reference(golden_mode4, name, precision):
+    """against the outputs of the reference ImplicitDecoder(mode=4), bsize strips included"""
+    w, dec, feat, size, bsize, want = _mode4_case(golden_mode4, name)
+    got = dec(precision)(torch.from_numpy(feat).cuda(), size, bsize).cpu().numpy()
+    assert got.shape == want.shape
+    err = float(np.abs(got - want).max())
+    assert err <= TOL[precision], (name, precision, err)
+    if name != "stress":
+        assert err <= TIGHT[precision], (name, precision, err)
+        assert _psnr_delta(got, want) < 0.01
+
+
+def test_mode4_row_tiles_host_entry_and_fp64(golden_mode4):
+    """row tiles (halo rows recomputed per tile) and the banded host entry are bit-identical to the full decode, with and
+    without bsize strips; the fp32 path against the fp64 oracle; bf16 I/O; the eval glue rides on the conv's store"""
+    w, dec, feat, size, _, want = _mode4_case(golden_mode4, "small")
+    x = torch.from_numpy(feat).cuda()
+    H_up, W_up = size
+    for precision in ("bf16", "fp32"):
+        d = dec(precision)
+        for bsize in (None, H_up * 10):
+            full = d(x, size, bsize)
+            tiles = torch.cat([d.forward_rows(x, size, a, b, bsize=bsize)
+                               for a, b in ((0, 1), (1, 19), (19, 50), (50, H_up - 1), (H_up - 1, H_up))], dim=2)
+            assert torch.equal(tiles, full), (precision, bsize)
+            ref = orc.decoder_forward(w, feat, size, mode=4, bsize=bsize)
+            assert float(np.abs(full.cpu().numpy() - ref).max()) <= TIGHT[precision]
+        assert torch.equal(d.decode_host(x.cpu().pin_memory(), size), d(x, size).cpu())
+    ref64 = orc.decoder_forward(w, feat, size, fp64=True, mode=4)
+    assert float(np.abs(dec("fp32")(x, size).cpu().numpy() - ref64).max()) <= 2e-6
+    d = dec("bf16")
+    y16 = d(x.bfloat16(), size)
+    assert y16.dtype == torch.bfloat16 and float((y16.float().cpu() - torch.from_numpy(want)).abs().max()) <= 1e-3
+    d.set_output_transform(sub=0.5, div=0.5, clamp=(0.0, 1.0), uint8=True)
+    u8 = d(x, size)
+    d.set_output_transform()
+    assert u8.dtype == torch.uint8
+    assert np.abs(u8.cpu().numpy().astype(np.int32) - orc.quantize_u8(orc.denorm_clamp(want)).astype(np.int32)).max() <= 1
+
+
+def test_mode4_contract_errors(golden_mode4):
+    w, dec, feat, size, _, _ = _mode4_case(golden_mode4, "small")
+    d = dec("bf16")
+    x = torch.from_numpy(feat).cuda()
+    H_up, W_up = size
+    with pytest.raises(diinn_b200._lib.DiinnError):          # strips of one column: reflect padding rejects them
+        d(x, size, H_up)
+    with pytest.raises(diinn_b200._lib.DiinnError):          # last strip one column wide (63 = 31 * 2 + 1)
+        d(x, size, H_up * 2)
+    with pytest.raises(diinn_b200._lib.DiinnError):          # bsize < H_up: the reference never terminates
+        d(x, size, H_up - 1)
+    with pytest.raises(diinn_b200._lib.DiinnError):          # 1-pixel-wide output
+        d(x, (8, 1))
+    coord, cell = (torch.from_numpy(v).cuda() for v in synth.make_query(3, 1, 64))
+    with pytest.raises(NotImplementedError):                 # the 3x3 conv needs the HR grid
+        d.query(x, coord, cell)
+    assert d(x, size, None).shape == (1, 3, H_up, W_up)      # the handle is still usable, bsize reset to None

@@ -160,3 +160,37 @@ def test_modes_1_2_match_reference(golden_modes, key):
     want = golden_modes[f"{key}.out"]
     assert got.shape == want.shape
     assert float(np.abs(got - want).max()) <= (2e-6 if kg == 1.0 else 2e-5)
+
+
+# ---- decoder mode 4: fixtures produced by the reference ImplicitDecoder(mode=4); the bsize cases
+# pin the per-strip reflect padding of batched_step (diinn.py:149-160)
+MODE4_CASES = ["small", "c1", "batch_bsize", "strips_uneven", "tiny", "stress"]
+
+
+def _mode4_case(g, name):
+    mode, fseed, B, H, W, H_up, W_up, bsize = (int(v) for v in g[f"m4.{name}.meta"])
+    kg, qg, lg = (float(v) for v in g[f"m4.{name}.gains"])
+    w = synth.make_weights(seed=mode, mode=mode, k_gain=kg, q_gain=qg, last_gain=lg)
+    return w, synth.make_feat(fseed, B, H, W), (H_up, W_up), (None if bsize < 0 else bsize), g[f"m4.{name}.out"]
+
+
+@pytest.mark.parametrize("name", MODE4_CASES)
+def test_mode4_matches_reference(golden_mode4, name):
+    w, feat, size, bsize, want = _mode4_case(golden_mode4, name)
+    assert w["last_layer.weight"].shape == (3, 256, 3, 3)
+    got = orc.decoder_forward(w, feat, size, mode=4, bsize=bsize)
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) <= (2e-6 if name != "stress" else 5e-5)
+
+
+def test_mode4_bsize_changes_the_result_and_bands_do_not(golden_mode4):
+    """the strips are part of the reference's mode-4 semantics: ignoring bsize gives a different image near strip borders;
+    a row band, by contrast, is a pure slice of the full result"""
+    w, feat, size, bsize, want = _mode4_case(golden_mode4, "strips_uneven")
+    whole = orc.decoder_forward(w, feat, size, mode=4)
+    assert float(np.abs(whole - want).max()) > 1e-4
+    strip = bsize // size[0]
+    interior = [c for c in range(size[1]) if 0 < c % strip < strip - 1 and c != size[1] - 1]
+    assert float(np.abs(whole[..., interior] - want[..., interior]).max()) <= 2e-6
+    band = orc.decoder_forward(w, feat, size, rows=(7, 19), mode=4, bsize=bsize)
+    assert np.array_equal(band, orc.decoder_forward(w, feat, size, mode=4, bsize=bsize)[:, :, 7:19])
