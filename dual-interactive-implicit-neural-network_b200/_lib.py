@@ -43,7 +43,7 @@ class OutputTransform(C.Structure):
 class WeightsF32(C.Structure):
     _fields_ = [("k_weight", C.c_void_p * 4), ("k_bias", C.c_void_p * 4), ("q_weight", C.c_void_p * 4),
                 ("q_bias", C.c_void_p * 4), ("last_weight", C.c_void_p), ("last_bias", C.c_void_p),
-                ("on_device", C.c_int)]
+                ("on_device", C.c_int), ("first_weight", C.c_void_p), ("first_bias", C.c_void_p)]
 
 
 _lib = None

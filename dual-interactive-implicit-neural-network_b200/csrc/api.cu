@@ -12,9 +12,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr size_t kAlign = 1024;
-inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
-
 // host twin of axis_index() in common.cuh (one rounded fp32 multiply, then floorf)
 inline int host_axis_index(const AxisParams& p, int j) {
   volatile float t = (static_cast<float>(j) + 0.5f) * p.scale;
@@ -26,13 +23,15 @@ struct DecodePlan {
   int lr_row0 = 0, lr_rows = 0;  // LR rows P must hold
   int fr0 = 0, frows = 0;        // LR rows (with +-1 halo, clipped) of the NHWC bf16 copy
   size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, off_chain = 0, off_q3 = 0, total = 0;
+  InitQPlan iq;                  // init_q=True: replaces P / the activation chunks / the chain scratch
   int qr0 = 0, qr1 = 0;          // mode 4: HR rows whose q_3 is dumped (the band +- 1 halo row, clipped to the image)
   int64_t chunk = 0;
 };
 
 constexpr int64_t kFp32Chunk = 1 << 17;  // HR pixels per activation ping-pong pass of the fp32 path
 
-DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int row1, int compute, int mode) {
+DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int row1, int compute, int mode,
+                       int init_q = 0) {
   DecodePlan p;
   const AxisParams ah = make_axis(H, H_up);
   p.qr0 = row0, p.qr1 = row1;
@@ -47,6 +46,14 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
   const int fr1 = (p.lr_row0 + p.lr_rows + 1 < H) ? p.lr_row0 + p.lr_rows + 1 : H;
   p.frows = fr1 - p.fr0;
   size_t off = 0;
+  if (init_q) {  // no LR-resolution P: everything is per HR pixel, chunk by chunk (csrc/init_q.cu)
+    if (compute != DIINN_COMPUTE_FP32) {
+      p.off_nhwc = off;
+      off += align_up(static_cast<size_t>(B) * p.frows * W * kC * sizeof(__nv_bfloat16));
+    }
+    p.iq = plan_initq(B, W_up, row1 - row0, compute, mode, off);
+    off = p.iq.end;
+  } else {
   p.off_P = off;
   off += align_up(static_cast<size_t>(B) * p.lr_rows * W * kPCols * sizeof(float));
   if (compute == DIINN_COMPUTE_FP32) {
@@ -63,6 +70,7 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
       p.off_chain = off;
       off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * p.lr_rows * W));
     }
+  }
   }
   if (mode == 4) {
     p.off_q3 = off;
@@ -164,10 +172,10 @@ int diinn_create(diinn_handle** out, const diinn_config* cfg) {
     return DIINN_ERR_BAD_ARG;
   }
   *out = nullptr;
-  if (cfg->mode < 1 || cfg->mode > 4 || cfg->init_q != 0 || cfg->in_channels != kC || cfg->hidden != kD ||
-      cfg->n_layers != kLayers) {
+  if (cfg->mode < 1 || cfg->mode > 4 || cfg->init_q < 0 || cfg->init_q > 1 || cfg->in_channels != kC ||
+      cfg->hidden != kD || cfg->n_layers != kLayers) {
     g_create_error =
-        "only mode in {1,2,3,4}, init_q=False, in_channels=64, hidden_dims=[256]*4 is implemented (diinn.py:57-90)";
+        "only mode in {1,2,3,4}, init_q in {0,1}, in_channels=64, hidden_dims=[256]*4 is implemented (diinn.py:40-92)";
     return DIINN_ERR_UNSUPPORTED_MODE;
   }
   int ndev = 0;
@@ -232,6 +240,10 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->trace_dev);
   cudaFree(h->WH32);
   cudaFree(h->WL4);
+  cudaFree(h->WF4);
+  cudaFree(h->WQ0_32);
+  cudaFree(h->WAg16);
+  cudaFree(h->WQ0g16);
   cudaFree(h->WH16);
   cudaFree(h->psnr_acc);
   cudaFree(h->host_feat_dev);
@@ -266,7 +278,7 @@ int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream)
 size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_up, int W_up, int row0, int row1,
                              int compute) {
   if (B < 1 || H < 1 || W < 1 || H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1) return 0;
-  return plan_decode(B, H, W, H_up, W_up, row0, row1, compute, h ? h->cfg.mode : 3).total;
+  return plan_decode(B, H, W, H_up, W_up, row0, row1, compute, h ? h->cfg.mode : 3, h ? h->cfg.init_q : 0).total;
 }
 
 static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
@@ -340,7 +352,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   if (row0 < 0 || row1 > H_up || row0 >= row1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad row range");
   if (static_cast<int64_t>(B) * H * W >= (1ll << 31) / kPCols * 512)
     return fail(h, DIINN_ERR_BAD_SHAPE, "feature map too large");
-  const DecodePlan plan = plan_decode(B, H, W, H_up, W_up, row0, row1, compute, h->cfg.mode);
+  const DecodePlan plan = plan_decode(B, H, W, H_up, W_up, row0, row1, compute, h->cfg.mode, h->cfg.init_q);
   if (!workspace || workspace_bytes < plan.total)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL,
                 "workspace too small: need " + std::to_string(plan.total) + " bytes");
@@ -383,7 +395,13 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
     return launch_last_conv3x3(h, q3, is_f32, B, H_up, W_up, strip, plan.qr0, plan.qr1 - plan.qr0, row0, row1, o, s);
   };
 
+  const bool init_q = h->cfg.init_q != 0;
   if (compute == DIINN_COMPUTE_FP32) {
+    if (init_q) {
+      float* q3f = mode4 ? reinterpret_cast<float*>(ws + plan.off_q3) : nullptr;
+      if ((rc = run_initq_fp32(h, feat, io_dtype, src, ob, ws, plan.iq, s, q3f))) return rc;
+      return mode4 ? last_conv(q3f, true) : DIINN_OK;
+    }
     if ((rc = launch_stage_a_fp32(h, feat, io_dtype, B, H, W, plan.lr_row0, plan.lr_rows, P, s))) return rc;
     if (chain_mode(h) && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, s))) return rc;
     float* q3f = mode4 ? reinterpret_cast<float*>(ws + plan.off_q3) : nullptr;
@@ -402,6 +420,22 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
       h->prof_events.push_back(e);
     }
   };
+  if (init_q) {  // no stage A: the gate reads the NHWC copy (or the caller's channels-last tensor) per HR pixel
+    mark();
+    const __nv_bfloat16* src_nhwc = nhwc;
+    int fr0 = plan.fr0, frows = plan.frows;
+    if (io_dtype == DIINN_IO_BF16_NHWC) {
+      src_nhwc = static_cast<const __nv_bfloat16*>(feat), fr0 = 0, frows = H;
+    } else if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, s))) {
+      return rc;
+    }
+    mark();
+    mark();
+    rc = run_initq_umma(h, src_nhwc, fr0, frows, src, ob, ws, plan.iq, compute == DIINN_COMPUTE_FP16ACC, s);
+    if (!rc && mode4) rc = last_conv(ob.q3, false);
+    mark();
+    return rc;
+  }
   mark();
   if (io_dtype == DIINN_IO_BF16_NHWC) {
     // encoder hand-off: the caller's tensor already is (B,H,W,64) bf16 -- stage A's TMA boxes read it in place
@@ -610,6 +644,8 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   if (!feat || !out || !coord || !cell) return fail(h, DIINN_ERR_BAD_ARG, "null pointer");
   if (h->cfg.mode == 4)
     return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "mode 4's 3x3 last conv is defined on the HR grid only: use diinn_decode");
+  if (h->cfg.init_q)
+    return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "init_q=True is implemented for the HR grid (diinn_decode) only");
   if (Q < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "Q must be positive");
   const int E = ensemble ? 4 : 1;
   if (static_cast<int64_t>(Q) * E >= (1ll << 31) / 8) return fail(h, DIINN_ERR_BAD_SHAPE, "too many queries per call");

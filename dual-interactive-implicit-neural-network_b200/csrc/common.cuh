@@ -83,6 +83,12 @@ struct PixelSource {
   float ratio;
   int B, H, W, H_up, W_up, row0, row1;
   int lr_row0, lr_rows;  // P holds LR rows [lr_row0, lr_row0 + lr_rows) of every batch image
+  // init_q=True (csrc/init_q.cu): the sine gate on x makes every K input a per-HR-pixel quantity, so P holds one row per
+  // pixel of the launch: row = g - p_base in the fp32 path's linear pixel order, (b, row - row0, col) in stage B's. The
+  // launch covers rows [row0,row1) of a band whose image offsets count from out_row0 (tensor path only).
+  int per_pixel_p;
+  long long p_base;
+  int out_row0;
   // query
   const float* coord;  // (B,Q,2)
   const float* cell;   // (B,Q,2)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstring>
 
 #include <string>
 #include <vector>
@@ -45,6 +46,13 @@ struct Handle {
   float* WH32 = nullptr;          // (3, 256, 256)
   __nv_bfloat16* WH16 = nullptr;  // (3, 256, 256)
   float* WL4 = nullptr;           // mode 4: last_layer.weight as (9 taps, 256, 4) fp32 = (Wl[0], Wl[1], Wl[2], 0) per (tap, f)
+  // init_q=True (csrc/init_q.cu): first_layer as (576, 4) fp32 = (w_relh, w_relw, w_ratio, bias) per unfolded channel,
+  // Q.0 (256, 576) in the reference's channel order (fp32 path), and the tensor path's row-major bf16 operands in tap-major
+  // channel order (k' = tap*64 + c): the x-facing K blocks (1024, 576) and Q.0 (256, 576)
+  float* WF4 = nullptr;
+  float* WQ0_32 = nullptr;
+  __nv_bfloat16* WAg16 = nullptr;
+  __nv_bfloat16* WQ0g16 = nullptr;
   SmallParams small{};            // host copy; passed by value to kernels
   diinn_output_transform out_tf{};  // eval glue fused into the output store (all zero = identity)
   int64_t bsize = 0;                // diinn_set_bsize: the reference's query-chunk size (0 = None); only mode 4 reads it
@@ -60,6 +68,17 @@ struct Handle {
   // copy streams + events of the banded host pipeline (upload band k+1 / download band k-1 while band k decodes)
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_h2d[8] = {}, ev_dec[8] = {};
+};
+
+constexpr size_t kWsAlign = 1024;  // every region of the caller's workspace starts on this boundary
+inline size_t align_up(size_t v) { return (v + kWsAlign - 1) / kWsAlign * kWsAlign; }
+
+// workspace of one init_q=True decode (csrc/init_q.cu), carved behind the regions every decode has
+struct InitQPlan {
+  int64_t chunk = 0;     // HR pixels per chunk (tensor path: chunk_rows whole HR rows of every batch image)
+  int chunk_rows = 0;
+  int64_t rows_pad = 0;  // chunk rounded up to the GEMM's M tile
+  size_t off_S = 0, off_XG = 0, off_PX = 0, off_QS = 0, off_q0 = 0, off_q1 = 0, off_chain = 0, end = 0;
 };
 
 inline int fail(Handle* h, int code, const std::string& msg) {
@@ -94,6 +113,14 @@ int launch_last_conv3x3(Handle* h, const void* q3, bool q3_is_f32, int B, int H_
                         int row0, int row1, const OutSpec& out, cudaStream_t s);
 int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,
                      float* qbuf1, int64_t chunk, cudaStream_t s, float* q3_dump = nullptr);
+int run_layers_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0, float* qbuf1,
+                    int64_t g0, int64_t g1, cudaStream_t s, float* q3_dump);
+// init_q=True (csrc/init_q.cu): gate, per-pixel x-facing GEMMs, then layers 1..3 with one P row per HR pixel
+InitQPlan plan_initq(int B, int W_up, int rows, int compute, int mode, size_t off);
+int run_initq_fp32(Handle* h, const void* feat, int io_dtype, const PixelSource& src, const OutSpec& out, char* ws,
+                   const InitQPlan& pl, cudaStream_t s, float* q3_dump);
+int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, const PixelSource& src, const OutSpec& out,
+                   char* ws, const InitQPlan& pl, bool f16acc, cudaStream_t s);
 // stage_a_umma.cu / stage_b_umma.cu
 int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H, int W, int fr0, int frows,
                         int lr_row0, int lr_rows, float* P, cudaStream_t s);

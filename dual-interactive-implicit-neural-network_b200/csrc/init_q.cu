@@ -1,0 +1,288 @@
+// init_q=True (diinn.py:48-51,113-115): before anything else `step` passes the synthetic input through
+//   first_layer = Conv2d(3, 576, 1) + sin          s_p  = sin(Wf (rel_h, rel_w, ratio)_p + bf)        (576 per HR pixel)
+// and gates the gathered unfolded features with it, x <- s_p * x_l(p). Q.0 then reads s_p (576 -> 256) instead of the
+// 3-vector, and every x-facing block of the K layers sees the gated x: nothing that multiplies x depends on the LR
+// cell alone any more, so stage A's hoist to LR resolution does not apply. What survives is the
+// split of each K layer into an x-facing and a q/k-facing block, evaluated per chunk of HR pixels:
+//
+//   gate     S  = s_p,  XG = s_p * x_l(p)                          (chunk x 576 each; x gathered with the nearest-exact
+//                                                                   index, zero-padded 3x3 neighbourhood)
+//   GEMM     PX = XG . WA^T   (chunk x 1024: the x-facing blocks of K.0..3)      QS = S . Q0^T   (chunk x 256)
+//   assemble PX += bk;  PX[:, :256] = relu(.) = k_0
+//   (modes 1 / 2: the k-fed chain of csrc/lr_chain.cu, now over HR pixels:  PX_i += WH_i . relu(PX_{i-1}))
+//   q_0      PX[:, :256] *= sin(QS + bq_0)
+//   stage B  layers 1..3 and the last layer exactly as without init_q, reading ONE PX ROW PER PIXEL (kPix variants of
+//            stage_b_umma_kernel / per_pixel_p in the fp32 kernels) and taking q_0 as given.
+//
+// fp32 path: CUDA-core SGEMMs in the reference's channel order (c*9 + tap). Tensor path: bf16 operands in tap-major order
+// (tap*64 + c, so the gate reads whole 128-byte channel vectors of the NHWC feature copy), the library's tcgen05 GEMM
+// (umma_selftest.cu), fp32 PX / QS. Executed arithmetic: 2 264 064 FLOP per HR pixel (nothing is shared between pixels).
+// Correct and on the tensor cores, not tuned: PX / XG / S round-trip through L2 / HBM (about 10 KB per pixel).
+#include "handle.h"
+#include "pixel.cuh"
+
+namespace diinn {
+
+constexpr int64_t kInitQChunkUmma = 148 * 128 * 2;  // HR pixels per tensor-path chunk: two waves of stage-B tiles
+constexpr int64_t kInitQChunkFp32 = 1 << 15;        // HR pixels per fp32-path chunk
+
+// ---------------------------------------------------------------------------------------------------------
+// gate: one CTA (192 threads, 3 channels each) per pixel. Column j of S / XG is unfolded channel
+//   kTapMajor ? (tap = j / 64, c = j % 64) : (c = j / 9, tap = j % 9)        -- reference channel index k = c*9 + tap.
+// Rows [g1 - g0, rows_pad) are zero-filled (padding up to the GEMM's M tile).
+// ---------------------------------------------------------------------------------------------------------
+struct FeatNCHW {      // the caller's (B,64,H,W) tensor
+  const void* ptr;
+  int bf16;
+  __device__ __forceinline__ float at(int b, int c, int hh, int ww, int H, int W) const {
+    const size_t i = ((static_cast<size_t>(b) * kC + c) * H + hh) * W + ww;
+    return bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(ptr)[i]) : static_cast<const float*>(ptr)[i];
+  }
+};
+struct FeatNHWC {      // (B, frows, W, 64) bf16 holding LR rows [fr0, fr0 + frows)
+  const __nv_bfloat16* ptr;
+  int fr0, frows;
+  __device__ __forceinline__ float at(int b, int c, int hh, int ww, int H, int W) const {
+    return __bfloat162float(ptr[((static_cast<size_t>(b) * frows + (hh - fr0)) * W + ww) * kC + c]);
+  }
+};
+
+__device__ __forceinline__ void store_gate(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_gate(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename Feat, typename TO, bool kTapMajor, bool kFastSin>
+__global__ void __launch_bounds__(192) initq_gate_kernel(PixelSource src, Feat feat, const float4* __restrict__ wf4,
+                                                         TO* __restrict__ S, TO* __restrict__ XG, int64_t g0, int64_t g1,
+                                                         int64_t rows_pad) {
+  for (int64_t row = blockIdx.x; row < rows_pad; row += gridDim.x) {
+    TO* srow = S + row * kUnfold;
+    TO* xrow = XG + row * kUnfold;
+    const int64_t g = g0 + row;
+    if (g >= g1) {
+      for (int j = threadIdx.x; j < kUnfold; j += 192) store_gate(srow + j, 0.f), store_gate(xrow + j, 0.f);
+      continue;
+    }
+    const PixInfo pi = pixel_info(src, g);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int j = threadIdx.x + 192 * i;
+      const int c = kTapMajor ? (j & 63) : j / 9;
+      const int tap = kTapMajor ? (j >> 6) : j % 9;
+      const float4 w = __ldg(wf4 + c * 9 + tap);
+      // same accumulation order as layer 0 of the init_q=False path: a 3-term dot product, then the bias
+      float t = __fmul_rn(w.x, pi.rel_h);
+      t = fmaf(w.y, pi.rel_w, t);
+      t = fmaf(w.z, pi.ratio, t);
+      t += w.w;
+      const float sv = kFastSin ? __sinf(t) : sinf(t);
+      const int hh = pi.ih + tap / 3 - 1, ww = pi.iw + tap % 3 - 1;
+      const float xv = (hh >= 0 && hh < src.H && ww >= 0 && ww < src.W) ? feat.at(pi.b, c, hh, ww, src.H, src.W) : 0.f;
+      store_gate(srow + j, sv);
+      store_gate(xrow + j, sv * xv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32: C(M x N, ldc) = A(M x K) . B(N x K)^T, 64x64 tiles, 256 threads, 4x4 per thread. K % 16 == 0, N % 64 == 0.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgemm_nt_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                       float* __restrict__ Cm, int64_t M, int K, int ldc) {
+  __shared__ float As[16][64 + 1];
+  __shared__ float Bs[16][64 + 1];
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int n0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, k = e & 15;
+      const int64_t m = m0 + r;
+      As[k][r] = m < M ? A[m * K + k0 + k] : 0.f;
+      Bs[k][r] = Bm[static_cast<size_t>(n0 + r) * K + k0 + k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i], b[i] = Bs[k][tx * 4 + i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Cm[m * ldc + n0 + tx * 4 + j] = acc[i][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// assemble (flags bit 0): PX[r][n] += bA[n], ReLU on n < 256.   q_0 (flags bit 1): PX[r][f] *= sin(QS[r][f] + bq0[f]).
+// One thread per 4 columns; rows < M only.
+// ---------------------------------------------------------------------------------------------------------
+template <bool kFastSin>
+__global__ void __launch_bounds__(256) initq_assemble_kernel(float* __restrict__ PX, const float* __restrict__ QS,
+                                                             const float* __restrict__ bA, const float* __restrict__ bq0,
+                                                             int64_t M, int flags) {
+  const int64_t total = M * (kPCols / 4);
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / (kPCols / 4);
+    const int n = static_cast<int>(e % (kPCols / 4)) * 4;
+    if (!(flags & 1) && n >= kD) continue;  // the q_0 pass touches block 0 only
+    float4 v = *reinterpret_cast<float4*>(PX + r * kPCols + n);
+    if (flags & 1) {
+      const float4 b = *reinterpret_cast<const float4*>(bA + n);
+      v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+      if (n < kD) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    }
+    if ((flags & 2) && n < kD) {
+      const float4 t = *reinterpret_cast<const float4*>(QS + r * kD + n);
+      const float4 b = *reinterpret_cast<const float4*>(bq0 + n);
+      const float a0 = t.x + b.x, a1 = t.y + b.y, a2 = t.z + b.z, a3 = t.w + b.w;
+      v.x *= kFastSin ? __sinf(a0) : sinf(a0);
+      v.y *= kFastSin ? __sinf(a1) : sinf(a1);
+      v.z *= kFastSin ? __sinf(a2) : sinf(a2);
+      v.w *= kFastSin ? __sinf(a3) : sinf(a3);
+    }
+    *reinterpret_cast<float4*>(PX + r * kPCols + n) = v;
+  }
+}
+
+// q_0 of the fp32 path leaves PX alone (the chain of modes 1 / 2 is finished by then) and fills the activation buffer
+__global__ void __launch_bounds__(256) initq_q0_fp32_kernel(const float* __restrict__ PX, const float* __restrict__ QS,
+                                                            const float* __restrict__ bq0, float* __restrict__ q, int64_t M) {
+  const int64_t total = M * kD;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / kD;
+    const int f = static_cast<int>(e % kD);
+    q[e] = PX[r * kPCols + f] * sinf(QS[e] + bq0[f]);
+  }
+}
+
+static unsigned capped_blocks(const Handle* h, int64_t want) {
+  const int64_t cap = static_cast<int64_t>(h->sm_count > 0 ? h->sm_count : 148) * 8;
+  return static_cast<unsigned>(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+InitQPlan plan_initq(int B, int W_up, int rows, int compute, int mode, size_t off) {
+  InitQPlan p;
+  const bool fp32 = compute == DIINN_COMPUTE_FP32;
+  const int64_t total = static_cast<int64_t>(B) * rows * W_up;
+  if (fp32) {
+    p.chunk = total < kInitQChunkFp32 ? total : kInitQChunkFp32;
+    p.rows_pad = p.chunk;
+  } else {
+    int64_t r = kInitQChunkUmma / (static_cast<int64_t>(B) * W_up);
+    if (r >= 8) r -= r % 8;  // whole 8-row stage-B patches, so only the band's last chunk has a partial tile row
+    r = r < 1 ? 1 : (r > rows ? rows : r);
+    p.chunk_rows = static_cast<int>(r);
+    p.chunk = static_cast<int64_t>(B) * r * W_up;
+    p.rows_pad = (p.chunk + 255) / 256 * 256;  // M tile of the CTA-pair GEMM
+  }
+  const size_t el = fp32 ? sizeof(float) : sizeof(__nv_bfloat16);
+  p.off_S = off;
+  off += align_up(static_cast<size_t>(p.rows_pad) * kUnfold * el);
+  p.off_XG = off;
+  off += align_up(static_cast<size_t>(p.rows_pad) * kUnfold * el);
+  p.off_PX = off;
+  off += align_up(static_cast<size_t>(p.rows_pad) * kPCols * sizeof(float));
+  p.off_QS = off;
+  off += align_up(static_cast<size_t>(p.rows_pad) * kD * sizeof(float));
+  if (fp32) {
+    p.off_q0 = off;
+    off += align_up(static_cast<size_t>(p.chunk) * kD * sizeof(float));
+    p.off_q1 = off;
+    off += align_up(static_cast<size_t>(p.chunk) * kD * sizeof(float));
+  } else if (mode == 1 || mode == 2) {
+    p.off_chain = off;
+    off += align_up(lr_chain_scratch_bytes(p.chunk));
+  }
+  p.end = off;
+  return p;
+}
+
+int run_initq_fp32(Handle* h, const void* feat, int io_dtype, const PixelSource& src_in, const OutSpec& out, char* ws,
+                   const InitQPlan& pl, cudaStream_t s, float* q3_dump) {
+  const int64_t total = static_cast<int64_t>(src_in.B) * (src_in.row1 - src_in.row0) * src_in.W_up;
+  float* S = reinterpret_cast<float*>(ws + pl.off_S);
+  float* XG = reinterpret_cast<float*>(ws + pl.off_XG);
+  float* PX = reinterpret_cast<float*>(ws + pl.off_PX);
+  float* QS = reinterpret_cast<float*>(ws + pl.off_QS);
+  float* q0 = reinterpret_cast<float*>(ws + pl.off_q0);
+  float* q1 = reinterpret_cast<float*>(ws + pl.off_q1);
+  const bool chain = h->cfg.mode == 1 || h->cfg.mode == 2;
+  const FeatNCHW f{feat, io_dtype != DIINN_IO_F32};
+  const float4* wf4 = reinterpret_cast<const float4*>(h->WF4);
+  for (int64_t g0 = 0; g0 < total; g0 += pl.chunk) {
+    const int64_t g1 = g0 + pl.chunk < total ? g0 + pl.chunk : total;
+    const int64_t M = g1 - g0;
+    PixelSource src = src_in;
+    src.per_pixel_p = 1, src.p_base = g0;
+    initq_gate_kernel<FeatNCHW, float, false, false><<<capped_blocks(h, M), 192, 0, s>>>(src, f, wf4, S, XG, g0, g1, M);
+    const unsigned mb = static_cast<unsigned>((M + 63) / 64);
+    sgemm_nt_kernel<<<dim3(mb, kPCols / 64), 256, 0, s>>>(XG, h->WA32, PX, M, kUnfold, kPCols);
+    sgemm_nt_kernel<<<dim3(mb, kD / 64), 256, 0, s>>>(S, h->WQ0_32, QS, M, kUnfold, kD);
+    initq_assemble_kernel<false><<<capped_blocks(h, (M * (kPCols / 4) + 255) / 256), 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 1);
+    h->launches += 4;
+    DIINN_CUDA_OK(h, cudaGetLastError());
+    int rc;
+    if (chain && (rc = run_lr_chain_fp32(h, PX, M, s))) return rc;
+    initq_q0_fp32_kernel<<<capped_blocks(h, (M * kD + 255) / 256), 256, 0, s>>>(PX, QS, h->bq_dev, q0, M);
+    h->launches += 1;
+    if ((rc = run_layers_fp32(h, src, out, PX, q0, q1, g0, g1, s, q3_dump))) return rc;
+  }
+  DIINN_CUDA_OK(h, cudaGetLastError());
+  return DIINN_OK;
+}
+
+int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, const PixelSource& src_in, const OutSpec& out,
+                   char* ws, const InitQPlan& pl, bool f16acc, cudaStream_t s) {
+  __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S);
+  __nv_bfloat16* XG = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_XG);
+  float* PX = reinterpret_cast<float*>(ws + pl.off_PX);
+  float* QS = reinterpret_cast<float*>(ws + pl.off_QS);
+  const bool chain = h->cfg.mode == 1 || h->cfg.mode == 2;
+  const FeatNHWC f{nhwc, fr0, frows};
+  const float4* wf4 = reinterpret_cast<const float4*>(h->WF4);
+  for (int a = src_in.row0; a < src_in.row1; a += pl.chunk_rows) {
+    const int b = a + pl.chunk_rows < src_in.row1 ? a + pl.chunk_rows : src_in.row1;
+    const int64_t M = static_cast<int64_t>(src_in.B) * (b - a) * src_in.W_up;
+    const int64_t Mp = (M + 255) / 256 * 256;
+    PixelSource src = src_in;
+    src.row0 = a, src.row1 = b;
+    src.per_pixel_p = 1, src.p_base = 0, src.out_row0 = src_in.row0;
+    initq_gate_kernel<FeatNHWC, __nv_bfloat16, true, true><<<capped_blocks(h, Mp), 192, 0, s>>>(src, f, wf4, S, XG, 0, M, Mp);
+    h->launches += 1;
+    DIINN_CUDA_OK(h, cudaGetLastError());
+    int rc;
+    if ((rc = launch_umma_selftest(h, XG, h->WAg16, PX, static_cast<int>(Mp), kPCols, kUnfold, 2, s))) return rc;
+    if ((rc = launch_umma_selftest(h, S, h->WQ0g16, QS, static_cast<int>(Mp), kD, kUnfold, 2, s))) return rc;
+    const unsigned ab = capped_blocks(h, (M * (kPCols / 4) + 255) / 256);
+    if (chain) {
+      initq_assemble_kernel<true><<<ab, 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 1);
+      h->launches += 1;
+      if ((rc = run_lr_chain_umma(h, PX, M, ws + pl.off_chain, s))) return rc;
+      initq_assemble_kernel<true><<<ab, 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 2);
+    } else {
+      initq_assemble_kernel<true><<<ab, 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 3);
+    }
+    h->launches += 1;
+    DIINN_CUDA_OK(h, cudaGetLastError());
+    if ((rc = launch_stage_b_umma(h, src, out, PX, 0, f16acc, s))) return rc;
+  }
+  return DIINN_OK;
+}
+
+}  // namespace diinn

@@ -71,13 +71,26 @@ __global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB3
   }
 }
 
+// init_q=True, tensor path: row-major bf16 operands of the library GEMM with the K index in tap-major channel order
+// (k' = tap*64 + c  <-  reference k = c*9 + tap): rows [0,1024) from WA32 (the x-facing K blocks), then Q.0's 256 rows
+__global__ void pack_initq_kernel(const float* __restrict__ WA32, const float* __restrict__ q0w,
+                                  __nv_bfloat16* __restrict__ WAg16, __nv_bfloat16* __restrict__ WQ0g16) {
+  const int n = blockIdx.x;  // 0..1279
+  const float* src = n < kPCols ? WA32 + static_cast<size_t>(n) * kUnfold : q0w + static_cast<size_t>(n - kPCols) * kUnfold;
+  __nv_bfloat16* dst = n < kPCols ? WAg16 + static_cast<size_t>(n) * kUnfold : WQ0g16 + static_cast<size_t>(n - kPCols) * kUnfold;
+  for (int j = threadIdx.x; j < kUnfold; j += blockDim.x) dst[j] = __float2bfloat16_rn(src[(j & 63) * 9 + (j >> 6)]);
+}
+
 int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   RefPtrs r{};
   float* staging = nullptr;
   const int mode = h->cfg.mode;
+  const bool init_q = h->cfg.init_q != 0;
+  if (init_q && (!w->first_weight || !w->first_bias))
+    return fail(h, DIINN_ERR_BAD_ARG, "init_q=True needs first_weight (576,3) and first_bias (576) (diinn.py:48-51)");
   const size_t kw_i = mode == 1 ? 256 * 256 : 256 * 832;
   const size_t sizes_kw[4] = {256 * 576, kw_i, kw_i, kw_i};
-  const size_t sizes_qw[4] = {256 * 3, 256 * 256, 256 * 256, 256 * 256};
+  const size_t sizes_qw[4] = {static_cast<size_t>(init_q ? 256 * 576 : 256 * 3), 256 * 256, 256 * 256, 256 * 256};
   size_t total = 0;
   for (int i = 0; i < 4; ++i) total += sizes_kw[i] + sizes_qw[i] + 512;
   total += 9 * 3 * 256 + 4;
@@ -129,8 +142,14 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   const cudaMemcpyKind kind = w->on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
   for (int i = 0; i < 4; ++i)
     DIINN_CUDA_OK(h, cudaMemcpyAsync(sp.bq[i], w->q_bias[i], sizeof(float) * kD, kind, s));
-  static thread_local float tmp_q0[kD * 3];
-  DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_q0, w->q_weight[0], sizeof(float) * kD * 3, kind, s));
+  static thread_local float tmp_q0[kD * 3];  // init_q=True: Q.0 is (256,576) and layer 0 never reads wq0 (left zero)
+  if (init_q) memset(tmp_q0, 0, sizeof(tmp_q0));
+  else DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_q0, w->q_weight[0], sizeof(float) * kD * 3, kind, s));
+  static thread_local float tmp_wf[kUnfold * 3], tmp_bf[kUnfold];
+  if (init_q) {
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_wf, w->first_weight, sizeof(tmp_wf), kind, s));
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_bf, w->first_bias, sizeof(tmp_bf), kind, s));
+  }
   static thread_local float tmp_wl[9 * 3 * kD];
   DIINN_CUDA_OK(h, cudaMemcpyAsync(tmp_wl, w->last_weight, sizeof(float) * 3 * kD * (mode == 4 ? 9 : 1), kind, s));
   DIINN_CUDA_OK(h, cudaMemcpyAsync(sp.bl, w->last_bias, sizeof(float) * 3, kind, s));
@@ -151,6 +170,24 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   }
   for (int f = 0; f < kD; f += 2)
     for (int c = 0; c < 4; ++c) sp.wq0_p[f >> 1][c] = make_float2(sp.wq0[f][c], sp.wq0[f + 1][c]);
+  if (init_q) {
+    static thread_local float wf4[kUnfold * 4];
+    for (int k = 0; k < kUnfold; ++k) {
+      for (int c = 0; c < 3; ++c) wf4[k * 4 + c] = tmp_wf[k * 3 + c];
+      wf4[k * 4 + 3] = tmp_bf[k];
+    }
+    if (!h->WF4) {
+      DIINN_CUDA_OK(h, cudaMalloc(&h->WF4, sizeof(wf4)));
+      DIINN_CUDA_OK(h, cudaMalloc(&h->WQ0_32, sizeof(float) * kD * kUnfold));
+      DIINN_CUDA_OK(h, cudaMalloc(&h->WAg16, sizeof(__nv_bfloat16) * kPCols * kUnfold));
+      DIINN_CUDA_OK(h, cudaMalloc(&h->WQ0g16, sizeof(__nv_bfloat16) * kD * kUnfold));
+    }
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WF4, wf4, sizeof(wf4), cudaMemcpyHostToDevice, s));
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WQ0_32, r.qw[0], sizeof(float) * kD * kUnfold, cudaMemcpyDeviceToDevice, s));
+    pack_initq_kernel<<<kPCols + kD, 192, 0, s>>>(h->WA32, h->WQ0_32, h->WAg16, h->WQ0g16);
+    h->launches += 1;
+    DIINN_CUDA_OK(h, cudaGetLastError());
+  }
   if (mode == 4) {
     // (c, f, ky, kx) -> (tap = ky*3 + kx, f, c) padded to float4
     static thread_local float wl4[9 * kD * 4];

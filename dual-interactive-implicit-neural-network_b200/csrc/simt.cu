@@ -8,59 +8,9 @@
 //                               q_i = k_i * sin(Q_i q_{i-1} + bq_i)                               diinn.py:137
 //                               rgb = last q_3 + bl                                               diinn.py:138
 #include "handle.h"
+#include "pixel.cuh"
 
 namespace diinn {
-
-// ---------------------------------------------------------------------------------------------------------
-// per-pixel bookkeeping
-// ---------------------------------------------------------------------------------------------------------
-struct PixInfo {
-  int p_idx;  // row of P
-  float rel_h, rel_w, ratio;
-  float area;  // ensemble rows only: |rel_h * rel_w| + 1e-9
-  int b, oh, ow;  // grid: batch / HR row / HR col; query: b, q, unused
-};
-
-__device__ __forceinline__ PixInfo pixel_info(const PixelSource& s, int64_t g) {
-  PixInfo pi;
-  if (s.mode == 0) {
-    const int nrows = s.row1 - s.row0;
-    const int64_t per_img = static_cast<int64_t>(nrows) * s.W_up;
-    const int b = static_cast<int>(g / per_img);
-    const int rem = static_cast<int>(g - b * per_img);
-    const int oh = s.row0 + rem / s.W_up;
-    const int ow = rem % s.W_up;
-    const int ih = axis_index(s.ax_h, oh), iw = axis_index(s.ax_w, ow);
-    pi.p_idx = (b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw;
-    pi.rel_h = axis_rel(s.ax_h, oh, ih);
-    pi.rel_w = axis_rel(s.ax_w, ow, iw);
-    pi.ratio = s.ratio;
-    pi.b = b;
-    pi.oh = oh;
-    pi.ow = ow;
-  } else {
-    const int64_t q = s.ensemble ? (g >> 2) : g;  // query index in (B*Q)
-    const int v = static_cast<int>(g & 3);
-    const int b = static_cast<int>(q / s.Q);
-    const float ch = s.coord[q * 2], cw = s.coord[q * 2 + 1];
-    int ih, iw;
-    if (s.ensemble) {
-      ih = ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi);
-      iw = ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi);
-    } else {
-      ih = query_index(s.ax_h, ch), iw = query_index(s.ax_w, cw);
-    }
-    pi.p_idx = (b * s.H + ih) * s.W + iw;
-    pi.rel_h = query_rel(s.ax_h, ch, ih);
-    pi.rel_w = query_rel(s.ax_w, cw, iw);
-    pi.ratio = __fmul_rn(__fmul_rn(__fmul_rn(s.cell[q * 2], s.cell[q * 2 + 1]), s.hw_f), 0.25f);
-    pi.area = __fadd_rn(fabsf(__fmul_rn(pi.rel_h, pi.rel_w)), 1e-9f);
-    pi.b = b;
-    pi.oh = static_cast<int>(q - static_cast<int64_t>(b) * s.Q);
-    pi.ow = 0;
-  }
-  return pi;
-}
 
 __device__ __forceinline__ int64_t total_pixels(const PixelSource& s) {
   return s.mode == 0 ? static_cast<int64_t>(s.B) * (s.row1 - s.row0) * s.W_up
@@ -378,30 +328,40 @@ __global__ void __launch_bounds__(256) last_fp32_kernel(PixelSource src, OutSpec
   }
 }
 
+// layers 1..3 and the RGB projection (or mode 4's q_3 dump) for the pixels [g0,g1) whose q_0 sits in qbuf0
+int run_layers_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0, float* qbuf1,
+                    int64_t g0, int64_t g1, cudaStream_t s, float* q3_dump) {
+  const unsigned nblk = static_cast<unsigned>((g1 - g0 + 63) / 64);
+  const float* bq_dev = h->bq_dev;
+  float* qi = qbuf0;
+  float* qo = qbuf1;
+  for (int li = 1; li < kLayers; ++li) {
+    // mode 4: the last layer writes q_3 of the chunk's pixels straight into the dump (grid order = its pixel-major
+    // order); the 3x3 conv (csrc/mode4.cu) replaces last_fp32_kernel once every chunk is done
+    float* dst = (q3_dump != nullptr && li == kLayers - 1) ? q3_dump + static_cast<size_t>(g0) * kD : qo;
+    layer_fp32_kernel<<<dim3(nblk, kD / 32), 256, 0, s>>>(src, qi, h->WB32 + static_cast<size_t>(li - 1) * 512 * kD,
+                                                          bq_dev + li * kD, P, li * kD, dst, g0, g1);
+    float* t = qi;
+    qi = qo;
+    qo = t;
+  }
+  if (q3_dump == nullptr)
+    last_fp32_kernel<<<static_cast<unsigned>((g1 - g0 + 7) / 8), 256, 0, s>>>(src, out, h->small, qi, g0, g1);
+  h->launches += q3_dump == nullptr ? 4 : 3;
+  DIINN_CUDA_OK(h, cudaGetLastError());
+  return DIINN_OK;
+}
+
 int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,
                      float* qbuf1, int64_t chunk, cudaStream_t s, float* q3_dump) {
   const int64_t total = src.mode == 0 ? static_cast<int64_t>(src.B) * (src.row1 - src.row0) * src.W_up
                                       : static_cast<int64_t>(src.B) * src.Q * (src.ensemble ? 4 : 1);
-  const float* bq_dev = h->bq_dev;
   for (int64_t g0 = 0; g0 < total; g0 += chunk) {
     const int64_t g1 = g0 + chunk < total ? g0 + chunk : total;
-    const unsigned nblk = static_cast<unsigned>((g1 - g0 + 63) / 64);
-    layer0_fp32_kernel<<<nblk, 256, 0, s>>>(src, h->small, P, qbuf0, g0, g1);
-    float* qi = qbuf0;
-    float* qo = qbuf1;
-    for (int li = 1; li < kLayers; ++li) {
-      // mode 4: the last layer writes q_3 of the chunk's pixels straight into the dump (grid order = its pixel-major
-      // order); the 3x3 conv (csrc/mode4.cu) replaces last_fp32_kernel once every chunk is done
-      float* dst = (q3_dump != nullptr && li == kLayers - 1) ? q3_dump + static_cast<size_t>(g0) * kD : qo;
-      layer_fp32_kernel<<<dim3(nblk, kD / 32), 256, 0, s>>>(src, qi, h->WB32 + static_cast<size_t>(li - 1) * 512 * kD,
-                                                            bq_dev + li * kD, P, li * kD, dst, g0, g1);
-      float* t = qi;
-      qi = qo;
-      qo = t;
-    }
-    if (q3_dump == nullptr)
-      last_fp32_kernel<<<static_cast<unsigned>((g1 - g0 + 7) / 8), 256, 0, s>>>(src, out, h->small, qi, g0, g1);
-    h->launches += q3_dump == nullptr ? 5 : 4;
+    layer0_fp32_kernel<<<static_cast<unsigned>((g1 - g0 + 63) / 64), 256, 0, s>>>(src, h->small, P, qbuf0, g0, g1);
+    h->launches += 1;
+    int rc = run_layers_fp32(h, src, out, P, qbuf0, qbuf1, g0, g1, s, q3_dump);
+    if (rc) return rc;
   }
   DIINN_CUDA_OK(h, cudaGetLastError());
   return DIINN_OK;

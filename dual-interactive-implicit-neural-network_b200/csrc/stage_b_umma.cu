@@ -78,7 +78,9 @@ struct RowCtx {
   bool valid;
 };
 
-template <int CG>
+// kPix (init_q=True, csrc/init_q.cu): P holds one row per HR pixel of the launch's rows [row0,row1) -- pixel-major
+// (b, row, col) -- instead of one per LR cell, and the launch covers a chunk of the band whose first row is out_row0.
+template <int CG, bool kPix = false>
 __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& o, const float* __restrict__ P,
                                            const Work& wk, int work, int rank, int r) {
   RowCtx rc;
@@ -92,14 +94,17 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
     rc.valid = oh < s.row1 && ow < s.W_up;
     const int ohc = min(oh, s.row1 - 1), owc = min(ow, s.W_up - 1);
     const int ih = axis_index(s.ax_h, ohc), iw = axis_index(s.ax_w, owc);
-    rc.prow = P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw) * kPCols;
+    if constexpr (kPix)
+      rc.prow = P + (static_cast<size_t>(b * (s.row1 - s.row0) + (ohc - s.row0)) * s.W_up + owc) * kPCols;
+    else
+      rc.prow = P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw) * kPCols;
 #if DIINN_ABL & 1
     rc.prow = P;
 #endif
     rc.rel_h = axis_rel(s.ax_h, ohc, ih);
     rc.rel_w = axis_rel(s.ax_w, owc, iw);
     rc.ratio = s.ratio;
-    rc.out_off = b * o.batch_stride + static_cast<int64_t>(ohc - s.row0) * o.row_stride + owc;
+    rc.out_off = b * o.batch_stride + static_cast<int64_t>(ohc - (kPix ? s.out_row0 : s.row0)) * o.row_stride + owc;
   } else {
     const int64_t total = static_cast<int64_t>(s.B) * s.Q * (s.ensemble ? 4 : 1);
     const int64_t g = (static_cast<int64_t>(work) * CG + rank) * kTileM + r;
@@ -206,13 +211,20 @@ __device__ __forceinline__ float act_sin(float x) {
 }
 
 // layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
-template <bool F16>
+template <bool F16, bool kPix = false>
 __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
                                             const SmallParams& sp, const float4 (&k0v)[4]) {
   const uint32_t chunk_base = act_base + kc * kChunkBytes;
   const int f0 = kc * 64 + wg * 16;
   const float* k0 = reinterpret_cast<const float*>(k0v);
   uint32_t pk[8];
+  if constexpr (kPix) {  // init_q=True: Q.0 reads the 576-wide gate, so q_0 was finished per pixel by csrc/init_q.cu
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) pk[j >> 1] = F16 ? pack_f16x2(k0[j], k0[j + 1]) : pack_bf16x2(k0[j], k0[j + 1]);
+    st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
+    st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
+    return;
+  }
   const float2 rh = make_float2(rc.rel_h, rc.rel_h), rw = make_float2(rc.rel_w, rc.rel_w), ra = make_float2(rc.ratio, rc.ratio);
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
@@ -308,7 +320,8 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
 }
 
 // kDump (mode 4): a separate instantiation, so the q_3 dump costs the RGB-projecting kernels neither a register nor a branch.
-template <int CG, bool F16, bool kDump>
+// kPix (init_q=True): see make_row / layer0_step.
+template <int CG, bool F16, bool kDump, bool kPix>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SmallParams sp,
                     const __grid_constant__ PixelSource src, const __grid_constant__ OutSpec out,
@@ -367,9 +380,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   if (warp == 0) {
     // ===================== weight producer (+ L2 prefetch of upcoming tiles' P rows) =====================
     uint32_t it = 0;
-    if (unit_id + n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, unit_id + n_units, rank, lane);
+    // (kPix: the per-pixel P of the chunk was written by the kernels right before this one, nothing to pull ahead)
+    if constexpr (!kPix)
+      if (unit_id + n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, unit_id + n_units, rank, lane);
     for (int work = unit_id; work < wk.n_work; work += n_units) {
-      if (work + 2 * n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, work + 2 * n_units, rank, lane);
+      if constexpr (!kPix)
+        if (work + 2 * n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, work + 2 * n_units, rank, lane);
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
       // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues
@@ -479,12 +495,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       // (the P prefetch is issued AFTER the proxy fence: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
       // which waits for every outstanding global load of the thread -- a prefetch issued just before it exposes its
       // whole L2 latency in every step; measured)
-      layer0_step<F16>(buf, kc0, fg, r, rcx, sp, ka);
+      layer0_step<F16, kPix>(buf, kc0, fg, r, rcx, sp, ka);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
       if (nb) load16(nb, ka);
-      layer0_step<F16>(buf, kc0 + 1, fg, r, rcx, sp, kb);
+      layer0_step<F16, kPix>(buf, kc0 + 1, fg, r, rcx, sp, kb);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
@@ -492,7 +508,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     };
 
     if (work < wk.n_work) {
-      rc = make_row<CG>(src, out, P, wk, work, rank, r);
+      rc = make_row<CG, kPix>(src, out, P, wk, work, rank, r);
       const float* p0 = rc.prow + fg * 16;
       load16(p0, ka);
       load16(p0 + 64, kb);
@@ -516,7 +532,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const uint32_t out_base = act0 + bout * kActBytes;
         const bool last = layer == 3;
         if (layer == 2 && has_next) {
-          rc_next = make_row<CG>(src, out, P, wk, next_work, rank, r);
+          rc_next = make_row<CG, kPix>(src, out, P, wk, next_work, rank, r);
           pn = rc_next.prow + fg * 16;
         }
 #pragma unroll 1
@@ -636,19 +652,19 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
 }  // namespace sb
 
-template <int CG, bool F16, bool kDump = false>
+template <int CG, bool F16, bool kDump = false, bool kPix = false>
 static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const PixelSource& src,
                           const OutSpec& out, const float* P, const sb::Work& wk, int* err_flag, long long* trace) {
   using namespace sb;
-  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, F16, kDump>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, F16, kDump, kPix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kSmemBytes)));
   if (getenv("DIINN_DEBUG_OCC")) {
     int nc = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, F16, kDump>, cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, F16, kDump, kPix>, cfg);
     fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
             cudaGetErrorString(e));
   }
-  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, F16, kDump>, tm, h->small, src, out, P, wk, err_flag, trace));
+  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, F16, kDump, kPix>, tm, h->small, src, out, P, wk, err_flag, trace));
   return DIINN_OK;
 }
 
@@ -692,20 +708,20 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = h->pdl ? 2 : 1;
+  // instantiations: kDump = mode 4 (q_3 dumped instead of projected), kPix = init_q=True (per-pixel P, q_0 given)
+  const bool dump = out.q3 != nullptr, pix = src.per_pixel_p != 0;
+  if (pix && src.mode != 0) return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "per-pixel P is implemented for the HR grid only");
+  const CUtensorMap& tm = cta_group == 1 ? (f16acc ? h->tmapWBh : h->tmapWB) : (f16acc ? h->tmapWBh_half : h->tmapWB_half);
   int rc;
-  if (out.q3 != nullptr) {  // mode 4: the q_3-dumping instantiations
-    if (cta_group == 1)
-      rc = f16acc ? launch_variant<1, true, true>(h, &cfg, h->tmapWBh, src, out, P, wk, err_flag, trace)
-                  : launch_variant<1, false, true>(h, &cfg, h->tmapWB, src, out, P, wk, err_flag, trace);
-    else
-      rc = f16acc ? launch_variant<2, true, true>(h, &cfg, h->tmapWBh_half, src, out, P, wk, err_flag, trace)
-                  : launch_variant<2, false, true>(h, &cfg, h->tmapWB_half, src, out, P, wk, err_flag, trace);
-  } else if (cta_group == 1)
-    rc = f16acc ? launch_variant<1, true>(h, &cfg, h->tmapWBh, src, out, P, wk, err_flag, trace)
-                : launch_variant<1, false>(h, &cfg, h->tmapWB, src, out, P, wk, err_flag, trace);
-  else
-    rc = f16acc ? launch_variant<2, true>(h, &cfg, h->tmapWBh_half, src, out, P, wk, err_flag, trace)
-                : launch_variant<2, false>(h, &cfg, h->tmapWB_half, src, out, P, wk, err_flag, trace);
+#define DIINN_SB_LAUNCH(CGv, F16v, DUMPv, PIXv) \
+  launch_variant<CGv, F16v, DUMPv, PIXv>(h, &cfg, tm, src, out, P, wk, err_flag, trace)
+#define DIINN_SB_PICK(CGv, F16v)                                                                        \
+  (dump ? (pix ? DIINN_SB_LAUNCH(CGv, F16v, true, true) : DIINN_SB_LAUNCH(CGv, F16v, true, false))       \
+        : (pix ? DIINN_SB_LAUNCH(CGv, F16v, false, true) : DIINN_SB_LAUNCH(CGv, F16v, false, false)))
+  if (cta_group == 1) rc = f16acc ? DIINN_SB_PICK(1, true) : DIINN_SB_PICK(1, false);
+  else rc = f16acc ? DIINN_SB_PICK(2, true) : DIINN_SB_PICK(2, false);
+#undef DIINN_SB_PICK
+#undef DIINN_SB_LAUNCH
   if (rc) return rc;
   h->launches += 1;
   return DIINN_OK;

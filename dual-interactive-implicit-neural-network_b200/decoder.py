@@ -36,7 +36,8 @@ def _stream(device) -> C.c_void_p:
 
 
 class FusedImplicitDecoder(nn.Module):
-    """B200-native DIINN query decoder (modes 1-4, init_q=False; mode 3 is the paper's / the benchmarked wiring).
+    """B200-native DIINN query decoder (modes 1-4, init_q False or True; mode 3 with init_q=False is the paper's / the
+    benchmarked wiring).
 
     precision: "bf16" -> tcgen05 tensor cores, bf16 operands / fp32 accumulation (default throughput path);
                "fp16acc" -> stage B with fp16 operands and fp16 TMEM accumulators (faster epilogue, opt-in);
@@ -48,20 +49,23 @@ class FusedImplicitDecoder(nn.Module):
                  init_q: bool = False, precision: str = "bf16"):
         super().__init__()
         hidden_dims = list(hidden_dims)
-        if mode not in (1, 2, 3, 4) or init_q:
+        if mode not in (1, 2, 3, 4):
             raise NotImplementedError(
                 "FusedImplicitDecoder implements mode=3 (the paper's final model, diinn.py:73-80), the k-fed wirings "
                 "mode=1 / mode=2 (diinn.py:57-72) and mode=4 (mode 3 with a 3x3 reflect-padded last conv, diinn.py:81-90), "
-                "all with init_q=False; init_q=True is a SURVEY.md section 8(f) 'next' row")
+                "each with init_q=False or True; the reference defines no other mode")
         if in_channels != 64 or hidden_dims != [256] * 4:
             raise NotImplementedError("only in_channels=64, hidden_dims=[256]*4 is implemented")
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
-        self.mode, self.init_q, self.precision = mode, init_q, precision
-        # identical module tree (hence state_dict keys and default init / RNG consumption) to diinn.py:53-92
+        self.mode, self.init_q, self.precision = mode, bool(init_q), precision
+        # identical module tree (hence state_dict keys and default init / RNG consumption) to diinn.py:46-92
+        last_k, last_q = in_channels * 9, 3
+        if self.init_q:  # sine gate on the unfolded features; Q.0 then reads its 576 channels (diinn.py:48-51)
+            self.first_layer = nn.Sequential(nn.Conv2d(3, in_channels * 9, 1), SineAct())
+            last_q = in_channels * 9
         self.K = nn.ModuleList()
         self.Q = nn.ModuleList()
-        last_k, last_q = in_channels * 9, 3
         for hd in hidden_dims:
             self.K.append(nn.Sequential(nn.Conv2d(last_k, hd, 1), nn.ReLU()))
             self.Q.append(nn.Sequential(nn.Conv2d(last_q, hd, 1), SineAct()))
@@ -78,7 +82,10 @@ class FusedImplicitDecoder(nn.Module):
         ts = []
         for i in range(4):
             ts += [self.K[i][0].weight, self.K[i][0].bias, self.Q[i][0].weight, self.Q[i][0].bias]
-        return ts + [self.last_layer.weight, self.last_layer.bias]
+        ts += [self.last_layer.weight, self.last_layer.bias]
+        if self.init_q:
+            ts += [self.first_layer[0].weight, self.first_layer[0].bias]
+        return ts
 
     def _ensure_handle(self, device: torch.device):
         lib = _lib.load()
@@ -87,7 +94,7 @@ class FusedImplicitDecoder(nn.Module):
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if self._handle is None or self._handle_device != idx:
             self.release()
-            cfg = _lib.Config(64, 256, 4, self.mode, 0, idx)
+            cfg = _lib.Config(64, 256, 4, self.mode, int(self.init_q), idx)
             h = C.c_void_p()
             _lib.check(lib, None, lib.diinn_create(C.byref(h), C.byref(cfg)))
             self._handle, self._handle_device, self._packed_versions = h, idx, None
@@ -106,6 +113,8 @@ class FusedImplicitDecoder(nn.Module):
                 w.k_weight[i], w.k_bias[i] = ws[4 * i].data_ptr(), ws[4 * i + 1].data_ptr()
                 w.q_weight[i], w.q_bias[i] = ws[4 * i + 2].data_ptr(), ws[4 * i + 3].data_ptr()
             w.last_weight, w.last_bias, w.on_device = ws[16].data_ptr(), ws[17].data_ptr(), 1
+            if self.init_q:
+                w.first_weight, w.first_bias = ws[18].data_ptr(), ws[19].data_ptr()
             _lib.check(lib, self._handle, lib.diinn_set_weights(self._handle, C.byref(w), _stream(device)))
             self._packed_versions = versions
         return lib, self._handle
@@ -234,6 +243,8 @@ class FusedImplicitDecoder(nn.Module):
         self._check_input(feat)
         if self.mode == 4:
             raise NotImplementedError("mode 4's 3x3 last conv is defined on the HR grid only: use forward()")
+        if self.init_q:
+            raise NotImplementedError("init_q=True is implemented for the HR grid only: use forward()")
         lib, h = self._ensure_handle(feat.device)
         if not (self._is_nhwc_bf16(feat) and self.precision != "fp32"):
             feat = feat.contiguous()

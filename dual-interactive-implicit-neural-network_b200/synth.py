@@ -64,34 +64,42 @@ def weight_names(n_layers: int = N_LAYERS):
     return names
 
 
-def weight_shapes(in_channels: int = IN_CHANNELS, hidden: int = HIDDEN, n_layers: int = N_LAYERS, mode: int = 3):
-    """name -> shape, identical to the reference state_dict (mode 1: K.i takes k only, diinn.py:57-64)."""
+def weight_shapes(in_channels: int = IN_CHANNELS, hidden: int = HIDDEN, n_layers: int = N_LAYERS, mode: int = 3,
+                  init_q: bool = False):
+    """name -> shape, identical to the reference state_dict (SURVEY.md §3.4; mode 1: K.i takes k only, diinn.py:57-64;
+    init_q: first_layer = Conv2d(3, 576, 1) and a 576-wide Q.0, diinn.py:48-53). The first_layer entries come LAST so that
+    every other tensor keeps its random stream."""
     unfold = in_channels * 9
     shapes = {}
     for i in range(n_layers):
         kin = unfold if i == 0 else (hidden if mode == 1 else hidden + unfold)
-        qin = 3 if i == 0 else hidden
+        qin = (unfold if init_q else 3) if i == 0 else hidden
         shapes[f"K.{i}.0.weight"] = (hidden, kin, 1, 1)
         shapes[f"K.{i}.0.bias"] = (hidden,)
         shapes[f"Q.{i}.0.weight"] = (hidden, qin, 1, 1)
         shapes[f"Q.{i}.0.bias"] = (hidden,)
     shapes["last_layer.weight"] = (3, hidden, 3, 3) if mode == 4 else (3, hidden, 1, 1)   # diinn.py:89-92
     shapes["last_layer.bias"] = (3,)
+    if init_q:
+        shapes["first_layer.0.weight"] = (unfold, 3, 1, 1)
+        shapes["first_layer.0.bias"] = (unfold,)
     return shapes
 
 
-def make_weights(seed: int = 0, k_gain: float = 1.0, q_gain: float = 1.0, last_gain: float = 1.0, mode: int = 3):
+def make_weights(seed: int = 0, k_gain: float = 1.0, q_gain: float = 1.0, last_gain: float = 1.0, mode: int = 3,
+                 init_q: bool = False, first_gain: float = 1.0):
     """Reference-layout decoder weights as a dict of float32 numpy arrays.
 
     k_gain/q_gain > 1 give the "stress" set of SURVEY.md §4 item 8 (activations O(1) instead of being
     dominated by last_layer.bias)."""
     out = {}
-    shapes = weight_shapes(mode=mode)
+    shapes = weight_shapes(mode=mode, init_q=init_q)
     for s, (name, shape) in enumerate(shapes.items()):
         wshape = shape if len(shape) == 4 else shapes[name.replace("bias", "weight")]
         fan_in = wshape[1] * wshape[2] * wshape[3]
         bound = 1.0 / np.sqrt(float(fan_in))
-        gain = k_gain if name.startswith("K.") else q_gain if name.startswith("Q.") else last_gain
+        gain = (k_gain if name.startswith("K.") else q_gain if name.startswith("Q.") else
+                first_gain if name.startswith("first_layer") else last_gain)
         out[name] = uniform(seed, 100 + s, shape, -bound * gain, bound * gain)
     return out
 

@@ -36,7 +36,7 @@ typedef enum diinn_status {
   DIINN_ERR_BAD_ARG = -1,
   DIINN_ERR_BAD_SHAPE = -2,
   DIINN_ERR_BAD_DTYPE = -3,
-  DIINN_ERR_UNSUPPORTED_MODE = -4,   /* anything but mode in {1,2,3,4}, init_q=False, 64 channels, 4x256 hidden */
+  DIINN_ERR_UNSUPPORTED_MODE = -4,   /* anything but mode in {1,2,3,4}, init_q in {0,1}, 64 channels, 4x256 hidden */
   DIINN_ERR_WORKSPACE_TOO_SMALL = -5,
   DIINN_ERR_CUDA = -6,
   DIINN_ERR_NO_WEIGHTS = -7,
@@ -64,11 +64,12 @@ typedef struct diinn_config {
   int n_layers;    /* 4 */
   int mode;        /* 3 (paper / benchmark wiring); 1 / 2: K chain fed by k instead of q (diinn.py:57-72,116-131);
                       4: mode 3 with a 3x3 reflect-padded last conv over the HR grid (diinn.py:73-90,140-147) */
-  int init_q;      /* 0 */
+  int init_q;      /* 0, or 1: sine gate on the unfolded features, first_layer + 576-wide Q.0 (diinn.py:48-51,113-115);
+                      grid decode only (diinn_query* return DIINN_ERR_UNSUPPORTED_MODE) */
   int device;      /* CUDA device ordinal the handle lives on */
 } diinn_config;
 
-/* The 18 tensors of the reference state_dict, fp32, contiguous, reference layout:
+/* The 18 (init_q=True: 20) tensors of the reference state_dict, fp32, contiguous, reference layout:
  *   k_weight[0] (256,576)  k_weight[1..3] (256,832) [mode 1: (256,256)]  q_weight[0] (256,3)  q_weight[1..3] (256,256)
  *   *_bias (256)           last_weight (3,256) [mode 4: (3,256,3,3)]       last_bias (3)
  * on_device != 0: pointers are device pointers on the handle's device; otherwise host pointers. */
@@ -80,6 +81,10 @@ typedef struct diinn_weights_f32 {
   const float* last_weight;
   const float* last_bias;
   int on_device;
+  /* init_q=True only (NULL otherwise): first_layer = Conv2d(3, 576, 1) of diinn.py:48-51, weight (576,3), bias (576);
+   * q_weight[0] is then (256,576). */
+  const float* first_weight;
+  const float* first_bias;
 } diinn_weights_f32;
 
 /* ---- lifetime -------------------------------------------------------------------------------------- */

@@ -116,12 +116,16 @@ def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False
 
     k = relu(K0 x); q = k * sin(Q0 syn); for i in 1..3: k = relu(K_i [q,x]); q = k * sin(Q_i q);
     out = last(q).  1x1 Conv2d == per-pixel affine map.
-    mode 2 (diinn.py:124-131): K_i takes [k,x] instead of [q,x]; mode 1 (diinn.py:116-123): K_i takes k alone."""
+    mode 2 (diinn.py:124-131): K_i takes [k,x] instead of [q,x]; mode 1 (diinn.py:116-123): K_i takes k alone.
+    init_q=True is recognised by the presence of first_layer in `weights`."""
     dt = np.float64 if fp64 else F32
     x = x.astype(dt)
     syn = syn.astype(dt)
     W = {k: v.astype(dt) for k, v in weights.items()}
     n_layers = sum(1 for k in W if k.startswith("K.") and k.endswith("weight"))
+    if "first_layer.0.weight" in W:   # init_q=True (diinn.py:48-51,113-115): sine gate on x, Q.0 reads the gate
+        syn = np.sin(syn @ _w2d(W["first_layer.0.weight"]).T + W["first_layer.0.bias"])
+        x = syn * x
     k = np.maximum(x @ _w2d(W["K.0.0.weight"]).T + W["K.0.0.bias"], 0)
     q = k * np.sin(syn @ _w2d(W["Q.0.0.weight"]).T + W["Q.0.0.bias"])
     if taps is not None:

@@ -38,3 +38,8 @@ def golden_modes():
 @pytest.fixture(scope="session")
 def golden_mode4():
     return np.load(os.path.join(GOLDEN, "mode4.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_initq():
+    return np.load(os.path.join(GOLDEN, "initq.npz"))

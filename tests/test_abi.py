@@ -36,8 +36,8 @@ def test_version_and_create_errors_without_gpu():
     lib = _lib.load()
     assert b"sm_100a" in lib.diinn_version()
     h = ctypes.c_void_p()
-    for bad in (_lib.Config(64, 256, 4, 5, 0, 0), _lib.Config(64, 256, 4, 3, 1, 0)):  # no such mode / init_q: not implemented
-        assert lib.diinn_create(ctypes.byref(h), ctypes.byref(bad)) == -4
+    for bad in (_lib.Config(64, 256, 4, 5, 0, 0), _lib.Config(64, 256, 4, 3, 2, 0), _lib.Config(32, 256, 4, 3, 0, 0)):
+        assert lib.diinn_create(ctypes.byref(h), ctypes.byref(bad)) == -4   # no such mode / init_q flag / width
         assert b"mode in {1,2,3,4}" in lib.diinn_last_error(None)
     assert lib.diinn_set_bsize(None, 0) == -1
     if not torch.cuda.is_available():
@@ -74,19 +74,21 @@ def test_same_default_init_as_reference_layout():
 
 
 def test_unsupported_wirings_raise():
-    for kw in (dict(mode=5), dict(mode=4, init_q=True), dict(mode=3, init_q=True), dict(mode=1, init_q=True),
-               dict(mode=3, in_channels=32), dict(mode=3, hidden_dims=[128] * 4)):
+    for kw in (dict(mode=5), dict(mode=0, init_q=True), dict(mode=3, in_channels=32), dict(mode=3, hidden_dims=[128] * 4)):
         with pytest.raises(NotImplementedError):
             diinn_b200.FusedImplicitDecoder(**kw)
 
 
+@pytest.mark.parametrize("init_q", [False, True])
 @pytest.mark.parametrize("mode", [1, 2, 3, 4])
-def test_every_wiring_mirrors_the_reference_module_tree(mode):
-    """state_dict keys / shapes per mode as diinn.py:53-92 builds them (mode 1: K.i takes k alone; mode 4: 3x3 last conv),
-    and the workspace of a mode-4 decode holds the q_3 dump of the band plus its halo rows"""
-    dec = diinn_b200.FusedImplicitDecoder(mode=mode)
+def test_every_wiring_mirrors_the_reference_module_tree(mode, init_q):
+    """state_dict keys / shapes per (mode, init_q) as diinn.py:46-92 builds them (mode 1: K.i takes k alone; mode 4: 3x3
+    last conv; init_q: first_layer and a 576-wide Q.0), first_layer registered first like the reference"""
+    dec = diinn_b200.FusedImplicitDecoder(mode=mode, init_q=init_q)
     shapes = {k: tuple(v.shape) for k, v in dec.state_dict().items()}
-    assert shapes == synth.weight_shapes(mode=mode)
+    assert shapes == synth.weight_shapes(mode=mode, init_q=init_q)
+    assert shapes["Q.0.0.weight"] == ((256, 576, 1, 1) if init_q else (256, 3, 1, 1))
+    assert (list(shapes)[0] == "first_layer.0.weight") == init_q
     assert shapes["K.1.0.weight"] == ((256, 256, 1, 1) if mode == 1 else (256, 832, 1, 1))
     assert shapes["last_layer.weight"] == ((3, 256, 3, 3) if mode == 4 else (3, 256, 1, 1))
     if mode == 4:

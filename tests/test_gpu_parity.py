@@ -700,3 +700,63 @@ def test_mode4_contract_errors(golden_mode4):
     with pytest.raises(NotImplementedError):                 # the 3x3 conv needs the HR grid
         d.query(x, coord, cell)
     assert d(x, size, None).shape == (1, 3, H_up, W_up)      # the handle is still usable, bsize reset to None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# init_q=True: sine gate on the unfolded features, per-HR-pixel x-facing GEMMs (csrc/init_q.cu)
+# ---------------------------------------------------------------------------------------------------------
+INITQ_CASES = ([f"iq{m}.{n}" for n in ("small", "batch_bsize") for m in (1, 2, 3, 4)]
+               + ["iq3.c1", "iq2.stress", "iq3.stress"])
+
+
+def _initq_case(g, key):
+    mode, fseed, B, H, W, H_up, W_up, bsize = (int(v) for v in g[f"{key}.meta"])
+    kg, qg, fg = (float(v) for v in g[f"{key}.gains"])
+    w = synth.make_weights(seed=20 + mode, mode=mode, init_q=True, k_gain=kg, q_gain=qg, first_gain=fg)
+    dec = lambda precision: diinn_b200.load_numpy_weights(  # noqa: E731
+        diinn_b200.FusedImplicitDecoder(mode=mode, init_q=True, precision=precision), w).cuda()
+    return mode, w, dec, synth.make_feat(fseed, B, H, W), (H_up, W_up), (None if bsize < 0 else bsize), g[f"{key}.out"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("key", INITQ_CASES)
+def test_init_q_matches_reference(golden_initq, key, precision):
+    """against the outputs of the reference ImplicitDecoder(mode, init_q=True), every mode"""
+    mode, w, dec, feat, size, bsize, want = _initq_case(golden_initq, key)
+    got = dec(precision)(torch.from_numpy(feat).cuda(), size, bsize).cpu().numpy()
+    assert got.shape == want.shape
+    err = float(np.abs(got - want).max())
+    assert err <= TOL[precision], (key, precision, err)
+    if not key.endswith("stress"):
+        assert err <= TIGHT[precision], (key, precision, err)
+        assert _psnr_delta(got, want) < 0.01
+
+
+@pytest.mark.parametrize("mode", [2, 3, 4])
+def test_init_q_row_tiles_chunks_and_io(golden_initq, mode):
+    """row tiles and the host entry are bit-identical to the full decode; a decode spanning several tensor-path chunks
+    (c2x2-sized output) agrees with the fp32 path; bf16 / channels-last feature maps; fp16acc; the fp64 oracle"""
+    _, w, dec, feat, size, _, want = _initq_case(golden_initq, f"iq{mode}.small")
+    x = torch.from_numpy(feat).cuda()
+    H_up = size[0]
+    for precision in ("bf16", "fp32"):
+        d = dec(precision)
+        full = d(x, size)
+        tiles = torch.cat([d.forward_rows(x, size, a, b) for a, b in ((0, 19), (19, 50), (50, H_up))], dim=2)
+        assert torch.equal(tiles, full), precision
+        assert torch.equal(d.decode_host(x.cpu().pin_memory(), size), full.cpu())
+    ref64 = orc.decoder_forward(w, feat, size, fp64=True, mode=mode)
+    assert float(np.abs(dec("fp32")(x, size).cpu().numpy() - ref64).max()) <= 2e-6
+    assert float(np.abs(dec("fp16acc")(x, size).cpu().numpy() - want).max()) <= TIGHT["fp16acc"]
+    d = dec("bf16")
+    x16 = x.bfloat16()
+    y16 = d(x16, size)
+    assert y16.dtype == torch.bfloat16 and float((y16.float().cpu() - torch.from_numpy(want)).abs().max()) <= 1e-3
+    assert torch.equal(d(x16.contiguous(memory_format=torch.channels_last), size), y16)
+    # several chunks (tensor path: 37 888 pixels each; fp32 path: 32 768)
+    big = torch.from_numpy(synth.make_feat(77, 1, 64, 64)).cuda()
+    a, b = d(big, (300, 400)), dec("fp32")(big, (300, 400))
+    assert float((a - b).abs().max()) <= TIGHT["bf16"]
+    coord, cell = (torch.from_numpy(v).cuda() for v in synth.make_query(3, 1, 64))
+    with pytest.raises(NotImplementedError):
+        d.query(x, coord, cell)

@@ -194,3 +194,31 @@ def test_mode4_bsize_changes_the_result_and_bands_do_not(golden_mode4):
     assert float(np.abs(whole[..., interior] - want[..., interior]).max()) <= 2e-6
     band = orc.decoder_forward(w, feat, size, rows=(7, 19), mode=4, bsize=bsize)
     assert np.array_equal(band, orc.decoder_forward(w, feat, size, mode=4, bsize=bsize)[:, :, 7:19])
+
+
+# ---- init_q=True: fixtures produced by the reference ImplicitDecoder(mode=1..4, init_q=True)
+INITQ_CASES = ([f"iq{m}.{n}" for n in ("small", "batch_bsize") for m in (1, 2, 3, 4)]
+               + ["iq3.c1", "iq2.stress", "iq3.stress"])
+
+
+def _initq_case(g, key):
+    mode, fseed, B, H, W, H_up, W_up, bsize = (int(v) for v in g[f"{key}.meta"])
+    kg, qg, fg = (float(v) for v in g[f"{key}.gains"])
+    w = synth.make_weights(seed=20 + mode, mode=mode, init_q=True, k_gain=kg, q_gain=qg, first_gain=fg)
+    return mode, w, synth.make_feat(fseed, B, H, W), (H_up, W_up), (None if bsize < 0 else bsize), g[f"{key}.out"]
+
+
+@pytest.mark.parametrize("key", INITQ_CASES)
+def test_init_q_matches_reference(golden_initq, key):
+    mode, w, feat, size, bsize, want = _initq_case(golden_initq, key)
+    assert w["Q.0.0.weight"].shape == (256, 576, 1, 1) and w["first_layer.0.weight"].shape == (576, 3, 1, 1)
+    got = orc.decoder_forward(w, feat, size, mode=mode, bsize=bsize)
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) <= (2e-6 if not key.endswith("stress") else 2e-5)
+
+
+def test_init_q_weights_leave_the_other_streams_alone():
+    """synth appends first_layer last: every tensor shared with init_q=False keeps its values (Q.0 changes fan-in)"""
+    a, b = synth.make_weights(seed=3, mode=3), synth.make_weights(seed=3, mode=3, init_q=True)
+    assert set(b) - set(a) == {"first_layer.0.weight", "first_layer.0.bias"}
+    assert all(np.array_equal(a[k], b[k]) for k in a if not k.startswith("Q.0.0."))
