@@ -22,7 +22,7 @@ inline int host_axis_index(const AxisParams& p, int j) {
 struct DecodePlan {
   int lr_row0 = 0, lr_rows = 0;  // LR rows P must hold
   int fr0 = 0, frows = 0;        // LR rows (with +-1 halo, clipped) of the NHWC bf16 copy
-  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, off_chain = 0, off_q3 = 0, total = 0;
+  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, off_chain = 0, off_q3 = 0, off_T = 0, total = 0;
   InitQPlan iq;                  // init_q=True: replaces P / the activation chunks / the chain scratch
   int qr0 = 0, qr1 = 0;          // mode 4: HR rows whose q_3 is dumped (the band +- 1 halo row, clipped to the image)
   int64_t chunk = 0;
@@ -76,6 +76,10 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
     p.off_q3 = off;
     off += align_up(static_cast<size_t>(B) * (p.qr1 - p.qr0) * W_up * kD *
                     (compute == DIINN_COMPUTE_FP32 ? sizeof(float) : sizeof(__nv_bfloat16)));
+    if (compute != DIINN_COMPUTE_FP32) {  // the 27 (tap, channel) projections of every dumped pixel, planar fp32
+      p.off_T = off;
+      off += align_up(static_cast<size_t>(B) * (p.qr1 - p.qr0) * W_up * 27 * sizeof(float));
+    }
   }
   p.total = off;
   return p;
@@ -240,6 +244,7 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->trace_dev);
   cudaFree(h->WH32);
   cudaFree(h->WL4);
+  cudaFree(h->WL27frag);
   cudaFree(h->WF4);
   cudaFree(h->WQ0_32);
   cudaFree(h->WAg16);
@@ -392,6 +397,9 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
       return fail(h, DIINN_ERR_BAD_SHAPE, "bsize leaves a column strip of width 1, which reflect padding rejects");
   }
   auto last_conv = [&](const void* q3, bool is_f32) {
+    if (!is_f32)
+      return launch_last_conv_umma_path(h, static_cast<const __nv_bfloat16*>(q3), reinterpret_cast<float*>(ws + plan.off_T), B,
+                                        H_up, W_up, strip, plan.qr0, plan.qr1 - plan.qr0, row0, row1, o, s);
     return launch_last_conv3x3(h, q3, is_f32, B, H_up, W_up, strip, plan.qr0, plan.qr1 - plan.qr0, row0, row1, o, s);
   };
 

@@ -46,6 +46,8 @@ struct Handle {
   float* WH32 = nullptr;          // (3, 256, 256)
   __nv_bfloat16* WH16 = nullptr;  // (3, 256, 256)
   float* WL4 = nullptr;           // mode 4: last_layer.weight as (9 taps, 256, 4) fp32 = (Wl[0], Wl[1], Wl[2], 0) per (tap, f)
+  uint32_t* WL27frag = nullptr;   // mode 4, tensor path: the same weights as mma.sync B fragments, (4 kb, 4 s, 8 n tiles, 32
+                                  // lanes) x uint2, bf16 hi (tiles 0..3) + lo (tiles 4..7) parts (csrc/mode4.cu)
   // init_q=True (csrc/init_q.cu): first_layer as (576, 4) fp32 = (w_relh, w_relw, w_ratio, bias) per unfolded channel,
   // Q.0 (256, 576) in the reference's channel order (fp32 path), and the tensor path's row-major bf16 operands in tap-major
   // channel order (k' = tap*64 + c): the x-facing K blocks (1024, 576) and Q.0 (256, 576)
@@ -109,6 +111,9 @@ int run_lr_chain_fp32(Handle* h, float* P, int64_t M, cudaStream_t s);
 int run_lr_chain_umma(Handle* h, float* P, int64_t M, void* scratch, cudaStream_t s);
 size_t lr_chain_scratch_bytes(int64_t M);
 // mode 4: 3x3 reflect-padded last conv over the dumped q_3 (csrc/mode4.cu)
+// tensor path: (pixels x 256) x (256 x 27) projection on mma.sync, then the 9-tap gather; T = (27, B*qrows*W_up) fp32 scratch
+int launch_last_conv_umma_path(Handle* h, const __nv_bfloat16* q3, float* T, int B, int H_up, int W_up, int strip, int qr0,
+                               int qrows, int row0, int row1, const OutSpec& out, cudaStream_t s);
 int launch_last_conv3x3(Handle* h, const void* q3, bool q3_is_f32, int B, int H_up, int W_up, int strip, int qr0, int qrows,
                         int row0, int row1, const OutSpec& out, cudaStream_t s);
 int run_stage_b_fp32(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, float* qbuf0,

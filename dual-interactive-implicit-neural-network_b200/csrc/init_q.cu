@@ -8,7 +8,7 @@
 //   gate     S  = s_p,  XG = s_p * x_l(p)                          (chunk x 576 each; x gathered with the nearest-exact
 //                                                                   index, zero-padded 3x3 neighbourhood)
 //   GEMM     PX = XG . WA^T   (chunk x 1024: the x-facing blocks of K.0..3)      QS = S . Q0^T   (chunk x 256)
-//   assemble PX += bk;  PX[:, :256] = relu(.) = k_0
+//   assemble PX += bk;  PX[:, :256] = relu(.) = k_0        (tensor path: fused into the GEMM's epilogue, with q_0 below)
 //   (modes 1 / 2: the k-fed chain of csrc/lr_chain.cu, now over HR pixels:  PX_i += WH_i . relu(PX_{i-1}))
 //   q_0      PX[:, :256] *= sin(QS + bq_0)
 //   stage B  layers 1..3 and the last layer exactly as without init_q, reading ONE PX ROW PER PIXEL (kPix variants of
@@ -27,7 +27,7 @@ constexpr int64_t kInitQChunkUmma = 148 * 128 * 2;  // HR pixels per tensor-path
 constexpr int64_t kInitQChunkFp32 = 1 << 15;        // HR pixels per fp32-path chunk
 
 // ---------------------------------------------------------------------------------------------------------
-// gate: one CTA (192 threads, 3 channels each) per pixel. Column j of S / XG is unfolded channel
+// gate: 192 threads, 3 channels each, 32 pixels per batch. Column j of S / XG is unfolded channel
 //   kTapMajor ? (tap = j / 64, c = j % 64) : (c = j / 9, tap = j % 9)        -- reference channel index k = c*9 + tap.
 // Rows [g1 - g0, rows_pad) are zero-filled (padding up to the GEMM's M tile).
 // ---------------------------------------------------------------------------------------------------------
@@ -54,31 +54,53 @@ template <typename Feat, typename TO, bool kTapMajor, bool kFastSin>
 __global__ void __launch_bounds__(192) initq_gate_kernel(PixelSource src, Feat feat, const float4* __restrict__ wf4,
                                                          TO* __restrict__ S, TO* __restrict__ XG, int64_t g0, int64_t g1,
                                                          int64_t rows_pad) {
-  for (int64_t row = blockIdx.x; row < rows_pad; row += gridDim.x) {
-    TO* srow = S + row * kUnfold;
-    TO* xrow = XG + row * kUnfold;
-    const int64_t g = g0 + row;
-    if (g >= g1) {
-      for (int j = threadIdx.x; j < kUnfold; j += 192) store_gate(srow + j, 0.f), store_gate(xrow + j, 0.f);
-      continue;
-    }
-    const PixInfo pi = pixel_info(src, g);
+  // batches of 32 rows: the first warp works out the 32 pixels' bookkeeping (index divisions, nearest-exact cell, relative
+  // coordinates), then every thread runs its three channels -- first_layer rows held in registers -- over the batch
+  __shared__ float s_syn[32][3];
+  __shared__ int s_loc[32][3];  // batch image, LR row, LR col
+  int c[3], dh[3], dw[3];
+  float4 w[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int j = threadIdx.x + 192 * i;
-      const int c = kTapMajor ? (j & 63) : j / 9;
-      const int tap = kTapMajor ? (j >> 6) : j % 9;
-      const float4 w = __ldg(wf4 + c * 9 + tap);
-      // same accumulation order as layer 0 of the init_q=False path: a 3-term dot product, then the bias
-      float t = __fmul_rn(w.x, pi.rel_h);
-      t = fmaf(w.y, pi.rel_w, t);
-      t = fmaf(w.z, pi.ratio, t);
-      t += w.w;
-      const float sv = kFastSin ? __sinf(t) : sinf(t);
-      const int hh = pi.ih + tap / 3 - 1, ww = pi.iw + tap % 3 - 1;
-      const float xv = (hh >= 0 && hh < src.H && ww >= 0 && ww < src.W) ? feat.at(pi.b, c, hh, ww, src.H, src.W) : 0.f;
-      store_gate(srow + j, sv);
-      store_gate(xrow + j, sv * xv);
+  for (int i = 0; i < 3; ++i) {
+    const int j = threadIdx.x + 192 * i;
+    c[i] = kTapMajor ? (j & 63) : j / 9;
+    const int tap = kTapMajor ? (j >> 6) : j % 9;
+    dh[i] = tap / 3 - 1, dw[i] = tap % 3 - 1;
+    w[i] = __ldg(wf4 + c[i] * 9 + tap);
+  }
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * 32; base < rows_pad; base += static_cast<int64_t>(gridDim.x) * 32) {
+    __syncthreads();  // the previous batch has been consumed
+    if (threadIdx.x < 32 && g0 + base + threadIdx.x < g1) {
+      const PixInfo pi = pixel_info(src, g0 + base + threadIdx.x);
+      s_syn[threadIdx.x][0] = pi.rel_h, s_syn[threadIdx.x][1] = pi.rel_w, s_syn[threadIdx.x][2] = pi.ratio;
+      s_loc[threadIdx.x][0] = pi.b, s_loc[threadIdx.x][1] = pi.ih, s_loc[threadIdx.x][2] = pi.iw;
+    }
+    __syncthreads();
+    const int n = static_cast<int>(rows_pad - base < 32 ? rows_pad - base : 32);
+    for (int r = 0; r < n; ++r) {
+      const int64_t row = base + r;
+      TO* srow = S + row * kUnfold;
+      TO* xrow = XG + row * kUnfold;
+      if (g0 + row >= g1) {  // padding up to the GEMM's M tile
+#pragma unroll
+        for (int i = 0; i < 3; ++i) store_gate(srow + threadIdx.x + 192 * i, 0.f), store_gate(xrow + threadIdx.x + 192 * i, 0.f);
+        continue;
+      }
+      const float rel_h = s_syn[r][0], rel_w = s_syn[r][1], ratio = s_syn[r][2];
+      const int b = s_loc[r][0], ih = s_loc[r][1], iw = s_loc[r][2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        // same accumulation order as layer 0 of the init_q=False path: a 3-term dot product, then the bias
+        float t = __fmul_rn(w[i].x, rel_h);
+        t = fmaf(w[i].y, rel_w, t);
+        t = fmaf(w[i].z, ratio, t);
+        t += w[i].w;
+        const float sv = kFastSin ? __sinf(t) : sinf(t);
+        const int hh = ih + dh[i], ww = iw + dw[i];
+        const float xv = (hh >= 0 && hh < src.H && ww >= 0 && ww < src.W) ? feat.at(b, c[i], hh, ww, src.H, src.W) : 0.f;
+        store_gate(srow + threadIdx.x + 192 * i, sv);
+        store_gate(xrow + threadIdx.x + 192 * i, sv * xv);
+      }
     }
   }
 }
@@ -230,7 +252,7 @@ int run_initq_fp32(Handle* h, const void* feat, int io_dtype, const PixelSource&
     const int64_t M = g1 - g0;
     PixelSource src = src_in;
     src.per_pixel_p = 1, src.p_base = g0;
-    initq_gate_kernel<FeatNCHW, float, false, false><<<capped_blocks(h, M), 192, 0, s>>>(src, f, wf4, S, XG, g0, g1, M);
+    initq_gate_kernel<FeatNCHW, float, false, false><<<capped_blocks(h, (M + 31) / 32), 192, 0, s>>>(src, f, wf4, S, XG, g0, g1, M);
     const unsigned mb = static_cast<unsigned>((M + 63) / 64);
     sgemm_nt_kernel<<<dim3(mb, kPCols / 64), 256, 0, s>>>(XG, h->WA32, PX, M, kUnfold, kPCols);
     sgemm_nt_kernel<<<dim3(mb, kD / 64), 256, 0, s>>>(S, h->WQ0_32, QS, M, kUnfold, kD);
@@ -263,23 +285,23 @@ int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, con
     PixelSource src = src_in;
     src.row0 = a, src.row1 = b;
     src.per_pixel_p = 1, src.p_base = 0, src.out_row0 = src_in.row0;
-    initq_gate_kernel<FeatNHWC, __nv_bfloat16, true, true><<<capped_blocks(h, Mp), 192, 0, s>>>(src, f, wf4, S, XG, 0, M, Mp);
+    initq_gate_kernel<FeatNHWC, __nv_bfloat16, true, true><<<capped_blocks(h, (Mp + 31) / 32), 192, 0, s>>>(src, f, wf4, S, XG, 0, M, Mp);
     h->launches += 1;
     DIINN_CUDA_OK(h, cudaGetLastError());
     int rc;
-    if ((rc = launch_umma_selftest(h, XG, h->WAg16, PX, static_cast<int>(Mp), kPCols, kUnfold, 2, s))) return rc;
+    // QS first: the big GEMM's epilogue finishes PX in registers -- bias, ReLU on block 0 and (modes 3 / 4) the q_0
+    // product with sin(QS + bq_0) -- so PX is written once and never re-read before stage B
     if ((rc = launch_umma_selftest(h, S, h->WQ0g16, QS, static_cast<int>(Mp), kD, kUnfold, 2, s))) return rc;
-    const unsigned ab = capped_blocks(h, (M * (kPCols / 4) + 255) / 256);
-    if (chain) {
-      initq_assemble_kernel<true><<<ab, 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 1);
-      h->launches += 1;
+    ChainEpilogue ce{};
+    ce.add_bias = h->bA, ce.relu_cols = kD;
+    if (!chain) ce.q0_arg = QS, ce.q0_bias = h->bq_dev;
+    if ((rc = launch_umma_selftest(h, XG, h->WAg16, PX, static_cast<int>(Mp), kPCols, kUnfold, 2, s, &ce))) return rc;
+    if (chain) {  // modes 1 / 2: q_0 only once the k-fed chain has read k_0
       if ((rc = run_lr_chain_umma(h, PX, M, ws + pl.off_chain, s))) return rc;
-      initq_assemble_kernel<true><<<ab, 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 2);
-    } else {
-      initq_assemble_kernel<true><<<ab, 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 3);
+      initq_assemble_kernel<true><<<capped_blocks(h, (M * (kPCols / 4) + 255) / 256), 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 2);
+      h->launches += 1;
+      DIINN_CUDA_OK(h, cudaGetLastError());
     }
-    h->launches += 1;
-    DIINN_CUDA_OK(h, cudaGetLastError());
     if ((rc = launch_stage_b_umma(h, src, out, PX, 0, f16acc, s))) return rc;
   }
   return DIINN_OK;

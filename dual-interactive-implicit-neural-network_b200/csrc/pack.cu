@@ -198,6 +198,41 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
       }
     if (!h->WL4) DIINN_CUDA_OK(h, cudaMalloc(&h->WL4, sizeof(wl4)));
     DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WL4, wl4, sizeof(wl4), cudaMemcpyHostToDevice, s));
+    // tensor path: W27[n = tap*3 + c][f] as mma.sync.m16n8k16 B fragments in the K permutation of last_conv_project_kernel
+    auto bf16_bits = [](float v) -> uint32_t {  // round to nearest even (the weights are finite)
+      uint32_t u;
+      memcpy(&u, &v, 4);
+      return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+    };
+    auto bf16_val = [](uint32_t b) -> float {
+      const uint32_t u = b << 16;
+      float v;
+      memcpy(&v, &u, 4);
+      return v;
+    };
+    static thread_local uint32_t frag[4 * 4 * 8 * 32 * 2];
+    for (int kb = 0; kb < 4; ++kb)
+      for (int st = 0; st < 4; ++st)
+        for (int j = 0; j < 8; ++j)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3;
+            const int n = 8 * (j & 3) + g;  // output column tap*3 + c; columns 27..31 are padding
+            uint32_t regs[2];
+            for (int half = 0; half < 2; ++half) {
+              const int f = kb * 64 + half * 32 + t * 8 + 2 * st;
+              uint32_t pk[2];
+              for (int e = 0; e < 2; ++e) {
+                const float wv = n < 27 ? tmp_wl[((n % 3) * kD + f + e) * 9 + n / 3] : 0.f;
+                const uint32_t hi = bf16_bits(wv);
+                pk[e] = j < 4 ? hi : bf16_bits(wv - bf16_val(hi));
+              }
+              regs[half] = pk[0] | (pk[1] << 16);
+            }
+            uint32_t* dst = frag + ((((kb * 4 + st) * 8 + j) * 32) + lane) * 2;
+            dst[0] = regs[0], dst[1] = regs[1];
+          }
+    if (!h->WL27frag) DIINN_CUDA_OK(h, cudaMalloc(&h->WL27frag, sizeof(frag)));
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WL27frag, frag, sizeof(frag), cudaMemcpyHostToDevice, s));
   }
   DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bq_dev, sp.bq, sizeof(float) * kLayers * kD, cudaMemcpyHostToDevice, s));
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));

@@ -149,9 +149,22 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tmem_ld_wait();
       if (row < M) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(drow + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 16; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (ce.add_bias != nullptr) {  // init_q=True: the per-pixel pre-activations are finished here (warp-uniform)
+            const int n = n0 + c0 + j;
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ce.add_bias + n));
+            o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
+            if (n < ce.relu_cols) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            if (ce.q0_arg != nullptr && n < kD) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(ce.q0_arg + static_cast<size_t>(row) * kD + n));
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(ce.q0_bias + n));
+              o.x *= __sinf(t.x + bq.x), o.y *= __sinf(t.y + bq.y), o.z *= __sinf(t.z + bq.z), o.w *= __sinf(t.w + bq.w);
+            }
+          }
+          *reinterpret_cast<float4*>(drow + c0 + j) = o;
+        }
       }
     }
   }
