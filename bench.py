@@ -342,6 +342,30 @@ def main():
                 del x
         dec._workspace = None
         torch.cuda.empty_cache()
+        # the other decoder wirings of the reference constructor on the headline shape (informative; parity in tests/)
+        with torch.no_grad():
+            b, h, w, hu, wu = synth.CONFIGS[args.workload]
+            x = torch.from_numpy(synth.make_feat(1, b, h, w)).to(dev)
+            for mode, init_q in ((1, False), (2, False), (4, False), (3, True)):
+                d2 = diinn_b200.load_numpy_weights(
+                    diinn_b200.FusedImplicitDecoder(mode=mode, init_q=init_q, precision=args.precision),
+                    synth.make_weights(seed=0, mode=mode, init_q=init_q)).to(dev)
+                for _ in range(2):
+                    d2(x, (hu, wu))
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                n_it = 3
+                for _ in range(n_it):
+                    d2(x, (hu, wu))
+                a1.record()
+                torch.cuda.synchronize()
+                ms = a0.elapsed_time(a1) / n_it
+                extra[f"{args.workload}_mode{mode}_init_q{int(init_q)}"] = {"ms": round(ms, 4), "px_per_s": b * hu * wu / ms * 1e3}
+                d2.release()
+                del d2
+            del x
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:

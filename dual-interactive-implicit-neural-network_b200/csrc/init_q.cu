@@ -18,6 +18,8 @@
 // (tap*64 + c, so the gate reads whole 128-byte channel vectors of the NHWC feature copy), the library's tcgen05 GEMM
 // (umma_selftest.cu), fp32 PX / QS. Executed arithmetic: 2 264 064 FLOP per HR pixel (nothing is shared between pixels).
 // Correct and on the tensor cores, not tuned: PX / XG / S round-trip through L2 / HBM (about 10 KB per pixel).
+#include <cstdlib>
+
 #include "handle.h"
 #include "pixel.cuh"
 
@@ -206,7 +208,12 @@ InitQPlan plan_initq(int B, int W_up, int rows, int compute, int mode, size_t of
     p.chunk = total < kInitQChunkFp32 ? total : kInitQChunkFp32;
     p.rows_pad = p.chunk;
   } else {
-    int64_t r = kInitQChunkUmma / (static_cast<int64_t>(B) * W_up);
+    static int64_t chunk_px = 0;  // DIINN_INITQ_CHUNK=<pixels>: measurement override
+    if (chunk_px == 0) {
+      const char* e = getenv("DIINN_INITQ_CHUNK");
+      chunk_px = (e && atoll(e) > 0) ? atoll(e) : kInitQChunkUmma;
+    }
+    int64_t r = chunk_px / (static_cast<int64_t>(B) * W_up);
     if (r >= 8) r -= r % 8;  // whole 8-row stage-B patches, so only the band's last chunk has a partial tile row
     r = r < 1 ? 1 : (r > rows ? rows : r);
     p.chunk_rows = static_cast<int>(r);

@@ -172,6 +172,26 @@ __device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const f
   }
 }
 
+// kPix (init_q=True): the tile's own P rows -- 16 consecutive pixels x 4 KB per patch row -- in 16 KB pieces, one per lane
+template <int CG>
+__device__ __forceinline__ void prefetch_tile_pixels(const PixelSource& s, const float* __restrict__ P, const Work& wk,
+                                                     int work, int rank, int lane) {
+  const int per_img = wk.tiles_y * wk.n_txp;
+  const int b = work / per_img;
+  const int rem = work - b * per_img;
+  const int ty = rem / wk.n_txp, txp = rem - ty * wk.n_txp;
+  const int oh0 = s.row0 + ty * kPatchH, ow0 = (txp * CG + rank) * kPatchW;
+  if (ow0 >= s.W_up) return;
+  const int nrows = min(kPatchH, s.row1 - oh0), ncols = min(kPatchW, s.W_up - ow0);
+  const int segs = (ncols + 3) >> 2;
+  for (int i = lane; i < nrows * segs; i += 32) {
+    const int r = i / segs, c0 = (i % segs) * 4;
+    const int nc = min(4, ncols - c0);
+    prefetch_l2_bulk(P + (static_cast<size_t>(b * (s.row1 - s.row0) + (oh0 + r - s.row0)) * s.W_up + ow0 + c0) * kPCols,
+                     static_cast<uint32_t>(nc) * kPCols * 4u);
+  }
+}
+
 // 16-byte unit `unit` (0..7) of row r inside a [128 x 128 B] SWIZZLE_128B chunk
 __device__ __forceinline__ uint32_t swz(uint32_t chunk_base, int r, int unit) {
   return chunk_base + r * 128 + ((unit ^ (r & 7)) << 4);
@@ -380,12 +400,13 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   if (warp == 0) {
     // ===================== weight producer (+ L2 prefetch of upcoming tiles' P rows) =====================
     uint32_t it = 0;
-    // (kPix: the per-pixel P of the chunk was written by the kernels right before this one, nothing to pull ahead)
-    if constexpr (!kPix)
-      if (unit_id + n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, unit_id + n_units, rank, lane);
+    auto prefetch = [&](int w_) {
+      if constexpr (kPix) prefetch_tile_pixels<CG>(src, P, wk, w_, rank, lane);
+      else prefetch_tile_rows<CG>(src, P, wk, w_, rank, lane);
+    };
+    if (unit_id + n_units < wk.n_work) prefetch(unit_id + n_units);
     for (int work = unit_id; work < wk.n_work; work += n_units) {
-      if constexpr (!kPix)
-        if (work + 2 * n_units < wk.n_work) prefetch_tile_rows<CG>(src, P, wk, work + 2 * n_units, rank, lane);
+      if (work + 2 * n_units < wk.n_work) prefetch(work + 2 * n_units);
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
       // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues

@@ -12,9 +12,10 @@
 namespace diinn {
 using namespace ptx;
 
-// two operand stages (2 x 32 KB with CTA pairs): with 256 TMEM columns per CTA two CTAs share an SM, so one tile's
-// epilogue runs under the other's loads and MMAs (the LR chain of modes 1 / 2 is epilogue / HBM bound)
-constexpr int kGemmStages = 2;
+// three operand stages (3 x 32 KB with CTA pairs): with 256 TMEM columns per CTA two CTAs still share an SM, so one tile's
+// epilogue runs under the other's loads and MMAs (the LR chain of modes 1 / 2 is epilogue / HBM bound), and the K loop
+// (9 steps for init_q's 576-wide operands) has two loads in flight behind the MMAs instead of one
+constexpr int kGemmStages = 3;
 
 template <int CG>
 __global__ void __launch_bounds__(192, 1)
@@ -143,27 +144,43 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
     } else
-    for (int c0 = 0; c0 < 256; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      if (row < M) {
+    {
+      // init_q=True (ce.add_bias): the per-pixel pre-activations are finished here -- bias, ReLU on the k_0 block and, in
+      // the first N tile, the product with sin(QS + bq_0). All of it warp-uniform; the operand loads of a 16-column step
+      // are issued while its TMEM load is in flight.
+      const bool fuse = ce.add_bias != nullptr;
+      const bool q0 = fuse && ce.q0_arg != nullptr && n0 < kD;
+      const size_t rq = static_cast<size_t>(row < M ? row : M - 1) * kD;
+      for (int c0 = 0; c0 < 256; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        float4 bv[4], tv[4];
+        if (fuse) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          if (ce.add_bias != nullptr) {  // init_q=True: the per-pixel pre-activations are finished here (warp-uniform)
-            const int n = n0 + c0 + j;
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ce.add_bias + n));
-            o.x += b.x, o.y += b.y, o.z += b.z, o.w += b.w;
-            if (n < ce.relu_cols) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            if (ce.q0_arg != nullptr && n < kD) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(ce.q0_arg + static_cast<size_t>(row) * kD + n));
-              const float4 bq = __ldg(reinterpret_cast<const float4*>(ce.q0_bias + n));
-              o.x *= __sinf(t.x + bq.x), o.y *= __sinf(t.y + bq.y), o.z *= __sinf(t.z + bq.z), o.w *= __sinf(t.w + bq.w);
-            }
+          for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(ce.add_bias + n0 + c0) + j);
+        }
+        if (q0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(ce.q0_arg + rq + c0) + j);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ce.q0_bias + c0) + j);
+            tv[j] = make_float4(t.x + b.x, t.y + b.y, t.z + b.z, t.w + b.w);
           }
-          *reinterpret_cast<float4*>(drow + c0 + j) = o;
+        }
+        tmem_ld_wait();
+        if (row < M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (fuse) {
+              o.x += bv[j].x, o.y += bv[j].y, o.z += bv[j].z, o.w += bv[j].w;
+              if (n0 + c0 < ce.relu_cols)
+                o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            }
+            if (q0) o.x *= __sinf(tv[j].x), o.y *= __sinf(tv[j].y), o.z *= __sinf(tv[j].z), o.w *= __sinf(tv[j].w);
+            *reinterpret_cast<float4*>(drow + c0 + 4 * j) = o;
+          }
         }
       }
     }
