@@ -413,7 +413,7 @@ def main():
             with open(pj) as f:
                 prof = json.load(f)
         line["roofline"] = {
-            "bound": "tensor", "kernel": "stage_b_umma_kernel<2, %s>" % ("true" if args.precision == "fp16acc" else "false"), "achieved": ach, "peak": peaks["bf16_sustained"],
+            "bound": "tensor", "kernel": "stage_b_umma_kernel<2, %s, false, false>" % ("true" if args.precision == "fp16acc" else "false"), "achieved": ach, "peak": peaks["bf16_sustained"],
             "unit": "TFLOP/s", "frac": ach / peaks["bf16_sustained"],
             "traffic": prof.get("dram_bytes_per_launch_c3") if args.workload == "c3" and world == 1 else None,
             "peak_source": peaks["source"] + "; sustained cuBLAS bf16 figure because the kernel is timed inside the step",
