@@ -214,7 +214,10 @@ InitQPlan plan_initq(int B, int W_up, int rows, int compute, int mode, size_t of
       chunk_px = (e && atoll(e) > 0) ? atoll(e) : kInitQChunkUmma;
     }
     int64_t r = chunk_px / (static_cast<int64_t>(B) * W_up);
-    if (r >= 8) r -= r % 8;  // whole 8-row stage-B patches, so only the band's last chunk has a partial tile row
+    // whole 8-row stage-B patches, so that only the band's last chunk has a partial tile row; very wide images (c4: 7 680
+    // columns) take one patch row per chunk as long as that stays within 4 chunks' worth of scratch
+    if (r >= 8) r -= r % 8;
+    else if (static_cast<int64_t>(B) * W_up * 8 <= 4 * chunk_px) r = 8;
     r = r < 1 ? 1 : (r > rows ? rows : r);
     p.chunk_rows = static_cast<int>(r);
     p.chunk = static_cast<int64_t>(B) * r * W_up;

@@ -142,17 +142,31 @@ def step_mode3(weights: dict, x: np.ndarray, syn: np.ndarray, fp64: bool = False
     return out.astype(dt)
 
 
-def last_conv3x3_reflect(weights: dict, q3: np.ndarray, fp64: bool = False) -> np.ndarray:
-    """mode 4 (diinn.py:89-90,146): q3 (B,H_up,W_up,256) -> (B,3,H_up,W_up) through Conv2d(256,3,3,padding=1,
-    padding_mode='reflect'): out[c,y,x] = b[c] + sum_{ky,kx,f} W[c,f,ky,kx] q3[refl(y+ky-1), refl(x+kx-1), f]."""
+def _reflect1(i: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    """torch 'reflect' padding by one element on [lo, hi): lo-1 -> lo+1, hi -> hi-2."""
+    return np.where(i < lo, 2 * lo - i, np.where(i >= hi, 2 * hi - 2 - i, i))
+
+
+def last_conv3x3_reflect(weights: dict, q3: np.ndarray, fp64: bool = False, rows=None, row_base: int = 0,
+                         H_up: int | None = None) -> np.ndarray:
+    """mode 4 (diinn.py:89-90,146): q3 (B,R,W_up,256) -> (B,3,rows,W_up) through Conv2d(256,3,3,padding=1,
+    padding_mode='reflect'): out[c,y,x] = b[c] + sum_{ky,kx,f} W[c,f,ky,kx] q3[refl(y+ky-1), refl(x+kx-1), f].
+
+    q3 holds HR rows [row_base, row_base + R) of an image H_up rows high (default: the whole image) and `rows`=(r0,r1)
+    selects the output rows; rows reflect at the IMAGE borders, so a band needs one halo row per side inside q3."""
     dt = np.float64 if fp64 else F32
     Wl = weights["last_layer.weight"].astype(dt)          # (3,256,3,3)
-    B, H, Wd, _ = q3.shape
-    qp = np.pad(q3.astype(dt), ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect")
-    out = np.zeros((B, 3, H, Wd), dtype=dt)
+    B, R, Wd, _ = q3.shape
+    H_up = R if H_up is None else H_up
+    r0, r1 = (row_base, row_base + R) if rows is None else rows
+    ys, xs = np.arange(r0, r1), np.arange(Wd)
+    q3 = q3.astype(dt)
+    out = np.zeros((B, 3, r1 - r0, Wd), dtype=dt)
     for ky in range(3):
+        yy = _reflect1(ys + ky - 1, 0, H_up) - row_base
         for kx in range(3):
-            out += np.einsum("bhwf,cf->bchw", qp[:, ky:ky + H, kx:kx + Wd], Wl[:, :, ky, kx]).astype(dt)
+            xx = _reflect1(xs + kx - 1, 0, Wd)
+            out += np.einsum("bhwf,cf->bchw", q3[:, yy][:, :, xx], Wl[:, :, ky, kx]).astype(dt)
     return (out + weights["last_layer.bias"].astype(dt).reshape(1, 3, 1, 1)).astype(dt)
 
 
@@ -169,12 +183,14 @@ def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool
     H_up, W_up = int(size[0]), int(size[1])
     r0, r1 = (0, H_up) if rows is None else (int(rows[0]), int(rows[1]))
     if mode == 4:
-        q3 = _q3_grid(weights, feat, (H_up, W_up), fp64, chunk)            # (B,H_up,W_up,256)
+        lo, hi = max(r0 - 1, 0), min(r1 + 1, H_up)                          # the band plus the rows its conv reads
+        q3 = _q3_grid(weights, feat, (H_up, W_up), fp64, chunk, rows=(lo, hi))   # (B,hi-lo,W_up,256)
         strip = W_up if bsize is None else int(bsize) // H_up
         if strip < 1:
             raise ValueError("bsize < H_up: batched_step makes no progress (diinn.py:155)")
-        outs = [last_conv3x3_reflect(weights, q3[:, :, a:a + strip], fp64=fp64) for a in range(0, W_up, strip)]
-        return np.concatenate(outs, axis=-1)[:, :, r0:r1]
+        outs = [last_conv3x3_reflect(weights, q3[:, :, a:a + strip], fp64=fp64, rows=(r0, r1), row_base=lo, H_up=H_up)
+                for a in range(0, W_up, strip)]
+        return np.concatenate(outs, axis=-1)
     ih, rh = rel_axis(H, H_up)
     iw, rw = rel_axis(W, W_up)
     ratio = ratio_value(H, W, H_up, W_up)
@@ -196,26 +212,28 @@ def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool
     return out
 
 
-def _q3_grid(weights: dict, feat: np.ndarray, size, fp64: bool, chunk: int) -> np.ndarray:
-    """mode 4: q_3 of every HR pixel, (B,H_up,W_up,256) -- the input of the 3x3 last conv (diinn.py:141-146)."""
+def _q3_grid(weights: dict, feat: np.ndarray, size, fp64: bool, chunk: int, rows=None) -> np.ndarray:
+    """mode 4: q_3 of the HR pixels of rows [rows[0], rows[1]) (default: all), (B,R,W_up,256) -- the input of the 3x3 last
+    conv (diinn.py:141-146)."""
     B, C, H, W = feat.shape
     H_up, W_up = size
+    g0, g1 = (0, H_up) if rows is None else rows
     ih, rh = rel_axis(H, H_up)
     iw, rw = rel_axis(W, W_up)
     ratio = ratio_value(H, W, H_up, W_up)
     u = np.ascontiguousarray(unfold3x3(feat).transpose(0, 2, 3, 1))
     n_hidden = weights["Q.3.0.weight"].shape[0]
-    q3 = np.empty((B, H_up, W_up, n_hidden), dtype=np.float64 if fp64 else F32)
+    q3 = np.empty((B, g1 - g0, W_up, n_hidden), dtype=np.float64 if fp64 else F32)
     rows_per_chunk = max(1, chunk // W_up)
     for b in range(B):
-        for a in range(0, H_up, rows_per_chunk):
-            e = min(a + rows_per_chunk, H_up)
+        for a in range(g0, g1, rows_per_chunk):
+            e = min(a + rows_per_chunk, g1)
             syn = np.empty((e - a, W_up, 3), dtype=F32)
             syn[..., 0] = rh[a:e, None]
             syn[..., 1] = rw[None, :]
             syn[..., 2] = ratio
             x = u[b][ih[a:e]][:, iw].reshape(-1, C * 9)
-            q3[b, a:e] = step_mode3(weights, x, syn.reshape(-1, 3), fp64=fp64, mode=4).reshape(e - a, W_up, -1)
+            q3[b, a - g0:e - g0] = step_mode3(weights, x, syn.reshape(-1, 3), fp64=fp64, mode=4).reshape(e - a, W_up, -1)
     return q3
 
 

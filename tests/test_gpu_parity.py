@@ -760,3 +760,61 @@ def test_init_q_row_tiles_chunks_and_io(golden_initq, mode):
     coord, cell = (torch.from_numpy(v).cuda() for v in synth.make_query(3, 1, 64))
     with pytest.raises(NotImplementedError):
         d.query(x, coord, cell)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the secondary wirings at the BASELINE full sizes (c3, c4): band oracles at the first / last rows and at shard boundaries
+# ---------------------------------------------------------------------------------------------------------
+def _wiring(mode, init_q, precision, seed=0):
+    w = synth.make_weights(seed=seed, mode=mode, init_q=init_q)
+    return w, diinn_b200.load_numpy_weights(
+        diinn_b200.FusedImplicitDecoder(mode=mode, init_q=init_q, precision=precision), w).cuda()
+
+
+@pytest.mark.parametrize("mode,init_q", [(4, False), (3, True), (4, True)])
+def test_config_c3_secondary_wirings(mode, init_q):
+    """full c3 decode on the tensor path: bands against the oracle, the 8-rank row tiling bit-identical, and the fp32 path
+    (band decodes) in agreement"""
+    B, H, W, H_up, W_up = synth.CONFIGS["c3"]
+    feat = synth.make_feat(1, B, H, W)
+    x = torch.from_numpy(feat).cuda()
+    size = (H_up, W_up)
+    w, dec16 = _wiring(mode, init_q, "bf16")
+    with torch.no_grad():
+        o16 = dec16(x, size)
+        tiled = torch.empty_like(o16)
+        for r0, r1 in diinn_b200.row_partition(H_up, 8):
+            dec16.forward_rows(x, size, r0, r1, out=tiled)
+        assert torch.equal(o16, tiled)
+        _, dec32 = _wiring(mode, init_q, "fp32")
+        bands = [(0, 2), (169, 171), (677, 679), (1354, 1356)]
+        o16n = o16.cpu().numpy()
+        assert np.isfinite(o16n).all()
+        for r0, r1 in bands:
+            ref = orc.decoder_forward(w, feat, size, rows=(r0, r1), mode=mode)
+            assert float(np.abs(o16n[:, :, r0:r1] - ref).max()) <= TIGHT["bf16"], (mode, init_q, r0, r1)
+            o32 = dec32.forward_rows(x, size, r0, r1).cpu().numpy()
+            assert float(np.abs(o32 - ref).max()) <= TIGHT["fp32"], (mode, init_q, r0, r1)
+
+
+@pytest.mark.parametrize("mode,init_q", [(4, False), (3, True)])
+def test_config_c4_secondary_wirings(mode, init_q):
+    """8K x12: mode 4 as a full decode (20 GB q_3 dump + projections), init_q on the shard-boundary and border bands
+    (a full init_q decode of 33 Mpx is 0.25 s of GPU time and adds nothing the bands do not cover)"""
+    B, H, W, H_up, W_up = synth.CONFIGS["c4"]
+    feat = synth.make_feat(1, B, H, W)
+    x = torch.from_numpy(feat).cuda()
+    size = (H_up, W_up)
+    w, dec16 = _wiring(mode, init_q, "bf16")
+    bands = [(0, 1), (539, 541), (4319, 4320)]
+    with torch.no_grad():
+        full = dec16(x, size) if mode == 4 else None
+        for r0, r1 in bands:
+            got = dec16.forward_rows(x, size, r0, r1)
+            if full is not None:
+                assert torch.equal(full[:, :, r0:r1], got)
+            ref = orc.decoder_forward(w, feat, size, rows=(r0, r1), mode=mode)
+            assert float(np.abs(got.cpu().numpy() - ref).max()) <= TIGHT["bf16"], (mode, init_q, r0, r1)
+        if full is None:   # a multi-chunk init_q tile: 24 rows of 7 680 pixels = three 8-row chunks
+            t = dec16.forward_rows(x, size, 532, 556)
+            assert torch.equal(t[:, :, 7:9], dec16.forward_rows(x, size, 539, 541))
