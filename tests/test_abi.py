@@ -135,6 +135,39 @@ def test_swap_decoder_keeps_call_site():
     assert all(torch.equal(before[k], after[k]) for k in before)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("mode,init_q", [(1, False), (3, False), (4, False), (2, True), (4, True)])
+def test_swap_decoder_on_the_real_reference_module(mode, init_q):
+    """the actual reference DIINN-style container with ImplicitDecoder(mode, init_q): swap_decoder keeps every parameter
+    (strict state_dict round trip, first_layer and the 3x3 last conv included) and the constructor flags"""
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.models.components.diinn import ImplicitDecoder
+    finally:
+        sys.path.remove("/root/reference")
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = torch.nn.Identity()
+            self.decoder = ImplicitDecoder(mode=mode, init_q=init_q)
+
+    torch.manual_seed(7)
+    net = Net()
+    before = {k: v.clone() for k, v in net.decoder.state_dict().items()}
+    diinn_b200.swap_decoder(net, precision="bf16")
+    dec = net.decoder
+    assert isinstance(dec, diinn_b200.FusedImplicitDecoder) and dec.mode == mode and dec.init_q == init_q
+    after = dec.state_dict()
+    assert list(after) == list(before)                       # same keys in the same order
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    # same default init for the same seed: the module tree consumes the RNG like the reference's
+    torch.manual_seed(7)
+    fresh = diinn_b200.FusedImplicitDecoder(mode=mode, init_q=init_q).state_dict()
+    assert all(torch.equal(before[k], fresh[k]) for k in before)
+
+
 def test_row_partition():
     parts = diinn_b200.row_partition(1356, 8)
     assert [b - a for a, b in parts] == [170, 170, 170, 170, 169, 169, 169, 169]
