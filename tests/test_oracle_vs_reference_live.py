@@ -68,3 +68,44 @@ def test_forward_on_random_shapes_every_wiring(ref_decoder_cls, mode, init_q):
         assert got.shape == ref.shape
         assert float(np.abs(got - ref).max()) <= 2e-6, (mode, init_q, H, W, H_up, W_up, bsize)
     torch.set_grad_enabled(True)
+
+
+def test_local_ensemble_on_random_queries(ref_decoder_cls):
+    """LIIF.query_rgb (liif.py:59-127, unmodified, its imnet replaced by an adapter around ImplicitDecoder.step) ==
+    oracle.query_ensemble on random feature-map shapes, random coordinates (borders and exact cell centres included) and
+    random cell sizes"""
+    torch.set_grad_enabled(False)
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.models.components.liif import LIIF
+    finally:
+        sys.path.remove("/root/reference")
+
+    class ImnetAdapter(torch.nn.Module):
+        def __init__(self, dec):
+            super().__init__()
+            self.dec = dec
+
+        def forward(self, inp):  # (N, 580) = [q_feat 576 | rel_coord 2 | rel_cell 2]  (liif.py:105-111)
+            n = inp.shape[0]
+            x = inp[:, :576].t().reshape(1, 576, n, 1)
+            ratio = inp[:, 578] * inp[:, 579] * 0.25
+            syn = torch.stack([inp[:, 576], inp[:, 577], ratio], 0).reshape(1, 3, n, 1)
+            return self.dec.step(x, syn)[0, :, :, 0].t()
+
+    w = synth.make_weights(seed=9, k_gain=1.5, q_gain=4.0)
+    dec = ref_decoder_cls(mode=3, init_q=False).eval()
+    dec.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in w.items()}, strict=True)
+    liif = LIIF().eval()
+    liif.imnet = ImnetAdapter(dec)
+    rng = np.random.default_rng(5)
+    for i in range(5):
+        B, H, W, Q = 1 + i % 2, int(rng.integers(2, 30)), int(rng.integers(2, 30)), 400
+        feat = synth.make_feat(60 + i, B, H, W)
+        coord, cell = synth.make_query(70 + i, B, Q, (2.0 / float(rng.integers(H, 6 * H)), 2.0 / float(rng.integers(W, 6 * W))))
+        coord[:, :40, 0] = np.linspace(-1, 1, 40, dtype=np.float32)                     # the image border ...
+        coord[:, 40:80, 1] = (-1 + (2 * np.arange(40) + 1) / 40).astype(np.float32)     # ... and cell centres of a 40-grid
+        ref = liif.query_rgb(torch.from_numpy(feat), torch.from_numpy(coord), torch.from_numpy(cell)).numpy()
+        got = orc.query_ensemble(w, feat, coord, cell)
+        assert float(np.abs(got - ref).max()) <= 2e-6, (i, B, H, W)
+    torch.set_grad_enabled(True)
