@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DIINN_B200_LIB") or os.path.join(HERE, "libdiinn_b200.so")  # override: ablation builds
 
 OK = 0
-COMPUTE_FP32, COMPUTE_BF16, COMPUTE_FP16ACC = 0, 1, 2
+COMPUTE_FP32, COMPUTE_BF16, COMPUTE_FP16, COMPUTE_FP32_SIMT = 0, 1, 2, 3
 IO_F32, IO_BF16, IO_BF16_NHWC = 0, 1, 2
 
 STATUS_NAMES = {
@@ -20,13 +20,17 @@ STATUS_NAMES = {
     -7: "DIINN_ERR_NO_WEIGHTS", -8: "DIINN_ERR_UNSUPPORTED_DEVICE",
 }
 
-# every symbol include/diinn_b200.h declares (tests/test_abi.py checks the .so exports them all)
+# every symbol include/diinn_b200.h (product surface) and include/diinn_b200_debug.h (taps, probes) declare;
+# tests/test_abi.py checks that the .so exports them all and that the lists match the headers
 SYMBOLS = [
     "diinn_create", "diinn_destroy", "diinn_last_error", "diinn_set_weights", "diinn_workspace_bytes",
-    "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query", "diinn_query_ensemble", "diinn_debug_gather",
-    "diinn_debug_query_gather", "diinn_debug_stage_a", "diinn_debug_umma_gemm", "diinn_debug_read_trace", "diinn_debug_umma_pace", "diinn_set_profiling", "diinn_get_kernel_times",
-    "diinn_launch_count",
+    "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query",
+    "diinn_query_ensemble", "diinn_set_profiling", "diinn_get_kernel_times", "diinn_launch_count",
     "diinn_version", "diinn_set_output_transform", "diinn_psnr", "diinn_set_bsize",
+]
+DEBUG_SYMBOLS = [
+    "diinn_debug_gather", "diinn_debug_query_gather", "diinn_debug_set_tap", "diinn_debug_stage_a", "diinn_debug_umma_gemm",
+    "diinn_debug_umma_pace", "diinn_debug_read_trace",
 ]
 
 
@@ -85,6 +89,8 @@ def load() -> C.CDLL:
     lib.diinn_debug_gather.restype = i
     lib.diinn_debug_query_gather.argtypes = [vp, i, i, i, vp, vp, i, vp, vp, vp, vp]
     lib.diinn_debug_query_gather.restype = i
+    lib.diinn_debug_set_tap.argtypes = [vp, vp]
+    lib.diinn_debug_set_tap.restype = i
     lib.diinn_debug_stage_a.argtypes = [vp, vp, i, i, i, i, vp, vp, sz, i, i, vp]
     lib.diinn_debug_stage_a.restype = i
     lib.diinn_debug_umma_gemm.argtypes = [vp, vp, vp, vp, i, i, i, i, vp]

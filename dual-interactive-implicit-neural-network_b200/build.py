@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdiinn_b200.so")
-SOURCES = ["api.cu", "pack.cu", "simt.cu", "umma_selftest.cu", "stage_a_umma.cu", "stage_b_umma.cu", "eval.cu", "lr_chain.cu", "mode4.cu", "init_q.cu"]
+SOURCES = ["api.cu", "pack.cu", "simt.cu", "gemm.cu", "stage_a_umma.cu", "stage_b_umma.cu", "eval.cu", "lr_chain.cu", "mode4.cu", "init_q.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

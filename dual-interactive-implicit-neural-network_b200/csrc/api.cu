@@ -12,6 +12,33 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it (a process that
+// drives several GPUs through PyTorch must not see torch.cuda.current_device() change under it).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// The tcgen05 kernels raise a device word when an internal invariant fails (operand buffers not 1024-byte aligned: the
+// swizzled layouts would be read wrongly). Read it back at a point where the stream is synchronised anyway.
+int check_err_flag(Handle* h) {
+  int v = 0;
+  if (h->err_flag && cudaMemcpy(&v, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && v != 0) {
+    cudaMemset(h->err_flag, 0, sizeof(int));
+    return fail(h, DIINN_ERR_CUDA, "a tcgen05 kernel reported an internal consistency failure (code " + std::to_string(v) +
+                                       "): its results are invalid");
+  }
+  return DIINN_OK;
+}
+
 // host twin of axis_index() in common.cuh (one rounded fp32 multiply, then floorf)
 inline int host_axis_index(const AxisParams& p, int j) {
   volatile float t = (static_cast<float>(j) + 0.5f) * p.scale;
@@ -22,13 +49,25 @@ inline int host_axis_index(const AxisParams& p, int j) {
 struct DecodePlan {
   int lr_row0 = 0, lr_rows = 0;  // LR rows P must hold
   int fr0 = 0, frows = 0;        // LR rows (with +-1 halo, clipped) of the NHWC bf16 copy
-  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, off_chain = 0, off_q3 = 0, off_T = 0, total = 0;
+  size_t off_P = 0, off_q0 = 0, off_q1 = 0, off_nhwc = 0, nhwc_plane = 0, off_chain = 0, off_q3 = 0, off_T = 0, total = 0;
   InitQPlan iq;                  // init_q=True: replaces P / the activation chunks / the chain scratch
   int qr0 = 0, qr1 = 0;          // mode 4: HR rows whose q_3 is dumped (the band +- 1 halo row, clipped to the image)
   int64_t chunk = 0;
 };
 
 constexpr int64_t kFp32Chunk = 1 << 17;  // HR pixels per activation ping-pong pass of the fp32 path
+
+inline bool is_simt(int compute) { return compute == DIINN_COMPUTE_FP32_SIMT; }
+inline bool is_split(int compute) { return compute == DIINN_COMPUTE_FP32; }
+// operand format of the tensor-core kernels for a compute mode
+inline int fmt_of(int compute) {
+  return compute == DIINN_COMPUTE_BF16 ? kFmtBf16 : compute == DIINN_COMPUTE_FP16 ? kFmtF16 : kFmtSplit;
+}
+// The fp32-precision tensor path covers every wiring except init_q=True, whose per-pixel x-facing GEMMs run on bf16 library
+// GEMMs; there fp32 precision means the CUDA-core path.
+inline int effective_compute(const Handle* h, int compute) {
+  return (compute == DIINN_COMPUTE_FP32 && h && h->cfg.init_q) ? DIINN_COMPUTE_FP32_SIMT : compute;
+}
 
 DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int row1, int compute, int mode,
                        int init_q = 0) {
@@ -46,8 +85,9 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
   const int fr1 = (p.lr_row0 + p.lr_rows + 1 < H) ? p.lr_row0 + p.lr_rows + 1 : H;
   p.frows = fr1 - p.fr0;
   size_t off = 0;
+  const size_t nhwc_planes = is_split(compute) ? 2 : 1;  // the split format keeps an fp16 residual plane next to the hi plane
   if (init_q) {  // no LR-resolution P: everything is per HR pixel, chunk by chunk (csrc/init_q.cu)
-    if (compute != DIINN_COMPUTE_FP32) {
+    if (!is_simt(compute)) {
       p.off_nhwc = off;
       off += align_up(static_cast<size_t>(B) * p.frows * W * kC * sizeof(__nv_bfloat16));
     }
@@ -56,7 +96,7 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
   } else {
   p.off_P = off;
   off += align_up(static_cast<size_t>(B) * p.lr_rows * W * kPCols * sizeof(float));
-  if (compute == DIINN_COMPUTE_FP32) {
+  if (is_simt(compute)) {
     const int64_t total = static_cast<int64_t>(B) * (row1 - row0) * W_up;
     p.chunk = total < kFp32Chunk ? total : kFp32Chunk;
     p.off_q0 = off;
@@ -65,8 +105,9 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
     off += align_up(static_cast<size_t>(p.chunk) * kD * sizeof(float));
   } else {
     p.off_nhwc = off;
-    off += align_up(static_cast<size_t>(B) * p.frows * W * kC * sizeof(__nv_bfloat16));
-    if (mode == 1 || mode == 2) {  // scratch of the LR-resolution K chain
+    p.nhwc_plane = align_up(static_cast<size_t>(B) * p.frows * W * kC * sizeof(__nv_bfloat16));
+    off += nhwc_planes * p.nhwc_plane;
+    if ((mode == 1 || mode == 2) && !is_split(compute)) {  // scratch of the LR-resolution K chain (split: fp32 chain in place)
       p.off_chain = off;
       off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * p.lr_rows * W));
     }
@@ -74,9 +115,9 @@ DecodePlan plan_decode(int B, int H, int W, int H_up, int W_up, int row0, int ro
   }
   if (mode == 4) {
     p.off_q3 = off;
-    off += align_up(static_cast<size_t>(B) * (p.qr1 - p.qr0) * W_up * kD *
-                    (compute == DIINN_COMPUTE_FP32 ? sizeof(float) : sizeof(__nv_bfloat16)));
-    if (compute != DIINN_COMPUTE_FP32) {  // the 27 (tap, channel) projections of every dumped pixel, planar fp32
+    const bool q3_f32 = is_simt(compute) || is_split(compute);
+    off += align_up(static_cast<size_t>(B) * (p.qr1 - p.qr0) * W_up * kD * (q3_f32 ? sizeof(float) : sizeof(__nv_bfloat16)));
+    if (!q3_f32) {  // the 27 (tap, channel) projections of every dumped pixel, planar fp32
       p.off_T = off;
       off += align_up(static_cast<size_t>(B) * (p.qr1 - p.qr0) * W_up * 27 * sizeof(float));
     }
@@ -94,10 +135,11 @@ int check_common(Handle* h, int B, int C, int H, int W, int io_dtype, int comput
   if (B < 1 || H < 1 || W < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "empty feature map");
   if (io_dtype != DIINN_IO_F32 && io_dtype != DIINN_IO_BF16 && io_dtype != DIINN_IO_BF16_NHWC)
     return fail(h, DIINN_ERR_BAD_DTYPE, "io_dtype");
-  if (io_dtype == DIINN_IO_BF16_NHWC && compute == DIINN_COMPUTE_FP32)
-    return fail(h, DIINN_ERR_BAD_DTYPE, "channels-last bf16 feature maps are taken by the tensor paths only");
-  if (compute != DIINN_COMPUTE_FP32 && compute != DIINN_COMPUTE_BF16 && compute != DIINN_COMPUTE_FP16ACC)
-    return fail(h, DIINN_ERR_BAD_DTYPE, "compute must be DIINN_COMPUTE_FP32, _BF16 or _FP16ACC");
+  if (compute != DIINN_COMPUTE_FP32 && compute != DIINN_COMPUTE_BF16 && compute != DIINN_COMPUTE_FP16 &&
+      compute != DIINN_COMPUTE_FP32_SIMT)
+    return fail(h, DIINN_ERR_BAD_DTYPE, "compute must be DIINN_COMPUTE_FP32, _BF16, _FP16 or _FP32_SIMT");
+  if (io_dtype == DIINN_IO_BF16_NHWC && (compute == DIINN_COMPUTE_FP32 || compute == DIINN_COMPUTE_FP32_SIMT))
+    return fail(h, DIINN_ERR_BAD_DTYPE, "channels-last bf16 feature maps are taken by the 16-bit-operand paths only");
   return DIINN_OK;
 }
 
@@ -168,7 +210,7 @@ static int make_tmap_4d(Handle* h, CUtensorMap* map, const void* base, CUtensorM
 
 extern "C" {
 
-const char* diinn_version(void) { return "diinn_b200 0.1 (sm_100a)"; }
+const char* diinn_version(void) { return "diinn_b200 0.2 (sm_100a)"; }
 
 int diinn_create(diinn_handle** out, const diinn_config* cfg) {
   if (!out || !cfg) {
@@ -210,7 +252,7 @@ int diinn_create(diinn_handle** out, const diinn_config* cfg) {
   }
   h->cfg = *cfg;
   h->sm_count = prop.multiProcessorCount;
-  cudaSetDevice(cfg->device);
+  DeviceGuard guard(cfg->device);
   // per-handle device scratch lives here so that decode / query never allocate (CUDA-graph capturable, one handle per
   // device or thread with no shared state)
   bool ok = cudaMalloc(&h->err_flag, sizeof(int)) == cudaSuccess && cudaMemset(h->err_flag, 0, sizeof(int)) == cudaSuccess;
@@ -232,14 +274,17 @@ int diinn_create(diinn_handle** out, const diinn_config* cfg) {
 
 void diinn_destroy(diinn_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaFree(h->WA32);
   cudaFree(h->bA);
   cudaFree(h->bq_dev);
   cudaFree(h->WB32);
-  cudaFree(h->WA16);
-  cudaFree(h->WB16);
-  cudaFree(h->WB16h);
+  for (int f = 0; f < 2; ++f) {
+    cudaFree(h->WA16[f]);
+    cudaFree(h->WB16[f]);
+  }
+  cudaFree(h->WA16lo);
+  cudaFree(h->WB16lo);
   cudaFree(h->err_flag);
   cudaFree(h->trace_dev);
   cudaFree(h->WH32);
@@ -276,18 +321,41 @@ int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream)
     if (!w->k_weight[i] || !w->k_bias[i] || !w->q_weight[i] || !w->q_bias[i])
       return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
   if (!w->last_weight || !w->last_bias) return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   return pack_weights(h, w, static_cast<cudaStream_t>(stream));
 }
 
 size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_up, int W_up, int row0, int row1,
                              int compute) {
   if (B < 1 || H < 1 || W < 1 || H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1) return 0;
-  return plan_decode(B, H, W, H_up, W_up, row0, row1, compute, h ? h->cfg.mode : 3, h ? h->cfg.init_q : 0).total;
+  return plan_decode(B, H, W, H_up, W_up, row0, row1, effective_compute(h, compute), h ? h->cfg.mode : 3,
+                     h ? h->cfg.init_q : 0).total;
 }
 
 static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, int W, int H_up, int W_up, int row0,
                        int row1, OutSpec o, void* workspace, size_t workspace_bytes, int compute, void* stream);
+
+// The LR-resolution half of a tensor-path decode: layout pass (skipped for a channels-last bf16 map, which stage A reads in
+// place as bf16 operands), stage A, and for modes 1 / 2 the K chain. nhwc / nhwc_lo / chain are workspace regions.
+static int run_lr_stages(Handle* h, const void* feat, int io_dtype, int fmt, int B, int H, int W, int fr0, int frows,
+                         int lr_row0, int lr_rows, float* P, char* nhwc, char* nhwc_lo, char* chain, cudaStream_t s,
+                         cudaEvent_t ev_after_layout = nullptr) {
+  int rc;
+  if (io_dtype == DIINN_IO_BF16_NHWC) {
+    if (ev_after_layout) cudaEventRecord(ev_after_layout, s);
+    rc = launch_stage_a_umma(h, feat, nullptr, kFmtBf16, B, H, W, 0, H, lr_row0, lr_rows, P, s);
+  } else {
+    if ((rc = launch_feat_to_nhwc(h, feat, io_dtype, fmt, B, H, W, fr0, fr0 + frows, nhwc, nhwc_lo, s))) return rc;
+    if (ev_after_layout) cudaEventRecord(ev_after_layout, s);
+    rc = launch_stage_a_umma(h, nhwc, nhwc_lo, fmt, B, H, W, fr0, frows, lr_row0, lr_rows, P, s);
+  }
+  if (rc) return rc;
+  if (h->cfg.mode == 1 || h->cfg.mode == 2) {
+    const int64_t M = static_cast<int64_t>(B) * lr_rows * W;
+    rc = fmt == kFmtSplit ? run_lr_chain_fp32(h, P, M, s) : run_lr_chain_umma(h, P, M, chain, s);
+  }
+  return rc;
+}
 
 int diinn_set_output_transform(diinn_handle* h, const diinn_output_transform* t) {
   if (!h) return DIINN_ERR_BAD_ARG;
@@ -350,6 +418,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   void* out = o.ptr;
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
+  compute = effective_compute(h, compute);
   if (io_dtype == DIINN_IO_BF16_NHWC) o.io_dtype = DIINN_IO_BF16;  // the image is bf16 NCHW either way
   if ((rc = apply_output_transform(h, &o))) return rc;
   if (!feat || !out) return fail(h, DIINN_ERR_BAD_ARG, "null feat/out");
@@ -361,7 +430,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   if (!workspace || workspace_bytes < plan.total)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL,
                 "workspace too small: need " + std::to_string(plan.total) + " bytes");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   float* P = reinterpret_cast<float*>(ws + plan.off_P);
@@ -404,7 +473,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   };
 
   const bool init_q = h->cfg.init_q != 0;
-  if (compute == DIINN_COMPUTE_FP32) {
+  if (is_simt(compute)) {
     if (init_q) {
       float* q3f = mode4 ? reinterpret_cast<float*>(ws + plan.off_q3) : nullptr;
       if ((rc = run_initq_fp32(h, feat, io_dtype, src, ob, ws, plan.iq, s, q3f))) return rc;
@@ -418,51 +487,46 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
       return rc;
     return mode4 ? last_conv(q3f, true) : DIINN_OK;
   }
-  if (mode4) ob.q3 = reinterpret_cast<__nv_bfloat16*>(ws + plan.off_q3);
-  __nv_bfloat16* nhwc = reinterpret_cast<__nv_bfloat16*>(ws + plan.off_nhwc);
-  auto mark = [&]() {
-    if (!h->profiling) return;
-    cudaEvent_t e;
-    if (cudaEventCreate(&e) == cudaSuccess) {
-      cudaEventRecord(e, s);
-      h->prof_events.push_back(e);
-    }
+  // ---- tensor-core paths: layout pass -> stage A -> (LR chain) -> stage B -> (mode 4: last conv)
+  const int fmt = fmt_of(compute);
+  const bool split = fmt == kFmtSplit;
+  if (mode4) {
+    if (split) ob.q3f = reinterpret_cast<float*>(ws + plan.off_q3);
+    else ob.q3 = reinterpret_cast<__nv_bfloat16*>(ws + plan.off_q3);
+  }
+  char* nhwc = ws + plan.off_nhwc;
+  char* nhwc_lo = split ? nhwc + plan.nhwc_plane : nullptr;
+  int ev = -1;  // profiling: 4 pre-created events per decode (diinn_set_profiling), none created here
+  if (h->profiling && h->prof_used + 4 <= h->prof_events.size()) ev = static_cast<int>(h->prof_used), h->prof_used += 4;
+  auto mark = [&](int i) {
+    if (ev >= 0) cudaEventRecord(h->prof_events[ev + i], s);
   };
   if (init_q) {  // no stage A: the gate reads the NHWC copy (or the caller's channels-last tensor) per HR pixel
-    mark();
-    const __nv_bfloat16* src_nhwc = nhwc;
+    mark(0);
+    const __nv_bfloat16* src_nhwc = reinterpret_cast<const __nv_bfloat16*>(nhwc);
     int fr0 = plan.fr0, frows = plan.frows;
     if (io_dtype == DIINN_IO_BF16_NHWC) {
       src_nhwc = static_cast<const __nv_bfloat16*>(feat), fr0 = 0, frows = H;
-    } else if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, s))) {
-      return rc;
+    } else if ((rc = launch_feat_to_nhwc(h, feat, io_dtype, kFmtBf16, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, nullptr, s))) {
+      return rc;  // (the gate and its library GEMMs take bf16 operands in every 16-bit compute mode)
     }
-    mark();
-    mark();
-    rc = run_initq_umma(h, src_nhwc, fr0, frows, src, ob, ws, plan.iq, compute == DIINN_COMPUTE_FP16ACC, s);
+    mark(1);
+    mark(2);
+    rc = run_initq_umma(h, src_nhwc, fr0, frows, src, ob, ws, plan.iq, fmt, s);
     if (!rc && mode4) rc = last_conv(ob.q3, false);
-    mark();
+    mark(3);
     return rc;
   }
-  mark();
-  if (io_dtype == DIINN_IO_BF16_NHWC) {
-    // encoder hand-off: the caller's tensor already is (B,H,W,64) bf16 -- stage A's TMA boxes read it in place
-    mark();
-    rc = launch_stage_a_umma(h, static_cast<const __nv_bfloat16*>(feat), B, H, W, 0, H, plan.lr_row0, plan.lr_rows, P, s);
-  } else {
-    if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, plan.fr0, plan.fr0 + plan.frows, nhwc, s)))
-      return rc;
-    mark();
-    rc = launch_stage_a_umma(h, nhwc, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, s);
-  }
-  if (rc) return rc;
-  if (chain_mode(h) &&
-      (rc = run_lr_chain_umma(h, P, static_cast<int64_t>(B) * plan.lr_rows * W, ws + plan.off_chain, s)))
+  mark(0);
+  // (encoder hand-off: a channels-last bf16 map is read in place as bf16 operands, whatever format stage B runs in -- a
+  // bf16 feature map holds no more than bf16 precision anyway)
+  if ((rc = run_lr_stages(h, feat, io_dtype, fmt, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, nhwc, nhwc_lo,
+                          ws + plan.off_chain, s, ev >= 0 ? h->prof_events[ev + 1] : nullptr)))
     return rc;
-  mark();
-  rc = launch_stage_b_umma(h, src, ob, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
-  if (!rc && mode4) rc = last_conv(ob.q3, false);
-  mark();
+  mark(2);
+  rc = launch_stage_b_umma(h, src, ob, P, 0, fmt, s, h->tap);
+  if (!rc && mode4) rc = split ? last_conv(ob.q3f, true) : last_conv(ob.q3, false);
+  mark(3);
   return rc;
 }
 
@@ -475,7 +539,7 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
     return fail(h, DIINN_ERR_BAD_DTYPE, "the host entry takes NCHW feature maps (its row bands upload channel planes)");
   if (H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1)
     return fail(h, DIINN_ERR_BAD_SHAPE, "bad size / row range");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t esz = io_dtype == DIINN_IO_F32 ? 4 : 2;
   const size_t osz = h->out_tf.quantize_u8 ? 1 : esz;  // output element size (uint8 with the quantising eval glue)
@@ -493,9 +557,9 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
     const int w5[5] = {2, 5, 5, 3, 1};
     bands = 5;
     for (int k = 0; k < 5; ++k) weights[k] = w5[k];
-  } else if (px >= (1 << 19)) {
-    bands = 2;
-    weights[0] = weights[1] = 1;
+  } else if (px >= (1 << 17)) {  // e.g. one rank's row tile of an 8-way sharded DIV2K image: still worth overlapping
+    bands = 3;
+    weights[0] = weights[1] = weights[2] = 1;
   }
   if (const char* e = getenv("DIINN_HOST_BANDS")) {
     int n = 0;
@@ -561,8 +625,10 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   for (int k = 0; k < bands; ++k) {
     const int a = edge[k], b = edge[k + 1];
     if (a >= b) continue;
-    // LR rows this band reads (nearest-exact rows of [a,b) plus the 3x3 halo), minus what is already up
-    int lr0 = host_axis_index(ah, a) - 1, lr1 = host_axis_index(ah, b - 1) + 2;
+    // LR rows this band reads (nearest-exact rows of [a,b) plus the 3x3 halo), minus what is already up. Mode 4 also
+    // evaluates q_3 on one HR halo row each side of the band (plan_decode: qr0 / qr1), whose LR rows must be there too.
+    const int ha = (h->cfg.mode == 4 && a > 0) ? a - 1 : a, hb = (h->cfg.mode == 4 && b < H_up) ? b + 1 : b;
+    int lr0 = host_axis_index(ah, ha) - 1, lr1 = host_axis_index(ah, hb - 1) + 2;
     lr0 = lr0 < 0 ? 0 : lr0;
     lr1 = lr1 > H ? H : lr1;
     if (!started) uploaded = lr0, started = true;
@@ -589,20 +655,21 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   }
   DIINN_CUDA_OK(h, cudaStreamSynchronize(h->s_d2h));
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
-  return DIINN_OK;
+  return check_err_flag(h);
 }
 
 size_t diinn_query_workspace_bytes(const diinn_handle* h, int B, int H, int W, int Q, int compute) {
   if (B < 1 || H < 1 || W < 1 || Q < 1) return 0;
   // same carving as a full-image decode whose "grid" has B*Q pixels
   size_t off = align_up(static_cast<size_t>(B) * H * W * kPCols * sizeof(float));
-  if (compute == DIINN_COMPUTE_FP32) {
+  if (is_simt(compute)) {
     const int64_t total = static_cast<int64_t>(B) * Q;
     const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;
     off += 2 * align_up(static_cast<size_t>(chunk) * kD * sizeof(float));
   } else {
-    off += align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
-    if (h && (h->cfg.mode == 1 || h->cfg.mode == 2)) off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * H * W));
+    off += (is_split(compute) ? 2 : 1) * align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+    if (h && (h->cfg.mode == 1 || h->cfg.mode == 2) && !is_split(compute))
+      off += align_up(lr_chain_scratch_bytes(static_cast<int64_t>(B) * H * W));
   }
   return off;
 }
@@ -660,7 +727,7 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   const size_t need = diinn_query_workspace_bytes(h, B, H, W, Q * E, compute);
   if (!workspace || workspace_bytes < need)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL, "workspace too small: need " + std::to_string(need) + " bytes");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);
   float* P = reinterpret_cast<float*>(ws);
@@ -670,7 +737,7 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   o.ptr = out;
   o.io_dtype = io_dtype == DIINN_IO_BF16_NHWC ? DIINN_IO_BF16 : io_dtype;
   if ((rc = apply_output_transform(h, &o))) return rc;
-  if (compute == DIINN_COMPUTE_FP32) {
+  if (is_simt(compute)) {
     const int64_t total = static_cast<int64_t>(B) * Q * E;
     const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;
     float* q0 = reinterpret_cast<float*>(ws + off);
@@ -679,25 +746,20 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
     if (chain_mode(h) && (rc = run_lr_chain_fp32(h, P, static_cast<int64_t>(B) * H * W, s))) return rc;
     return run_stage_b_fp32(h, src, o, P, q0, q1, chunk, s);
   }
-  const __nv_bfloat16* nhwc = static_cast<const __nv_bfloat16*>(feat);  // channels-last bf16: read in place
-  if (io_dtype != DIINN_IO_BF16_NHWC) {
-    __nv_bfloat16* conv = reinterpret_cast<__nv_bfloat16*>(ws + off);
-    if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, conv, s))) return rc;
-    nhwc = conv;
-  }
-  if ((rc = launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s))) return rc;
-  if (chain_mode(h)) {
-    char* chain = ws + off + align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
-    if ((rc = run_lr_chain_umma(h, P, static_cast<int64_t>(B) * H * W, chain, s))) return rc;
-  }
-  return launch_stage_b_umma(h, src, o, P, 0, compute == DIINN_COMPUTE_FP16ACC, s);
+  const int fmt = fmt_of(compute);
+  const size_t plane = align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+  char* nhwc = ws + off;
+  char* nhwc_lo = fmt == kFmtSplit ? nhwc + plane : nullptr;
+  char* chain = nhwc + (fmt == kFmtSplit ? 2 : 1) * plane;
+  if ((rc = run_lr_stages(h, feat, io_dtype, fmt, B, H, W, 0, H, 0, H, P, nhwc, nhwc_lo, chain, s))) return rc;
+  return launch_stage_b_umma(h, src, o, P, 0, fmt, s);
 }
 
 int diinn_debug_gather(diinn_handle* h, int H, int W, int H_up, int W_up, int32_t* ih, int32_t* iw, float* rel_h,
                        float* rel_w, void* stream) {
   if (!h || !ih || !iw || !rel_h || !rel_w) return DIINN_ERR_BAD_ARG;
   if (H < 1 || W < 1 || H_up < 1 || W_up < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad shape");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   return launch_axis_tables(h, make_axis(H, H_up), make_axis(W, W_up), ih, iw, rel_h, rel_w,
                             static_cast<cudaStream_t>(stream));
 }
@@ -706,9 +768,15 @@ int diinn_debug_query_gather(diinn_handle* h, int B, int H, int W, const float* 
                              int32_t* idx, float* rel, float* ratio, void* stream) {
   if (!h || !coord || !cell || !idx || !rel || !ratio) return DIINN_ERR_BAD_ARG;
   if (B < 1 || H < 1 || W < 1 || Q < 1) return fail(h, DIINN_ERR_BAD_SHAPE, "bad shape");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   return launch_query_gather(h, make_query_source(B, H, W, coord, cell, Q), idx, rel, ratio,
                              static_cast<cudaStream_t>(stream));
+}
+
+int diinn_debug_set_tap(diinn_handle* h, int32_t* tap) {
+  if (!h) return DIINN_ERR_BAD_ARG;
+  h->tap = reinterpret_cast<int4*>(tap);
+  return DIINN_OK;
 }
 
 int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, int W, float* P, void* workspace,
@@ -716,17 +784,19 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
   if (!feat || !P) return fail(h, DIINN_ERR_BAD_ARG, "null pointer");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (compute == DIINN_COMPUTE_FP32) return launch_stage_a_fp32(h, feat, io_dtype, B, H, W, 0, H, P, s);
-  const size_t need = align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+  if (is_simt(compute)) return launch_stage_a_fp32(h, feat, io_dtype, B, H, W, 0, H, P, s);
+  const int fmt = fmt_of(compute);
+  const size_t plane = align_up(static_cast<size_t>(B) * H * W * kC * sizeof(__nv_bfloat16));
+  const size_t need = (fmt == kFmtSplit ? 2 : 1) * plane;
   if (!workspace || workspace_bytes < need)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL, "workspace too small: need " + std::to_string(need) + " bytes");
-  if (io_dtype == DIINN_IO_BF16_NHWC)
-    return launch_stage_a_umma(h, static_cast<const __nv_bfloat16*>(feat), B, H, W, 0, H, 0, H, P, s);
-  __nv_bfloat16* nhwc = static_cast<__nv_bfloat16*>(workspace);
-  if ((rc = launch_feat_to_nhwc_bf16(h, feat, io_dtype, B, H, W, 0, H, nhwc, s))) return rc;
-  return launch_stage_a_umma(h, nhwc, B, H, W, 0, H, 0, H, P, s);
+  char* nhwc = static_cast<char*>(workspace);
+  if (io_dtype == DIINN_IO_BF16_NHWC) return launch_stage_a_umma(h, feat, nullptr, kFmtBf16, B, H, W, 0, H, 0, H, P, s);
+  char* lo = fmt == kFmtSplit ? nhwc + plane : nullptr;
+  if ((rc = launch_feat_to_nhwc(h, feat, io_dtype, fmt, B, H, W, 0, H, nhwc, lo, s))) return rc;
+  return launch_stage_a_umma(h, nhwc, lo, fmt, B, H, W, 0, H, 0, H, P, s);
 }
 
 int diinn_debug_umma_pace(diinn_handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma,
@@ -735,25 +805,39 @@ int diinn_debug_umma_pace(diinn_handle* h, int cta_group, int n_cols, int iters,
   if ((cta_group != 1 && cta_group != 2) || n_cols < 16 || n_cols > 256 || n_cols % 16 || iters < 1 || n_ctas < cta_group ||
       n_ctas % cta_group)
     return fail(h, DIINN_ERR_BAD_SHAPE, "bad pace-probe arguments");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   return launch_umma_pace(h, cta_group, n_cols, iters, n_ctas, cyc_per_mma, noise, static_cast<cudaStream_t>(stream));
 }
 
+constexpr size_t kProfDecodes = 2048;  // decodes per profiling window (4 events each), created when profiling is enabled
+
 int diinn_set_profiling(diinn_handle* h, int enable) {
   if (!h) return DIINN_ERR_BAD_ARG;
-  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-  h->prof_events.clear();
+  DeviceGuard guard(h->cfg.device);
+  h->prof_used = 0;
   h->profiling = enable != 0;
+  if (h->profiling && h->prof_events.empty()) {
+    // all events are created HERE, never inside a decode (diinn_decode stays allocation-free and graph-capturable)
+    h->prof_events.reserve(4 * kProfDecodes);
+    for (size_t i = 0; i < 4 * kProfDecodes; ++i) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      h->prof_events.push_back(e);
+    }
+  } else if (!h->profiling) {
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    h->prof_events.clear();
+  }
   return DIINN_OK;
 }
 
 int diinn_get_kernel_times(diinn_handle* h, double* ms_layout, double* ms_stage_a, double* ms_stage_b,
                            int64_t* n_decodes) {
   if (!h || !ms_layout || !ms_stage_a || !ms_stage_b || !n_decodes) return DIINN_ERR_BAD_ARG;
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   *ms_layout = *ms_stage_a = *ms_stage_b = 0.0;
   *n_decodes = 0;
-  const size_t n = h->prof_events.size() / 4;
+  const size_t n = h->prof_used / 4;
   for (size_t i = 0; i < n; ++i) {
     cudaEvent_t* e = &h->prof_events[4 * i];
     DIINN_CUDA_OK(h, cudaEventSynchronize(e[3]));
@@ -764,15 +848,14 @@ int diinn_get_kernel_times(diinn_handle* h, double* ms_layout, double* ms_stage_
     *ms_layout += a, *ms_stage_a += b, *ms_stage_b += c;
   }
   *n_decodes = static_cast<int64_t>(n);
-  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-  h->prof_events.clear();
-  return DIINN_OK;
+  h->prof_used = 0;  // the events are reused by the next window
+  return check_err_flag(h);
 }
 
 int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n) {
   if (!h || !host_out || n < 1 || n > 1024) return DIINN_ERR_BAD_ARG;
   if (!h->trace_dev) return fail(h, DIINN_ERR_BAD_ARG, "no trace: run a bf16 decode with DIINN_TRACE=1 first");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   DIINN_CUDA_OK(h, cudaDeviceSynchronize());
   DIINN_CUDA_OK(h, cudaMemcpy(host_out, h->trace_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
   return DIINN_OK;
@@ -785,7 +868,7 @@ int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* 
       (cta_group != 1 && cta_group != 2 && cta_group != 11 && cta_group != 12))
     return fail(h, DIINN_ERR_BAD_SHAPE, "need M%128==0, N%256==0, K%64==0, cta_group in {1,2,11,12}");
   if (cta_group % 10 == 2 && M % 256) return fail(h, DIINN_ERR_BAD_SHAPE, "cta_group 2 needs M%256==0");
-  cudaSetDevice(h->cfg.device);
+  DeviceGuard guard(h->cfg.device);
   return launch_umma_selftest(h, A, B, D, M, N, K, cta_group, static_cast<cudaStream_t>(stream));
 }
 

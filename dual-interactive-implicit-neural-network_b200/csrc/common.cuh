@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/diinn_b200.h"
+#include "../../include/diinn_b200_debug.h"
 
 namespace diinn {
 
@@ -117,6 +118,7 @@ struct OutSpec {
   // bf16, pixel-major (pixel offset = the channel-0 offset computed from batch_stride / row_stride, x 256); csrc/mode4.cu
   // then runs the convolution. nullptr everywhere else.
   __nv_bfloat16* q3;
+  float* q3f;  // the same dump in fp32 (the fp32-precision tensor path, DIINN_COMPUTE_FP32); at most one of q3 / q3f is set
   // eval glue fused into the store (diinn_set_output_transform): bit 0 affine, bit 1 clamp, bit 2 uint8 quantisation
   int t_flags;
   float t_scale, t_bias, t_lo, t_hi;
@@ -156,7 +158,7 @@ struct SmallParams {
   float2 wq0_p[kD / 2][4]; // (w_relh, w_relw, w_ratio, bq0) x (f, f+1)
 };
 
-// Optional fused epilogue of the library GEMM (umma_selftest.cu) for the LR-resolution K chain of modes 1 / 2
+// Optional fused epilogue of the library GEMM (gemm.cu) for the LR-resolution K chain of modes 1 / 2
 // (lr_chain.cu): instead of D = A.B^T it does  P[m0 + r][256 layer + n] += acc  and hands the next layer its A operand,
 // A_next[r][n] = bf16(relu(that)).
 struct ChainEpilogue {

@@ -11,6 +11,11 @@
 
 namespace diinn {
 
+// operand formats of the tensor-core kernels (template parameter FMT of stage A / stage B)
+constexpr int kFmtBf16 = 0;   // bf16 operands
+constexpr int kFmtF16 = 1;    // fp16 operands (saturating conversions)
+constexpr int kFmtSplit = 2;  // fp16 hi + lo split, three MMAs per product: fp32-level precision on the tensor pipe
+
 struct Handle {
   diinn_config cfg{};
   int sm_count = 0;
@@ -20,9 +25,11 @@ struct Handle {
   // optional per-kernel timing of the tcgen05 path (diinn_set_profiling): 4 events per decode
   bool profiling = false;
   bool pdl = true;  // programmatic dependent launch of stage A / stage B (DIINN_NO_PDL=1 at diinn_create turns it off)
-  std::vector<cudaEvent_t> prof_events;
+  std::vector<cudaEvent_t> prof_events;  // created by diinn_set_profiling(1), 4 per decode, reused window after window
+  size_t prof_used = 0;
   long long* trace_dev = nullptr;  // DIINN_TRACE=1: 1024 clock64 samples of the last stage-B launch
   int* err_flag = nullptr;         // device word the tcgen05 kernels raise on an internal consistency failure
+  int4* tap = nullptr;             // diinn_debug_set_tap: per-pixel (ih, iw, rel) tap of the fused stage-B kernel
 
   // ---- fp32 CUDA-core path ----
   float* WA32 = nullptr;  // (1024, 576): rows [0,256) K.0; rows 256*i.. K.i[:,256:832]; reference k order c*9+tap
@@ -30,18 +37,19 @@ struct Handle {
   float bA_host[kPCols] = {};  // host copy: travels to the tcgen05 stage-A kernel as a by-value parameter
   float* bq_dev = nullptr;  // (4, 256): Q biases (device copy of small.bq)
   float* WB32 = nullptr;  // (3, 512, 256): layer i=1..3: rows [0,256) K.i[:, :256], rows [256,512) Q.i
-  // ---- tcgen05 path (bf16) ----
-  __nv_bfloat16* WA16 = nullptr;  // (4 n-blocks, 9 taps, 256 rows, 64 ch): K index permuted to tap*64 + c
-  __nv_bfloat16* WB16 = nullptr;  // (3 layers, 2 halves, 4 k-chunks, 256 rows, 64): rows [0,128) K-part, [128,256) Q-part
-  CUtensorMap tmapWA{};           // 2-D (64, 9216 rows), box (64, 256|128), 128B swizzle
-  CUtensorMap tmapWA_half{};
-  CUtensorMap tmapWB{};           // 2-D (64, 6144 rows)
-  CUtensorMap tmapWB_half{};
-  // fp16 twin of WB16 for the fp16-accumulator variant; inside every 256-row tile the K and Q rows are interleaved in
-  // 16-feature blocks (K f -> 32*(f/16) + f%16, Q f -> that + 16) so one packed TMEM load returns both branches
-  __half* WB16h = nullptr;
-  CUtensorMap tmapWBh{};
-  CUtensorMap tmapWBh_half{};
+  // ---- tcgen05 paths ----
+  // WA16[f]: (4 n-blocks, 9 taps, 256 rows, 64 ch), K index permuted to tap*64 + c; f = 0: bf16, f = 1: fp16 (= the hi part of
+  // the split format); WA16lo: fp16 residual W - fp16(W). WB16[f] / WB16lo likewise: (3 layers, 2 halves, 4 k-chunks, 256
+  // rows, 64) with rows [0,128) K-part, [128,256) Q-part. 16-bit storage; the element type only matters to the MMA.
+  uint16_t* WA16[2] = {nullptr, nullptr};
+  uint16_t* WA16lo = nullptr;
+  uint16_t* WB16[2] = {nullptr, nullptr};
+  uint16_t* WB16lo = nullptr;
+  // TMA maps, [format][cta_group - 1]: 2-D (64, rows), box (64, 256) for single CTAs and (64, 128) for CTA pairs, 128B swizzle
+  CUtensorMap tmapWA[2][2]{};
+  CUtensorMap tmapWAlo[2]{};
+  CUtensorMap tmapWB[2][2]{};
+  CUtensorMap tmapWBlo[2]{};
   // modes 1 / 2 (K chain entirely at LR resolution): the k-facing 256x256 blocks of K.1..3, row-major [n][k]
   float* WH32 = nullptr;          // (3, 256, 256)
   __nv_bfloat16* WH16 = nullptr;  // (3, 256, 256)
@@ -98,8 +106,10 @@ inline int fail(Handle* h, int code, const std::string& msg) {
 // ---- implemented across the .cu files -------------------------------------------------------------------
 // pack.cu
 int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s);
-int launch_feat_to_nhwc_bf16(Handle* h, const void* feat, int io_dtype, int B, int H, int W, int r0, int r1,
-                             __nv_bfloat16* dst, cudaStream_t s);
+// feat (B,64,H,W) NCHW fp32 | bf16, LR rows [r0,r1) -> (B, r1-r0, W, 64) 16-bit elements of operand format fmt (dst), plus
+// the fp16 residual plane dst_lo for kFmtSplit
+int launch_feat_to_nhwc(Handle* h, const void* feat, int io_dtype, int fmt, int B, int H, int W, int r0, int r1, void* dst,
+                        void* dst_lo, cudaStream_t s);
 // simt.cu
 int launch_axis_tables(Handle* h, const AxisParams& ah, const AxisParams& aw, int32_t* ih, int32_t* iw,
                        float* rel_h, float* rel_w, cudaStream_t s);
@@ -125,13 +135,14 @@ InitQPlan plan_initq(int B, int W_up, int rows, int compute, int mode, size_t of
 int run_initq_fp32(Handle* h, const void* feat, int io_dtype, const PixelSource& src, const OutSpec& out, char* ws,
                    const InitQPlan& pl, cudaStream_t s, float* q3_dump);
 int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, const PixelSource& src, const OutSpec& out,
-                   char* ws, const InitQPlan& pl, bool f16acc, cudaStream_t s);
+                   char* ws, const InitQPlan& pl, int fmt, cudaStream_t s);
 // stage_a_umma.cu / stage_b_umma.cu
-int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H, int W, int fr0, int frows,
-                        int lr_row0, int lr_rows, float* P, cudaStream_t s);
-int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group,
-                        bool f16acc, cudaStream_t s);
-// umma_selftest.cu
+// feat_nhwc: (B, frows, W, 64) 16-bit elements in the operand format fmt; feat_lo: the fp16 residual plane (kFmtSplit only)
+int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, int fmt, int B, int H, int W, int fr0,
+                        int frows, int lr_row0, int lr_rows, float* P, cudaStream_t s);
+int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group, int fmt,
+                        cudaStream_t s, int4* tap = nullptr);
+// gemm.cu
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
                          cudaStream_t s, const ChainEpilogue* chain = nullptr);
 int launch_umma_pace(Handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma, int noise,

@@ -16,7 +16,7 @@
 //
 // fp32 path: CUDA-core SGEMMs in the reference's channel order (c*9 + tap). Tensor path: bf16 operands in tap-major order
 // (tap*64 + c, so the gate reads whole 128-byte channel vectors of the NHWC feature copy), the library's tcgen05 GEMM
-// (umma_selftest.cu), fp32 PX / QS. Executed arithmetic: 2 264 064 FLOP per HR pixel (nothing is shared between pixels).
+// (gemm.cu), fp32 PX / QS. Executed arithmetic: 2 264 064 FLOP per HR pixel (nothing is shared between pixels).
 // Correct and on the tensor cores, not tuned: PX / XG / S round-trip through L2 / HBM (about 10 KB per pixel).
 #include <cstdlib>
 
@@ -202,7 +202,7 @@ static unsigned capped_blocks(const Handle* h, int64_t want) {
 // ---------------------------------------------------------------------------------------------------------
 InitQPlan plan_initq(int B, int W_up, int rows, int compute, int mode, size_t off) {
   InitQPlan p;
-  const bool fp32 = compute == DIINN_COMPUTE_FP32;
+  const bool fp32 = compute == DIINN_COMPUTE_FP32_SIMT;
   const int64_t total = static_cast<int64_t>(B) * rows * W_up;
   if (fp32) {
     p.chunk = total < kInitQChunkFp32 ? total : kInitQChunkFp32;
@@ -280,7 +280,7 @@ int run_initq_fp32(Handle* h, const void* feat, int io_dtype, const PixelSource&
 }
 
 int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, const PixelSource& src_in, const OutSpec& out,
-                   char* ws, const InitQPlan& pl, bool f16acc, cudaStream_t s) {
+                   char* ws, const InitQPlan& pl, int fmt, cudaStream_t s) {
   __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S);
   __nv_bfloat16* XG = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_XG);
   float* PX = reinterpret_cast<float*>(ws + pl.off_PX);
@@ -312,7 +312,7 @@ int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, con
       h->launches += 1;
       DIINN_CUDA_OK(h, cudaGetLastError());
     }
-    if ((rc = launch_stage_b_umma(h, src, out, PX, 0, f16acc, s))) return rc;
+    if ((rc = launch_stage_b_umma(h, src, out, PX, 0, fmt, s))) return rc;
   }
   return DIINN_OK;
 }

@@ -9,7 +9,7 @@
 // unchanged with ZERO K rows: relu(0 + P_i) = k_i, q_i = k_i * sin(Q_i q_{i-1} + bq_i).
 //
 // fp32 path: a plain tiled SGEMM on CUDA cores (exact fp32 FMA). Tensor path: per chunk of <= 32768 LR pixels,
-// one relu + bf16 conversion of block 0, then per layer the library's tcgen05 GEMM (umma_selftest.cu, 128x256 tiles,
+// one relu + bf16 conversion of block 0, then per layer the library's tcgen05 GEMM (gemm.cu, 128x256 tiles,
 // fp32 accumulation) with a fused epilogue: P_i += acc, and the next layer's A operand bf16(relu(P_i)) written
 // alongside (ChainEpilogue). Modes 1 / 2 are outside the benchmarked configuration.
 #include "handle.h"

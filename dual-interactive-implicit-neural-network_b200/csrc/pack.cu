@@ -12,9 +12,21 @@
 // Because every term multiplying x depends only on the LR pixel, the four x-facing blocks are stacked into one
 // (1024 x 576) matrix evaluated once per LR pixel ("stage A"); the per-HR-pixel work ("stage B") keeps only the
 // 256x256 q-facing blocks of K.1..3 next to Q.1..3.
+#include <cuda_fp16.h>
+
 #include "handle.h"
 
 namespace diinn {
+
+// the three 16-bit renderings of one fp32 weight: bf16, fp16 (saturating), fp16 residual after the fp16 part
+__device__ __forceinline__ void put_formats(float v, size_t idx, uint16_t* __restrict__ bf, uint16_t* __restrict__ hi,
+                                            uint16_t* __restrict__ lo) {
+  bf[idx] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+  const float vc = fminf(fmaxf(v, -65504.f), 65504.f);
+  const __half hh = __float2half_rn(vc);
+  hi[idx] = __half_as_ushort(hh);
+  lo[idx] = __half_as_ushort(__float2half_rn(vc - __half2float(hh)));
+}
 
 struct RefPtrs {
   const float* kw[4];
@@ -26,7 +38,8 @@ struct RefPtrs {
 };
 
 __global__ void pack_stage_a_kernel(RefPtrs r, int mode, float* __restrict__ WA32, float* __restrict__ bA,
-                                    __nv_bfloat16* __restrict__ WA16) {
+                                    uint16_t* __restrict__ WA_bf, uint16_t* __restrict__ WA_hi,
+                                    uint16_t* __restrict__ WA_lo) {
   const int n = blockIdx.x;  // 0..1023
   const int layer = n >> 8, row = n & 255;
   const int stride = layer == 0 ? kUnfold : kD + kUnfold;
@@ -38,13 +51,13 @@ __global__ void pack_stage_a_kernel(RefPtrs r, int mode, float* __restrict__ WA3
     WA32[static_cast<size_t>(n) * kUnfold + k] = v;
     const int c = k / 9, tap = k % 9;
     // (n-block, tap, row, c)
-    WA16[((static_cast<size_t>(layer) * 9 + tap) * 256 + row) * kC + c] = __float2bfloat16_rn(v);
+    put_formats(v, ((static_cast<size_t>(layer) * 9 + tap) * 256 + row) * kC + c, WA_bf, WA_hi, WA_lo);
   }
   if (threadIdx.x == 0) bA[n] = r.kb[layer][row];
 }
 
-__global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB32, __nv_bfloat16* __restrict__ WB16,
-                                    __half* __restrict__ WB16h, float* __restrict__ WH32,
+__global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB32, uint16_t* __restrict__ WB_bf,
+                                    uint16_t* __restrict__ WB_hi, uint16_t* __restrict__ WB_lo, float* __restrict__ WH32,
                                     __nv_bfloat16* __restrict__ WH16) {
   const int n = blockIdx.x;   // 0..511
   const int li = blockIdx.y;  // 0..2 -> reference layer li+1
@@ -55,8 +68,6 @@ __global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB3
   const bool to_chain = !is_q && (mode == 1 || mode == 2);  // k-facing block: LR chain instead of stage B
   const int half = row >> 7;                              // which 128-feature half of the layer output
   const int tile_row = (is_q ? 128 : 0) + (row & 127);    // K-part rows [0,128), Q-part rows [128,256)
-  const int fh = row & 127;                               // fp16 twin: K/Q interleaved in 16-feature blocks
-  const int tile_row_h = 32 * (fh >> 4) + (is_q ? 16 : 0) + (fh & 15);
   for (int k = threadIdx.x; k < kD; k += blockDim.x) {
     float v = src[k];
     if (to_chain) {
@@ -66,8 +77,7 @@ __global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB3
     }
     WB32[(static_cast<size_t>(li) * 512 + n) * kD + k] = v;
     const int kc = k >> 6, e = k & 63;
-    WB16[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row) * 64 + e] = __float2bfloat16_rn(v);
-    WB16h[((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row_h) * 64 + e] = __float2half_rn(v);
+    put_formats(v, ((((static_cast<size_t>(li) * 2 + half) * 4 + kc) * 256) + tile_row) * 64 + e, WB_bf, WB_hi, WB_lo);
   }
 }
 
@@ -94,11 +104,20 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   size_t total = 0;
   for (int i = 0; i < 4; ++i) total += sizes_kw[i] + sizes_qw[i] + 512;
   total += 9 * 3 * 256 + 4;
+  // host weights are staged on the device for the packing kernels; the guard frees the staging on every exit path
+  struct StagingGuard {
+    float** p;
+    ~StagingGuard() {
+      if (*p) cudaFree(*p);
+    }
+  } staging_guard{&staging};
   if (!w->on_device) {
     DIINN_CUDA_OK(h, cudaMalloc(&staging, total * sizeof(float)));
     float* p = staging;
+    cudaError_t up_err = cudaSuccess;
     auto up = [&](const float* src, size_t n) -> const float* {
-      cudaMemcpyAsync(p, src, n * sizeof(float), cudaMemcpyHostToDevice, s);
+      const cudaError_t e = cudaMemcpyAsync(p, src, n * sizeof(float), cudaMemcpyHostToDevice, s);
+      if (e != cudaSuccess && up_err == cudaSuccess) up_err = e;
       const float* d = p;
       p += n;
       return d;
@@ -111,6 +130,7 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     }
     r.lw = up(w->last_weight, mode == 4 ? 768 * 9 : 768);
     r.lb = up(w->last_bias, 3);
+    DIINN_CUDA_OK(h, up_err);
   } else {
     for (int i = 0; i < 4; ++i) {
       r.kw[i] = w->k_weight[i];
@@ -126,14 +146,17 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     DIINN_CUDA_OK(h, cudaMalloc(&h->bA, sizeof(float) * kPCols));
     DIINN_CUDA_OK(h, cudaMalloc(&h->WB32, sizeof(float) * 3 * 512 * kD));
     DIINN_CUDA_OK(h, cudaMalloc(&h->bq_dev, sizeof(float) * kLayers * kD));
-    DIINN_CUDA_OK(h, cudaMalloc(&h->WA16, sizeof(__nv_bfloat16) * kPCols * kUnfold));
-    DIINN_CUDA_OK(h, cudaMalloc(&h->WB16, sizeof(__nv_bfloat16) * 3 * 512 * kD));
-    DIINN_CUDA_OK(h, cudaMalloc(&h->WB16h, sizeof(__half) * 3 * 512 * kD));
+    for (int f = 0; f < 2; ++f) {
+      DIINN_CUDA_OK(h, cudaMalloc(&h->WA16[f], sizeof(uint16_t) * kPCols * kUnfold));
+      DIINN_CUDA_OK(h, cudaMalloc(&h->WB16[f], sizeof(uint16_t) * 3 * 512 * kD));
+    }
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WA16lo, sizeof(uint16_t) * kPCols * kUnfold));
+    DIINN_CUDA_OK(h, cudaMalloc(&h->WB16lo, sizeof(uint16_t) * 3 * 512 * kD));
     DIINN_CUDA_OK(h, cudaMalloc(&h->WH32, sizeof(float) * 3 * kD * kD));
     DIINN_CUDA_OK(h, cudaMalloc(&h->WH16, sizeof(__nv_bfloat16) * 3 * kD * kD));
   }
-  pack_stage_a_kernel<<<kPCols, 192, 0, s>>>(r, mode, h->WA32, h->bA, h->WA16);
-  pack_stage_b_kernel<<<dim3(512, 3), 128, 0, s>>>(r, mode, h->WB32, h->WB16, h->WB16h, h->WH32, h->WH16);
+  pack_stage_a_kernel<<<kPCols, 192, 0, s>>>(r, mode, h->WA32, h->bA, h->WA16[0], h->WA16[1], h->WA16lo);
+  pack_stage_b_kernel<<<dim3(512, 3), 128, 0, s>>>(r, mode, h->WB32, h->WB16[0], h->WB16[1], h->WB16lo, h->WH32, h->WH16);
   h->launches += 2;
   DIINN_CUDA_OK(h, cudaGetLastError());
 
@@ -236,28 +259,31 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
   }
   DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bq_dev, sp.bq, sizeof(float) * kLayers * kD, cudaMemcpyHostToDevice, s));
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
-  if (staging) cudaFree(staging);
 
   // TMA descriptors over the bf16 tiles (rows of 64 bf16 = 128 B, 128B swizzle applied by TMA on the way in)
   int rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWA, h->WA16, 64, 4 * 9 * 256, 64, 256))) return rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWA_half, h->WA16, 64, 4 * 9 * 256, 64, 128))) return rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB, h->WB16, 64, 3 * 2 * 4 * 256, 64, 256))) return rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWB_half, h->WB16, 64, 3 * 2 * 4 * 256, 64, 128))) return rc;
   // (same element size and no arithmetic in a TMA copy: the bf16 descriptor type moves fp16 bits unchanged)
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh, h->WB16h, 64, 3 * 2 * 4 * 256, 64, 256))) return rc;
-  if ((rc = make_tmap_2d_bf16(h, &h->tmapWBh_half, h->WB16h, 64, 3 * 2 * 4 * 256, 64, 128))) return rc;
+  for (int cg = 0; cg < 2; ++cg) {
+    const uint32_t box_rows = cg == 0 ? 256 : 128;  // CTA pairs split every 256-row tile by N halves
+    for (int f = 0; f < 2; ++f) {
+      if ((rc = make_tmap_2d_bf16(h, &h->tmapWA[f][cg], h->WA16[f], 64, 4 * 9 * 256, 64, box_rows))) return rc;
+      if ((rc = make_tmap_2d_bf16(h, &h->tmapWB[f][cg], h->WB16[f], 64, 3 * 2 * 4 * 256, 64, box_rows))) return rc;
+    }
+    if ((rc = make_tmap_2d_bf16(h, &h->tmapWAlo[cg], h->WA16lo, 64, 4 * 9 * 256, 64, box_rows))) return rc;
+    if ((rc = make_tmap_2d_bf16(h, &h->tmapWBlo[cg], h->WB16lo, 64, 3 * 2 * 4 * 256, 64, box_rows))) return rc;
+  }
   h->has_weights = true;
   return DIINN_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// feat (B,64,H,W) NCHW fp32|bf16, LR rows [r0,r1) -> (B, r1-r0, W, 64) bf16, the layout stage A's TMA im2col
-// boxes read (one 128-byte row per LR pixel and tap). Coalesced both ways through a padded smem tile.
+// feat (B,64,H,W) NCHW fp32|bf16, LR rows [r0,r1) -> (B, r1-r0, W, 64) in the 16-bit operand format FMT, the layout
+// stage A's TMA im2col boxes read (one 128-byte row per LR pixel and tap); the split format also writes the fp16
+// residual plane. Coalesced both ways through a padded smem tile.
 // ---------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void feat_to_nhwc_bf16_kernel(const T* __restrict__ feat, __nv_bfloat16* __restrict__ dst, int H, int W,
-                                         int r0, int rows) {
+template <typename T, int FMT>
+__global__ void feat_to_nhwc_kernel(const T* __restrict__ feat, uint32_t* __restrict__ dst, uint32_t* __restrict__ dst_lo,
+                                    int H, int W, int r0, int rows) {
   __shared__ float tile[kC][33];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // stage A may be scheduled while we drain (PDL)
   const int w0 = blockIdx.x * 32;
@@ -275,20 +301,42 @@ __global__ void feat_to_nhwc_bf16_kernel(const T* __restrict__ feat, __nv_bfloat
   for (int p = ty; p < 32; p += 8) {
     const int w = w0 + p;
     if (w < W) {
-      __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * tx][p], tile[2 * tx + 1][p]);
-      reinterpret_cast<__nv_bfloat162*>(dst + ((static_cast<size_t>(b) * rows + row) * W + w) * kC)[tx] = v;
+      const float a = tile[2 * tx][p], c = tile[2 * tx + 1][p];
+      const size_t o = ((static_cast<size_t>(b) * rows + row) * W + w) * (kC / 2) + tx;
+      if constexpr (FMT == kFmtBf16) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(a, c);
+        dst[o] = *reinterpret_cast<const uint32_t*>(&v);
+      } else {
+        const float ac = fminf(fmaxf(a, -65504.f), 65504.f), cc = fminf(fmaxf(c, -65504.f), 65504.f);
+        const __half2 v = __floats2half2_rn(ac, cc);
+        dst[o] = *reinterpret_cast<const uint32_t*>(&v);
+        if constexpr (FMT == kFmtSplit) {
+          const float2 back = __half22float2(v);
+          const __half2 l = __floats2half2_rn(ac - back.x, cc - back.y);
+          dst_lo[o] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+      }
     }
   }
 }
 
-int launch_feat_to_nhwc_bf16(Handle* h, const void* feat, int io_dtype, int B, int H, int W, int r0, int r1,
-                             __nv_bfloat16* dst, cudaStream_t s) {
+int launch_feat_to_nhwc(Handle* h, const void* feat, int io_dtype, int fmt, int B, int H, int W, int r0, int r1, void* dst,
+                        void* dst_lo, cudaStream_t s) {
   dim3 grid((W + 31) / 32, r1 - r0, B);
-  if (io_dtype == DIINN_IO_F32)
-    feat_to_nhwc_bf16_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(feat), dst, H, W, r0, r1 - r0);
-  else
-    feat_to_nhwc_bf16_kernel<__nv_bfloat16>
-        <<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), dst, H, W, r0, r1 - r0);
+  uint32_t* d = static_cast<uint32_t*>(dst);
+  uint32_t* dl = static_cast<uint32_t*>(dst_lo);
+  if (fmt == kFmtSplit && !dst_lo) return fail(h, DIINN_ERR_BAD_ARG, "layout pass: the split format needs the residual plane");
+#define DIINN_LAYOUT(T, FMTv) feat_to_nhwc_kernel<T, FMTv><<<grid, 256, 0, s>>>(static_cast<const T*>(feat), d, dl, H, W, r0, r1 - r0)
+  if (io_dtype == DIINN_IO_F32) {
+    if (fmt == kFmtBf16) DIINN_LAYOUT(float, kFmtBf16);
+    else if (fmt == kFmtF16) DIINN_LAYOUT(float, kFmtF16);
+    else DIINN_LAYOUT(float, kFmtSplit);
+  } else {
+    if (fmt == kFmtBf16) DIINN_LAYOUT(__nv_bfloat16, kFmtBf16);
+    else if (fmt == kFmtF16) DIINN_LAYOUT(__nv_bfloat16, kFmtF16);
+    else DIINN_LAYOUT(__nv_bfloat16, kFmtSplit);
+  }
+#undef DIINN_LAYOUT
   h->launches += 1;
   DIINN_CUDA_OK(h, cudaGetLastError());
   return DIINN_OK;

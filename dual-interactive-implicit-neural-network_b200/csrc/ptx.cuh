@@ -197,6 +197,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_acc16(int M, int N) {
   return (0u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// instruction descriptor, kind::f16: fp16 x fp16 -> fp32 accumulators, A and B K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
 // instruction descriptor, kind::f16: bf16 x bf16 -> fp32, A and B K-major
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
@@ -300,6 +305,12 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// saturating form: |x| > 65504 becomes +-65504 instead of inf (fp16 operands of the tensor paths)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 // the two fp16 halves of a register as floats (lo = lower 16 bits)

@@ -1,4 +1,4 @@
-// fp32 CUDA-core path of the DIINN query decoder (DIINN_COMPUTE_FP32) plus the coordinate / index kernels shared
+// fp32 CUDA-core path of the DIINN query decoder (DIINN_COMPUTE_FP32_SIMT) plus the coordinate / index kernels shared
 // by every path. True fp32 FMA arithmetic end to end: this is the path that meets the fp32 tolerance (1e-4) with
 // margin on any weight set; the throughput path is the tcgen05 one (stage_a_umma.cu / stage_b_umma.cu).
 //

@@ -16,6 +16,11 @@
 //
 // 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA), warp 2 = TMEM allocator, warps 4..7 = epilogue.
 // CG=2 runs CTA pairs (cta_group::2, M = 256 = two 8x16 LR patches, B split by N halves between the CTAs).
+//
+// Operand formats (FMT, handle.h): bf16, fp16, or the fp16 hi + lo SPLIT of the fp32-precision path, where every (n-block,
+// tap) becomes three ring stages -- (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) -- accumulated into the same TMEM columns.
+// Small launches (an 8-way row shard of a DIV2K image has 96 pixel tiles for 74 CTA pairs) split every tile's four
+// N-blocks into 2 or 4 work items so that the last wave is not mostly idle (Geo::nsplit).
 #include <cstdlib>
 
 #include "handle.h"
@@ -58,15 +63,18 @@ struct Geo {
   int B, H, W;            // feature map
   int fr0;                // first LR row held by the NHWC copy
   int lr_row0, lr_rows;   // LR rows to produce (rows of P per image)
-  int tiles_y, n_txp, n_work;
+  int tiles_y, n_txp, n_work;  // n_work = pixel tiles x nsplit
+  int nsplit;             // work items per pixel tile: each covers 4 / nsplit consecutive N-blocks (1, 2 or 4)
 };
 
-template <int CG>
+template <int CG, int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
-stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmW,
+stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmFlo,
+                    const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                     const __grid_constant__ CUtensorMap tmP, const __grid_constant__ BiasParams bias, const Geo g,
                     int* __restrict__ err_flag) {
   using C = Cfg<CG>;
+  constexpr int kTerms = FMT == kFmtSplit ? 3 : 1;  // ring stages per (n-block, tap)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_ring = smem;
   Smem& sm = *reinterpret_cast<Smem*>(smem + kRingBytes);
@@ -82,6 +90,10 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
     prefetch_tensormap(&tmF);
     prefetch_tensormap(&tmW);
     prefetch_tensormap(&tmP);
+    if constexpr (kTerms == 3) {
+      prefetch_tensormap(&tmFlo);
+      prefetch_tensormap(&tmWlo);
+    }
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&sm.w_full[i], 1);
       mbar_init(&sm.w_empty[i], 1);
@@ -98,6 +110,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_ptr;
   const int per_img = g.tiles_y * g.n_txp;
+  const int nb_cnt = 4 / g.nsplit;  // N-blocks per work item
   grid_dep_launch();  // stage B's CTAs may be scheduled as ours retire ...
   grid_dep_wait();    // ... and we read feat_nhwc only once the layout kernel has completed (PDL, see ptx.cuh)
 
@@ -106,50 +119,57 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
       uint32_t it = 0;
       int t = 0;
       for (int work = unit_id; work < g.n_work; work += n_units, ++t) {
-        const int b = work / per_img;
-        const int rem = work - b * per_img;
+        const int tile = work / g.nsplit, part = work - tile * g.nsplit;
+        const int b = tile / per_img;
+        const int rem = tile - b * per_img;
         const int ty = rem / g.n_txp, txp = rem - ty * g.n_txp;
         const int h0 = g.lr_row0 + ty * kPatchH;
         const int w0 = (txp * CG + rank) * kPatchW;
+        const int s_beg = part * nb_cnt * 9, s_end = s_beg + nb_cnt * 9;
 #pragma unroll 1
-        for (int s36 = 0; s36 < 36; ++s36, ++it) {  // (n-block, tap): the A tap tile is re-fetched per n-block (L2 hits)
+        for (int s36 = s_beg; s36 < s_end; ++s36) {  // (n-block, tap): the A tap tile is re-fetched per n-block (L2 hits)
           const int tap = s36 % 9;
-          const int st = it % C::kStages;
-          mbar_wait(&sm.w_empty[st], ((it / C::kStages) & 1) ^ 1);
-          if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
-            uint8_t* dst = s_ring + st * C::kStageBytes;
-            const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
-            if constexpr (CG == 1) {
-              tma_load_4d(dst, &tmF, &sm.w_full[st], 0, c1, c2, b);
-              tma_load_2d(dst + kTapBytes, &tmW, &sm.w_full[st], 0, s36 * 256);
-            } else {
-              tma_load_4d_2sm(dst, &tmF, &sm.w_full[st], 0, c1, c2, b);
-              tma_load_2d_2sm(dst + kTapBytes, &tmW, &sm.w_full[st], 0, s36 * 256 + rank * 128);
+          const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
+#pragma unroll 1
+          for (int term = 0; term < kTerms; ++term, ++it) {  // split: (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo)
+            const CUtensorMap* mf = (kTerms == 3 && term == 1) ? &tmFlo : &tmF;
+            const CUtensorMap* mw = (kTerms == 3 && term == 2) ? &tmWlo : &tmW;
+            const int st = it % C::kStages;
+            mbar_wait(&sm.w_empty[st], ((it / C::kStages) & 1) ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
+              uint8_t* dst = s_ring + st * C::kStageBytes;
+              if constexpr (CG == 1) {
+                tma_load_4d(dst, mf, &sm.w_full[st], 0, c1, c2, b);
+                tma_load_2d(dst + kTapBytes, mw, &sm.w_full[st], 0, s36 * 256);
+              } else {
+                tma_load_4d_2sm(dst, mf, &sm.w_full[st], 0, c1, c2, b);
+                tma_load_2d_2sm(dst + kTapBytes, mw, &sm.w_full[st], 0, s36 * 256 + rank * 128);
+              }
             }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (leader) {  // whole warp loops, tcgen05 instructions under elect_one() (see stage_b_umma.cu)
-      constexpr uint32_t idesc = umma_idesc_bf16(128 * CG, 256);
+      constexpr uint32_t idesc = FMT == kFmtBf16 ? umma_idesc_bf16(128 * CG, 256) : umma_idesc_f16(128 * CG, 256);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0, slot_use = 0;
       int t = 0;
       for (int work = unit_id; work < g.n_work; work += n_units, ++t) {
 #pragma unroll 1
-        for (int nb = 0; nb < 4; ++nb, ++slot_use) {
-          const int slot = nb & 1;
+        for (int nb = 0; nb < nb_cnt; ++nb, ++slot_use) {
+          const int slot = slot_use & 1;
           const uint32_t use = slot_use >> 1;  // how many times this slot was used before
           if constexpr (CG == 2) mbar_wait_cluster(&sm.tmem_empty[slot], (use & 1) ^ 1);
           else mbar_wait(&sm.tmem_empty[slot], (use & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_u + slot * 256;
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap, ++it) {
+          for (int tap = 0; tap < 9 * kTerms; ++tap, ++it) {
             const int st = it % C::kStages;
             mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
             tc_fence_after();
@@ -161,7 +181,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
                 umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
                               (tap | k) != 0 ? 1u : 0u);
               umma_commit<CG>(&sm.w_empty[st]);
-              if (tap == 8) umma_commit<CG>(&sm.tmem_full[slot]);
+              if (tap == 9 * kTerms - 1) umma_commit<CG>(&sm.tmem_full[slot]);
             }
             __syncwarp();
           }
@@ -176,14 +196,15 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
     const uint32_t srow = sbuf + lane * 128;  // this lane's tile row (TMEM lane) inside the warp's 32-row block
     uint32_t slot_use = 0;
     for (int work = unit_id; work < g.n_work; work += n_units) {
-      const int b = work / per_img;
-      const int rem = work - b * per_img;
+      const int tile = work / g.nsplit, part = work - tile * g.nsplit;
+      const int b = tile / per_img;
+      const int rem = tile - b * per_img;
       const int ty = rem / g.n_txp, txp = rem - ty * g.n_txp;
       const int h0 = ty * kPatchH + 2 * quarter;          // relative to lr_row0; this warp owns patch rows 2q, 2q+1
       const int w0 = (txp * CG + rank) * kPatchW;
 #pragma unroll 1
-      for (int nb = 0; nb < 4; ++nb, ++slot_use) {
-        const int slot = nb & 1;
+      for (int nb = part * nb_cnt; nb < (part + 1) * nb_cnt; ++nb, ++slot_use) {
+        const int slot = slot_use & 1;
         mbar_wait(&sm.tmem_full[slot], (slot_use >> 1) & 1);
         tc_fence_after();
         const uint32_t tslot = tmem_base + lane_bits + slot * 256;
@@ -231,8 +252,8 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
 
 }  // namespace sa
 
-int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H, int W, int fr0, int frows,
-                        int lr_row0, int lr_rows, float* P, cudaStream_t s) {
+int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, int fmt, int B, int H, int W, int fr0,
+                        int frows, int lr_row0, int lr_rows, float* P, cudaStream_t s) {
   using namespace sa;
   static int env_cg = -1;
   if (env_cg < 0) {
@@ -241,14 +262,17 @@ int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H,
   }
   const int cta_group = env_cg;
   int* err_flag = h->err_flag;
-  CUtensorMap tmF;
+  if (fmt < 0 || fmt > kFmtSplit) return fail(h, DIINN_ERR_BAD_DTYPE, "stage A: unknown operand format");
+  if (fmt == kFmtSplit && !feat_lo) return fail(h, DIINN_ERR_BAD_ARG, "stage A: the split format needs the residual plane");
+  CUtensorMap tmF, tmFlo;
   const uint64_t dims[4] = {static_cast<uint64_t>(kC), static_cast<uint64_t>(W), static_cast<uint64_t>(frows),
                             static_cast<uint64_t>(B)};
   const uint64_t strides[3] = {kC * 2ull, static_cast<uint64_t>(W) * kC * 2ull,
                                static_cast<uint64_t>(frows) * W * kC * 2ull};
   const uint32_t box[4] = {kC, kPatchW, kPatchH, 1};
-  int rc = make_tmap_4d_bf16(h, &tmF, feat_nhwc, dims, strides, box);
+  int rc = make_tmap_4d_bf16(h, &tmF, feat_nhwc, dims, strides, box);  // 16-bit elements: the type only matters to the MMA
   if (rc) return rc;
+  if ((rc = make_tmap_4d_bf16(h, &tmFlo, fmt == kFmtSplit ? feat_lo : feat_nhwc, dims, strides, box))) return rc;
   CUtensorMap tmP;
   const uint64_t pdims[4] = {static_cast<uint64_t>(kPCols), static_cast<uint64_t>(W), static_cast<uint64_t>(lr_rows),
                              static_cast<uint64_t>(B)};
@@ -263,8 +287,29 @@ int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H,
   const int tiles_x = (W + kPatchW - 1) / kPatchW;
   g.tiles_y = (lr_rows + kPatchH - 1) / kPatchH;
   g.n_txp = (tiles_x + cta_group - 1) / cta_group;
-  g.n_work = B * g.tiles_y * g.n_txp;
-  int units = h->sm_count / cta_group;
+  const int n_tiles = B * g.tiles_y * g.n_txp;
+  const int max_units = h->sm_count / cta_group;
+  // N-block split: the split with the fewest (fractional) waves wins, ties go to the coarser one (less A re-fetch set-up)
+  g.nsplit = 1;
+  {
+    static int env_ns = -1;
+    if (env_ns < 0) {
+      const char* e = getenv("DIINN_STAGE_A_NSPLIT");
+      env_ns = e ? atoi(e) : 0;
+    }
+    if (env_ns == 1 || env_ns == 2 || env_ns == 4) {
+      g.nsplit = env_ns;
+    } else {
+      double best = 1e30;
+      for (int ns = 1; ns <= 4; ns *= 2) {
+        const int items = n_tiles * ns;
+        const double waves = static_cast<double>((items + max_units - 1) / max_units) / ns;
+        if (waves < best - 1e-9) best = waves, g.nsplit = ns;
+      }
+    }
+  }
+  g.n_work = n_tiles * g.nsplit;
+  int units = max_units;
   if (units > g.n_work) units = g.n_work;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(units * cta_group, 1, 1);
@@ -280,15 +325,25 @@ int launch_stage_a_umma(Handle* h, const __nv_bfloat16* feat_nhwc, int B, int H,
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = h->pdl ? 2 : 1;
+  const int ci = cta_group - 1;
+  const CUtensorMap& tmW = h->tmapWA[fmt == kFmtBf16 ? 0 : 1][ci];
+  const CUtensorMap& tmWlo = h->tmapWAlo[ci];
+#define DIINN_SA_LAUNCH(CGv, FMTv)                                                                                        \
+  do {                                                                                                                    \
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<CGv, FMTv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          static_cast<int>(kSmemBytes)));                                                 \
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<CGv, FMTv>, tmF, tmFlo, tmW, tmWlo, tmP, bias, g, err_flag)); \
+  } while (0)
   if (cta_group == 1) {
-    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(kSmemBytes)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<1>, tmF, h->tmapWA, tmP, bias, g, err_flag));
+    if (fmt == kFmtBf16) DIINN_SA_LAUNCH(1, kFmtBf16);
+    else if (fmt == kFmtF16) DIINN_SA_LAUNCH(1, kFmtF16);
+    else DIINN_SA_LAUNCH(1, kFmtSplit);
   } else {
-    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(kSmemBytes)));
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<2>, tmF, h->tmapWA_half, tmP, bias, g, err_flag));
+    if (fmt == kFmtBf16) DIINN_SA_LAUNCH(2, kFmtBf16);
+    else if (fmt == kFmtF16) DIINN_SA_LAUNCH(2, kFmtF16);
+    else DIINN_SA_LAUNCH(2, kFmtSplit);
   }
+#undef DIINN_SA_LAUNCH
   h->launches += 1;
   return DIINN_OK;
 }

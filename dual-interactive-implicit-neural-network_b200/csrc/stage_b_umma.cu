@@ -23,6 +23,14 @@
 // operand (the chunk that gates the next layer is one step behind the layer's last MMA). The control warpgroup gives
 // its registers away (setmaxnreg) so each epilogue thread can hold two prefetched slices of P next to its accumulators.
 //
+// Operand formats (template FMT): 0 = bf16 operands, 1 = fp16 operands (11-bit mantissa: 8x less operand noise at the same
+// tensor rate; conversions saturate at +-65504), 2 = fp16 hi + lo SPLIT -- every activation and weight is the sum of two
+// fp16 numbers (22 mantissa bits) and each product is evaluated as a_hi w_hi + a_lo w_hi + a_hi w_lo (three MMAs into
+// the same fp32 accumulator; the dropped a_lo w_lo term is 2^-22 relative). That is the fp32-PRECISION path on the
+// tensor pipe (precision="fp32", DIINN_COMPUTE_FP32): activations stay in ONE 128 KB buffer (hi | lo halves), rewritten
+// in place once all MMAs of a layer have retired, and the sine is range-reduced (Cody-Waite) before MUFU.SIN.
+// Accumulation is fp32 in TMEM in every format.
+//
 // Measured alternatives that did NOT pay: two 8-warp groups (one per half slot), four 128-column
 // slots with per-slot groups, three slots (256|128|128), fp16 accumulators, packed FFMA2 for the RGB projection.
 #include <cstdio>
@@ -68,6 +76,8 @@ static_assert(kSmemBytes <= 232448, "exceeds 227 KB of dynamic shared memory");
 struct Work {
   int n_work;          // work items per CTA pair (CG=2) / CTA (CG=1)
   int tiles_y, n_txp;  // grid mode
+  int4* tap;           // debug (diinn_debug_stage_b_rows): per output pixel (ih, iw, bits(rel_h), bits(rel_w)) as THIS kernel
+                       // derives them, indexed by the pixel's channel-0 output offset; nullptr in product calls
 };
 
 struct RowCtx {
@@ -82,7 +92,7 @@ struct RowCtx {
 // (b, row, col) -- instead of one per LR cell, and the launch covers a chunk of the band whose first row is out_row0.
 template <int CG, bool kPix = false>
 __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& o, const float* __restrict__ P,
-                                           const Work& wk, int work, int rank, int r) {
+                                           const Work& wk, int work, int rank, int r, bool write_tap = false) {
   RowCtx rc;
   if (s.mode == 0) {
     const int per_img = wk.tiles_y * wk.n_txp;
@@ -105,6 +115,8 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
     rc.rel_w = axis_rel(s.ax_w, owc, iw);
     rc.ratio = s.ratio;
     rc.out_off = b * o.batch_stride + static_cast<int64_t>(ohc - (kPix ? s.out_row0 : s.row0)) * o.row_stride + owc;
+    if (wk.tap != nullptr && write_tap && rc.valid)
+      wk.tap[rc.out_off] = make_int4(ih, iw, __float_as_int(rc.rel_h), __float_as_int(rc.rel_w));
   } else {
     const int64_t total = static_cast<int64_t>(s.B) * s.Q * (s.ensemble ? 4 : 1);
     const int64_t g = (static_cast<int64_t>(work) * CG + rank) * kTileM + r;
@@ -222,94 +234,116 @@ __device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[
   for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p) + j);
 }
 
+// Sine of the Q branch (SineAct, diinn.py:21-26). MUFU.SIN works on x / 2pi rounded to fp32, so its absolute error grows as
+// ~6e-8 |x| (1e-5 at |x| = 200): far inside the 16-bit-operand paths' budget for any sane argument. The split (fp32-
+// precision) path first removes the whole turns with a two-constant Cody-Waite reduction, which keeps the error at the
+// MUFU's own ~5e-7 for |x| up to ~1e5.
+template <bool kReduce>
 __device__ __forceinline__ float act_sin(float x) {
 #if DIINN_ABL & 4
   return x * 0.5f;
 #else
+  if constexpr (kReduce) {
+    const float k = __fadd_rn(__fmaf_rn(x, 0.15915494309189535f, 12582912.f), -12582912.f);  // rint(x / 2pi)
+    x = __fmaf_rn(k, -6.28318548202514648f, x);      // fp32(2pi)
+    x = __fmaf_rn(k, 1.74845553146951715e-7f, x);    // fp32(2pi) - 2pi
+  }
   return __sinf(x);
 #endif
 }
 
+// operand conversion of FMT: two fp32 -> one packed register of bf16 (FMT 0) or saturating fp16 (FMT 1, 2)
+template <int FMT>
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+  if constexpr (FMT == 0) return pack_bf16x2(lo, hi);
+  else return pack_f16x2_sat(lo, hi);
+}
+// split formats: the fp16 residual of (a, b) after their fp16 part `hi16`
+__device__ __forceinline__ uint32_t pack_residual(float a, float b, uint32_t hi16) {
+  float ha, hb;
+  unpack_f16x2(hi16, ha, hb);
+  return pack_f16x2_sat(__fsub_rn(a, ha), __fsub_rn(b, hb));
+}
+
 // layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
-template <bool F16, bool kPix = false>
+// Split formats write the fp16 residual into the lo half of the buffer (same swizzled position, kActBytes further on).
+template <int FMT, bool kPix = false>
 __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
                                             const SmallParams& sp, const float4 (&k0v)[4]) {
+  constexpr bool kSplit = FMT == 2;
   const uint32_t chunk_base = act_base + kc * kChunkBytes;
   const int f0 = kc * 64 + wg * 16;
   const float* k0 = reinterpret_cast<const float*>(k0v);
-  uint32_t pk[8];
+  uint32_t pk[8], pl[8];
   if constexpr (kPix) {  // init_q=True: Q.0 reads the 576-wide gate, so q_0 was finished per pixel by csrc/init_q.cu
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) pk[j >> 1] = F16 ? pack_f16x2(k0[j], k0[j + 1]) : pack_bf16x2(k0[j], k0[j + 1]);
-    st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
-    st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
-    return;
-  }
-  const float2 rh = make_float2(rc.rel_h, rc.rel_h), rw = make_float2(rc.rel_w, rc.rel_w), ra = make_float2(rc.ratio, rc.ratio);
+    for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_op<FMT>(k0[j], k0[j + 1]);
+  } else {
+    const float2 rh = make_float2(rc.rel_h, rc.rel_h), rw = make_float2(rc.rel_w, rc.rel_w), ra = make_float2(rc.ratio, rc.ratio);
 #pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    // packed fp32x2 (two features per instruction; per feature the same three fused multiply-adds as the scalar form)
-    const float2* w = &sp.wq0_p[(f0 + j) >> 1][0];
-    float2 t = __ffma2_rn(w[0], rh, w[3]);
-    t = __ffma2_rn(w[1], rw, t);
-    t = __ffma2_rn(w[2], ra, t);
-    const float2 q = __fmul2_rn(make_float2(k0[j], k0[j + 1]), make_float2(act_sin(t.x), act_sin(t.y)));
-    pk[j >> 1] = F16 ? pack_f16x2(q.x, q.y) : pack_bf16x2(q.x, q.y);
+    for (int j = 0; j < 16; j += 2) {
+      // packed fp32x2 (two features per instruction; per feature the same three fused multiply-adds as the scalar form)
+      const float2* w = &sp.wq0_p[(f0 + j) >> 1][0];
+      float2 t = __ffma2_rn(w[0], rh, w[3]);
+      t = __ffma2_rn(w[1], rw, t);
+      t = __ffma2_rn(w[2], ra, t);
+      const float2 q = __fmul2_rn(make_float2(k0[j], k0[j + 1]), make_float2(act_sin<kSplit>(t.x), act_sin<kSplit>(t.y)));
+      pk[j >> 1] = pack_op<FMT>(q.x, q.y);
+      if constexpr (kSplit) pl[j >> 1] = pack_residual(q.x, q.y, pk[j >> 1]);
+    }
   }
   st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
   st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
-}
-
-// ---- epilogue of 16 features [128h + 64c + 16wg, +16) of one row, reference layer `layer` (1..3) ------------------
-// raw accumulator registers of one step: fp32 accumulators = 16 K + 16 Q columns (32 regs); fp16 accumulators (K and Q
-// rows interleaved in 16-feature blocks by pack.cu) = 32 columns packed two per register (16 regs)
-template <bool F16>
-struct Raw {
-  uint32_t v[F16 ? 16 : 32];
-};
-
-template <bool F16>
-__device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw<F16>& raw) {  // issue only; caller waits
-#if DIINN_ABL & 16
-#pragma unroll
-  for (int i = 0; i < (F16 ? 16 : 32); ++i) raw.v[i] = tslot + col + i;
-  return;
-#endif
-  if constexpr (F16) {
-    tmem_ld32_pack16(tslot + 2 * col, raw.v);
-  } else {
-    tmem_ld16(tslot + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[0]));
-    tmem_ld16(tslot + 128 + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[16]));
+  if constexpr (kSplit) {
+    st_shared_v4(swz(chunk_base + kActBytes, r, wg * 2), pl[0], pl[1], pl[2], pl[3]);
+    st_shared_v4(swz(chunk_base + kActBytes, r, wg * 2 + 1), pl[4], pl[5], pl[6], pl[7]);
   }
 }
 
+// ---- epilogue of 16 features [128h + 64c + 16wg, +16) of one row, reference layer `layer` (1..3) ------------------
+// raw accumulator registers of one step: 16 K + 16 Q columns of fp32
+struct Raw {
+  uint32_t v[32];
+};
+
+__device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw& raw) {  // issue only; caller waits
+#if DIINN_ABL & 16
+#pragma unroll
+  for (int i = 0; i < 32; ++i) raw.v[i] = tslot + col + i;
+  return;
+#endif
+  tmem_ld16(tslot + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[0]));
+  tmem_ld16(tslot + 128 + col, *reinterpret_cast<uint32_t(*)[16]>(&raw.v[16]));
+}
+
 // kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
-template <bool kLast, bool F16, bool kDump = false>
-__device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
+// kDump (mode 4): q_3 goes to HBM for the 3x3 last conv -- bf16 (q3row) from the 16-bit-operand formats, fp32 (q3row_f) from
+// the split format.
+template <bool kLast, int FMT, bool kDump = false>
+__device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
                                          const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3],
-                                         __nv_bfloat16* q3row = nullptr) {
+                                         __nv_bfloat16* q3row = nullptr, float* q3row_f = nullptr) {
+  constexpr bool kSplit = FMT == 2;
   const int col = c * 64 + wg * 16;
   const int f0 = h * 128 + col;
   const float* kx = reinterpret_cast<const float*>(kxv);
-  uint32_t pk[8];
+  uint32_t pk[8], pl[8];
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
-    float ak[2], aq[2];
-    if constexpr (F16) {
-      unpack_f16x2(raw.v[j >> 1], ak[0], ak[1]);
-      unpack_f16x2(raw.v[8 + (j >> 1)], aq[0], aq[1]);
-    } else {
-      ak[0] = __uint_as_float(raw.v[j]), ak[1] = __uint_as_float(raw.v[j + 1]);
-      aq[0] = __uint_as_float(raw.v[16 + j]), aq[1] = __uint_as_float(raw.v[16 + j + 1]);
-    }
+    const float ak[2] = {__uint_as_float(raw.v[j]), __uint_as_float(raw.v[j + 1])};
+    const float aq[2] = {__uint_as_float(raw.v[16 + j]), __uint_as_float(raw.v[16 + j + 1])};
     // packed fp32x2 adds / multiplies (Blackwell FADD2 / FMUL2)
     float2 k2 = __fadd2_rn(make_float2(ak[0], ak[1]), make_float2(kx[j], kx[j + 1]));
     k2.x = fmaxf(k2.x, 0.f), k2.y = fmaxf(k2.y, 0.f);
     const float2 t2 = __fadd2_rn(make_float2(aq[0], aq[1]), *reinterpret_cast<const float2*>(&sp.bq[layer][f0 + j]));
-    const float2 q2 = __fmul2_rn(k2, make_float2(act_sin(t2.x), act_sin(t2.y)));
+    const float2 q2 = __fmul2_rn(k2, make_float2(act_sin<kSplit>(t2.x), act_sin<kSplit>(t2.y)));
     const float q[2] = {q2.x, q2.y};
-    if constexpr (kLast && kDump) {  // mode 4: q_3 goes to HBM as bf16 for the 3x3 last conv
-      pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+    if constexpr (kLast && kDump) {
+      if constexpr (kSplit) {
+        if (q3row_f != nullptr) *reinterpret_cast<float2*>(q3row_f + f0 + j) = q2;
+      } else {
+        pk[j >> 1] = pack_bf16x2(q[0], q[1]);
+      }
     } else if constexpr (kLast) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -319,9 +353,12 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
         rgb[2] = fmaf(w.z, q[e], rgb[2]);
       }
     }
-    if constexpr (!kLast) pk[j >> 1] = F16 ? pack_f16x2(q[0], q[1]) : pack_bf16x2(q[0], q[1]);
+    if constexpr (!kLast) {
+      pk[j >> 1] = pack_op<FMT>(q[0], q[1]);
+      if constexpr (kSplit) pl[j >> 1] = pack_residual(q[0], q[1], pk[j >> 1]);
+    }
   }
-  if constexpr (kLast && kDump) {
+  if constexpr (kLast && kDump && !kSplit) {
     if (q3row != nullptr) {  // rows outside the image / band have no store target
       uint4* dst = reinterpret_cast<uint4*>(q3row + f0);
       dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -335,19 +372,26 @@ __device__ __forceinline__ void epi_math(const Raw<F16>& raw, uint32_t out_base,
 #else
     st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
     st_shared_v4(swz(chunk_base, r, wg * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
+    if constexpr (kSplit) {
+      st_shared_v4(swz(chunk_base + kActBytes, r, wg * 2), pl[0], pl[1], pl[2], pl[3]);
+      st_shared_v4(swz(chunk_base + kActBytes, r, wg * 2 + 1), pl[4], pl[5], pl[6], pl[7]);
+    }
 #endif
   }
 }
 
 // kDump (mode 4): a separate instantiation, so the q_3 dump costs the RGB-projecting kernels neither a register nor a branch.
 // kPix (init_q=True): see make_row / layer0_step.
-template <int CG, bool F16, bool kDump, bool kPix>
+template <int CG, int FMT, bool kDump, bool kPix>
 __global__ void __launch_bounds__(kThreads, 1)
-stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ SmallParams sp,
+stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
+                    const __grid_constant__ SmallParams sp,
                     const __grid_constant__ PixelSource src, const __grid_constant__ OutSpec out,
                     const float* __restrict__ P, const __grid_constant__ Work wk,
                     int* __restrict__ err_flag, long long* __restrict__ trace) {
   using C = Cfg<CG>;
+  constexpr bool kSplit = FMT == 2;
+  static_assert(!(kSplit && kPix), "the split format is not wired for per-pixel P (init_q=True runs on the fp32 CUDA-core path)");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_act = smem;                     // 2 x 64 KB
   uint8_t* s_w = smem + 2 * kActBytes;       // 96 KB of weight stages
@@ -375,6 +419,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmW);
+    if constexpr (kSplit) prefetch_tensormap(&tmWlo);
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(&sm.w_full[i], 1);
       mbar_init(&sm.w_empty[i], 1);
@@ -410,7 +455,11 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
       // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues
-      for (int s24 = 0; s24 < 24; ++s24, ++it) {  // (layer-1, half, kc) in MMA consumption order
+      // (layer-1, half, kc) in MMA consumption order; the split format streams the hi and then the lo tile of each
+      constexpr int kLoads = kSplit ? 48 : 24;
+      for (int sl = 0; sl < kLoads; ++sl, ++it) {
+        const int s24 = kSplit ? (sl >> 1) : sl;
+        const CUtensorMap* tm = (kSplit && (sl & 1)) ? &tmWlo : &tmW;
         const int st = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1;
         mbar_wait(&sm.w_empty[st], ph ^ 1);
@@ -418,9 +467,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
           void* dst = s_w + st * C::kStageBytes;
           if constexpr (CG == 1)
-            tma_load_2d(dst, &tmW, &sm.w_full[st], 0, s24 * 256);
+            tma_load_2d(dst, tm, &sm.w_full[st], 0, s24 * 256);
           else
-            tma_load_2d_2sm(dst, &tmW, &sm.w_full[st], 0, s24 * 256 + rank * 128);
+            tma_load_2d_2sm(dst, tm, &sm.w_full[st], 0, s24 * 256 + rank * 128);
         }
         __syncwarp();
       }
@@ -433,7 +482,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // from a divergent single-lane region instead, each UTCHMMA costs an ELECT + 5x R2UR.BROADCAST waterfall
     // (~100 clk), which capped the tensor pipe at ~200 clk per MMA instead of 128.
     if (leader) {
-      constexpr uint32_t idesc = F16 ? umma_idesc_f16_acc16(128 * CG, 256) : umma_idesc_bf16(128 * CG, 256);
+      constexpr uint32_t idesc = FMT == 0 ? umma_idesc_bf16(128 * CG, 256) : umma_idesc_f16(128 * CG, 256);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0;            // weight stage counter
       uint32_t act_phase = 0;     // bit b: parity to wait for on act_ready[b][*]
@@ -443,7 +492,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const int X = t & 1;
 #pragma unroll 1
         for (int layer = 1; layer <= 3; ++layer) {
-          const int bin = (layer == 2) ? (X ^ 1) : X;  // L1: buf X, L2: buf X^1, L3: buf X
+          // L1: buf X, L2: buf X^1, L3: buf X; the split format has ONE buffer (hi half | lo half), rewritten in place
+          const int bin = kSplit ? 0 : ((layer == 2) ? (X ^ 1) : X);
           const uint32_t a_base = act0 + bin * kActBytes;
           const uint32_t aph = (act_phase >> bin) & 1;
 #pragma unroll 1
@@ -472,10 +522,30 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                 for (int k = 0; k < 4; ++k)
                   umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
                                 (kc | k) != 0 ? 1u : 0u);
+                if constexpr (kSplit) {  // a_lo . w_hi on the same weight stage
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + kActBytes + k * 32), umma_desc_sw128(b0 + k * 32), idesc, 1u);
+                }
                 umma_commit<CG>(&sm.w_empty[st]);
-                if (kc == 3) umma_commit<CG>(&sm.tmem_full[h]);
+                if (!kSplit && kc == 3) umma_commit<CG>(&sm.tmem_full[h]);
               }
               __syncwarp();
+              if constexpr (kSplit) {  // a_hi . w_lo on the next stage
+                ++it;
+                const int st2 = it % C::kStages;
+                mbar_wait(&sm.w_full[st2], (it / C::kStages) & 1);
+                tc_fence_after();
+                const uint32_t b1 = smem_u32(s_w + st2 * C::kStageBytes);
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b1 + k * 32), idesc, 1u);
+                  umma_commit<CG>(&sm.w_empty[st2]);
+                  if (kc == 3) umma_commit<CG>(&sm.tmem_full[h]);
+                }
+                __syncwarp();
+              }
             }
             if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 9);
           }
@@ -516,12 +586,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       // (the P prefetch is issued AFTER the proxy fence: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
       // which waits for every outstanding global load of the thread -- a prefetch issued just before it exposes its
       // whole L2 latency in every step; measured)
-      layer0_step<F16, kPix>(buf, kc0, fg, r, rcx, sp, ka);
+      layer0_step<FMT, kPix>(buf, kc0, fg, r, rcx, sp, ka);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
       if (nb) load16(nb, ka);
-      layer0_step<F16, kPix>(buf, kc0 + 1, fg, r, rcx, sp, kb);
+      layer0_step<FMT, kPix>(buf, kc0 + 1, fg, r, rcx, sp, kb);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
@@ -529,7 +599,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     };
 
     if (work < wk.n_work) {
-      rc = make_row<CG, kPix>(src, out, P, wk, work, rank, r);
+      rc = make_row<CG, kPix>(src, out, P, wk, work, rank, r, fg == 0);
       const float* p0 = rc.prow + fg * 16;
       load16(p0, ka);
       load16(p0 + 64, kb);
@@ -546,21 +616,29 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       float rgb[3] = {0.f, 0.f, 0.f};  // this warp's share of the RGB projection (scalar FFMA: measured faster than FFMA2 here)
       // mode 4: this row's q_3 vector in the dump buffer (rows outside the image / band get no store target)
       __nv_bfloat16* q3row = nullptr;
-      if constexpr (kDump) q3row = rc.valid ? out.q3 + rc.out_off * kD : nullptr;
+      float* q3row_f = nullptr;  // the split format dumps fp32
+      if constexpr (kDump && !kSplit) q3row = rc.valid ? out.q3 + rc.out_off * kD : nullptr;
+      if constexpr (kDump && kSplit) q3row_f = rc.valid ? out.q3f + rc.out_off * kD : nullptr;
 #pragma unroll 1
       for (int layer = 1; layer <= 3; ++layer) {
-        const int bout = (layer == 2) ? X : (X ^ 1);  // L1 writes X^1, L2 writes X, (L3 writes nothing)
+        // L1 writes X^1, L2 writes X, (L3 writes nothing); split format: the one buffer, in place
+        const int bout = kSplit ? 0 : ((layer == 2) ? X : (X ^ 1));
         const uint32_t out_base = act0 + bout * kActBytes;
         const bool last = layer == 3;
         if (layer == 2 && has_next) {
-          rc_next = make_row<CG, kPix>(src, out, P, wk, next_work, rank, r);
+          rc_next = make_row<CG, kPix>(src, out, P, wk, next_work, rank, r, fg == 0);
           pn = rc_next.prow + fg * 16;
         }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+          // Split format: this layer's epilogue (and the next tile's layer 0) overwrite the buffer the layer's MMAs read, so
+          // nothing may be written before ALL of them have retired, i.e. before half slot 1 is complete.
+          if constexpr (kSplit) {
+            if (h == 0) mbar_wait(&sm.tmem_full[1], full_uses & 1);
+          }
           // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs: complete, because
           // this warp has itself consumed tmem_full[1] of layer 2. Its four chunks are interleaved with layer 3's halves.
-          if (last && has_next) layer0_unit(X ^ 1, 2 * h, rc_next, pw + 3 * kD + h * 128);
+          if (last && has_next) layer0_unit(kSplit ? 0 : (X ^ 1), 2 * h, rc_next, pw + 3 * kD + h * 128);
           // unit after this one: the other half / the next layer / layer 0 of the next tile / the next tile's layer 1
           const float* nb;
           if (!last) nb = (h == 0) ? pw + layer * kD + 128 : (layer == 1 || !has_next) ? pw + (layer + 1) * kD : pn;
@@ -570,9 +648,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           mbar_wait(&sm.tmem_full[h], full_uses & 1);
           tc_fence_after();
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 1);
-          Raw<F16> ra, rb;
-          epi_load<F16>(tslot, fg * 16, ra);
-          if constexpr (F16) epi_load<F16>(tslot, 64 + fg * 16, rb);
+          Raw ra, rb;
+          epi_load(tslot, fg * 16, ra);
           tmem_ld_wait();
 #if DIINN_TOUCH_KA
           { float tch = ka[0].x + ka[1].y + ka[2].z + ka[3].w; asm volatile("" ::"f"(tch) : "memory"); }
@@ -580,18 +657,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 0);
 #endif
-          if constexpr (F16) {  // both loads have landed: hand the slot back before any math
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
-            if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
-          }
-          if (last) epi_math<true, F16, kDump>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row);
-          else epi_math<false, F16>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
+          if (last) epi_math<true, FMT, kDump>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row, q3row_f);
+          else epi_math<false, FMT>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
 #endif
-          if constexpr (!F16) epi_load<F16>(tslot, 64 + fg * 16, rb);
+          epi_load(tslot, 64 + fg * 16, rb);
           if (!last) {
             fence_proxy_async_smem();
             __syncwarp();
@@ -599,18 +670,16 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           }
           if (nb) load16(nb, ka);  // after the fence (see layer0_unit)
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
-          if constexpr (!F16) {
-            tmem_ld_wait();
+          tmem_ld_wait();
 #if DIINN_FINE_TRACE
-            if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 2);
+          if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 2);
 #endif
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
-            if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
-          }
-          if (last) epi_math<true, F16, kDump>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row);
-          else epi_math<false, F16>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
+          if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
+          if (last) epi_math<true, FMT, kDump>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row, q3row_f);
+          else epi_math<false, FMT>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
 #endif
@@ -673,24 +742,27 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
 }  // namespace sb
 
-template <int CG, bool F16, bool kDump = false, bool kPix = false>
-static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const PixelSource& src,
-                          const OutSpec& out, const float* P, const sb::Work& wk, int* err_flag, long long* trace) {
+template <int CG, int FMT, bool kDump = false, bool kPix = false>
+static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const CUtensorMap& tm_lo,
+                          const PixelSource& src, const OutSpec& out, const float* P, const sb::Work& wk, int* err_flag,
+                          long long* trace) {
   using namespace sb;
-  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, F16, kDump, kPix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, FMT, kDump, kPix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kSmemBytes)));
   if (getenv("DIINN_DEBUG_OCC")) {
     int nc = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, F16, kDump, kPix>, cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix>, cfg);
     fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
             cudaGetErrorString(e));
   }
-  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, F16, kDump, kPix>, tm, h->small, src, out, P, wk, err_flag, trace));
+  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix>, tm, tm_lo, h->small, src, out, P, wk,
+                                      err_flag, trace));
   return DIINN_OK;
 }
 
-int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group,
-                        bool f16acc, cudaStream_t s) {
+// fmt: kFmtBf16 / kFmtF16 / kFmtSplit (handle.h). tap: debug only (see sb::Work).
+int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group, int fmt,
+                        cudaStream_t s, int4* tap) {
   using namespace sb;
   if (cta_group == 0) {
     static int env_cg = -1;
@@ -704,6 +776,7 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   long long* trace = h->trace_dev;
 
   Work wk{};
+  wk.tap = tap;
   if (src.mode == 0) {
     const int tiles_x = (src.W_up + kPatchW - 1) / kPatchW;
     wk.tiles_y = (src.row1 - src.row0 + kPatchH - 1) / kPatchH;
@@ -730,17 +803,25 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   cfg.attrs = attr;
   cfg.numAttrs = h->pdl ? 2 : 1;
   // instantiations: kDump = mode 4 (q_3 dumped instead of projected), kPix = init_q=True (per-pixel P, q_0 given)
-  const bool dump = out.q3 != nullptr, pix = src.per_pixel_p != 0;
+  const bool dump = out.q3 != nullptr || out.q3f != nullptr, pix = src.per_pixel_p != 0;
   if (pix && src.mode != 0) return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "per-pixel P is implemented for the HR grid only");
-  const CUtensorMap& tm = cta_group == 1 ? (f16acc ? h->tmapWBh : h->tmapWB) : (f16acc ? h->tmapWBh_half : h->tmapWB_half);
+  if (fmt < 0 || fmt > kFmtSplit) return fail(h, DIINN_ERR_BAD_DTYPE, "stage B: unknown operand format");
+  if (fmt == kFmtSplit && pix) return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "the split format is not wired for per-pixel P");
+  if (dump && ((fmt == kFmtSplit) != (out.q3f != nullptr)))
+    return fail(h, DIINN_ERR_BAD_ARG, "stage B: the split format dumps fp32 q_3, the 16-bit formats bf16");
+  const int ci = cta_group - 1;
+  const CUtensorMap& tm = h->tmapWB[fmt == kFmtBf16 ? 0 : 1][ci];
+  const CUtensorMap& tm_lo = h->tmapWBlo[ci];
   int rc;
-#define DIINN_SB_LAUNCH(CGv, F16v, DUMPv, PIXv) \
-  launch_variant<CGv, F16v, DUMPv, PIXv>(h, &cfg, tm, src, out, P, wk, err_flag, trace)
-#define DIINN_SB_PICK(CGv, F16v)                                                                        \
-  (dump ? (pix ? DIINN_SB_LAUNCH(CGv, F16v, true, true) : DIINN_SB_LAUNCH(CGv, F16v, true, false))       \
-        : (pix ? DIINN_SB_LAUNCH(CGv, F16v, false, true) : DIINN_SB_LAUNCH(CGv, F16v, false, false)))
-  if (cta_group == 1) rc = f16acc ? DIINN_SB_PICK(1, true) : DIINN_SB_PICK(1, false);
-  else rc = f16acc ? DIINN_SB_PICK(2, true) : DIINN_SB_PICK(2, false);
+#define DIINN_SB_LAUNCH(CGv, FMTv, DUMPv, PIXv) \
+  launch_variant<CGv, FMTv, DUMPv, PIXv>(h, &cfg, tm, tm_lo, src, out, P, wk, err_flag, trace)
+#define DIINN_SB_PICK(CGv, FMTv)                                                                        \
+  (dump ? (pix ? DIINN_SB_LAUNCH(CGv, FMTv, true, true) : DIINN_SB_LAUNCH(CGv, FMTv, true, false))       \
+        : (pix ? DIINN_SB_LAUNCH(CGv, FMTv, false, true) : DIINN_SB_LAUNCH(CGv, FMTv, false, false)))
+#define DIINN_SB_PICK_SPLIT(CGv) (dump ? DIINN_SB_LAUNCH(CGv, 2, true, false) : DIINN_SB_LAUNCH(CGv, 2, false, false))
+  if (cta_group == 1) rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(1) : fmt == kFmtF16 ? DIINN_SB_PICK(1, 1) : DIINN_SB_PICK(1, 0);
+  else rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(2) : fmt == kFmtF16 ? DIINN_SB_PICK(2, 1) : DIINN_SB_PICK(2, 0);
+#undef DIINN_SB_PICK_SPLIT
 #undef DIINN_SB_PICK
 #undef DIINN_SB_LAUNCH
   if (rc) return rc;

@@ -17,7 +17,8 @@ import torch.nn as nn
 
 from . import _lib
 
-_PRECISIONS = {"fp32": _lib.COMPUTE_FP32, "bf16": _lib.COMPUTE_BF16, "fp16acc": _lib.COMPUTE_FP16ACC}
+_PRECISIONS = {"fp32": _lib.COMPUTE_FP32, "bf16": _lib.COMPUTE_BF16, "fp16": _lib.COMPUTE_FP16,
+               "fp32_simt": _lib.COMPUTE_FP32_SIMT}
 
 
 class SineAct(nn.Module):
@@ -39,14 +40,20 @@ class FusedImplicitDecoder(nn.Module):
     """B200-native DIINN query decoder (modes 1-4, init_q False or True; mode 3 with init_q=False is the paper's / the
     benchmarked wiring).
 
-    precision: "bf16" -> tcgen05 tensor cores, bf16 operands / fp32 accumulation (default throughput path);
-               "fp16acc" -> stage B with fp16 operands and fp16 TMEM accumulators (faster epilogue, opt-in);
-               "fp32" -> fp32 FMA on CUDA cores end to end (exact-fp32 parity path).
+    precision (all on tcgen05 tensor cores with fp32 TMEM accumulation unless noted; envelopes in include/diinn_b200.h):
+        "fp16" (default) -> fp16 operands: the throughput path; 8x less operand noise than bf16 at the same tensor rate
+        "bf16"           -> bf16 operands (the format north_star names; misses 1e-2 once activations are O(1))
+        "fp32"           -> fp32 PRECISION: fp16 hi+lo split operands, three MMAs per product (<= 1e-4 also on O(1)
+                            activations); init_q=True falls back to "fp32_simt"
+        "fp32_simt"      -> exact fp32 FMA on CUDA cores end to end (cross-check path)
+        "auto"           -> "fp16", unless a calibration decode of a crop of the first input (re-run when the weights
+                            change) differs from the "fp32" path by more than ``auto_tol`` / 2: then "fp32"
     The I/O dtype follows ``x.dtype`` (float32 or bfloat16), as in the reference where out.dtype == x.dtype.
+    Forward-only: calling it with autograd enabled on trainable parameters or inputs raises.
     """
 
     def __init__(self, in_channels: int = 64, hidden_dims: Sequence[int] = (256, 256, 256, 256), mode: int = 1,
-                 init_q: bool = False, precision: str = "bf16"):
+                 init_q: bool = False, precision: str = "fp16", auto_tol: float = 1e-2):
         super().__init__()
         hidden_dims = list(hidden_dims)
         if mode not in (1, 2, 3, 4):
@@ -56,9 +63,12 @@ class FusedImplicitDecoder(nn.Module):
                 "each with init_q=False or True; the reference defines no other mode")
         if in_channels != 64 or hidden_dims != [256] * 4:
             raise NotImplementedError("only in_channels=64, hidden_dims=[256]*4 is implemented")
-        if precision not in _PRECISIONS:
-            raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
+        if precision not in _PRECISIONS and precision != "auto":
+            raise ValueError(f"precision must be one of {list(_PRECISIONS) + ['auto']}")
         self.mode, self.init_q, self.precision = mode, bool(init_q), precision
+        self.auto_tol = float(auto_tol)
+        self._auto_choice = None      # ("fp16" | "fp32", measured max-abs difference) once calibrated
+        self._auto_versions = None
         # identical module tree (hence state_dict keys and default init / RNG consumption) to diinn.py:46-92
         last_k, last_q = in_channels * 9, 3
         if self.init_q:  # sine gate on the unfolded features; Q.0 then reads its 576 channels (diinn.py:48-51)
@@ -153,11 +163,15 @@ class FusedImplicitDecoder(nn.Module):
         raise TypeError(f"unsupported dtype {x.dtype}: the decoder takes float32 or bfloat16 feature maps")
 
     def _check_input(self, x: torch.Tensor):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            if x.requires_grad:
-                raise RuntimeError("FusedImplicitDecoder is forward-only: call it under torch.no_grad()")
         if x.dim() != 4 or x.shape[1] != 64:
             raise ValueError(f"expected a (B,64,H,W) feature map, got {tuple(x.shape)}")
+        if x.device.type != "cuda":
+            raise RuntimeError("FusedImplicitDecoder runs on CUDA (sm_100a) only; there is no CPU fallback")
+        # The reference decoder is trainable; this one has no backward. Returning a tensor without a grad_fn to a caller
+        # that expects gradients (trainable parameters, or an input that requires grad) would silently train nothing.
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError("FusedImplicitDecoder is forward-only (no backward pass): call it under torch.no_grad() "
+                               "or freeze it with requires_grad_(False) and detach the input")
 
     # ------------------------------------------------------------------ reference interface
     # ------------------------------------------------------------------ eval glue fused into the output store
@@ -190,6 +204,42 @@ class FusedImplicitDecoder(nn.Module):
         H_up, W_up = int(size[0]), int(size[1])
         return self.forward_rows(x, (H_up, W_up), 0, H_up, bsize=bsize)
 
+    # ------------------------------------------------------------------ precision routing
+    def _compute(self, x: Optional[torch.Tensor] = None, size=None) -> int:
+        if self.precision != "auto":
+            return _PRECISIONS[self.precision]
+        versions = tuple((t.data_ptr(), t._version) for t in self._ref_tensors())
+        if self._auto_choice is None or self._auto_versions != versions:
+            if x is None:
+                return _PRECISIONS["fp16"]
+            self.calibrate(x, size)
+        return _PRECISIONS[self._auto_choice[0]]
+
+    def calibrate(self, x: torch.Tensor, size=None) -> float:
+        """precision="auto": decode a crop (<= 32x32 LR pixels of every image, same scale factor) with the fp16-operand path
+        and with the fp32-precision path and keep "fp16" only if they agree to auto_tol / 2. Returns the measured max-abs
+        difference. Weight sets that amplify operand noise (SIREN-style gains) route to "fp32" this way."""
+        B, _, H, W = x.shape
+        h, w = min(H, 32), min(W, 32)
+        if size is None:
+            size = (4 * H, 4 * W)
+        hu = max(2, min(256, int(round(h * int(size[0]) / H))))
+        wu = max(2, min(256, int(round(w * int(size[1]) / W))))
+        crop = x[:, :, :h, :w].float().contiguous()
+        keep = self.precision, self._workspace
+        outs = []
+        try:
+            for prec in ("fp16", "fp32"):
+                self.precision = prec
+                with torch.no_grad():
+                    outs.append(self.forward_rows(crop, (hu, wu), 0, hu).float())
+        finally:
+            self.precision, self._workspace = keep
+        diff = float((outs[0] - outs[1]).abs().max())
+        self._auto_choice = ("fp16" if diff <= 0.5 * self.auto_tol else "fp32", diff)
+        self._auto_versions = tuple((t.data_ptr(), t._version) for t in self._ref_tensors())
+        return diff
+
     def forward_rows(self, x: torch.Tensor, size, row0: int, row1: int, out: Optional[torch.Tensor] = None,
                      peer_ptrs: Optional[Sequence[int]] = None, multicast_ptr: int = 0, bsize: Optional[int] = None):
         """HR rows [row0,row1) only -> (B,3,row1-row0,W_up), or written in place into rows [row0,row1) of a full
@@ -198,12 +248,12 @@ class FusedImplicitDecoder(nn.Module):
         lib, h = self._ensure_handle(x.device)
         if self.mode == 4:
             _lib.check(lib, h, lib.diinn_set_bsize(h, 0 if bsize is None else int(bsize)))
-        if not (self._is_nhwc_bf16(x) and self.precision != "fp32"):
+        comp = self._compute(x, size)
+        if not (self._is_nhwc_bf16(x) and comp in (_lib.COMPUTE_BF16, _lib.COMPUTE_FP16)):
             x = x.contiguous()
         B, Cc, H, W = x.shape
         H_up, W_up = int(size[0]), int(size[1])
         io = self._io_dtype(x)
-        comp = _PRECISIONS[self.precision]
         nbytes = lib.diinn_workspace_bytes(h, B, H, W, H_up, W_up, row0, row1, comp)
         if nbytes == 0:
             raise _lib.DiinnError(-2, f"bad shape/rows: feat {tuple(x.shape)}, size {(H_up, W_up)}, rows {(row0, row1)}")
@@ -246,7 +296,8 @@ class FusedImplicitDecoder(nn.Module):
         if self.init_q:
             raise NotImplementedError("init_q=True is implemented for the HR grid only: use forward()")
         lib, h = self._ensure_handle(feat.device)
-        if not (self._is_nhwc_bf16(feat) and self.precision != "fp32"):
+        comp = self._compute(feat)
+        if not (self._is_nhwc_bf16(feat) and comp in (_lib.COMPUTE_BF16, _lib.COMPUTE_FP16)):
             feat = feat.contiguous()
         B, Cc, H, W = feat.shape
         Q = coord.shape[1]
@@ -255,7 +306,6 @@ class FusedImplicitDecoder(nn.Module):
         if coord.shape != (B, Q, 2) or cell.shape != (B, Q, 2):
             raise ValueError("coord and cell must be (B,Q,2)")
         io = self._io_dtype(feat)
-        comp = _PRECISIONS[self.precision]
         nbytes = lib.diinn_query_workspace_bytes(h, B, H, W, Q * (4 if local_ensemble else 1), comp)
         ws = self._get_workspace(nbytes, feat.device)
         out = torch.empty((B, Q, 3), dtype=self._out_dtype(feat), device=feat.device)
@@ -281,7 +331,7 @@ class FusedImplicitDecoder(nn.Module):
         if out_host is None:
             out_host = torch.empty((B, 3, row1 - row0, W_up), dtype=self._out_dtype(feat_host)).pin_memory()
         io = self._io_dtype(feat_host)
-        comp = _PRECISIONS[self.precision]
+        comp = self._compute()
         _lib.check(lib, h, lib.diinn_decode_host(h, _ptr(feat_host), B, Cc, H, W, H_up, W_up, row0, row1,
                                                  _ptr(out_host), io, comp, _stream(device)))
         return out_host
@@ -317,10 +367,28 @@ class FusedImplicitDecoder(nn.Module):
         x = x.contiguous()
         B, Cc, H, W = x.shape
         P = torch.empty((B * H * W, 1024), dtype=torch.float32, device=x.device)
-        ws = self._get_workspace(B * H * W * 64 * 2 + 4096, x.device)
+        ws = self._get_workspace(2 * (B * H * W * 64 * 2 + 4096), x.device)
         _lib.check(lib, h, lib.diinn_debug_stage_a(h, _ptr(x), B, Cc, H, W, _ptr(P), _ptr(ws), ws.numel(),
-                                                   self._io_dtype(x), _PRECISIONS[self.precision], _stream(x.device)))
+                                                   self._io_dtype(x), self._compute(), _stream(x.device)))
         return P
+
+    def debug_rows(self, x: torch.Tensor, size):
+        """(ih, iw, rel_h, rel_w) per output pixel as the FUSED stage-B kernel derives them (diinn_debug_set_tap), for a
+        B=1 tensor-path decode: four (H_up, W_up) tensors, to be compared bit for bit with _make_pos_encoding."""
+        if x.shape[0] != 1 or self._compute(x, size) == _lib.COMPUTE_FP32_SIMT:
+            raise ValueError("debug_rows taps the tensor-path kernel on a single image")
+        lib, h = self._ensure_handle(x.device)
+        H_up, W_up = int(size[0]), int(size[1])
+        tap = torch.full((3 * H_up * W_up, 4), -1, dtype=torch.int32, device=x.device)
+        _lib.check(lib, h, lib.diinn_debug_set_tap(h, _ptr(tap)))
+        try:
+            with torch.no_grad():
+                self.forward_rows(x, (H_up, W_up), 0, H_up)
+            torch.cuda.synchronize(x.device)
+        finally:
+            _lib.check(lib, h, lib.diinn_debug_set_tap(h, C.c_void_p(0)))
+        t = tap[:H_up * W_up].view(H_up, W_up, 4)
+        return t[..., 0], t[..., 1], t[..., 2].contiguous().view(torch.float32), t[..., 3].contiguous().view(torch.float32)
 
     def debug_umma_gemm(self, A: torch.Tensor, Bm: torch.Tensor, cta_group: int = 2) -> torch.Tensor:
         """tcgen05 self-test: (M,K) bf16 x (N,K) bf16 ^T -> (M,N) fp32."""
@@ -333,7 +401,7 @@ class FusedImplicitDecoder(nn.Module):
         return D
 
     def set_profiling(self, enable: bool, device=None):
-        """Record CUDA events around the three kernels of every bf16-path decode (see diinn_set_profiling)."""
+        """Record CUDA events around the three kernels of every tensor-path decode (see diinn_set_profiling)."""
         device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         lib, h = self._ensure_handle(device)
         _lib.check(lib, h, lib.diinn_set_profiling(h, 1 if enable else 0))
@@ -373,7 +441,7 @@ def load_numpy_weights(decoder: FusedImplicitDecoder, weights: dict) -> FusedImp
     return decoder
 
 
-def swap_decoder(model: nn.Module, precision: str = "bf16") -> nn.Module:
+def swap_decoder(model: nn.Module, precision: str = "fp16") -> nn.Module:
     """Replace the reference decoder inside a ``DIINN`` (diinn.py:8-19) or an ``SRLitModule`` (``.net``,
     sr_module.py:93) by a FusedImplicitDecoder carrying the same parameters. Call sites stay unchanged."""
     net = model.net if hasattr(model, "net") and hasattr(model.net, "decoder") else model

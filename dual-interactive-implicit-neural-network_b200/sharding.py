@@ -42,6 +42,7 @@ def band_partition(n_rows: int, world: int, bands: int) -> Tuple[int, List[List[
 
 _side_streams = {}
 _symm_images = {}
+_symm_turn = {}
 last_fused_mode = None  # how the last decode_sharded_fused call reached the peers (for reports)
 
 
@@ -62,12 +63,13 @@ def broadcast_features(x: torch.Tensor, src: int, group: Optional[dist.ProcessGr
     return x
 
 
-def _symmetric_image(shape, dtype, device, group):
+def _symmetric_image(shape, dtype, device, group, slot=0):
     """A (B,3,H_up,W_up) image buffer allocated in symmetric memory and mapped into every rank of `group`
-    (torch.distributed._symmetric_memory): returns (local tensor, handle with .buffer_ptrs / .multicast_ptr / .barrier)."""
+    (torch.distributed._symmetric_memory): returns (local tensor, handle with .buffer_ptrs / .multicast_ptr / .barrier).
+    `slot` distinguishes the two buffers decode_sharded_fused alternates between."""
     import torch.distributed._symmetric_memory as symm_mem
     pg = group if group is not None else dist.group.WORLD
-    key = (tuple(shape), dtype, device.index, pg.group_name)
+    key = (tuple(shape), dtype, device.index, pg.group_name, slot)
     if key not in _symm_images:
         buf = symm_mem.empty(*shape, dtype=dtype, device=device)
         hdl = symm_mem.rendezvous(buf, pg.group_name)
@@ -80,10 +82,13 @@ def decode_sharded_fused(decoder, x: torch.Tensor, size, group: Optional[dist.Pr
     """Fused decode + assembly: the stage-B kernel of every rank stores each RGB value of its row tile straight into
     the image buffers of ALL ranks over NVLink (one `multimem.st` through the NVSwitch multicast mapping when the
     fabric offers it, else one peer store per rank), so the transfer rides under the math tile by tile and no
-    collective is launched; two symmetric-memory barriers order buffer reuse and completion.
+    collective is launched. ONE symmetric-memory barrier per call (completion: every rank's stores have landed
+    everywhere). The barrier that used to protect buffer reuse is gone: calls alternate between two symmetric buffers,
+    and a rank can only enter call k+1 -- which overwrites the buffer of call k-1 -- after the completion barrier of call
+    k, which every rank joins after (in stream order) its own reads of call k-1's image.
 
     Returns the assembled (B,3,H_up,W_up) image on every rank. clone=False returns the symmetric buffer itself, which
-    the next call with the same shape overwrites. feat_src: see decode_sharded.
+    stays valid until the SECOND next call with the same shape. feat_src: see decode_sharded.
     multicast: True / False / "auto" -- measured at 8 GPUs the single `multimem.st` wins on small row tiles (c3: 0.293 vs
     0.308 ms) and the eight peer stores on large ones (c4: 2.52 vs 2.64 ms); "auto" switches at 2 Mpx per rank."""
     if feat_src is not None:
@@ -93,17 +98,20 @@ def decode_sharded_fused(decoder, x: torch.Tensor, size, group: Optional[dist.Pr
     H_up, W_up = int(size[0]), int(size[1])
     B = x.shape[0]
     odt = _out_dtype(decoder, x)   # uint8 when the decoder's eval glue quantises: a quarter of the bytes over NVLink
-    buf, hdl = _symmetric_image((B, 3, H_up, W_up), odt, x.device, group)
+    pg = group if group is not None else dist.group.WORLD
+    tkey = ((B, 3, H_up, W_up), odt, x.device.index, pg.group_name)
+    slot = _symm_turn.get(tkey, 0)
+    _symm_turn[tkey] = slot ^ 1
+    buf, hdl = _symmetric_image((B, 3, H_up, W_up), odt, x.device, group, slot)
     r0, r1 = row_partition(H_up, world)[rank]
     if multicast == "auto":
         multicast = B * (r1 - r0) * W_up < (1 << 21)
     mc = int(hdl.multicast_ptr) if (multicast and odt == torch.float32) else 0  # 0 when the fabric has no multicast
     global last_fused_mode
     last_fused_mode = "nvswitch-multicast multimem.st" if mc else f"{world} peer stores per value"
-    hdl.barrier(channel=0)  # every rank is done reading the previous image held in these buffers
     if r1 > r0:
         decoder.forward_rows(x, (H_up, W_up), r0, r1, out=buf, peer_ptrs=list(hdl.buffer_ptrs), multicast_ptr=mc)
-    hdl.barrier(channel=1)  # every rank's stores have landed everywhere
+    hdl.barrier(channel=slot)  # every rank's stores have landed everywhere (and its reads of the other buffer are done)
     return buf.clone() if clone else buf
 
 

@@ -43,13 +43,19 @@ typedef enum diinn_status {
   DIINN_ERR_UNSUPPORTED_DEVICE = -8
 } diinn_status;
 
-/* arithmetic path */
+/* arithmetic path. Every tensor-core mode accumulates in fp32 (TMEM) and keeps P, biases, relu, sin, the coordinates and the
+ * RGB projection in fp32; the modes differ in how activations, features and weights enter the MMAs.
+ * Accuracy envelope (max-abs against the fp32 reference; tests/test_gpu_parity.py):
+ *   default-init weights (|out| < 0.06)      FP32 <= 2e-6    FP16 ~3e-6    BF16 ~2e-5
+ *   gain-scaled weights, O(1) activations    FP32 <= 1e-4    FP16 ~2e-3    BF16 ~1.6e-2  (K x3, Q x10: bf16 misses the 1e-2
+ *   contract there, fp16 operands keep it -- which is why FP16 is the default 16-bit mode of the Python layer)
+ * Sine arguments: MUFU.SIN's error grows as ~6e-8 |x|; DIINN_COMPUTE_FP32 range-reduces first (error ~5e-7 for |x| < 1e5). */
 typedef enum diinn_compute {
-  DIINN_COMPUTE_FP32 = 0, /* fp32 FMA on CUDA cores end to end (exact-fp32 path; slow, used for fp32 parity)   */
-  DIINN_COMPUTE_BF16 = 1, /* tcgen05 tensor cores: bf16 operands, fp32 TMEM accumulation, fp32 bias/sin/relu     */
-  DIINN_COMPUTE_FP16ACC = 2 /* stage B with fp16 operands AND fp16 TMEM accumulators (read back two per register, which
-                               halves the TMEM->register traffic that bounds the fp32-accumulator kernel); stage A, P,
-                               biases, sin, relu stay as in _BF16. Opt-in: ~1e-3 relative error on pre-activations. */
+  DIINN_COMPUTE_FP32 = 0, /* fp32 PRECISION on the tensor cores: every operand is an fp16 hi + lo pair (22 mantissa bits) and
+                             every product three MMAs (hi.hi + lo.hi + hi.lo). init_q=True decodes fall back to _FP32_SIMT. */
+  DIINN_COMPUTE_BF16 = 1, /* bf16 operands                                                                                 */
+  DIINN_COMPUTE_FP16 = 2, /* fp16 operands (saturating conversions): same tensor rate as bf16, 8x less operand noise        */
+  DIINN_COMPUTE_FP32_SIMT = 3 /* exact fp32 FMA on CUDA cores end to end (cross-check path, ~40x slower)                     */
 } diinn_compute;
 
 /* element type of the feat / out buffers. DIINN_IO_BF16_NHWC (the encoder hand-off): feat is bf16 in
@@ -93,8 +99,8 @@ void diinn_destroy(diinn_handle* h);
 const char* diinn_last_error(const diinn_handle* h);
 
 /* Repack the reference-layout weights into the library's layouts (fp32 hoisted matrices for the CUDA-core
- * path; bf16, K-permuted, 128B-swizzle tiles for the tcgen05 path). Replaces ImplicitDecoder.__init__ /
- * load_state_dict (diinn.py:40-92). */
+ * path; bf16 / fp16 / fp16 hi+lo, K-permuted, 128B-swizzle tiles for the tcgen05 paths). Replaces
+ * ImplicitDecoder.__init__ / load_state_dict (diinn.py:40-92). */
 int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream);
 
 /* ---- the hot path ---------------------------------------------------------------------------------- */
@@ -179,44 +185,20 @@ int diinn_query_ensemble(diinn_handle* h, const void* feat, int B, int C, int H,
                          const float* cell, int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype,
                          int compute, void* stream);
 
-/* ---- debug taps for the bit-exact tests -------------------------------------------------------------- */
-/* Per-axis nearest-exact source index and scaled relative coordinate, exactly the values
- * _make_pos_encoding (diinn.py:94-110) produces: ih[H_up], iw[W_up] int32; rel_h[H_up], rel_w[W_up] fp32. */
-int diinn_debug_gather(diinn_handle* h, int H, int W, int H_up, int W_up, int32_t* ih, int32_t* iw,
-                       float* rel_h, float* rel_w, void* stream);
-/* Same for the query entry: idx[B*Q] = ih*W+iw, rel[B*Q*2], ratio[B*Q]. */
-int diinn_debug_query_gather(diinn_handle* h, int B, int H, int W, const float* coord, const float* cell, int Q,
-                             int32_t* idx, float* rel, float* ratio, void* stream);
-/* LR-resolution hoisted pre-activations P (B*H*W, 1024) fp32 = [relu(K0 x) | K_i[:,256:] x + b_i, i=1..3]. */
-int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, int W, float* P, void* workspace,
-                        size_t workspace_bytes, int io_dtype, int compute, void* stream);
-/* tcgen05 self-test: D(M x N fp32) = A(M x K bf16, row-major) * B(N x K bf16, row-major)^T through the same
- * TMA / UMMA-descriptor / TMEM plumbing the fused kernels use. M%128==0, N%256==0, K%64==0. cta_group 1|2;
- * 11|12 = the same with A, B holding fp16 and fp16 TMEM accumulators read back with tcgen05.ld.pack::16b. */
-int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
-                          int cta_group, void* stream);
-
-/* Tensor-pipe pace probe: `iters` back-to-back tcgen05.mma (M = 128*cta_group, N = n_cols, K = 16, bf16) on resident
- * shared-memory operands in n_ctas CTAs; cyc_per_mma[n_ctas / cta_group] (device) receives clock64 cycles per MMA.
- * noise: 16 extra warps per CTA hammer the idle TMEM half (bit 0), shared memory (bit 1) or the MUFU (bit 2) meanwhile. */
-int diinn_debug_umma_pace(diinn_handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma,
-                          int noise, void* stream);
-
 /* Per-kernel device timing of the tcgen05 path, measured with CUDA events recorded on the caller's stream around
  * the three kernels of every diinn_decode (layout pass, stage A, stage B) while enabled. diinn_get_kernel_times
  * synchronises on the recorded events, returns the summed milliseconds and the number of decodes, and resets.
- * bench.py uses it for the roofline of the dominant kernel (stage B). */
-int diinn_set_profiling(diinn_handle* h, int enable);
+ * bench.py uses it for the roofline of the dominant kernel (stage B). Both calls, like diinn_decode_host, also read the
+ * device-side consistency flag of the tcgen05 kernels and return DIINN_ERR_CUDA if one of them raised it. */
+int diinn_set_profiling(diinn_handle* h, int enable);  /* enable: creates the event pool (2048 decodes per window) */
 int diinn_get_kernel_times(diinn_handle* h, double* ms_layout, double* ms_stage_a, double* ms_stage_b,
                            int64_t* n_decodes);
-
-/* DIINN_TRACE=1 in the environment makes the fused stage-B kernel record clock64() at its pipeline events (leader
- * CTA of the first CTA pair, first 8 tiles); this copies the first n (<=1024) samples to host_out. */
-int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n);
 
 /* Number of kernels this library launched on the handle since creation (bench.py's gpu_launches). */
 int64_t diinn_launch_count(const diinn_handle* h);
 const char* diinn_version(void);
+
+/* Debug taps and hardware probes live in diinn_b200_debug.h (same library). */
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 #include <stdio.h>
 #include "diinn_b200.h"
+#include "diinn_b200_debug.h"
 int main(void) {
   diinn_config cfg = {64, 256, 4, 3, 0, 0};
   diinn_handle* h = NULL;

@@ -22,13 +22,16 @@ def _ensure_built():
 
 def test_header_symbols_are_exported():
     _ensure_built()
-    header = open(os.path.join(ROOT, "include", "diinn_b200.h")).read()
-    declared = set(re.findall(r"\b(diinn_[a-z_0-9]+)\s*\(", header))
-    declared -= {"diinn_status", "diinn_compute", "diinn_io_dtype"}
-    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     lib = ctypes.CDLL(_lib.LIB_PATH)
-    for name in declared:
-        assert hasattr(lib, name), name
+    # product surface and debug taps / probes live in separate headers; both are exported by the one library
+    for fname, symbols in (("diinn_b200.h", _lib.SYMBOLS), ("diinn_b200_debug.h", _lib.DEBUG_SYMBOLS)):
+        header = open(os.path.join(ROOT, "include", fname)).read()
+        declared = set(re.findall(r"\b(diinn_[a-z_0-9]+)\s*\(", header))
+        declared -= {"diinn_status", "diinn_compute", "diinn_io_dtype"}
+        assert declared == set(symbols), (fname, declared ^ set(symbols))
+        for name in declared:
+            assert hasattr(lib, name), name
+    assert not [n for n in _lib.SYMBOLS if "debug" in n]      # nothing debug-flavoured on the product surface
 
 
 def test_version_and_create_errors_without_gpu():

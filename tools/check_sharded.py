@@ -14,7 +14,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
-dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="bf16"), synth.make_weights(seed=0)).to(dev)
+dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="fp16"), synth.make_weights(seed=0)).to(dev)
 ok = True
 for name, bands in (("c1", 1), ("c1", 3), ("c3", None), ("c3", 2), ("c5", 1)):
     B, H, W, H_up, W_up = synth.CONFIGS[name]

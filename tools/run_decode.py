@@ -8,7 +8,7 @@ import diinn_b200  # noqa: E402
 from diinn_b200 import synth  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
-precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+precision = sys.argv[2] if len(sys.argv) > 2 else "fp16"
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 mode = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 init_q = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False

@@ -10,7 +10,7 @@ from diinn_b200 import synth  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 B, H, W, H_up, W_up = synth.CONFIGS[name]
-dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="bf16"),
+dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="fp16"),
                                     synth.make_weights(seed=0)).cuda()
 feat = torch.from_numpy(synth.make_feat(1, B, H, W)).pin_memory()
 out = torch.empty((B, 3, H_up, W_up), dtype=torch.float32).pin_memory()

@@ -27,7 +27,7 @@ def timed(fn, n=10):
 
 with torch.no_grad():
     for mode in (3, 2, 1):
-        dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=mode, precision="bf16"),
+        dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=mode, precision="fp16"),
                                             synth.make_weights(seed=0, mode=mode)).cuda()
         dec.set_profiling(True)
         ms = timed(lambda: dec(x, (H_up, W_up)))
@@ -36,7 +36,7 @@ with torch.no_grad():
         print(f"{name} mode {mode}: {ms:.3f} ms/decode  (layout {kt['layout_ms'] / n:.3f}, stage A + LR chain {kt['stage_a_ms'] / n:.3f}, "
               f"stage B {kt['stage_b_ms'] / n:.3f})")
         dec.set_profiling(False)
-    dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="bf16"), synth.make_weights(seed=0)).cuda()
+    dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="fp16"), synth.make_weights(seed=0)).cuda()
     base = timed(lambda: dec(x, (H_up, W_up)))
     dec.set_output_transform(sub=0.5, div=0.5, clamp=(0, 1))
     t1 = timed(lambda: dec(x, (H_up, W_up)))

@@ -14,7 +14,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
-dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="bf16"), synth.make_weights(seed=0)).to(dev)
+dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="fp16"), synth.make_weights(seed=0)).to(dev)
 B, H, W, H_up, W_up = synth.CONFIGS[name]
 x = torch.from_numpy(synth.make_feat(1, B, H, W)).to(dev)
 r0, r1 = diinn_b200.row_partition(H_up, world)[rank]

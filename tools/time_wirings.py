@@ -30,7 +30,7 @@ with torch.no_grad():
     for init_q in (False, True):
         for mode in (3, 4, 2, 1):
             w = synth.make_weights(seed=0, mode=mode, init_q=init_q)
-            dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=mode, init_q=init_q, precision="bf16"), w).cuda()
+            dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=mode, init_q=init_q, precision="fp16"), w).cuda()
             dec(x, (H_up, W_up))
             n0 = dec.launch_count()
             dec(x, (H_up, W_up))

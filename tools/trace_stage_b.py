@@ -18,7 +18,7 @@ from diinn_b200 import synth, _lib  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 B, H, W, H_up, W_up = synth.CONFIGS[name]
-dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision=(sys.argv[2] if len(sys.argv) > 2 else "bf16")),
+dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision=(sys.argv[2] if len(sys.argv) > 2 else "fp16")),
                                     synth.make_weights(seed=0)).cuda()
 x = torch.from_numpy(synth.make_feat(1, B, H, W)).cuda()
 with torch.no_grad():
