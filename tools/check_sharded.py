@@ -40,6 +40,22 @@ for name, mc in (("c1", False), ("c3", False), ("c1", True), ("c3", True), ("c5"
             print(f"rank {rank} fused {name} multicast={mc}: EXCEPTION {type(e).__name__}: {e}", flush=True)
     ok &= same
     print(f"rank {rank}/{world} fused {name} multicast={mc}: bit-identical={same}", flush=True)
+# encoder hand-off: only rank 0 holds the real feature map, the others receive it by broadcast --
+# NCHW fp32 and channels-last bf16 (the layout stage A reads in place)
+for name in ("c1", "c3"):
+    B, H, W, H_up, W_up = synth.CONFIGS[name]
+    real = torch.from_numpy(synth.make_feat(1, B, H, W)).to(dev)
+    for fmt in ("nchw_f32", "nhwc_bf16"):
+        src = real if fmt == "nchw_f32" else real.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        x = src.clone(memory_format=torch.preserve_format) if rank == 0 else torch.zeros_like(src, memory_format=torch.preserve_format)
+        with torch.no_grad():
+            full = dec(src, (H_up, W_up))
+            sh = diinn_b200.decode_sharded_fused(dec, x, (H_up, W_up), feat_src=0)
+            sh2 = diinn_b200.decode_sharded(dec, x, (H_up, W_up), feat_src=0)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(full, sh)) and bool(torch.equal(full, sh2)) and bool(torch.equal(x, src))
+        ok &= same
+        print(f"rank {rank}/{world} broadcast hand-off {name} {fmt}: bit-identical={same}", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
