@@ -126,14 +126,18 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
         const int h0 = g.lr_row0 + ty * kPatchH;
         const int w0 = (txp * CG + rank) * kPatchW;
         const int s_beg = part * nb_cnt * 9, s_end = s_beg + nb_cnt * 9;
+        // (n-block, term, tap): the A tap tile is re-fetched per n-block and term (L2 hits). Split format: the small terms
+        // (x_lo, w_hi) and (x_hi, w_lo) of all nine taps first, then (x_hi, w_hi) -- the tensor core truncates when it adds
+        // an MMA's result to the accumulator, so the adds at full magnitude should be as few as possible (9, not 27).
 #pragma unroll 1
-        for (int s36 = s_beg; s36 < s_end; ++s36) {  // (n-block, tap): the A tap tile is re-fetched per n-block (L2 hits)
-          const int tap = s36 % 9;
+        for (int sq = s_beg * kTerms; sq < s_end * kTerms; ++sq, ++it) {
+          const int nbq = sq / (9 * kTerms), rq = sq - nbq * 9 * kTerms;
+          const int term = rq / 9, tap = rq - term * 9;
+          const int s36 = nbq * 9 + tap;
           const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
-#pragma unroll 1
-          for (int term = 0; term < kTerms; ++term, ++it) {  // split: (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo)
-            const CUtensorMap* mf = (kTerms == 3 && term == 1) ? &tmFlo : &tmF;
-            const CUtensorMap* mw = (kTerms == 3 && term == 2) ? &tmWlo : &tmW;
+          {
+            const CUtensorMap* mf = (kTerms == 3 && term == 0) ? &tmFlo : &tmF;
+            const CUtensorMap* mw = (kTerms == 3 && term == 1) ? &tmWlo : &tmW;
             const int st = it % C::kStages;
             mbar_wait(&sm.w_empty[st], ((it / C::kStages) & 1) ^ 1);
             if (elect_one()) {

@@ -66,8 +66,9 @@ struct Smem {  // after the big buffers
   uint64_t act_ready[2][4];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t a01_free;   // split format: the layer's MMAs no longer read K-chunks 0, 1 of the (in-place) activation buffer
   uint32_t tmem_ptr;
-  uint32_t pad[3];
+  uint32_t pad[1];
   float partial[3][kTileM][3];  // RGB partial sums of the three non-reducing warp sets
 };
 constexpr size_t kSmemBytes = 2 * kActBytes + kWBytesTotal + sizeof(Smem);
@@ -429,6 +430,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_init(&sm.tmem_full[i], 1);
       mbar_init(&sm.tmem_empty[i], kEpiWarps * CG);
     }
+    mbar_init(&sm.a01_free, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CG>(&sm.tmem_ptr, 512);
@@ -455,11 +457,18 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
       // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues
-      // (layer-1, half, kc) in MMA consumption order; the split format streams the hi and then the lo tile of each
-      constexpr int kLoads = kSplit ? 48 : 24;
+      // (layer-1, half, kc) in MMA consumption order. Split format, per (layer, half) and K-chunk pair g: hi, lo tiles of
+      // chunks 2g, 2g+1 (for the small a_lo.w_hi and a_hi.w_lo terms), then their hi tiles again (a_hi.w_hi) -- see the MMA issuer
+      constexpr int kLoads = kSplit ? 72 : 24;
       for (int sl = 0; sl < kLoads; ++sl, ++it) {
-        const int s24 = kSplit ? (sl >> 1) : sl;
-        const CUtensorMap* tm = (kSplit && (sl & 1)) ? &tmWlo : &tmW;
+        int s24 = sl;
+        const CUtensorMap* tm = &tmW;
+        if constexpr (kSplit) {
+          const int lh = sl / 12, j = sl % 12, g = j / 6, jj = j % 6;  // jj: 0..3 = (kc, hi|lo) of the small terms, 4..5 = hi again
+          const int kc = 2 * g + (jj < 4 ? (jj >> 1) : jj - 4);
+          s24 = lh * 4 + kc;
+          if (jj < 4 && (jj & 1)) tm = &tmWlo;
+        }
         const int st = it % C::kStages;
         const uint32_t ph = (it / C::kStages) & 1;
         mbar_wait(&sm.w_empty[st], ph ^ 1);
@@ -504,47 +513,58 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             tc_fence_after();
             if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10);
             const uint32_t d_tmem = tmem_u + h * 256;
-#pragma unroll 1
-            for (int kc = 0; kc < 4; ++kc, ++it) {
-              if (h == 0) {  // half 1 re-reads chunks whose readiness half 0 already observed
-                if constexpr (CG == 2) mbar_wait_cluster(&sm.act_ready[bin][kc], aph);
-                else mbar_wait(&sm.act_ready[bin][kc], aph);
-              }
-              if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 1 + 2 * kc);
+            // one weight stage = four K = 16 MMAs of A chunk `a0` against it
+            auto stage_mmas = [&](uint32_t a0, bool first, bool commit_full) {
               const int st = it % C::kStages;
               mbar_wait(&sm.w_full[st], (it / C::kStages) & 1);
               tc_fence_after();
-              if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 2 + 2 * kc);
-              const uint32_t a0 = a_base + kc * kChunkBytes;
               const uint32_t b0 = smem_u32(s_w + st * C::kStageBytes);
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b0 + k * 32), idesc,
-                                (kc | k) != 0 ? 1u : 0u);
-                if constexpr (kSplit) {  // a_lo . w_hi on the same weight stage
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + kActBytes + k * 32), umma_desc_sw128(b0 + k * 32), idesc, 1u);
-                }
+                                (first && k == 0) ? 0u : 1u);
                 umma_commit<CG>(&sm.w_empty[st]);
-                if (!kSplit && kc == 3) umma_commit<CG>(&sm.tmem_full[h]);
+                if (commit_full) umma_commit<CG>(&sm.tmem_full[h]);
               }
               __syncwarp();
-              if constexpr (kSplit) {  // a_hi . w_lo on the next stage
-                ++it;
-                const int st2 = it % C::kStages;
-                mbar_wait(&sm.w_full[st2], (it / C::kStages) & 1);
-                tc_fence_after();
-                const uint32_t b1 = smem_u32(s_w + st2 * C::kStageBytes);
-                if (elect_one()) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16<CG>(d_tmem, umma_desc_sw128(a0 + k * 32), umma_desc_sw128(b1 + k * 32), idesc, 1u);
-                  umma_commit<CG>(&sm.w_empty[st2]);
-                  if (kc == 3) umma_commit<CG>(&sm.tmem_full[h]);
+              ++it;
+            };
+            auto wait_chunk = [&](int kc) {
+              if (h == 0) {  // half 1 re-reads chunks whose readiness half 0 already observed
+                if constexpr (CG == 2) mbar_wait_cluster(&sm.act_ready[bin][kc], aph);
+                else mbar_wait(&sm.act_ready[bin][kc], aph);
+              }
+            };
+            if constexpr (!kSplit) {
+#pragma unroll 1
+              for (int kc = 0; kc < 4; ++kc) {
+                wait_chunk(kc);
+                if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 1 + 2 * kc);
+                stage_mmas(a_base + kc * kChunkBytes, kc == 0, kc == 3);
+                if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 2 + 2 * kc);
+              }
+            } else {
+              // Split format. The tensor core adds every MMA's result to the fp32 accumulator with truncation, so each add at
+              // full accumulator magnitude costs up to one ulp: the small terms (a_lo.w_hi, a_hi.w_lo: 2^-11 of the result)
+              // of a K-chunk pair go in BEFORE that pair's a_hi.w_hi. Chunk pairs (0,1) then (2,3), so that chunks 0, 1 of the
+              // in-place activation buffer are dead halfway through half 1 and half 0's epilogue can start overwriting them.
+#pragma unroll 1
+              for (int g = 0; g < 2; ++g) {
+#pragma unroll 1
+                for (int kc = 2 * g; kc < 2 * g + 2; ++kc) {
+                  wait_chunk(kc);
+                  const uint32_t a0 = a_base + kc * kChunkBytes;
+                  stage_mmas(a0 + kActBytes, kc == 0, false);  // a_lo . w_hi
+                  stage_mmas(a0, false, false);                // a_hi . w_lo
                 }
-                __syncwarp();
+#pragma unroll 1
+                for (int kc = 2 * g; kc < 2 * g + 2; ++kc)
+                  stage_mmas(a_base + kc * kChunkBytes, false, kc == 3);  // a_hi . w_hi
+                if (g == 0 && h == 1) {
+                  if (elect_one()) umma_commit<CG>(&sm.a01_free);
+                  __syncwarp();
+                }
               }
             }
             if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 9);
@@ -631,10 +651,11 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          // Split format: this layer's epilogue (and the next tile's layer 0) overwrite the buffer the layer's MMAs read, so
-          // nothing may be written before ALL of them have retired, i.e. before half slot 1 is complete.
+          // Split format: this layer's epilogue (and the next tile's layer 0) overwrite the buffer the layer's MMAs read:
+          // K-chunks 0, 1 once half 1 is past them (a01_free), chunks 2, 3 once half slot 1 is complete.
           if constexpr (kSplit) {
-            if (h == 0) mbar_wait(&sm.tmem_full[1], full_uses & 1);
+            if (h == 0) mbar_wait(&sm.a01_free, full_uses & 1);       // chunks 0, 1 (this half's output, layer 0's first pair)
+            else mbar_wait(&sm.tmem_full[1], full_uses & 1);          // chunks 2, 3: every MMA of the layer has retired
           }
           // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs: complete, because
           // this warp has itself consumed tmem_full[1] of layer 2. Its four chunks are interleaved with layer 3's halves.
