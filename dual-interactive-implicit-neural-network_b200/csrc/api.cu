@@ -285,6 +285,8 @@ void diinn_destroy(diinn_handle* h) {
   }
   cudaFree(h->WA16lo);
   cudaFree(h->WB16lo);
+  cudaFree(h->WSel16[0]);
+  cudaFree(h->WSel16[1]);
   cudaFree(h->err_flag);
   cudaFree(h->trace_dev);
   cudaFree(h->WH32);
@@ -337,17 +339,18 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
 
 // The LR-resolution half of a tensor-path decode: layout pass (skipped for a channels-last bf16 map, which stage A reads in
 // place as bf16 operands), stage A, and for modes 1 / 2 the K chain. nhwc / nhwc_lo / chain are workspace regions.
+// p16: P is written as fp16 (what stage B's select-MMA variant consumes, stage_b_wants_p16); never with the K chain.
 static int run_lr_stages(Handle* h, const void* feat, int io_dtype, int fmt, int B, int H, int W, int fr0, int frows,
-                         int lr_row0, int lr_rows, float* P, char* nhwc, char* nhwc_lo, char* chain, cudaStream_t s,
+                         int lr_row0, int lr_rows, float* P, bool p16, char* nhwc, char* nhwc_lo, char* chain, cudaStream_t s,
                          cudaEvent_t ev_after_layout = nullptr) {
   int rc;
   if (io_dtype == DIINN_IO_BF16_NHWC) {
     if (ev_after_layout) cudaEventRecord(ev_after_layout, s);
-    rc = launch_stage_a_umma(h, feat, nullptr, kFmtBf16, B, H, W, 0, H, lr_row0, lr_rows, P, s);
+    rc = launch_stage_a_umma(h, feat, nullptr, kFmtBf16, B, H, W, 0, H, lr_row0, lr_rows, P, p16, s);
   } else {
     if ((rc = launch_feat_to_nhwc(h, feat, io_dtype, fmt, B, H, W, fr0, fr0 + frows, nhwc, nhwc_lo, s))) return rc;
     if (ev_after_layout) cudaEventRecord(ev_after_layout, s);
-    rc = launch_stage_a_umma(h, nhwc, nhwc_lo, fmt, B, H, W, fr0, frows, lr_row0, lr_rows, P, s);
+    rc = launch_stage_a_umma(h, nhwc, nhwc_lo, fmt, B, H, W, fr0, frows, lr_row0, lr_rows, P, p16, s);
   }
   if (rc) return rc;
   if (h->cfg.mode == 1 || h->cfg.mode == 2) {
@@ -520,8 +523,9 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   mark(0);
   // (encoder hand-off: a channels-last bf16 map is read in place as bf16 operands, whatever format stage B runs in -- a
   // bf16 feature map holds no more than bf16 precision anyway)
-  if ((rc = run_lr_stages(h, feat, io_dtype, fmt, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, nhwc, nhwc_lo,
-                          ws + plan.off_chain, s, ev >= 0 ? h->prof_events[ev + 1] : nullptr)))
+  const bool p16 = stage_b_wants_p16(h, src, fmt);
+  if ((rc = run_lr_stages(h, feat, io_dtype, fmt, B, H, W, plan.fr0, plan.frows, plan.lr_row0, plan.lr_rows, P, p16, nhwc,
+                          nhwc_lo, ws + plan.off_chain, s, ev >= 0 ? h->prof_events[ev + 1] : nullptr)))
     return rc;
   mark(2);
   rc = launch_stage_b_umma(h, src, ob, P, 0, fmt, s, h->tap);
@@ -751,7 +755,7 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   char* nhwc = ws + off;
   char* nhwc_lo = fmt == kFmtSplit ? nhwc + plane : nullptr;
   char* chain = nhwc + (fmt == kFmtSplit ? 2 : 1) * plane;
-  if ((rc = run_lr_stages(h, feat, io_dtype, fmt, B, H, W, 0, H, 0, H, P, nhwc, nhwc_lo, chain, s))) return rc;
+  if ((rc = run_lr_stages(h, feat, io_dtype, fmt, B, H, W, 0, H, 0, H, P, false, nhwc, nhwc_lo, chain, s))) return rc;
   return launch_stage_b_umma(h, src, o, P, 0, fmt, s);
 }
 
@@ -793,10 +797,11 @@ int diinn_debug_stage_a(diinn_handle* h, const void* feat, int B, int C, int H, 
   if (!workspace || workspace_bytes < need)
     return fail(h, DIINN_ERR_WORKSPACE_TOO_SMALL, "workspace too small: need " + std::to_string(need) + " bytes");
   char* nhwc = static_cast<char*>(workspace);
-  if (io_dtype == DIINN_IO_BF16_NHWC) return launch_stage_a_umma(h, feat, nullptr, kFmtBf16, B, H, W, 0, H, 0, H, P, s);
+  if (io_dtype == DIINN_IO_BF16_NHWC)
+    return launch_stage_a_umma(h, feat, nullptr, kFmtBf16, B, H, W, 0, H, 0, H, P, false, s);
   char* lo = fmt == kFmtSplit ? nhwc + plane : nullptr;
   if ((rc = launch_feat_to_nhwc(h, feat, io_dtype, fmt, B, H, W, 0, H, nhwc, lo, s))) return rc;
-  return launch_stage_a_umma(h, nhwc, lo, fmt, B, H, W, 0, H, 0, H, P, s);
+  return launch_stage_a_umma(h, nhwc, lo, fmt, B, H, W, 0, H, 0, H, P, false, s);
 }
 
 int diinn_debug_umma_pace(diinn_handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma,

@@ -50,6 +50,10 @@ struct Handle {
   CUtensorMap tmapWAlo[2]{};
   CUtensorMap tmapWB[2][2]{};
   CUtensorMap tmapWBlo[2]{};
+  // select-MMA variant of stage B: the constant Q-branch tiles of B_sel, (3 layers, 2 halves, 2 feature blocks, K_sel rows, 64)
+  // fp16 with bq_hi in row K_sel-2 and bq_lo in row K_sel-1, for K_sel = 16 ([0]) and 32 ([1])
+  uint16_t* WSel16[2] = {nullptr, nullptr};
+  CUtensorMap tmapSelB[2]{};
   // modes 1 / 2 (K chain entirely at LR resolution): the k-facing 256x256 blocks of K.1..3, row-major [n][k]
   float* WH32 = nullptr;          // (3, 256, 256)
   __nv_bfloat16* WH16 = nullptr;  // (3, 256, 256)
@@ -138,10 +142,13 @@ int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, con
                    char* ws, const InitQPlan& pl, int fmt, cudaStream_t s);
 // stage_a_umma.cu / stage_b_umma.cu
 // feat_nhwc: (B, frows, W, 64) 16-bit elements in the operand format fmt; feat_lo: the fp16 residual plane (kFmtSplit only)
+// P: fp32 (B*lr_rows*W, 1024), or with p16 the same matrix in fp16 (what stage B's select-MMA variant consumes)
 int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, int fmt, int B, int H, int W, int fr0,
-                        int frows, int lr_row0, int lr_rows, float* P, cudaStream_t s);
-int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group, int fmt,
+                        int frows, int lr_row0, int lr_rows, void* P, bool p16, cudaStream_t s);
+// P: fp32 rows, or fp16 rows when stage_b_wants_p16(h, src, fmt) (the select-MMA variant, which feeds P to the tensor core)
+int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const void* P, int cta_group, int fmt,
                         cudaStream_t s, int4* tap = nullptr);
+bool stage_b_wants_p16(const Handle* h, const PixelSource& src, int fmt);
 // gemm.cu
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
                          cudaStream_t s, const ChainEpilogue* chain = nullptr);

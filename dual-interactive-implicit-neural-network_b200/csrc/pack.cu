@@ -258,6 +258,31 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WL27frag, frag, sizeof(frag), cudaMemcpyHostToDevice, s));
   }
   DIINN_CUDA_OK(h, cudaMemcpyAsync(h->bq_dev, sp.bq, sizeof(float) * kLayers * kD, cudaMemcpyHostToDevice, s));
+  {
+    // select-MMA variant of stage B: the Q-branch tiles of B_sel. Per (layer 1..3, half, 64-feature block) a K_sel x 64 fp16
+    // tile that is zero except for its last two rows, bq_hi and bq_lo = fp16(bq - bq_hi): the one-hot rows of A_sel carry a
+    // 1.0 in both slots, so the accumulators of the Q branch start at bq to 22 bits.
+    static thread_local uint16_t tab[3 * 2 * 2 * 32 * 64];
+    for (int v = 0; v < 2; ++v) {
+      const int ks = v == 0 ? 16 : 32;
+      memset(tab, 0, sizeof(tab));
+      for (int lh = 0; lh < 6; ++lh)
+        for (int fb = 0; fb < 2; ++fb)
+          for (int e = 0; e < 64; ++e) {
+            const float b = sp.bq[lh / 2 + 1][(lh & 1) * 128 + fb * 64 + e];
+            const float bc = b < -65504.f ? -65504.f : (b > 65504.f ? 65504.f : b);
+            const __half hi = __float2half_rn(bc);
+            const __half lo = __float2half_rn(bc - __half2float(hi));
+            uint16_t* t = tab + (static_cast<size_t>(lh * 2 + fb) * ks) * 64;
+            t[(ks - 2) * 64 + e] = __half_as_ushort(hi);
+            t[(ks - 1) * 64 + e] = __half_as_ushort(lo);
+          }
+      const size_t bytes = sizeof(uint16_t) * 3 * 2 * 2 * ks * 64;
+      if (!h->WSel16[v]) DIINN_CUDA_OK(h, cudaMalloc(&h->WSel16[v], bytes));
+      DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WSel16[v], tab, bytes, cudaMemcpyHostToDevice, s));
+      DIINN_CUDA_OK(h, cudaStreamSynchronize(s));  // tab is reused
+    }
+  }
   DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
 
   // TMA descriptors over the bf16 tiles (rows of 64 bf16 = 128 B, 128B swizzle applied by TMA on the way in)
@@ -271,6 +296,10 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     }
     if ((rc = make_tmap_2d_bf16(h, &h->tmapWAlo[cg], h->WA16lo, 64, 4 * 9 * 256, 64, box_rows))) return rc;
     if ((rc = make_tmap_2d_bf16(h, &h->tmapWBlo[cg], h->WB16lo, 64, 3 * 2 * 4 * 256, 64, box_rows))) return rc;
+  }
+  for (int v = 0; v < 2; ++v) {
+    const uint32_t ks = v == 0 ? 16 : 32;
+    if ((rc = make_tmap_2d_bf16(h, &h->tmapSelB[v], h->WSel16[v], 64, 3 * 2 * 2 * ks, 64, ks))) return rc;
   }
   h->has_weights = true;
   return DIINN_OK;

@@ -197,6 +197,26 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_acc16(int M, int N) {
   return (0u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// K-major, 64-byte-swizzle operand tile: rows of 64 B (32 16-bit elements), 8-row groups 512 B apart (SBO), layout type 4
+// (SWIZZLE_64B). +32 B steps UMMA_K inside the swizzle atom. 512-byte aligned base.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t addr) {
+  const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// MN-major, 128-byte-swizzle operand tile (cute: Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): each K
+// index is a 128-byte row of 64 consecutive M/N elements, 8 K-rows form a 1 KB atom; atoms along K are sbo_bytes apart,
+// atoms along M/N (the next 64 elements) lbo_bytes apart. 1024-byte aligned base; + 2 * sbo_bytes steps UMMA_K = 16.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = ((addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+// instruction descriptor, kind::f16: fp16 x fp16 -> fp32, A K-major, B MN-major (bit 16)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_bmn(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
 // instruction descriptor, kind::f16: fp16 x fp16 -> fp32 accumulators, A and B K-major
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |

@@ -19,6 +19,9 @@
 //
 // Operand formats (FMT, handle.h): bf16, fp16, or the fp16 hi + lo SPLIT of the fp32-precision path, where every (n-block,
 // tap) becomes three ring stages -- (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) -- accumulated into the same TMEM columns.
+// kP16: P is written as fp16 (saturating), 2 KB per LR pixel -- the form stage B's select-MMA variant consumes as a tensor-core
+// operand; the epilogue then packs 64 columns per staging round, so a TMA store moves a full 128-byte swizzle row per pixel
+// and an N-block takes 4 store rounds instead of 8.
 // Small launches (an 8-way row shard of a DIV2K image has 96 pixel tiles for 74 CTA pairs) split every tile's four
 // N-blocks into 2 or 4 work items so that the last wave is not mostly idle (Geo::nsplit).
 #include <cstdlib>
@@ -67,7 +70,7 @@ struct Geo {
   int nsplit;             // work items per pixel tile: each covers 4 / nsplit consecutive N-blocks (1, 2 or 4)
 };
 
-template <int CG, int FMT>
+template <int CG, int FMT, bool kP16>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmFlo,
                     const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
@@ -212,30 +215,59 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
         mbar_wait(&sm.tmem_full[slot], (slot_use >> 1) & 1);
         tc_fence_after();
         const uint32_t tslot = tmem_base + lane_bits + slot * 256;
+        if constexpr (!kP16) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld16(tslot + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          tmem_ld16(tslot + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-          tmem_ld_wait();
-          const int n0 = nb * 256 + c0;
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld16(tslot + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld16(tslot + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            tmem_ld_wait();
+            const int n0 = nb * 256 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + bias.b[n0 + j];
-            if (nb == 0) x = fmaxf(x, 0.f);  // first 256 columns are k0 = relu(K0 x + b0)
-            v[j] = __float_as_uint(x);
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(v[j]) + bias.b[n0 + j];
+              if (nb == 0) x = fmaxf(x, 0.f);  // first 256 columns are k0 = relu(K0 x + b0)
+              v[j] = __float_as_uint(x);
+            }
+            // the previous TMA store of this warp must have finished reading the staging block
+            if (lane == 0) bulk_wait_group_read0();
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              st_shared_v4(srow + ((u ^ (lane & 7)) << 4), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmP, sm.store[quarter], n0, w0, h0, b);
+              bulk_commit_group();
+            }
           }
-          // the previous TMA store of this warp must have finished reading the staging block
-          if (lane == 0) bulk_wait_group_read0();
-          __syncwarp();
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 64) {
+            uint32_t v[64];
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            st_shared_v4(srow + ((u ^ (lane & 7)) << 4), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&tmP, sm.store[quarter], n0, w0, h0, b);
-            bulk_commit_group();
+            for (int q4 = 0; q4 < 4; ++q4) tmem_ld16(tslot + c0 + 16 * q4, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * q4]));
+            tmem_ld_wait();
+            const int n0 = nb * 256 + c0;
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+              float x0 = __uint_as_float(v[j]) + bias.b[n0 + j], x1 = __uint_as_float(v[j + 1]) + bias.b[n0 + j + 1];
+              if (nb == 0) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
+              pk[j >> 1] = pack_f16x2_sat(x0, x1);
+            }
+            if (lane == 0) bulk_wait_group_read0();
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              st_shared_v4(srow + ((u ^ (lane & 7)) << 4), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmP, sm.store[quarter], n0, w0, h0, b);  // tmP: fp16 map, box (64 cols, 16 w, 2 h)
+              bulk_commit_group();
+            }
           }
         }
         tc_fence_before();
@@ -257,7 +289,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
 }  // namespace sa
 
 int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, int fmt, int B, int H, int W, int fr0,
-                        int frows, int lr_row0, int lr_rows, float* P, cudaStream_t s) {
+                        int frows, int lr_row0, int lr_rows, void* P, bool p16, cudaStream_t s) {
   using namespace sa;
   static int env_cg = -1;
   if (env_cg < 0) {
@@ -268,6 +300,7 @@ int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, i
   int* err_flag = h->err_flag;
   if (fmt < 0 || fmt > kFmtSplit) return fail(h, DIINN_ERR_BAD_DTYPE, "stage A: unknown operand format");
   if (fmt == kFmtSplit && !feat_lo) return fail(h, DIINN_ERR_BAD_ARG, "stage A: the split format needs the residual plane");
+  if (fmt == kFmtSplit && p16) return fail(h, DIINN_ERR_BAD_ARG, "stage A: the split format writes fp32 P");
   CUtensorMap tmF, tmFlo;
   const uint64_t dims[4] = {static_cast<uint64_t>(kC), static_cast<uint64_t>(W), static_cast<uint64_t>(frows),
                             static_cast<uint64_t>(B)};
@@ -280,10 +313,13 @@ int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, i
   CUtensorMap tmP;
   const uint64_t pdims[4] = {static_cast<uint64_t>(kPCols), static_cast<uint64_t>(W), static_cast<uint64_t>(lr_rows),
                              static_cast<uint64_t>(B)};
-  const uint64_t pstrides[3] = {kPCols * 4ull, static_cast<uint64_t>(W) * kPCols * 4ull,
-                                static_cast<uint64_t>(lr_rows) * W * kPCols * 4ull};
-  const uint32_t pbox[4] = {32, kPatchW, 2, 1};
-  if ((rc = make_tmap_4d_f32(h, &tmP, P, pdims, pstrides, pbox))) return rc;
+  const uint64_t pesz = p16 ? 2 : 4;
+  const uint64_t pstrides[3] = {kPCols * pesz, static_cast<uint64_t>(W) * kPCols * pesz,
+                                static_cast<uint64_t>(lr_rows) * W * kPCols * pesz};
+  const uint32_t pbox[4] = {p16 ? 64u : 32u, kPatchW, 2, 1};   // 128 bytes of columns either way
+  rc = p16 ? make_tmap_4d_bf16(h, &tmP, P, pdims, pstrides, pbox)   // (16-bit elements; TMA does no arithmetic)
+           : make_tmap_4d_f32(h, &tmP, P, pdims, pstrides, pbox);
+  if (rc) return rc;
   static_assert(sizeof(BiasParams) == sizeof(float) * kPCols, "bias block");
   const BiasParams& bias = *reinterpret_cast<const BiasParams*>(h->bA_host);
   Geo g{};
@@ -332,21 +368,24 @@ int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, i
   const int ci = cta_group - 1;
   const CUtensorMap& tmW = h->tmapWA[fmt == kFmtBf16 ? 0 : 1][ci];
   const CUtensorMap& tmWlo = h->tmapWAlo[ci];
-#define DIINN_SA_LAUNCH(CGv, FMTv)                                                                                        \
-  do {                                                                                                                    \
-    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<CGv, FMTv>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                          static_cast<int>(kSmemBytes)));                                                 \
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<CGv, FMTv>, tmF, tmFlo, tmW, tmWlo, tmP, bias, g, err_flag)); \
+#define DIINN_SA_LAUNCH(CGv, FMTv, P16v)                                                                                   \
+  do {                                                                                                                     \
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<CGv, FMTv, P16v>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          static_cast<int>(kSmemBytes)));                                                  \
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<CGv, FMTv, P16v>, tmF, tmFlo, tmW, tmWlo, tmP, bias, g,   \
+                                        err_flag));                                                                        \
   } while (0)
-  if (cta_group == 1) {
-    if (fmt == kFmtBf16) DIINN_SA_LAUNCH(1, kFmtBf16);
-    else if (fmt == kFmtF16) DIINN_SA_LAUNCH(1, kFmtF16);
-    else DIINN_SA_LAUNCH(1, kFmtSplit);
-  } else {
-    if (fmt == kFmtBf16) DIINN_SA_LAUNCH(2, kFmtBf16);
-    else if (fmt == kFmtF16) DIINN_SA_LAUNCH(2, kFmtF16);
-    else DIINN_SA_LAUNCH(2, kFmtSplit);
-  }
+#define DIINN_SA_PICK(CGv)                                                  \
+  do {                                                                      \
+    if (fmt == kFmtSplit) DIINN_SA_LAUNCH(CGv, kFmtSplit, false);           \
+    else if (fmt == kFmtBf16 && p16) DIINN_SA_LAUNCH(CGv, kFmtBf16, true);  \
+    else if (fmt == kFmtBf16) DIINN_SA_LAUNCH(CGv, kFmtBf16, false);        \
+    else if (p16) DIINN_SA_LAUNCH(CGv, kFmtF16, true);                      \
+    else DIINN_SA_LAUNCH(CGv, kFmtF16, false);                              \
+  } while (0)
+  if (cta_group == 1) DIINN_SA_PICK(1);
+  else DIINN_SA_PICK(2);
+#undef DIINN_SA_PICK
 #undef DIINN_SA_LAUNCH
   h->launches += 1;
   return DIINN_OK;

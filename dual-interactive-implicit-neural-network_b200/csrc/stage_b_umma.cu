@@ -31,6 +31,15 @@
 // in place once all MMAs of a layer have retired, and the sine is range-reduced (Cody-Waite) before MUFU.SIN.
 // Accumulation is fp32 in TMEM in every format.
 //
+// Select-MMA variant (template kSel; grid decodes whose CTA-pair patch touches at most 30 LR cells, i.e. scale factors from
+// about x3.6 up -- c1, c2x4, c3, c4): the two ADDS of every epilogue element move into the tensor core. relu(accK + P[l]) needs
+// the LR cell's hoisted row P[l]; sin(accQ + bq) needs the Q bias. Both are linear in a one-hot row vector: with
+//   A_sel[row]  = e_slot(l(row)) + e_bias_hi + e_bias_lo                 (128 x K_sel fp16, K_sel = 16 or 32, built per tile)
+//   B_sel       = [ P16 rows of the pair's LR patch ; 0 ; 0 ]  for the K-branch columns (one TMA 4-D box out of the fp16 P
+//                 stage A writes for this variant), [ 0 ; bq_hi ; bq_lo ] for the Q-branch columns (constant table)
+// one or two extra K = 16 MMAs per half slot (MN-major B: a P row IS a row of N values) pre-load the accumulators with
+// P[l] and bq, and the epilogue shrinks to relu(accK) * sin(accQ): no P loads, no bias loads, two adds fewer per pair.
+//
 // Measured alternatives that did NOT pay: two 8-warp groups (one per half slot), four 128-column
 // slots with per-slot groups, three slots (256|128|128), fp16 accumulators, packed FFMA2 for the RGB projection.
 #include <cstdio>
@@ -44,20 +53,28 @@ using namespace ptx;
 
 namespace sb {
 constexpr int kTileM = 128;
-constexpr int kPatchH = 8, kPatchW = 16;
+// a CTA tile is a patch of 128 HR pixels, 2^pw_log2 wide (Work::pw_log2): 8x16 by default, 4x32 / 2x64 / 16x8 when that
+// leaves fewer (partly idle) waves for the launch -- e.g. the 170-row shard of an 8-way split DIV2K image: 19 waves
+// instead of 20. A row's arithmetic does not depend on its tile, so the image is bit-identical whatever the shape.
+constexpr int kPatchWLog2Default = 4;
 constexpr int kActBytes = kTileM * kD * 2;       // 64 KB: one activation buffer (4 K-chunks x 16 KB)
 constexpr int kChunkBytes = kTileM * 128;        // 16 KB: 128 rows x 128 B
-constexpr int kWBytesTotal = 80 * 1024;          // weight stages
+constexpr int kSelBytes = 8 * 1024;              // select variant: one B_sel stage (2 x K_sel rows x 128 B)
+constexpr int kASelBytes = 8 * 1024;             // select variant: one A_sel buffer (128 rows x 64 B, 64B swizzle); two of them
 constexpr int kThreads = 640;
 constexpr int kEpiWarps = 16;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kRegsCtrl = 40, kRegsEpi = 104;
 
-template <int CG>
+template <int CG, bool kSel>
 struct Cfg {
   static constexpr int kStageRows = 256 / CG;
   static constexpr int kStageBytes = kStageRows * 128;
-  static constexpr int kStages = kWBytesTotal / kStageBytes;  // 3 (CG=1) or 6 (CG=2)
+  static constexpr int kWBytes = (kSel ? 64 : 80) * 1024;      // weight ring: 5 stages per CTA of a pair, 4 with kSel
+  static constexpr int kStages = kWBytes / kStageBytes;
+  static constexpr int kSelOff = 2 * kActBytes + kWBytes;      // B_sel stage
+  static constexpr int kASelOff = kSelOff + kSelBytes;         // A_sel buffers
+  static constexpr int kCtrlOff = kSel ? kASelOff + 2 * kASelBytes : 2 * kActBytes + kWBytes;  // struct Smem
 };
 
 struct Smem {  // after the big buffers
@@ -67,22 +84,30 @@ struct Smem {  // after the big buffers
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t a01_free;   // split format: the layer's MMAs no longer read K-chunks 0, 1 of the (in-place) activation buffer
+  uint64_t sel_full, sel_empty;  // select variant: the B_sel stage
   uint32_t tmem_ptr;
   uint32_t pad[1];
   float partial[3][kTileM][3];  // RGB partial sums of the three non-reducing warp sets
 };
-constexpr size_t kSmemBytes = 2 * kActBytes + kWBytesTotal + sizeof(Smem);
-static_assert(kSmemBytes <= 232448, "exceeds 227 KB of dynamic shared memory");
+template <int CG, bool kSel>
+constexpr size_t smem_bytes() { return Cfg<CG, kSel>::kCtrlOff + sizeof(Smem); }
+static_assert(smem_bytes<2, true>() <= 232448 && smem_bytes<2, false>() <= 232448, "exceeds 227 KB of dynamic shared memory");
 
 struct Work {
   int n_work;          // work items per CTA pair (CG=2) / CTA (CG=1)
   int tiles_y, n_txp;  // grid mode
+  int pw_log2;         // log2 of the patch width in pixels (3..6); patch height = 128 >> pw_log2
+  int ksel;            // select variant: K_sel (16 or 32); slots [0, box_r*box_c) = LR cells of the pair's patch, the last two = bias
+  int box_r, box_c;    // select variant: LR rows x columns of the TMA box that fetches a pair's P16 patch
+  uint32_t sel_lbo, sel_sbo, sel_kstep;  // select variant: B_sel descriptor strides (bytes): 64-feature blocks, 8-row K groups,
+                                         // and the start-address step of the second K = 16 MMA
   int4* tap;           // debug (diinn_debug_stage_b_rows): per output pixel (ih, iw, bits(rel_h), bits(rel_w)) as THIS kernel
                        // derives them, indexed by the pixel's channel-0 output offset; nullptr in product calls
 };
 
 struct RowCtx {
-  const float* prow;  // P row of this pixel's LR cell
+  const float* prow;  // P row of this pixel's LR cell (select variant: the fp16 row, see p16row())
+  int slot;           // select variant: index of the LR cell inside the pair's patch box
   float rel_h, rel_w, ratio;
   float area;  // ensemble rows: |rel_h * rel_w| + 1e-9
   int64_t out_off;  // offset of channel 0
@@ -91,24 +116,41 @@ struct RowCtx {
 
 // kPix (init_q=True, csrc/init_q.cu): P holds one row per HR pixel of the launch's rows [row0,row1) -- pixel-major
 // (b, row, col) -- instead of one per LR cell, and the launch covers a chunk of the band whose first row is out_row0.
-template <int CG, bool kPix = false>
-__device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& o, const float* __restrict__ P,
+// origin of a CTA pair's (or CTA's) patch and of its LR patch: shared by make_row (slots) and the producer (TMA coordinates)
+template <int CG>
+__device__ __forceinline__ void pair_origin(const PixelSource& s, const Work& wk, int ty, int txp, int& ih0, int& iw0) {
+  const int pw = 1 << wk.pw_log2, ph = kTileM >> wk.pw_log2;
+  ih0 = axis_index(s.ax_h, min(s.row0 + ty * ph, s.row1 - 1));
+  iw0 = axis_index(s.ax_w, min(txp * CG * pw, s.W_up - 1));
+}
+
+template <int CG, bool kPix = false, bool kSel = false>
+__device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& o, const void* __restrict__ Pv,
                                            const Work& wk, int work, int rank, int r, bool write_tap = false) {
   RowCtx rc;
+  const float* P = static_cast<const float*>(Pv);
+  rc.slot = 0;
   if (s.mode == 0) {
     const int per_img = wk.tiles_y * wk.n_txp;
     const int b = work / per_img;
     const int rem = work - b * per_img;
     const int ty = rem / wk.n_txp, txp = rem - ty * wk.n_txp;
-    const int oh = s.row0 + ty * kPatchH + (r >> 4);
-    const int ow = (txp * CG + rank) * kPatchW + (r & 15);
+    const int pw = 1 << wk.pw_log2, ph = kTileM >> wk.pw_log2;
+    const int oh = s.row0 + ty * ph + (r >> wk.pw_log2);
+    const int ow = (txp * CG + rank) * pw + (r & (pw - 1));
     rc.valid = oh < s.row1 && ow < s.W_up;
     const int ohc = min(oh, s.row1 - 1), owc = min(ow, s.W_up - 1);
     const int ih = axis_index(s.ax_h, ohc), iw = axis_index(s.ax_w, owc);
-    if constexpr (kPix)
+    if constexpr (kPix) {
       rc.prow = P + (static_cast<size_t>(b * (s.row1 - s.row0) + (ohc - s.row0)) * s.W_up + owc) * kPCols;
-    else
+    } else if constexpr (kSel) {  // fp16 P: half the row pitch in bytes (kept as a float pointer; see p16row())
+      rc.prow = P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw) * (kPCols / 2);
+      int ih0, iw0;
+      pair_origin<CG>(s, wk, ty, txp, ih0, iw0);
+      rc.slot = (ih - ih0) * wk.box_c + (iw - iw0);
+    } else {
       rc.prow = P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw) * kPCols;
+    }
 #if DIINN_ABL & 1
     rc.prow = P;
 #endif
@@ -148,16 +190,20 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
 // P is produced by stage A right before this kernel and is far larger than L2 for real images, so a tile's first
 // touch of its P rows would be an HBM-latency load in the middle of the epilogue. The producer warp therefore pulls
 // the P rows of the tile two work items ahead into L2 (whole 4 KB rows, one bulk prefetch per LR row segment).
-template <int CG>
-__device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const float* __restrict__ P, const Work& wk,
+// kEsz: bytes per P element (4, or 2 for the select variant's fp16 P)
+template <int CG, int kEsz = 4>
+__device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const void* __restrict__ Pv, const Work& wk,
                                                    int work, int rank, int lane) {
+  const char* P = static_cast<const char*>(Pv);
+  constexpr size_t kRow = static_cast<size_t>(kPCols) * kEsz;  // bytes per P row
   if (s.mode == 0) {
     const int per_img = wk.tiles_y * wk.n_txp;
     const int b = work / per_img;
     const int rem = work - b * per_img;
     const int ty = rem / wk.n_txp, txp = rem - ty * wk.n_txp;
-    const int oh0 = min(s.row0 + ty * kPatchH, s.row1 - 1), oh1 = min(oh0 + kPatchH - 1, s.row1 - 1);
-    const int ow0 = min((txp * CG + rank) * kPatchW, s.W_up - 1), ow1 = min(ow0 + kPatchW - 1, s.W_up - 1);
+    const int pw = 1 << wk.pw_log2, ph = kTileM >> wk.pw_log2;
+    const int oh0 = min(s.row0 + ty * ph, s.row1 - 1), oh1 = min(oh0 + ph - 1, s.row1 - 1);
+    const int ow0 = min((txp * CG + rank) * pw, s.W_up - 1), ow1 = min(ow0 + pw - 1, s.W_up - 1);
     const int ih0 = axis_index(s.ax_h, oh0), ih1 = axis_index(s.ax_h, oh1);
     const int iw0 = axis_index(s.ax_w, ow0), iw1 = axis_index(s.ax_w, ow1);
     const int ncols = iw1 - iw0 + 1;
@@ -166,8 +212,8 @@ __device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const f
     for (int i = lane; i < n; i += 32) {
       const int ih = ih0 + i / segs, c0 = (i % segs) * 4;
       const int nc = min(4, ncols - c0);
-      prefetch_l2_bulk(P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw0 + c0) * kPCols,
-                       static_cast<uint32_t>(nc) * kPCols * 4u);
+      prefetch_l2_bulk(P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw0 + c0) * kRow,
+                       static_cast<uint32_t>(nc * kRow));
     }
   } else {
     const int64_t total = static_cast<int64_t>(s.B) * s.Q * (s.ensemble ? 4 : 1);
@@ -180,7 +226,7 @@ __device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const f
       const float ch = __ldg(s.coord + qi * 2), cw = __ldg(s.coord + qi * 2 + 1);
       const int ih = s.ensemble ? ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi) : query_index(s.ax_h, ch);
       const int iw = s.ensemble ? ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi) : query_index(s.ax_w, cw);
-      prefetch_l2_bulk(P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kPCols, kPCols * 4u);
+      prefetch_l2_bulk(P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kRow, static_cast<uint32_t>(kRow));
     }
   }
 }
@@ -193,9 +239,10 @@ __device__ __forceinline__ void prefetch_tile_pixels(const PixelSource& s, const
   const int b = work / per_img;
   const int rem = work - b * per_img;
   const int ty = rem / wk.n_txp, txp = rem - ty * wk.n_txp;
-  const int oh0 = s.row0 + ty * kPatchH, ow0 = (txp * CG + rank) * kPatchW;
+  const int pw = 1 << wk.pw_log2, ph = kTileM >> wk.pw_log2;
+  const int oh0 = s.row0 + ty * ph, ow0 = (txp * CG + rank) * pw;
   if (ow0 >= s.W_up) return;
-  const int nrows = min(kPatchH, s.row1 - oh0), ncols = min(kPatchW, s.W_up - ow0);
+  const int nrows = min(ph, s.row1 - oh0), ncols = min(pw, s.W_up - ow0);
   const int segs = (ncols + 3) >> 2;
   for (int i = lane; i < nrows * segs; i += 32) {
     const int r = i / segs, c0 = (i % segs) * 4;
@@ -234,6 +281,11 @@ __device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[
 #pragma unroll
   for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p) + j);
 }
+// select variant: 16 fp16 values (32 B) of a P16 row, kept raw in v[0], v[1] until layer0_step unpacks them
+__device__ __forceinline__ void load16h(const uint16_t* __restrict__ p, float4 (&v)[4]) {
+  v[0] = __ldg(reinterpret_cast<const float4*>(p));
+  v[1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
 
 // Sine of the Q branch (SineAct, diinn.py:21-26). MUFU.SIN works on x / 2pi rounded to fp32, so its absolute error grows as
 // ~6e-8 |x| (1e-5 at |x| = 200): far inside the 16-bit-operand paths' budget for any sane argument. The split (fp32-
@@ -268,13 +320,19 @@ __device__ __forceinline__ uint32_t pack_residual(float a, float b, uint32_t hi1
 
 // layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
 // Split formats write the fp16 residual into the lo half of the buffer (same swizzled position, kActBytes further on).
-template <int FMT, bool kPix = false>
+template <int FMT, bool kPix = false, bool kSel = false>
 __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
                                             const SmallParams& sp, const float4 (&k0v)[4]) {
   constexpr bool kSplit = FMT == 2;
   const uint32_t chunk_base = act_base + kc * kChunkBytes;
   const int f0 = kc * 64 + wg * 16;
-  const float* k0 = reinterpret_cast<const float*>(k0v);
+  float k0h[16];
+  if constexpr (kSel) {  // fp16 P: 16 values in the first 32 bytes
+    const uint32_t* raw = reinterpret_cast<const uint32_t*>(k0v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) unpack_f16x2(raw[j], k0h[2 * j], k0h[2 * j + 1]);
+  }
+  const float* k0 = kSel ? k0h : reinterpret_cast<const float*>(k0v);
   uint32_t pk[8], pl[8];
   if constexpr (kPix) {  // init_q=True: Q.0 reads the 576-wide gate, so q_0 was finished per pixel by csrc/init_q.cu
 #pragma unroll
@@ -320,7 +378,7 @@ __device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw& raw) {  /
 // kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
 // kDump (mode 4): q_3 goes to HBM for the 3x3 last conv -- bf16 (q3row) from the 16-bit-operand formats, fp32 (q3row_f) from
 // the split format.
-template <bool kLast, int FMT, bool kDump = false>
+template <bool kLast, int FMT, bool kDump = false, bool kSel = false>
 __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
                                          const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3],
                                          __nv_bfloat16* q3row = nullptr, float* q3row_f = nullptr) {
@@ -333,10 +391,13 @@ __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int 
   for (int j = 0; j < 16; j += 2) {
     const float ak[2] = {__uint_as_float(raw.v[j]), __uint_as_float(raw.v[j + 1])};
     const float aq[2] = {__uint_as_float(raw.v[16 + j]), __uint_as_float(raw.v[16 + j + 1])};
-    // packed fp32x2 adds / multiplies (Blackwell FADD2 / FMUL2)
-    float2 k2 = __fadd2_rn(make_float2(ak[0], ak[1]), make_float2(kx[j], kx[j + 1]));
+    // packed fp32x2 adds / multiplies (Blackwell FADD2 / FMUL2); the select variant's accumulators already hold P[l] and bq
+    float2 k2 = make_float2(ak[0], ak[1]), t2 = make_float2(aq[0], aq[1]);
+    if constexpr (!kSel) {
+      k2 = __fadd2_rn(k2, make_float2(kx[j], kx[j + 1]));
+      t2 = __fadd2_rn(t2, *reinterpret_cast<const float2*>(&sp.bq[layer][f0 + j]));
+    }
     k2.x = fmaxf(k2.x, 0.f), k2.y = fmaxf(k2.y, 0.f);
-    const float2 t2 = __fadd2_rn(make_float2(aq[0], aq[1]), *reinterpret_cast<const float2*>(&sp.bq[layer][f0 + j]));
     const float2 q2 = __fmul2_rn(k2, make_float2(act_sin<kSplit>(t2.x), act_sin<kSplit>(t2.y)));
     const float q[2] = {q2.x, q2.y};
     if constexpr (kLast && kDump) {
@@ -383,20 +444,25 @@ __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int 
 
 // kDump (mode 4): a separate instantiation, so the q_3 dump costs the RGB-projecting kernels neither a register nor a branch.
 // kPix (init_q=True): see make_row / layer0_step.
-template <int CG, int FMT, bool kDump, bool kPix>
+// tmWlo: the fp16 residual weights (split format). tmSelP / tmSelB (select variant): the 4-D map of the fp16 P whose box is
+// one pair's LR patch x 64 features, and the 2-D map of the constant Q-bias tiles. P: fp32 rows, fp16 rows with kSel.
+template <int CG, int FMT, bool kDump, bool kPix, bool kSel>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
+                    const __grid_constant__ CUtensorMap tmSelP, const __grid_constant__ CUtensorMap tmSelB,
                     const __grid_constant__ SmallParams sp,
                     const __grid_constant__ PixelSource src, const __grid_constant__ OutSpec out,
-                    const float* __restrict__ P, const __grid_constant__ Work wk,
+                    const void* __restrict__ P, const __grid_constant__ Work wk,
                     int* __restrict__ err_flag, long long* __restrict__ trace) {
-  using C = Cfg<CG>;
+  using C = Cfg<CG, kSel>;
   constexpr bool kSplit = FMT == 2;
   static_assert(!(kSplit && kPix), "the split format is not wired for per-pixel P (init_q=True runs on the fp32 CUDA-core path)");
+  static_assert(!kSel || (CG == 2 && !kSplit && !kPix), "select variant: CTA pairs, 16-bit operand formats, LR-resolution P");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_act = smem;                     // 2 x 64 KB
-  uint8_t* s_w = smem + 2 * kActBytes;       // 96 KB of weight stages
-  Smem& sm = *reinterpret_cast<Smem*>(smem + 2 * kActBytes + kWBytesTotal);
+  uint8_t* s_w = smem + 2 * kActBytes;       // weight stages
+  Smem& sm = *reinterpret_cast<Smem*>(smem + C::kCtrlOff);
+  const uint32_t sel0 = smem_u32(smem + C::kSelOff), asel0 = smem_u32(smem + C::kASelOff);  // select variant only
 
   // warp index through a shuffle: ptxas then knows it is warp-uniform, so everything indexed by it (feature offsets
   // into the constant-bank parameters, TMEM columns) goes through uniform registers / LDCU instead of the ADU
@@ -431,7 +497,19 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_init(&sm.tmem_empty[i], kEpiWarps * CG);
     }
     mbar_init(&sm.a01_free, 1);
+    mbar_init(&sm.sel_full, 1);
+    mbar_init(&sm.sel_empty, 1);
+    if constexpr (kSel) {
+      prefetch_tensormap(&tmSelP);
+      prefetch_tensormap(&tmSelB);
+    }
     fence_barrier_init();
+  }
+  if constexpr (kSel) {
+    // the B_sel stage starts all-zero: the P16 box fills rows [0, box_r*box_c) of the K-branch CTA's tile and nothing ever
+    // writes the rows behind them (the bias slots and the padding up to K_sel must multiply to zero there)
+    for (int i = threadIdx.x; i < kSelBytes / 16; i += kThreads) st_shared_v4(sel0 + i * 16, 0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   if (warp == 2) tmem_alloc<CG>(&sm.tmem_ptr, 512);
   tc_fence_before();
@@ -446,10 +524,26 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   setmaxnreg_dec<kRegsCtrl>();
   if (warp == 0) {
     // ===================== weight producer (+ L2 prefetch of upcoming tiles' P rows) =====================
-    uint32_t it = 0;
+    uint32_t it = 0, sel_it = 0;
     auto prefetch = [&](int w_) {
-      if constexpr (kPix) prefetch_tile_pixels<CG>(src, P, wk, w_, rank, lane);
-      else prefetch_tile_rows<CG>(src, P, wk, w_, rank, lane);
+      if constexpr (kPix) prefetch_tile_pixels<CG>(src, static_cast<const float*>(P), wk, w_, rank, lane);
+      else prefetch_tile_rows<CG, kSel ? 2 : 4>(src, P, wk, w_, rank, lane);
+    };
+    // one weight stage: tile s24 of the (layer-1, half, kc) sequence out of map tm
+    auto load_w = [&](const CUtensorMap* tm, int s24) {
+      const int st = it % C::kStages;
+      const uint32_t ph = (it / C::kStages) & 1;
+      mbar_wait(&sm.w_empty[st], ph ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
+        void* dst = s_w + st * C::kStageBytes;
+        if constexpr (CG == 1)
+          tma_load_2d(dst, tm, &sm.w_full[st], 0, s24 * 256);
+        else
+          tma_load_2d_2sm(dst, tm, &sm.w_full[st], 0, s24 * 256 + rank * 128);
+      }
+      __syncwarp();
+      ++it;
     };
     if (unit_id + n_units < wk.n_work) prefetch(unit_id + n_units);
     for (int work = unit_id; work < wk.n_work; work += n_units) {
@@ -457,30 +551,47 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
       // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues
-      // (layer-1, half, kc) in MMA consumption order. Split format, per (layer, half) and K-chunk pair g: hi, lo tiles of
-      // chunks 2g, 2g+1 (for the small a_lo.w_hi and a_hi.w_lo terms), then their hi tiles again (a_hi.w_hi) -- see the MMA issuer
-      constexpr int kLoads = kSplit ? 72 : 24;
-      for (int sl = 0; sl < kLoads; ++sl, ++it) {
-        int s24 = sl;
-        const CUtensorMap* tm = &tmW;
-        if constexpr (kSplit) {
+      if constexpr (kSplit) {
+        // per (layer, half) and K-chunk pair g: hi, lo tiles of chunks 2g, 2g+1 (for the small a_lo.w_hi and a_hi.w_lo
+        // terms), then their hi tiles again (a_hi.w_hi) -- see the MMA issuer
+        for (int sl = 0; sl < 72; ++sl) {
           const int lh = sl / 12, j = sl % 12, g = j / 6, jj = j % 6;  // jj: 0..3 = (kc, hi|lo) of the small terms, 4..5 = hi again
           const int kc = 2 * g + (jj < 4 ? (jj >> 1) : jj - 4);
-          s24 = lh * 4 + kc;
-          if (jj < 4 && (jj & 1)) tm = &tmWlo;
+          load_w((jj < 4 && (jj & 1)) ? &tmWlo : &tmW, lh * 4 + kc);
         }
-        const int st = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
-        mbar_wait(&sm.w_empty[st], ph ^ 1);
-        if (elect_one()) {
-          if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
-          void* dst = s_w + st * C::kStageBytes;
-          if constexpr (CG == 1)
-            tma_load_2d(dst, tm, &sm.w_full[st], 0, s24 * 256);
-          else
-            tma_load_2d_2sm(dst, tm, &sm.w_full[st], 0, s24 * 256 + rank * 128);
+      } else {
+        int b_img = 0, ih0 = 0, iw0 = 0;
+        if constexpr (kSel) {
+          const int per_img = wk.tiles_y * wk.n_txp;
+          b_img = work / per_img;
+          const int rem = work - b_img * per_img;
+          const int ty = rem / wk.n_txp, txp = rem - ty * wk.n_txp;
+          pair_origin<CG>(src, wk, ty, txp, ih0, iw0);
         }
-        __syncwarp();
+        for (int lh = 0; lh < 6; ++lh) {  // (layer-1, half)
+          if constexpr (kSel) {
+            // B_sel stage of this half slot: the K-branch CTA (rank 0: features [128h, 128h+128) of P's block `layer`)
+            // fetches the pair's LR patch out of the fp16 P, the Q-branch CTA the constant bias tile
+            const uint32_t fb_stride = static_cast<uint32_t>(wk.ksel) * 128u;
+            mbar_wait(&sm.sel_empty, (sel_it & 1) ^ 1);
+            if (elect_one()) {
+              if (leader)
+                mbar_arrive_expect_tx(&sm.sel_full, 2u * 128u * static_cast<uint32_t>(wk.box_r * wk.box_c + wk.ksel));
+              uint8_t* dst = smem + C::kSelOff;
+              if (rank == 0) {
+                const int f0 = ((lh >> 1) + 1) * kD + (lh & 1) * 128;
+                tma_load_4d_2sm(dst, &tmSelP, &sm.sel_full, f0, iw0, ih0 - src.lr_row0, b_img);
+                tma_load_4d_2sm(dst + fb_stride, &tmSelP, &sm.sel_full, f0 + 64, iw0, ih0 - src.lr_row0, b_img);
+              } else {
+                tma_load_2d_2sm(dst, &tmSelB, &sm.sel_full, 0, (lh * 2 + 0) * wk.ksel);
+                tma_load_2d_2sm(dst + fb_stride, &tmSelB, &sm.sel_full, 0, (lh * 2 + 1) * wk.ksel);
+              }
+            }
+            __syncwarp();
+            ++sel_it;
+          }
+          for (int kc = 0; kc < 4; ++kc) load_w(&tmW, lh * 4 + kc);
+        }
       }
     }
     __syncwarp();
@@ -494,6 +605,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       constexpr uint32_t idesc = FMT == 0 ? umma_idesc_bf16(128 * CG, 256) : umma_idesc_f16(128 * CG, 256);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0;            // weight stage counter
+      uint32_t sel_it = 0;        // B_sel stage counter (select variant)
       uint32_t act_phase = 0;     // bit b: parity to wait for on act_ready[b][*]
       uint32_t slot_uses = 0;     // completed uses per TMEM slot (same for both slots at layer granularity)
       int t = 0;
@@ -536,12 +648,30 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                 else mbar_wait(&sm.act_ready[bin][kc], aph);
               }
             };
+            if constexpr (kSel) {
+              // accumulators start as  [ P16[l(row)] | bq ]  = A_sel (one-hot rows) x B_sel; K-chunk 0's barrier also covers
+              // this tile's A_sel rows (every epilogue warp writes its share before it signals chunk 0)
+              wait_chunk(0);
+              mbar_wait(&sm.sel_full, sel_it & 1);
+              tc_fence_after();
+              const uint32_t a_sel = asel0 + (t & 1) * kASelBytes;
+              constexpr uint32_t idesc_sel = umma_idesc_f16_bmn(128 * CG, 256);
+              if (elect_one()) {
+                umma_bf16<CG>(d_tmem, umma_desc_k_sw64(a_sel), umma_desc_mn_sw128(sel0, wk.sel_lbo, wk.sel_sbo), idesc_sel, 0u);
+                if (wk.ksel == 32)
+                  umma_bf16<CG>(d_tmem, umma_desc_k_sw64(a_sel + 32),
+                                umma_desc_mn_sw128(sel0 + wk.sel_kstep, wk.sel_lbo, wk.sel_sbo), idesc_sel, 1u);
+                umma_commit<CG>(&sm.sel_empty);
+              }
+              __syncwarp();
+              ++sel_it;
+            }
             if constexpr (!kSplit) {
 #pragma unroll 1
               for (int kc = 0; kc < 4; ++kc) {
                 wait_chunk(kc);
                 if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 1 + 2 * kc);
-                stage_mmas(a_base + kc * kChunkBytes, kc == 0, kc == 3);
+                stage_mmas(a_base + kc * kChunkBytes, kc == 0 && !kSel, kc == 3);
                 if (lane == 0) DIINN_TR(t, (layer - 1) * 20 + h * 10 + 2 + 2 * kc);
               }
             } else {
@@ -601,38 +731,59 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
     // this warp's share of K-chunks [kc0, kc0 + 2) of layer 0 for the tile described by rcx -> activation buffer
     // `bufidx`; nb = P slice base of the next unit (nullptr: none)
-    auto layer0_unit = [&](int bufidx, int kc0, const RowCtx& rcx, const float* nb) {
+    // (select variant: nb counts fp16 elements of the P16 row, and asel >= 0 names the A_sel buffer this tile's one-hot
+    // rows go to, written before K-chunk 0 is signalled)
+    auto load_p = [&](const float* q, float4 (&v)[4]) {
+      if constexpr (kSel) load16h(reinterpret_cast<const uint16_t*>(q), v);
+      else load16(q, v);
+    };
+    constexpr int kP64 = kSel ? 32 : 64;  // 64 P columns, in units of the float pointer that carries the row
+    auto layer0_unit = [&](int bufidx, int kc0, const RowCtx& rcx, const float* nb, int asel = -1) {
       const uint32_t buf = act0 + bufidx * kActBytes;
+      if constexpr (kSel) {
+        if (asel >= 0) {
+          // this row's A_sel: 1.0 at its LR cell's slot and at the two bias slots (K_sel-2: bq_hi, K_sel-1: bq_lo); this
+          // warp writes 16-byte unit fg = slots [8 fg, 8 fg + 8) of the 64-byte row (64B swizzle: unit ^= (row >> 1) & 3)
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int s0 = 8 * fg + 2 * j;
+            w[j] = (rcx.slot == s0 ? 0x3C00u : 0u) | (rcx.slot == s0 + 1 ? 0x3C000000u : 0u);
+          }
+          if (fg == (wk.ksel >> 3) - 1) w[3] = 0x3C003C00u;
+          st_shared_v4(asel0 + asel * kASelBytes + r * 64 + ((fg ^ ((r >> 1) & 3)) << 4), w[0], w[1], w[2], w[3]);
+        }
+      }
       // (the P prefetch is issued AFTER the proxy fence: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
       // which waits for every outstanding global load of the thread -- a prefetch issued just before it exposes its
       // whole L2 latency in every step; measured)
-      layer0_step<FMT, kPix>(buf, kc0, fg, r, rcx, sp, ka);
+      layer0_step<FMT, kPix, kSel>(buf, kc0, fg, r, rcx, sp, ka);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
-      if (nb) load16(nb, ka);
-      layer0_step<FMT, kPix>(buf, kc0 + 1, fg, r, rcx, sp, kb);
+      if (nb) load_p(nb, ka);
+      layer0_step<FMT, kPix, kSel>(buf, kc0 + 1, fg, r, rcx, sp, kb);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
-      if (nb) load16(nb + 64, kb);
+      if (nb) load_p(nb + kP64, kb);
     };
 
     if (work < wk.n_work) {
-      rc = make_row<CG, kPix>(src, out, P, wk, work, rank, r, fg == 0);
-      const float* p0 = rc.prow + fg * 16;
-      load16(p0, ka);
-      load16(p0 + 64, kb);
-      layer0_unit(0, 0, rc, p0 + 128);  // first tile -> buffer 0
-      layer0_unit(0, 2, rc, p0 + kD);
+      rc = make_row<CG, kPix, kSel>(src, out, P, wk, work, rank, r, fg == 0);
+      const float* p0 = rc.prow + fg * (kSel ? 8 : 16);
+      load_p(p0, ka);
+      load_p(p0 + kP64, kb);
+      layer0_unit(0, 0, rc, p0 + 2 * kP64, 0);  // first tile -> buffer 0 (A_sel buffer 0)
+      layer0_unit(0, 2, rc, kSel ? nullptr : p0 + kD);
     }
     for (; work < wk.n_work; work += n_units, ++t) {
       const int X = t & 1;
       const int next_work = work + n_units;
       const bool has_next = next_work < wk.n_work;
       RowCtx rc_next{};
-      const float* const pw = rc.prow + fg * 16;  // this warp's column of the tile row's P entry
-      const float* pn = nullptr;                  // same for the next tile
+      const float* const pw = rc.prow + fg * (kSel ? 8 : 16);  // this warp's column of the tile row's P entry
+      const float* pn = nullptr;                               // same for the next tile
       float rgb[3] = {0.f, 0.f, 0.f};  // this warp's share of the RGB projection (scalar FFMA: measured faster than FFMA2 here)
       // mode 4: this row's q_3 vector in the dump buffer (rows outside the image / band get no store target)
       __nv_bfloat16* q3row = nullptr;
@@ -646,8 +797,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const uint32_t out_base = act0 + bout * kActBytes;
         const bool last = layer == 3;
         if (layer == 2 && has_next) {
-          rc_next = make_row<CG, kPix>(src, out, P, wk, next_work, rank, r, fg == 0);
-          pn = rc_next.prow + fg * 16;
+          rc_next = make_row<CG, kPix, kSel>(src, out, P, wk, next_work, rank, r, fg == 0);
+          pn = rc_next.prow + fg * (kSel ? 8 : 16);
+          if constexpr (kSel) {  // only layer 0 reads P here: the next tile's first two k_0 slices, a whole layer ahead
+            load_p(pn, ka);
+            load_p(pn + kP64, kb);
+          }
         }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -659,10 +814,14 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           }
           // Layer 0 of the next tile goes into buffer X^1, whose last readers are layer 2's MMAs: complete, because
           // this warp has itself consumed tmem_full[1] of layer 2. Its four chunks are interleaved with layer 3's halves.
-          if (last && has_next) layer0_unit(kSplit ? 0 : (X ^ 1), 2 * h, rc_next, pw + 3 * kD + h * 128);
+          if (last && has_next) {
+            if constexpr (kSel) layer0_unit(X ^ 1, 2 * h, rc_next, h == 0 ? pn + 2 * kP64 : nullptr, h == 0 ? ((t + 1) & 1) : -1);
+            else layer0_unit(kSplit ? 0 : (X ^ 1), 2 * h, rc_next, pw + 3 * kD + h * 128);
+          }
           // unit after this one: the other half / the next layer / layer 0 of the next tile / the next tile's layer 1
           const float* nb;
-          if (!last) nb = (h == 0) ? pw + layer * kD + 128 : (layer == 1 || !has_next) ? pw + (layer + 1) * kD : pn;
+          if constexpr (kSel) nb = nullptr;  // the accumulators arrive with P[l] and bq in them
+          else if (!last) nb = (h == 0) ? pw + layer * kD + 128 : (layer == 1 || !has_next) ? pw + (layer + 1) * kD : pn;
           else nb = has_next ? (h == 0 ? pn + 128 : pn + kD) : (h == 0 ? pw + 3 * kD + 128 : nullptr);
           const uint32_t tslot = tlane + h * 256;
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
@@ -678,8 +837,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 0);
 #endif
-          if (last) epi_math<true, FMT, kDump>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row, q3row_f);
-          else epi_math<false, FMT>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
+          if (last) epi_math<true, FMT, kDump, kSel>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row, q3row_f);
+          else epi_math<false, FMT, false, kSel>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
 #endif
@@ -699,8 +858,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           __syncwarp();
           if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
-          if (last) epi_math<true, FMT, kDump>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row, q3row_f);
-          else epi_math<false, FMT>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
+          if (last) epi_math<true, FMT, kDump, kSel>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row, q3row_f);
+          else epi_math<false, FMT, false, kSel>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
 #endif
@@ -763,56 +922,142 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
 }  // namespace sb
 
-template <int CG, int FMT, bool kDump = false, bool kPix = false>
+template <int CG, int FMT, bool kDump, bool kPix, bool kSel>
 static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const CUtensorMap& tm_lo,
-                          const PixelSource& src, const OutSpec& out, const float* P, const sb::Work& wk, int* err_flag,
-                          long long* trace) {
+                          const CUtensorMap& tm_selp, const CUtensorMap& tm_selb, const PixelSource& src, const OutSpec& out,
+                          const void* P, const sb::Work& wk, int* err_flag, long long* trace) {
   using namespace sb;
-  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, FMT, kDump, kPix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kSmemBytes)));
+  constexpr int kBytes = static_cast<int>(smem_bytes<CG, kSel>());
+  cfg->dynamicSmemBytes = kBytes;
+  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
   if (getenv("DIINN_DEBUG_OCC")) {
     int nc = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix>, cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, cfg);
     fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
             cudaGetErrorString(e));
   }
-  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix>, tm, tm_lo, h->small, src, out, P, wk,
-                                      err_flag, trace));
+  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, tm, tm_lo, tm_selp, tm_selb,
+                                      h->small, src, out, P, wk, err_flag, trace));
   return DIINN_OK;
 }
 
-// fmt: kFmtBf16 / kFmtF16 / kFmtSplit (handle.h). tap: debug only (see sb::Work).
-int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const float* P, int cta_group, int fmt,
-                        cudaStream_t s, int4* tap) {
+namespace {
+
+// host twin of axis_index() (common.cuh): one rounded fp32 multiply, then floorf
+inline int host_axis_index(const AxisParams& p, int j) {
+  volatile float t = (static_cast<float>(j) + 0.5f) * p.scale;
+  const int i = static_cast<int>(floorf(t));
+  return i < p.n_in - 1 ? i : p.n_in - 1;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Geometry of one stage-B launch: patch shape, work items, and whether the select-MMA variant applies (then P is fp16).
+struct Plan {
+  sb::Work wk{};
+  int cta_group = 2;
+  bool sel = false;
+};
+
+Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, bool chain_mode) {
   using namespace sb;
+  Plan pl;
   if (cta_group == 0) {
     static int env_cg = -1;
-    if (env_cg < 0) {
-      const char* e = getenv("DIINN_CTA_GROUP");
-      env_cg = (e && e[0] == '1') ? 1 : 2;
-    }
+    if (env_cg < 0) env_cg = env_int("DIINN_CTA_GROUP", 2) == 1 ? 1 : 2;
     cta_group = env_cg;
   }
-  int* err_flag = h->err_flag;   // per-handle device scratch, allocated by diinn_create (no allocation in decode)
-  long long* trace = h->trace_dev;
-
-  Work wk{};
-  wk.tap = tap;
-  if (src.mode == 0) {
-    const int tiles_x = (src.W_up + kPatchW - 1) / kPatchW;
-    wk.tiles_y = (src.row1 - src.row0 + kPatchH - 1) / kPatchH;
-    wk.n_txp = (tiles_x + cta_group - 1) / cta_group;
-    wk.n_work = src.B * wk.tiles_y * wk.n_txp;
-  } else {
+  pl.cta_group = cta_group;
+  Work& wk = pl.wk;
+  wk.pw_log2 = kPatchWLog2Default;
+  const bool pix = src.per_pixel_p != 0;
+  if (src.mode != 0) {
     const int64_t total = static_cast<int64_t>(src.B) * src.Q * (src.ensemble ? 4 : 1);
     wk.n_work = static_cast<int>((total + kTileM * cta_group - 1) / (kTileM * cta_group));
+    return pl;
   }
+  // Select variant: CTA pairs, 16-bit formats, LR-resolution P that no LR chain rewrites, and a pair patch of <= 30 LR cells.
+  // Whether it applies must NOT depend on the row range or the patch shape a launch ends up with: row tiles of one image
+  // have to be bit-identical to the full decode, and the two variants differ in the last bits (fp16 P added inside the
+  // tensor core vs fp32 P added by the epilogue). So the decision is taken for the DEFAULT patch shape from a bound that
+  // only knows the scale factors -- n pixels of an axis touch at most floor((n - 1) * n_in / n_up) + 2 source cells -- and
+  // the wave-count search below only considers shapes on the same side of it.
+  static const int env_nosel = env_int("DIINN_NO_SEL", 0);
+  const bool sel_candidate = cta_group == 2 && fmt != kFmtSplit && !pix && !chain_mode && !env_nosel;
+  auto box_of = [&](int l2, int max_rows, int& br, int& bc) {
+    const int pw = 1 << l2, ph = kTileM >> l2;
+    br = static_cast<int>(floor(static_cast<double>(ph - 1) * src.H / src.H_up)) + 2;
+    bc = static_cast<int>(floor(static_cast<double>(2 * pw - 1) * src.W / src.W_up)) + 2;
+    br = br < max_rows ? br : max_rows;
+    bc = bc < src.W ? bc : src.W;
+  };
+  auto sel_ok = [&](int l2) {
+    int br, bc;
+    box_of(l2, src.H, br, bc);  // (whole-image extents: the same answer for every row tile)
+    return sel_candidate && br * bc + 2 <= 32;
+  };
+  pl.sel = sel_ok(kPatchWLog2Default);
+  // patch shape: fewest waves over the launch's CTA (pair)s; ties keep the default 8x16 (DIINN_PATCH_W_LOG2 pins it)
+  static const int env_pw = env_int("DIINN_PATCH_W_LOG2", -1);
+  const int max_units = h->sm_count / cta_group > 0 ? h->sm_count / cta_group : 1;
+  long long best_waves = -1;
+  const int cand[4] = {4, 5, 3, 6};
+  for (int ci = 0; ci < 4; ++ci) {
+    const int l2 = cand[ci];
+    if (env_pw >= 3 && env_pw <= 6 && l2 != env_pw && sel_ok(env_pw) == pl.sel) continue;
+    if (pix && l2 != kPatchWLog2Default) continue;  // per-pixel P (init_q): the chunk geometry assumes 8-row patches
+    if (sel_ok(l2) != pl.sel) continue;
+    const int pw = 1 << l2, ph = kTileM >> l2;
+    const long long n = static_cast<long long>(src.B) * ((src.row1 - src.row0 + ph - 1) / ph) *
+                        (((src.W_up + pw - 1) / pw + cta_group - 1) / cta_group);
+    const long long waves = (n + max_units - 1) / max_units;
+    if (best_waves < 0 || waves < best_waves) best_waves = waves, wk.pw_log2 = l2;
+  }
+  const int pw = 1 << wk.pw_log2, ph = kTileM >> wk.pw_log2;
+  const int tiles_x = (src.W_up + pw - 1) / pw;
+  wk.tiles_y = (src.row1 - src.row0 + ph - 1) / ph;
+  wk.n_txp = (tiles_x + cta_group - 1) / cta_group;
+  wk.n_work = src.B * wk.tiles_y * wk.n_txp;
+  if (pl.sel) {
+    box_of(wk.pw_log2, src.lr_rows, wk.box_r, wk.box_c);  // (the P16 tensor of this launch holds lr_rows LR rows)
+    wk.ksel = wk.box_r * wk.box_c + 2 <= 16 ? 16 : 32;
+    // B_sel tile of one CTA: two 64-feature blocks of K_sel rows x 128 B; MN-major SWIZZLE_128B atoms are 8 K-rows (1 KB)
+    wk.sel_lbo = static_cast<uint32_t>(env_int("DIINN_SEL_LBO", wk.ksel * 128));
+    wk.sel_sbo = static_cast<uint32_t>(env_int("DIINN_SEL_SBO", 1024));
+    wk.sel_kstep = static_cast<uint32_t>(env_int("DIINN_SEL_KSTEP", 2048));
+  }
+  return pl;
+}
+
+}  // namespace
+
+// Does the stage-B launch for this source take the select-MMA variant, i.e. must stage A write P as fp16?
+bool stage_b_wants_p16(const Handle* h, const PixelSource& src, int fmt) {
+  return make_plan(h, src, 0, fmt, h->cfg.mode == 1 || h->cfg.mode == 2).sel;
+}
+
+// fmt: kFmtBf16 / kFmtF16 / kFmtSplit (handle.h). P: fp32 rows -- fp16 rows when stage_b_wants_p16() says so. tap: debug only.
+int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const void* P, int cta_group, int fmt,
+                        cudaStream_t s, int4* tap) {
+  using namespace sb;
+  if (fmt < 0 || fmt > kFmtSplit) return fail(h, DIINN_ERR_BAD_DTYPE, "stage B: unknown operand format");
+  Plan pl = make_plan(h, src, cta_group, fmt, h->cfg.mode == 1 || h->cfg.mode == 2);
+  cta_group = pl.cta_group;
+  Work& wk = pl.wk;
+  wk.tap = tap;
+  int* err_flag = h->err_flag;   // per-handle device scratch, allocated by diinn_create (no allocation in decode)
+  long long* trace = h->trace_dev;
+  const bool pix = src.per_pixel_p != 0;
+
   int units = h->sm_count / cta_group;
   if (units > wk.n_work) units = wk.n_work;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(units * cta_group, 1, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -824,25 +1069,40 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   cfg.attrs = attr;
   cfg.numAttrs = h->pdl ? 2 : 1;
   // instantiations: kDump = mode 4 (q_3 dumped instead of projected), kPix = init_q=True (per-pixel P, q_0 given)
-  const bool dump = out.q3 != nullptr || out.q3f != nullptr, pix = src.per_pixel_p != 0;
+  const bool dump = out.q3 != nullptr || out.q3f != nullptr;
   if (pix && src.mode != 0) return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "per-pixel P is implemented for the HR grid only");
-  if (fmt < 0 || fmt > kFmtSplit) return fail(h, DIINN_ERR_BAD_DTYPE, "stage B: unknown operand format");
   if (fmt == kFmtSplit && pix) return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "the split format is not wired for per-pixel P");
   if (dump && ((fmt == kFmtSplit) != (out.q3f != nullptr)))
     return fail(h, DIINN_ERR_BAD_ARG, "stage B: the split format dumps fp32 q_3, the 16-bit formats bf16");
   const int ci = cta_group - 1;
   const CUtensorMap& tm = h->tmapWB[fmt == kFmtBf16 ? 0 : 1][ci];
   const CUtensorMap& tm_lo = h->tmapWBlo[ci];
+  CUtensorMap tm_selp = tm;  // placeholders unless the select variant runs
+  const CUtensorMap& tm_selb = pl.sel ? h->tmapSelB[wk.ksel == 16 ? 0 : 1] : tm;
+  if (pl.sel) {
+    // fp16 P as (1024 features, W, LR rows, B); box = 64 features x the pair's LR patch
+    const uint64_t dims[4] = {static_cast<uint64_t>(kPCols), static_cast<uint64_t>(src.W), static_cast<uint64_t>(src.lr_rows),
+                              static_cast<uint64_t>(src.B)};
+    const uint64_t strides[3] = {kPCols * 2ull, static_cast<uint64_t>(src.W) * kPCols * 2ull,
+                                 static_cast<uint64_t>(src.lr_rows) * src.W * kPCols * 2ull};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(wk.box_c), static_cast<uint32_t>(wk.box_r), 1};
+    int rc0 = make_tmap_4d_bf16(h, &tm_selp, P, dims, strides, box);  // (16-bit elements; TMA does no arithmetic)
+    if (rc0) return rc0;
+  }
   int rc;
-#define DIINN_SB_LAUNCH(CGv, FMTv, DUMPv, PIXv) \
-  launch_variant<CGv, FMTv, DUMPv, PIXv>(h, &cfg, tm, tm_lo, src, out, P, wk, err_flag, trace)
-#define DIINN_SB_PICK(CGv, FMTv)                                                                        \
-  (dump ? (pix ? DIINN_SB_LAUNCH(CGv, FMTv, true, true) : DIINN_SB_LAUNCH(CGv, FMTv, true, false))       \
-        : (pix ? DIINN_SB_LAUNCH(CGv, FMTv, false, true) : DIINN_SB_LAUNCH(CGv, FMTv, false, false)))
-#define DIINN_SB_PICK_SPLIT(CGv) (dump ? DIINN_SB_LAUNCH(CGv, 2, true, false) : DIINN_SB_LAUNCH(CGv, 2, false, false))
-  if (cta_group == 1) rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(1) : fmt == kFmtF16 ? DIINN_SB_PICK(1, 1) : DIINN_SB_PICK(1, 0);
+#define DIINN_SB_LAUNCH(CGv, FMTv, DUMPv, PIXv, SELv) \
+  launch_variant<CGv, FMTv, DUMPv, PIXv, SELv>(h, &cfg, tm, tm_lo, tm_selp, tm_selb, src, out, P, wk, err_flag, trace)
+#define DIINN_SB_PICK(CGv, FMTv)                                                                                     \
+  (dump ? (pix ? DIINN_SB_LAUNCH(CGv, FMTv, true, true, false) : DIINN_SB_LAUNCH(CGv, FMTv, true, false, false))       \
+        : (pix ? DIINN_SB_LAUNCH(CGv, FMTv, false, true, false) : DIINN_SB_LAUNCH(CGv, FMTv, false, false, false)))
+#define DIINN_SB_PICK_SEL(FMTv) (dump ? DIINN_SB_LAUNCH(2, FMTv, true, false, true) : DIINN_SB_LAUNCH(2, FMTv, false, false, true))
+#define DIINN_SB_PICK_SPLIT(CGv) \
+  (dump ? DIINN_SB_LAUNCH(CGv, 2, true, false, false) : DIINN_SB_LAUNCH(CGv, 2, false, false, false))
+  if (pl.sel) rc = fmt == kFmtF16 ? DIINN_SB_PICK_SEL(1) : DIINN_SB_PICK_SEL(0);
+  else if (cta_group == 1) rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(1) : fmt == kFmtF16 ? DIINN_SB_PICK(1, 1) : DIINN_SB_PICK(1, 0);
   else rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(2) : fmt == kFmtF16 ? DIINN_SB_PICK(2, 1) : DIINN_SB_PICK(2, 0);
 #undef DIINN_SB_PICK_SPLIT
+#undef DIINN_SB_PICK_SEL
 #undef DIINN_SB_PICK
 #undef DIINN_SB_LAUNCH
   if (rc) return rc;

@@ -30,6 +30,20 @@ with torch.no_grad():
             ok = err <= tol
             bad += not ok
             print(f"mode {mode} {prec:9s} err {err:.3e} (tol {tol:.0e}) {'OK' if ok else 'FAIL'}  [{time.time() - t0:.2f}s]", flush=True)
+    # the select-MMA variant of stage B (CTA-pair patches of <= 30 LR cells: x4 -> K_sel 32, x12 -> K_sel 16), odd sizes
+    w = synth.make_weights(seed=0)
+    for (b_, h_, w_, hu_, wu_) in ((1, 24, 24, 96, 96), (2, 19, 23, 77, 93), (1, 9, 11, 108, 132), (1, 48, 48, 192, 192)):
+        f_ = synth.make_feat(5, b_, h_, w_)
+        ref_ = orc.decoder_forward(w, f_, (hu_, wu_))
+        x_ = torch.from_numpy(f_).cuda()
+        for prec in ("fp16", "bf16"):
+            dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision=prec), w).cuda()
+            out = dec(x_, (hu_, wu_))
+            torch.cuda.synchronize()
+            err = float(np.abs(out.cpu().numpy() - ref_).max())
+            ok = err <= TOL[prec]
+            bad += not ok
+            print(f"sel {h_}x{w_}->{hu_}x{wu_} B={b_} {prec}: err {err:.3e} {'OK' if ok else 'FAIL'}", flush=True)
     # stress weights: absolute errors
     w = synth.make_weights(seed=0, k_gain=3.0, q_gain=10.0)
     ref = orc.decoder_forward(w, feat, size)
