@@ -652,8 +652,10 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
               // accumulators start as  [ P16[l(row)] | bq ]  = A_sel (one-hot rows) x B_sel; K-chunk 0's barrier also covers
               // this tile's A_sel rows (every epilogue warp writes its share before it signals chunk 0)
               wait_chunk(0);
+              if (lane == 0) DIINN_TR(t, 112 + (layer - 1) * 4 + h * 2);
               mbar_wait(&sm.sel_full, sel_it & 1);
               tc_fence_after();
+              if (lane == 0) DIINN_TR(t, 113 + (layer - 1) * 4 + h * 2);
               const uint32_t a_sel = asel0 + (t & 1) * kASelBytes;
               constexpr uint32_t idesc_sel = umma_idesc_f16_bmn(128 * CG, 256);
               if (elect_one()) {

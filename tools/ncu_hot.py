@@ -7,10 +7,12 @@ rep = sys.argv[1]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+hi = his[0]
 h = rows[hi]
 col = {k: i for i, k in enumerate(h)}
-data = rows[hi + 1:]
+end = next((i for i in range(hi + 1, len(rows)) if not rows[i] or rows[i][0] == "Kernel Name"), len(rows))  # first launch only
+data = [r for r in rows[hi + 1:end] if len(r) == len(h)]
 stalls = ["stall_barrier", "stall_branch_resolving", "stall_long_sb", "stall_math", "stall_membar", "stall_mio",
           "stall_not_selected", "stall_selected", "stall_short_sb", "stall_wait", "stall_dispatch", "stall_no_inst",
           "stall_lg", "stall_sleep"]

@@ -36,7 +36,9 @@ for t in range(1, 5):
         for h in range(2):
             m = tr[t, layer * 20 + h * 10: layer * 20 + h * 10 + 10] - t0
             e = tr[t, 64 + layer * 10 + h * 5: 64 + layer * 10 + h * 5 + 5] - t0
-            print(f" L{layer + 1}.h{h} MMA slot_free {m[0]:7d} | act/w ready kc0 {m[1]:7d}/{m[2]:7d} kc1 {m[3]:7d}/{m[4]:7d} "
+            sw = tr[t, 112 + layer * 4 + h * 2: 114 + layer * 4 + h * 2] - t0
+            print(f" L{layer + 1}.h{h} sel: chunk0 ready {sw[0]:7d} B_sel landed {sw[1]:7d}")
+            print(f" L{layer + 1}.h{h} MMA slot_free {m[0]:7d} | act ready / issued kc0 {m[1]:7d}/{m[2]:7d} kc1 {m[3]:7d}/{m[4]:7d} "
                   f"kc2 {m[5]:7d}/{m[6]:7d} kc3 {m[7]:7d}/{m[8]:7d} issued {m[9]:7d} || EPI wait {e[0]:7d} full {e[1]:7d} "
                   f"c0 {e[2]:7d} c1 {e[3]:7d} freed {e[4]:7d}")
     for h in range(2):
