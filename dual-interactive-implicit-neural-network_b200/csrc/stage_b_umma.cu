@@ -281,10 +281,16 @@ __device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[
 #pragma unroll
   for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p) + j);
 }
-// select variant: 16 fp16 values (32 B) of a P16 row, kept raw in v[0], v[1] until layer0_step unpacks them
+// select variant: 16 fp16 values (32 B) of a P16 row, kept raw in v[0], v[1] until layer0_step unpacks them. ONE 256-bit load
+// (LDG.E.256): the 32 rows of a warp sit in ~8 LR cells 2 KB apart, so every load instruction costs ~8 L1 wavefronts whatever
+// its width -- half the instructions of two 128-bit loads, half the queue time (same-box A/B on c3: 1.91 -> 1.80 ms).
+// Measured and rejected: all four k_0 slices of a tile fetched together one layer ahead, or fetched right before the epilogue
+// warps' tensor-core waits (both ~1.92-1.97 ms: the load issue itself backs up the warps); see DESIGN.md section 4.1.
 __device__ __forceinline__ void load16h(const uint16_t* __restrict__ p, float4 (&v)[4]) {
-  v[0] = __ldg(reinterpret_cast<const float4*>(p));
-  v[1] = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "l"(p));
 }
 
 // Sine of the Q branch (SineAct, diinn.py:21-26). MUFU.SIN works on x / 2pi rounded to fp32, so its absolute error grows as
