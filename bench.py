@@ -511,8 +511,9 @@ def main():
         if os.path.exists(pj):
             with open(pj) as f:
                 prof = json.load(f)
-        # a timed region of well under a second runs at boost clocks (burst regime); longer ones settle under the power cap
-        burst = ms_total < 1000.0
+        # a timed region of tens of milliseconds runs at boost clocks (burst regime); after ~50-100 ms the 1 kW power cap
+        # pulls the clocks down and the sustained cuBLAS figure is the comparable one (both fractions are reported)
+        burst = ms_total < 100.0
         peak = peaks["bf16_burst"] if burst else peaks["bf16_sustained"]
         fmt = {"fp16": 1, "bf16": 0, "fp32": 2}[args.precision]
         line["roofline"] = {

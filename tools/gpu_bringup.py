@@ -159,18 +159,18 @@ def _bf16(cg):
 
 
 @stage
-def fp16acc():
+def fp16():
     np, torch, diinn_b200, synth, orc = _setup()
     for name in ["x1_batch", "c1", "odd2", "frac", "stress"]:
         weights, feat, size, ref = _case(name)
-        dec = _decoder(weights, "fp16acc")
+        dec = _decoder(weights, "fp16")
         with torch.no_grad():
             out = dec(torch.from_numpy(feat).cuda(), size)
         torch.cuda.synchronize()
         e = np.abs(out.cpu().numpy() - ref)
-        print(f"fp16acc {name}: max-abs err {e.max():.3e} mean {e.mean():.3e} (|ref| max {np.abs(ref).max():.3f})")
+        print(f"fp16 {name}: max-abs err {e.max():.3e} mean {e.mean():.3e} (|ref| max {np.abs(ref).max():.3f})")
     weights = synth.make_weights(seed=0)
-    for prec in ("fp16acc", "bf16"):
+    for prec in ("fp16", "bf16"):
         for name in ["c2x2", "c2x4", "c3", "c4"]:
             B, H, W, H_up, W_up = synth.CONFIGS[name]
             x = torch.from_numpy(synth.make_feat(1, B, H, W)).cuda()

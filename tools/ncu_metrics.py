@@ -7,7 +7,7 @@ import sys
 rep = sys.argv[1]
 pats = sys.argv[2:] or [
     r"^gpu__time_duration\.sum$", r"^sm__cycles_elapsed\.max$", r"sm__cycles_elapsed\.max\.per_second",
-    r"sm__pipe_tensor_cycles_active_realtime\.avg\.pct", r"^smsp__issue_active\.avg\.pct_of_peak_sustained_active$",
+    r"sm__pipe_tensor_cycles_active_realtime\.avg\.pct", r"^sm__pipe_tensor_cycles_active\.avg\.pct", r"hmma_cycles_active_realtime\.avg$", r"^smsp__issue_active\.avg\.pct_of_peak_sustained_active$",
     r"^smsp__inst_executed\.sum$", r"^sm__inst_executed_pipe_[a-z_]+\.avg\.pct_of_peak_sustained_active$",
     r"^dram__bytes_(read|write)\.sum$", r"^lts__t_bytes\.sum$", r"lts__t_sectors_op_read\.sum$",
     r"^l1tex__data_pipe_lsu_wavefronts\.avg\.pct", r"^smsp__average_warps?_issue_stalled_[a-z_]+_per_issue_active",
