@@ -156,6 +156,8 @@ struct SmallParams {
   float bl[4];             // last_layer.bias (+pad)
   // wq0 again for feature PAIRS (f, f+1), component-major, for the packed fp32x2 (FFMA2) layer 0 of the tensor path:
   float2 wq0_p[kD / 2][4]; // (w_relh, w_relw, w_ratio, bq0) x (f, f+1)
+  int q0_folded;           // stage B, grid decodes: wq0_p[.][3] already holds w_ratio * ratio + bq0 (the launcher folds it)
+  int pad_[3];
 };
 
 // Optional fused epilogue of the library GEMM (gemm.cu) for the LR-resolution K chain of modes 1 / 2

@@ -333,7 +333,7 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
   const uint32_t chunk_base = act_base + kc * kChunkBytes;
   const int f0 = kc * 64 + wg * 16;
   float k0h[16];
-  if constexpr (kSel) {  // fp16 P: 16 values in the first 32 bytes
+  if constexpr (kSel && FMT != 1) {  // fp16 P: 16 values in the first 32 bytes (fp16 operands multiply them in half2, below)
     const uint32_t* raw = reinterpret_cast<const uint32_t*>(k0v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) unpack_f16x2(raw[j], k0h[2 * j], k0h[2 * j + 1]);
@@ -344,17 +344,30 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
 #pragma unroll
     for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_op<FMT>(k0[j], k0[j + 1]);
   } else {
+    // Layer 0 is bound by the FMA pipe (packed FFMA2 / FMUL2 and the fp16 -> fp32 unpacks all issue there), so:
+    //  * grid decodes fold the per-image constant w_ratio * ratio + b into the bias on the host (sp.q0_folded): two FFMA2
+    //    per feature pair instead of three;
+    //  * the select variant with fp16 operands multiplies k_0 (already fp16) by the sine in half2 -- one F2FP + one HMUL2
+    //    per pair instead of two unpacks + FMUL2 + F2FP (|k_0 sin| <= |k_0|: no overflow).
     const float2 rh = make_float2(rc.rel_h, rc.rel_h), rw = make_float2(rc.rel_w, rc.rel_w), ra = make_float2(rc.ratio, rc.ratio);
+    const bool folded = sp.q0_folded != 0;
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-      // packed fp32x2 (two features per instruction; per feature the same three fused multiply-adds as the scalar form)
+      // packed fp32x2 (two features per instruction)
       const float2* w = &sp.wq0_p[(f0 + j) >> 1][0];
       float2 t = __ffma2_rn(w[0], rh, w[3]);
       t = __ffma2_rn(w[1], rw, t);
-      t = __ffma2_rn(w[2], ra, t);
-      const float2 q = __fmul2_rn(make_float2(k0[j], k0[j + 1]), make_float2(act_sin<kSplit>(t.x), act_sin<kSplit>(t.y)));
-      pk[j >> 1] = pack_op<FMT>(q.x, q.y);
-      if constexpr (kSplit) pl[j >> 1] = pack_residual(q.x, q.y, pk[j >> 1]);
+      if (!folded) t = __ffma2_rn(w[2], ra, t);
+      const float2 sn = make_float2(act_sin<kSplit>(t.x), act_sin<kSplit>(t.y));
+      if constexpr (kSel && FMT == 1) {
+        const uint32_t k0raw = reinterpret_cast<const uint32_t*>(k0v)[j >> 1];
+        const uint32_t s16 = pack_f16x2_sat(sn.x, sn.y);
+        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pk[j >> 1]) : "r"(k0raw), "r"(s16));
+      } else {
+        const float2 q = __fmul2_rn(make_float2(k0[j], k0[j + 1]), sn);
+        pk[j >> 1] = pack_op<FMT>(q.x, q.y);
+        if constexpr (kSplit) pl[j >> 1] = pack_residual(q.x, q.y, pk[j >> 1]);
+      }
     }
   }
   st_shared_v4(swz(chunk_base, r, wg * 2), pk[0], pk[1], pk[2], pk[3]);
@@ -944,6 +957,19 @@ static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap&
     cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, cfg);
     fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
             cudaGetErrorString(e));
+  }
+  if (src.mode == 0 && !kPix) {
+    // grid decode: `ratio` is one constant per image, so Q.0's w_ratio * ratio + b is folded into the bias here
+    static thread_local SmallParams spf;
+    spf = h->small;
+    for (int i = 0; i < kD / 2; ++i) {
+      spf.wq0_p[i][3].x = fmaf(spf.wq0_p[i][2].x, src.ratio, spf.wq0_p[i][3].x);
+      spf.wq0_p[i][3].y = fmaf(spf.wq0_p[i][2].y, src.ratio, spf.wq0_p[i][3].y);
+    }
+    spf.q0_folded = 1;
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, tm, tm_lo, tm_selp, tm_selb, spf,
+                                        src, out, P, wk, err_flag, trace));
+    return DIINN_OK;
   }
   DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, tm, tm_lo, tm_selp, tm_selb,
                                       h->small, src, out, P, wk, err_flag, trace));
