@@ -277,9 +277,16 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
 #define DIINN_TRACE_BUILD DIINN_FINE_TRACE
 #endif
 
+// 16 fp32 values (64 B) of a P row as two 256-bit loads (LDG.E.256): a warp's 32 rows sit in ~8 LR cells 4 KB apart, so every
+// load instruction costs ~8 L1 wavefronts whatever its width -- half the instructions of four 128-bit loads
 __device__ __forceinline__ void load16(const float* __restrict__ p, float4 (&v)[4]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const float4*>(p) + j);
+  for (int j = 0; j < 2; ++j)
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[8 * j]), "=r"(u[8 * j + 1]), "=r"(u[8 * j + 2]), "=r"(u[8 * j + 3]), "=r"(u[8 * j + 4]),
+                   "=r"(u[8 * j + 5]), "=r"(u[8 * j + 6]), "=r"(u[8 * j + 7])
+                 : "l"(p + 8 * j));
 }
 // select variant: 16 fp16 values (32 B) of a P16 row, kept raw in v[0], v[1] until layer0_step unpacks them. ONE 256-bit load
 // (LDG.E.256): the 32 rows of a warp sit in ~8 LR cells 2 KB apart, so every load instruction costs ~8 L1 wavefronts whatever
