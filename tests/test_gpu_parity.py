@@ -249,6 +249,33 @@ def test_row_tiles_bit_identical(w0, precision, world):
     assert torch.equal(full, parts)
 
 
+def test_patch_shapes_and_stage_a_splits_are_bit_identical():
+    """A launch may pick another stage-B patch shape (8x16 / 4x32 / 16x8 / 2x64) or split stage A's N-blocks over more work
+    items to fill its last wave; neither may change a bit of the image. The shapes are pinned through the environment
+    (read once per process, hence subprocesses), on a x4 decode (select-MMA variant) and a x2.3 decode (classic variant)."""
+    import hashlib
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, torch; sys.path.insert(0, %r)\n"
+        "import diinn_b200; from diinn_b200 import synth\n"
+        "w = synth.make_weights(seed=0); h = hashlib.sha256()\n"
+        "for (B, H, W, hu, wu) in ((2, 23, 31, 91, 125), (1, 16, 20, 37, 51)):\n"
+        "    x = torch.from_numpy(synth.make_feat(6, B, H, W)).cuda()\n"
+        "    for prec in ('fp16', 'bf16', 'fp32'):\n"
+        "        d = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision=prec), w).cuda()\n"
+        "        with torch.no_grad():\n"
+        "            h.update(d(x, (hu, wu)).cpu().numpy().tobytes())\n"
+        "print('HASH', h.hexdigest())\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = {}
+    for env in ({}, {"DIINN_PATCH_W_LOG2": "3"}, {"DIINN_PATCH_W_LOG2": "5"}, {"DIINN_PATCH_W_LOG2": "6"},
+                {"DIINN_STAGE_A_NSPLIT": "1"}, {"DIINN_STAGE_A_NSPLIT": "2"}, {"DIINN_STAGE_A_NSPLIT": "4"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        seen[str(env)] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][0]
+    assert len(set(seen.values())) == 1, seen
+
+
 def test_decode_multi_writes_every_peer_buffer(w0):
     """diinn_decode_multi (fused multi-GPU assembly) on one GPU: two 'peer' image buffers both receive the row tile,
     bit-identical to a plain decode; rows outside the tile stay untouched."""
