@@ -100,6 +100,9 @@ struct PixelSource {
   int ensemble;
   float sh_h[2], sh_w[2];  // fp32(v/n + 1e-6) for v = -1, +1
   float clamp_lo, clamp_hi;
+  // query list decoded by LIIF's own imnet (diinn_set_weights_liif): lookups as LIIF.query_rgb does them with or without
+  // the ensemble, rel_cell = cell * (H, W) instead of `ratio`
+  int liif;
 };
 
 constexpr int kMaxPeers = 8;

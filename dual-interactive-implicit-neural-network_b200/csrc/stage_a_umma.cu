@@ -68,6 +68,7 @@ struct Geo {
   int lr_row0, lr_rows;   // LR rows to produce (rows of P per image)
   int tiles_y, n_txp, n_work;  // n_work = pixel tiles x nsplit
   int nsplit;             // work items per pixel tile: each covers 4 / nsplit consecutive N-blocks (1, 2 or 4)
+  int no_relu0;           // LIIF's imnet: block 0 is the feature part of the first Linear, its ReLU comes after the per-query part
 };
 
 template <int CG, int FMT, bool kP16>
@@ -226,7 +227,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float x = __uint_as_float(v[j]) + bias.b[n0 + j];
-              if (nb == 0) x = fmaxf(x, 0.f);  // first 256 columns are k0 = relu(K0 x + b0)
+              if (nb == 0 && !g.no_relu0) x = fmaxf(x, 0.f);  // first 256 columns are k0 = relu(K0 x + b0)
               v[j] = __float_as_uint(x);
             }
             // the previous TMA store of this warp must have finished reading the staging block
@@ -254,7 +255,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
               float x0 = __uint_as_float(v[j]) + bias.b[n0 + j], x1 = __uint_as_float(v[j + 1]) + bias.b[n0 + j + 1];
-              if (nb == 0) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
+              if (nb == 0 && !g.no_relu0) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
               pk[j >> 1] = pack_f16x2_sat(x0, x1);
             }
             if (lane == 0) bulk_wait_group_read0();
@@ -331,6 +332,7 @@ int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, i
   const int max_units = h->sm_count / cta_group;
   // N-block split: the split with the fewest (fractional) waves wins, ties go to the coarser one (less A re-fetch set-up)
   g.nsplit = 1;
+  g.no_relu0 = h->liif ? 1 : 0;
   {
     static int env_ns = -1;
     if (env_ns < 0) {

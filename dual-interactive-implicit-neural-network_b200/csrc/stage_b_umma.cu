@@ -110,6 +110,7 @@ struct RowCtx {
   int slot;           // select variant: index of the LR cell inside the pair's patch box
   float rel_h, rel_w, ratio;
   float area;  // ensemble rows: |rel_h * rel_w| + 1e-9
+  float cell_w;  // kLiif only: rel_cell = cell * (H, W) (liif.py:107-110) travels as (ratio, cell_w)
   int64_t out_off;  // offset of channel 0
   bool valid;
 };
@@ -124,7 +125,7 @@ __device__ __forceinline__ void pair_origin(const PixelSource& s, const Work& wk
   iw0 = axis_index(s.ax_w, min(txp * CG * pw, s.W_up - 1));
 }
 
-template <int CG, bool kPix = false, bool kSel = false>
+template <int CG, bool kPix = false, bool kSel = false, bool kLiif = false>
 __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& o, const void* __restrict__ Pv,
                                            const Work& wk, int work, int rank, int r, bool write_tap = false) {
   RowCtx rc;
@@ -173,13 +174,21 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
     if (s.ensemble) {
       ih = ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi);
       iw = ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi);
+    } else if constexpr (kLiif) {  // local_ensemble=False: no shift, but the same clamp + grid_sample lookup (liif.py:76,95-99)
+      ih = ensemble_index(s.ax_h, ch, 0.f, s.clamp_lo, s.clamp_hi);
+      iw = ensemble_index(s.ax_w, cw, 0.f, s.clamp_lo, s.clamp_hi);
     } else {
       ih = query_index(s.ax_h, ch), iw = query_index(s.ax_w, cw);
     }
     rc.prow = P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kPCols;
     rc.rel_h = query_rel(s.ax_h, ch, ih);
     rc.rel_w = query_rel(s.ax_w, cw, iw);
-    rc.ratio = __fmul_rn(__fmul_rn(__fmul_rn(__ldg(s.cell + qi * 2), __ldg(s.cell + qi * 2 + 1)), s.hw_f), 0.25f);
+    if constexpr (kLiif) {
+      rc.ratio = __fmul_rn(__ldg(s.cell + qi * 2), s.ax_h.n_in_f);
+      rc.cell_w = __fmul_rn(__ldg(s.cell + qi * 2 + 1), s.ax_w.n_in_f);
+    } else {
+      rc.ratio = __fmul_rn(__fmul_rn(__fmul_rn(__ldg(s.cell + qi * 2), __ldg(s.cell + qi * 2 + 1)), s.hw_f), 0.25f);
+    }
     rc.area = __fadd_rn(fabsf(__fmul_rn(rc.rel_h, rc.rel_w)), 1e-9f);
     if (s.ensemble) rc.valid = rc.valid && v == 0;  // lane 4j stores the blended query
     rc.out_off = qi * 3;
@@ -224,8 +233,10 @@ __device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const v
       const int v = static_cast<int>(g & 3);
       const int b = static_cast<int>(qi / s.Q);
       const float ch = __ldg(s.coord + qi * 2), cw = __ldg(s.coord + qi * 2 + 1);
-      const int ih = s.ensemble ? ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi) : query_index(s.ax_h, ch);
-      const int iw = s.ensemble ? ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi) : query_index(s.ax_w, cw);
+      const int ih = s.ensemble ? ensemble_index(s.ax_h, ch, s.sh_h[v >> 1], s.clamp_lo, s.clamp_hi)
+                     : s.liif   ? ensemble_index(s.ax_h, ch, 0.f, s.clamp_lo, s.clamp_hi) : query_index(s.ax_h, ch);
+      const int iw = s.ensemble ? ensemble_index(s.ax_w, cw, s.sh_w[v & 1], s.clamp_lo, s.clamp_hi)
+                     : s.liif   ? ensemble_index(s.ax_w, cw, 0.f, s.clamp_lo, s.clamp_hi) : query_index(s.ax_w, cw);
       prefetch_l2_bulk(P + static_cast<size_t>((b * s.H + ih) * s.W + iw) * kRow, static_cast<uint32_t>(kRow));
     }
   }
@@ -333,7 +344,7 @@ __device__ __forceinline__ uint32_t pack_residual(float a, float b, uint32_t hi1
 
 // layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
 // Split formats write the fp16 residual into the lo half of the buffer (same swizzled position, kActBytes further on).
-template <int FMT, bool kPix = false, bool kSel = false>
+template <int FMT, bool kPix = false, bool kSel = false, bool kLiif = false>
 __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
                                             const SmallParams& sp, const float4 (&k0v)[4]) {
   constexpr bool kSplit = FMT == 2;
@@ -350,6 +361,22 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
   if constexpr (kPix) {  // init_q=True: Q.0 reads the 576-wide gate, so q_0 was finished per pixel by csrc/init_q.cu
 #pragma unroll
     for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_op<FMT>(k0[j], k0[j + 1]);
+  } else if constexpr (kLiif) {
+    // LIIF's imnet, first Linear(580, 256) + ReLU (mlp.py:9-12): the 576 feature columns were applied per LR cell by stage A
+    // (k0 = W1[:, :576] x_l + b1, no ReLU there); the four coordinate columns (rel_h, rel_w, cell_h H, cell_w W) are per query
+    const float2 rh = make_float2(rc.rel_h, rc.rel_h), rw = make_float2(rc.rel_w, rc.rel_w);
+    const float2 chh = make_float2(rc.ratio, rc.ratio), cww = make_float2(rc.cell_w, rc.cell_w);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const float2* w = &sp.wq0_p[(f0 + j) >> 1][0];
+      float2 t = __ffma2_rn(w[0], rh, make_float2(k0[j], k0[j + 1]));
+      t = __ffma2_rn(w[1], rw, t);
+      t = __ffma2_rn(w[2], chh, t);
+      t = __ffma2_rn(w[3], cww, t);
+      const float qx = fmaxf(t.x, 0.f), qy = fmaxf(t.y, 0.f);
+      pk[j >> 1] = pack_op<FMT>(qx, qy);
+      if constexpr (kSplit) pl[j >> 1] = pack_residual(qx, qy, pk[j >> 1]);
+    }
   } else {
     // Layer 0 is bound by the FMA pipe (packed FFMA2 / FMUL2 and the fp16 -> fp32 unpacks all issue there), so:
     //  * grid decodes fold the per-image constant w_ratio * ratio + b into the bias on the host (sp.q0_folded): two FFMA2
@@ -404,7 +431,7 @@ __device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw& raw) {  /
 // kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
 // kDump (mode 4): q_3 goes to HBM for the 3x3 last conv -- bf16 (q3row) from the 16-bit-operand formats, fp32 (q3row_f) from
 // the split format.
-template <bool kLast, int FMT, bool kDump = false, bool kSel = false>
+template <bool kLast, int FMT, bool kDump = false, bool kSel = false, bool kLiif = false>
 __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
                                          const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3],
                                          __nv_bfloat16* q3row = nullptr, float* q3row_f = nullptr) {
@@ -424,7 +451,8 @@ __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int 
       t2 = __fadd2_rn(t2, *reinterpret_cast<const float2*>(&sp.bq[layer][f0 + j]));
     }
     k2.x = fmaxf(k2.x, 0.f), k2.y = fmaxf(k2.y, 0.f);
-    const float2 q2 = __fmul2_rn(k2, make_float2(act_sin<kSplit>(t2.x), act_sin<kSplit>(t2.y)));
+    // (kLiif: a plain ReLU layer of LIIF's imnet -- the Q-branch columns were multiplied by zero weights and are ignored)
+    const float2 q2 = kLiif ? k2 : __fmul2_rn(k2, make_float2(act_sin<kSplit>(t2.x), act_sin<kSplit>(t2.y)));
     const float q[2] = {q2.x, q2.y};
     if constexpr (kLast && kDump) {
       if constexpr (kSplit) {
@@ -472,7 +500,8 @@ __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int 
 // kPix (init_q=True): see make_row / layer0_step.
 // tmWlo: the fp16 residual weights (split format). tmSelP / tmSelB (select variant): the 4-D map of the fp16 P whose box is
 // one pair's LR patch x 64 features, and the 2-D map of the constant Q-bias tiles. P: fp32 rows, fp16 rows with kSel.
-template <int CG, int FMT, bool kDump, bool kPix, bool kSel>
+// kLiif: LIIF's imnet (ReLU MLP 580 -> 256^4 -> 3, liif.py:26 / mlp.py) instead of the dual-interactive layers, query lists only.
+template <int CG, int FMT, bool kDump, bool kPix, bool kSel, bool kLiif>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                     const __grid_constant__ CUtensorMap tmSelP, const __grid_constant__ CUtensorMap tmSelB,
@@ -484,6 +513,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   constexpr bool kSplit = FMT == 2;
   static_assert(!(kSplit && kPix), "the split format is not wired for per-pixel P (init_q=True runs on the fp32 CUDA-core path)");
   static_assert(!kSel || (CG == 2 && !kSplit && !kPix), "select variant: CTA pairs, 16-bit operand formats, LR-resolution P");
+  static_assert(!kLiif || (!kSel && !kPix && !kDump), "LIIF's imnet runs on the classic kernel (query lists, fp32 P)");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_act = smem;                     // 2 x 64 KB
   uint8_t* s_w = smem + 2 * kActBytes;       // weight stages
@@ -785,12 +815,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       // (the P prefetch is issued AFTER the proxy fence: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
       // which waits for every outstanding global load of the thread -- a prefetch issued just before it exposes its
       // whole L2 latency in every step; measured)
-      layer0_step<FMT, kPix, kSel>(buf, kc0, fg, r, rcx, sp, ka);
+      layer0_step<FMT, kPix, kSel, kLiif>(buf, kc0, fg, r, rcx, sp, ka);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
       if (nb) load_p(nb, ka);
-      layer0_step<FMT, kPix, kSel>(buf, kc0 + 1, fg, r, rcx, sp, kb);
+      layer0_step<FMT, kPix, kSel, kLiif>(buf, kc0 + 1, fg, r, rcx, sp, kb);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
@@ -798,7 +828,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     };
 
     if (work < wk.n_work) {
-      rc = make_row<CG, kPix, kSel>(src, out, P, wk, work, rank, r, fg == 0);
+      rc = make_row<CG, kPix, kSel, kLiif>(src, out, P, wk, work, rank, r, fg == 0);
       const float* p0 = rc.prow + fg * (kSel ? 8 : 16);
       load_p(p0, ka);
       load_p(p0 + kP64, kb);
@@ -825,7 +855,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const uint32_t out_base = act0 + bout * kActBytes;
         const bool last = layer == 3;
         if (layer == 2 && has_next) {
-          rc_next = make_row<CG, kPix, kSel>(src, out, P, wk, next_work, rank, r, fg == 0);
+          rc_next = make_row<CG, kPix, kSel, kLiif>(src, out, P, wk, next_work, rank, r, fg == 0);
           pn = rc_next.prow + fg * (kSel ? 8 : 16);
           if constexpr (kSel) {  // only layer 0 reads P here: the next tile's first two k_0 slices, a whole layer ahead
             load_p(pn, ka);
@@ -865,8 +895,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 0);
 #endif
-          if (last) epi_math<true, FMT, kDump, kSel>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row, q3row_f);
-          else epi_math<false, FMT, false, kSel>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
+          if (last) epi_math<true, FMT, kDump, kSel, kLiif>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row, q3row_f);
+          else epi_math<false, FMT, false, kSel, kLiif>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
 #endif
@@ -886,8 +916,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           __syncwarp();
           if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
-          if (last) epi_math<true, FMT, kDump, kSel>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row, q3row_f);
-          else epi_math<false, FMT, false, kSel>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
+          if (last) epi_math<true, FMT, kDump, kSel, kLiif>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row, q3row_f);
+          else epi_math<false, FMT, false, kSel, kLiif>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
 #endif
@@ -950,18 +980,18 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
 }  // namespace sb
 
-template <int CG, int FMT, bool kDump, bool kPix, bool kSel>
+template <int CG, int FMT, bool kDump, bool kPix, bool kSel, bool kLiif = false>
 static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const CUtensorMap& tm_lo,
                           const CUtensorMap& tm_selp, const CUtensorMap& tm_selb, const PixelSource& src, const OutSpec& out,
                           const void* P, const sb::Work& wk, int* err_flag, long long* trace) {
   using namespace sb;
   constexpr int kBytes = static_cast<int>(smem_bytes<CG, kSel>());
   cfg->dynamicSmemBytes = kBytes;
-  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>,
+  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
   if (getenv("DIINN_DEBUG_OCC")) {
     int nc = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>, cfg);
     fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
             cudaGetErrorString(e));
   }
@@ -974,11 +1004,11 @@ static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap&
       spf.wq0_p[i][3].y = fmaf(spf.wq0_p[i][2].y, src.ratio, spf.wq0_p[i][3].y);
     }
     spf.q0_folded = 1;
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, tm, tm_lo, tm_selp, tm_selb, spf,
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>, tm, tm_lo, tm_selp, tm_selb, spf,
                                         src, out, P, wk, err_flag, trace));
     return DIINN_OK;
   }
-  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel>, tm, tm_lo, tm_selp, tm_selb,
+  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>, tm, tm_lo, tm_selp, tm_selb,
                                       h->small, src, out, P, wk, err_flag, trace));
   return DIINN_OK;
 }
@@ -1139,7 +1169,14 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
 #define DIINN_SB_PICK_SEL(FMTv) (dump ? DIINN_SB_LAUNCH(2, FMTv, true, false, true) : DIINN_SB_LAUNCH(2, FMTv, false, false, true))
 #define DIINN_SB_PICK_SPLIT(CGv) \
   (dump ? DIINN_SB_LAUNCH(CGv, 2, true, false, false) : DIINN_SB_LAUNCH(CGv, 2, false, false, false))
-  if (pl.sel) rc = fmt == kFmtF16 ? DIINN_SB_PICK_SEL(1) : DIINN_SB_PICK_SEL(0);
+  if (src.liif) {
+    if (src.mode != 1 || dump || pix || cta_group != 2)
+      return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "LIIF's imnet runs on query lists with CTA pairs only");
+#define DIINN_SB_LIIF(FMTv) \
+  launch_variant<2, FMTv, false, false, false, true>(h, &cfg, tm, tm_lo, tm_selp, tm_selb, src, out, P, wk, err_flag, trace)
+    rc = fmt == kFmtSplit ? DIINN_SB_LIIF(2) : fmt == kFmtF16 ? DIINN_SB_LIIF(1) : DIINN_SB_LIIF(0);
+#undef DIINN_SB_LIIF
+  } else if (pl.sel) rc = fmt == kFmtF16 ? DIINN_SB_PICK_SEL(1) : DIINN_SB_PICK_SEL(0);
   else if (cta_group == 1) rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(1) : fmt == kFmtF16 ? DIINN_SB_PICK(1, 1) : DIINN_SB_PICK(1, 0);
   else rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(2) : fmt == kFmtF16 ? DIINN_SB_PICK(2, 1) : DIINN_SB_PICK(2, 0);
 #undef DIINN_SB_PICK_SPLIT
