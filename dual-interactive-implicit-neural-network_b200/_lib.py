@@ -26,7 +26,7 @@ SYMBOLS = [
     "diinn_create", "diinn_destroy", "diinn_last_error", "diinn_set_weights", "diinn_workspace_bytes",
     "diinn_decode", "diinn_decode_multi", "diinn_decode_host", "diinn_query_workspace_bytes", "diinn_query",
     "diinn_query_ensemble", "diinn_set_profiling", "diinn_get_kernel_times", "diinn_launch_count",
-    "diinn_version", "diinn_set_output_transform", "diinn_psnr", "diinn_set_bsize",
+    "diinn_version", "diinn_set_output_transform", "diinn_psnr", "diinn_set_bsize", "diinn_set_weights_liif",
 ]
 DEBUG_SYMBOLS = [
     "diinn_debug_gather", "diinn_debug_query_gather", "diinn_debug_set_tap", "diinn_debug_stage_a", "diinn_debug_umma_gemm",
@@ -50,6 +50,10 @@ class WeightsF32(C.Structure):
                 ("on_device", C.c_int), ("first_weight", C.c_void_p), ("first_bias", C.c_void_p)]
 
 
+class LiifWeightsF32(C.Structure):
+    _fields_ = [("weight", C.c_void_p * 5), ("bias", C.c_void_p * 5), ("on_device", C.c_int)]
+
+
 _lib = None
 
 
@@ -71,6 +75,8 @@ def load() -> C.CDLL:
     lib.diinn_last_error.restype = C.c_char_p
     lib.diinn_set_weights.argtypes = [vp, C.POINTER(WeightsF32), vp]
     lib.diinn_set_weights.restype = i
+    lib.diinn_set_weights_liif.argtypes = [vp, C.POINTER(LiifWeightsF32), vp]
+    lib.diinn_set_weights_liif.restype = i
     lib.diinn_workspace_bytes.argtypes = [vp, i, i, i, i, i, i, i, i]
     lib.diinn_workspace_bytes.restype = sz
     lib.diinn_decode.argtypes = [vp, vp, i, i, i, i, i, i, i, i, vp, i64, i64, i64, vp, sz, i, i, vp]

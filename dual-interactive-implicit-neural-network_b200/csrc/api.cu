@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "handle.h"
 
@@ -324,7 +325,56 @@ int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream)
       return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
   if (!w->last_weight || !w->last_bias) return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
   DeviceGuard guard(h->cfg.device);
+  h->liif = false;
   return pack_weights(h, w, static_cast<cudaStream_t>(stream));
+}
+
+// LIIF's imnet = MLP(580, 3, [256]*4) (liif.py:19-26, mlp.py:5-15) expressed in the decoder's own layouts, so that the same
+// two kernels evaluate it:
+//   Linear 0 (256,580): columns [0,576) multiply the unfolded features -> stage A block 0 (k_weight[0], bias b_0, NO ReLU
+//                       there: Geo::no_relu0); columns 576..579 multiply (rel_h, rel_w, cell_h H, cell_w W) per query ->
+//                       the four per-feature constants of stage B's layer 0 (SmallParams::wq0_p)
+//   Linear i (256,256), i = 1..3: the q-facing block of K.i, with zero x-facing columns, so P block i = b_i for every LR cell
+//   Q.1..3 = 0 (the kLiif instantiation of stage B ignores the gate), Linear 4 (3,256) = last_layer.
+int diinn_set_weights_liif(diinn_handle* h, const diinn_liif_weights_f32* w, void* stream) {
+  if (!h || !w) return DIINN_ERR_BAD_ARG;
+  for (int i = 0; i < 5; ++i)
+    if (!w->weight[i] || !w->bias[i]) return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
+  if (h->cfg.mode != 3 || h->cfg.init_q)
+    return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "LIIF's imnet is hosted by a mode=3, init_q=0 handle");
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  constexpr int kIn = kUnfold + 4;
+  std::vector<float> w0(static_cast<size_t>(kD) * kIn), wi(3 * static_cast<size_t>(kD) * kD), wl(3 * kD), b(4 * kD + 3);
+  const cudaMemcpyKind kind = w->on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(w0.data(), w->weight[0], w0.size() * sizeof(float), kind, s));
+  for (int i = 0; i < 3; ++i)
+    DIINN_CUDA_OK(h, cudaMemcpyAsync(wi.data() + static_cast<size_t>(i) * kD * kD, w->weight[i + 1], sizeof(float) * kD * kD, kind, s));
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(wl.data(), w->weight[4], wl.size() * sizeof(float), kind, s));
+  for (int i = 0; i < 4; ++i) DIINN_CUDA_OK(h, cudaMemcpyAsync(b.data() + i * kD, w->bias[i], sizeof(float) * kD, kind, s));
+  DIINN_CUDA_OK(h, cudaMemcpyAsync(b.data() + 4 * kD, w->bias[4], sizeof(float) * 3, kind, s));
+  DIINN_CUDA_OK(h, cudaStreamSynchronize(s));
+  std::vector<float> k0(static_cast<size_t>(kD) * kUnfold), ki(3 * static_cast<size_t>(kD) * (kD + kUnfold), 0.f), q0(kD * 3),
+      q0b(kD), zeros(static_cast<size_t>(kD) * kD, 0.f);
+  for (int n = 0; n < kD; ++n) {
+    memcpy(&k0[static_cast<size_t>(n) * kUnfold], &w0[static_cast<size_t>(n) * kIn], sizeof(float) * kUnfold);
+    for (int c = 0; c < 3; ++c) q0[n * 3 + c] = w0[static_cast<size_t>(n) * kIn + kUnfold + c];
+    q0b[n] = w0[static_cast<size_t>(n) * kIn + kUnfold + 3];
+    for (int i = 0; i < 3; ++i)
+      memcpy(&ki[(static_cast<size_t>(i) * kD + n) * (kD + kUnfold)], &wi[(static_cast<size_t>(i) * kD + n) * kD], sizeof(float) * kD);
+  }
+  diinn_weights_f32 v{};
+  v.k_weight[0] = k0.data(), v.k_bias[0] = b.data();
+  v.q_weight[0] = q0.data(), v.q_bias[0] = q0b.data();
+  for (int i = 1; i < 4; ++i) {
+    v.k_weight[i] = ki.data() + static_cast<size_t>(i - 1) * kD * (kD + kUnfold), v.k_bias[i] = b.data() + i * kD;
+    v.q_weight[i] = zeros.data(), v.q_bias[i] = zeros.data();
+  }
+  v.last_weight = wl.data(), v.last_bias = b.data() + 4 * kD;
+  v.on_device = 0;
+  const int rc = pack_weights(h, &v, s);  // synchronises the stream before it returns: the host vectors may go
+  h->liif = rc == DIINN_OK;
+  return rc;
 }
 
 size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_up, int W_up, int row0, int row1,
@@ -421,6 +471,9 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
   void* out = o.ptr;
   int rc = check_common(h, B, C, H, W, io_dtype, compute);
   if (rc) return rc;
+  if (h->liif)
+    return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "the handle holds LIIF's imnet (diinn_set_weights_liif): use diinn_query / "
+                                               "diinn_query_ensemble with the grid's coordinates (liif.py:47-57,151-158)");
   compute = effective_compute(h, compute);
   if (io_dtype == DIINN_IO_BF16_NHWC) o.io_dtype = DIINN_IO_BF16;  // the image is bf16 NCHW either way
   if ((rc = apply_output_transform(h, &o))) return rc;
@@ -736,12 +789,14 @@ static int query_impl(diinn_handle* h, const void* feat, int B, int C, int H, in
   char* ws = static_cast<char*>(workspace);
   float* P = reinterpret_cast<float*>(ws);
   size_t off = align_up(static_cast<size_t>(B) * H * W * kPCols * sizeof(float));
-  const PixelSource src = make_query_source(B, H, W, coord, cell, Q, ensemble);
+  PixelSource src = make_query_source(B, H, W, coord, cell, Q, ensemble);
+  src.liif = h->liif ? 1 : 0;
   OutSpec o{};
   o.ptr = out;
   o.io_dtype = io_dtype == DIINN_IO_BF16_NHWC ? DIINN_IO_BF16 : io_dtype;
   if ((rc = apply_output_transform(h, &o))) return rc;
   if (is_simt(compute)) {
+    if (h->liif) return fail(h, DIINN_ERR_UNSUPPORTED_MODE, "LIIF's imnet runs on the tensor paths (FP32 / FP16 / BF16) only");
     const int64_t total = static_cast<int64_t>(B) * Q * E;
     const int64_t chunk = total < kFp32Chunk ? total : kFp32Chunk;
     float* q0 = reinterpret_cast<float*>(ws + off);

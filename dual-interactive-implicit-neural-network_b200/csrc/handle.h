@@ -20,6 +20,7 @@ struct Handle {
   diinn_config cfg{};
   int sm_count = 0;
   bool has_weights = false;
+  bool liif = false;  // the weights are LIIF's imnet (diinn_set_weights_liif): query entries only, see api.cu
   std::string err;
   int64_t launches = 0;
   // optional per-kernel timing of the tcgen05 path (diinn_set_profiling): 4 events per decode

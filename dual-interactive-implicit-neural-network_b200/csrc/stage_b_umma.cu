@@ -1015,13 +1015,6 @@ static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap&
 
 namespace {
 
-// host twin of axis_index() (common.cuh): one rounded fp32 multiply, then floorf
-inline int host_axis_index(const AxisParams& p, int j) {
-  volatile float t = (static_cast<float>(j) + 0.5f) * p.scale;
-  const int i = static_cast<int>(floorf(t));
-  return i < p.n_in - 1 ? i : p.n_in - 1;
-}
-
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;

@@ -104,6 +104,22 @@ def make_weights(seed: int = 0, k_gain: float = 1.0, q_gain: float = 1.0, last_g
     return out
 
 
+LIIF_IMNET_SHAPES = {"layers.0.weight": (256, 580), "layers.0.bias": (256,), "layers.2.weight": (256, 256), "layers.2.bias": (256,),
+                     "layers.4.weight": (256, 256), "layers.4.bias": (256,), "layers.6.weight": (256, 256), "layers.6.bias": (256,),
+                     "layers.8.weight": (3, 256), "layers.8.bias": (3,)}
+
+
+def make_liif_weights(seed: int = 0, gain: float = 1.0):
+    """LIIF's imnet = MLP(580, 3, [256]*4) (liif.py:26, mlp.py:5-15) in state_dict layout, nn.Linear-style bounds
+    (uniform(+-1/sqrt(fan_in))); gain > 1 scales the hidden layers for O(1) activations."""
+    out = {}
+    for s, (name, shape) in enumerate(LIIF_IMNET_SHAPES.items()):
+        fan_in = LIIF_IMNET_SHAPES[name.replace("bias", "weight")][1]
+        bound = (1.0 if name.startswith("layers.8") else gain) / np.sqrt(float(fan_in))
+        out[name] = uniform(seed, 300 + s, shape, -bound, bound)
+    return out
+
+
 def make_feat(seed: int, B: int, H: int, W: int, C: int = IN_CHANNELS, std: float = 0.34) -> np.ndarray:
     """Synthetic encoder output (B,C,H,W); std 0.34 matches the random-init RDN feature std."""
     return normalish(seed, 7, (B, C, H, W), std)

@@ -185,6 +185,22 @@ int diinn_query_ensemble(diinn_handle* h, const void* feat, int B, int C, int H,
                          const float* cell, int Q, void* out, void* workspace, size_t workspace_bytes, int io_dtype,
                          int compute, void* stream);
 
+/* "Next" row 1 of SURVEY.md section 8(f), second half: LIIF-proper decoding. The handle (created with mode=3, init_q=0) takes
+ * the weights of LIIF's own imnet = MLP(580, 3, [256]*4) (liif.py:19-26, mlp.py:5-15; state_dict keys imnet.layers.{0,2,4,6,8}):
+ *   weight[0] (256,580)   weight[1..3] (256,256)   weight[4] (3,256)   bias[i] (256) / (3)      fp32, contiguous
+ * whose 580 inputs are [unfolded features 576 | rel_coord 2 | rel_cell 2] (liif.py:105-111). Afterwards diinn_query is
+ * LIIF.query_rgb(feat, coord, cell) with local_ensemble=False and diinn_query_ensemble the same with local_ensemble=True
+ * (feat_unfold=True, cell_decode=True; liif.py:59-127): lookups by grid_sample(nearest) on the clamped coordinate, ReLU
+ * layers, area blend. The feature part of the first Linear is evaluated once per LR cell by the same stage-A kernel, the
+ * rest per query by the same stage-B kernel. diinn_decode* return DIINN_ERR_UNSUPPORTED_MODE on such a handle (LIIF.forward
+ * queries the grid's own coordinates, liif.py:151-158); diinn_set_weights switches it back. Tensor paths only. */
+typedef struct diinn_liif_weights_f32 {
+  const float* weight[5];
+  const float* bias[5];
+  int on_device;
+} diinn_liif_weights_f32;
+int diinn_set_weights_liif(diinn_handle* h, const diinn_liif_weights_f32* w, void* stream);
+
 /* Per-kernel device timing of the tcgen05 path, measured with CUDA events recorded on the caller's stream around
  * the three kernels of every diinn_decode (layout pass, stage A, stage B) while enabled. diinn_get_kernel_times
  * synchronises on the recorded events, returns the summed milliseconds and the number of decodes, and resets.

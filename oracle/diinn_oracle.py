@@ -17,6 +17,7 @@ PyTorch/ATen (not vendored in the reference tree; the reference pins no torch ve
                               wirings, diinn.py:116-131,140-147).
 * ``last_conv3x3_reflect`` <- mode 4's last_layer, Conv2d(256, 3, 3, padding=1, padding_mode='reflect'), diinn.py:89-90.
 * ``decoder_forward``      <- diinn.py:163-173 (bsize chunking, diinn.py:149-160, is pure scheduling).
+* ``liif_query_rgb``       <- LIIF.query_rgb with its own imnet MLP(580,3,[256]*4), liif.py:59-127 + mlp.py:5-20.
 * ``query``                <- the (feat, coord, cell) superset entry of SURVEY.md section 8(b); on a regular
                               grid it reproduces ``decoder_forward`` (tested).
 
@@ -315,6 +316,72 @@ def query_ensemble(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.
             acc = acc + p_ * (a_ / tot).astype(dt)[:, None]
         out[b] = acc
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# "next" row 1, second half: LIIF-proper decoding -- LIIF.query_rgb with its own imnet = MLP(580, 3, [256]*4)
+# (/root/reference/src/models/components/liif.py:59-127, mlp.py:5-20), feat_unfold=True, cell_decode=True.
+# Pinned by tests/golden/liif.npz (the unmodified reference run by tests/golden/make_golden_liif.py).
+# --------------------------------------------------------------------------------------------------
+def liif_imnet(weights: dict, inp: np.ndarray, fp64: bool = False) -> np.ndarray:
+    """MLP.forward (mlp.py:17-20): Linear + ReLU four times, then Linear. weights: 'layers.{0,2,4,6,8}.{weight,bias}'."""
+    dt = np.float64 if fp64 else F32
+    x = inp.astype(dt)
+    for i in (0, 2, 4, 6):
+        x = np.maximum(x @ weights[f"layers.{i}.weight"].astype(dt).T + weights[f"layers.{i}.bias"].astype(dt), 0)
+    return (x @ weights["layers.8.weight"].astype(dt).T + weights["layers.8.bias"].astype(dt)).astype(dt)
+
+
+def liif_query_rgb(weights: dict, feat: np.ndarray, coord: np.ndarray, cell: np.ndarray, local_ensemble: bool = True,
+                   fp64: bool = False) -> np.ndarray:
+    """feat (B,64,H,W), coord / cell (B,Q,2) as (h,w) -> (B,Q,3)  (liif.py:59-127).
+
+    Per shift (vx, vy) in [(-1,-1), (-1,1), (1,-1), (1,1)] (one unshifted pass without the ensemble, liif.py:71-77):
+      lookup index / rel_coord as ``ensemble_index_rel`` (liif.py:88-104; v = 0: no shift and eps_shift = 0, same clamp),
+      rel_cell = cell * (H, W) in fp32 (liif.py:107-110), inp = [unfold(feat)[idx] | rel_coord | rel_cell] (580 wide),
+      pred = imnet(inp), area = |rel_h * rel_w| + 1e-9; the areas are swapped diagonally and normalised (liif.py:117-127)."""
+    B, C, H, W = feat.shape
+    u = np.ascontiguousarray(unfold3x3(feat).transpose(0, 2, 3, 1))
+    dt = np.float64 if fp64 else F32
+    out = np.zeros(coord.shape[:2] + (3,), dtype=dt)
+    shifts = [(-1, -1), (-1, 1), (1, -1), (1, 1)] if local_ensemble else [(0, 0)]
+    for b in range(B):
+        ce = cell[b].astype(F32)
+        rel_cell = np.stack([(ce[:, 0] * F32(H)).astype(F32), (ce[:, 1] * F32(W)).astype(F32)], axis=1)
+        preds, areas = [], []
+        for vx, vy in shifts:
+            ih, rh = _liif_index_rel(coord[b, :, 0], H, vx)
+            iw, rw = _liif_index_rel(coord[b, :, 1], W, vy)
+            inp = np.concatenate([u[b][ih, iw], np.stack([rh, rw], axis=1), rel_cell], axis=1).astype(F32)
+            preds.append(liif_imnet(weights, inp, fp64=fp64))
+            areas.append((np.abs((rh * rw).astype(F32)) + F32(1e-9)).astype(F32))
+        tot = areas[0]
+        for a_ in areas[1:]:
+            tot = (tot + a_).astype(F32)
+        if local_ensemble:
+            areas = [areas[3], areas[2], areas[1], areas[0]]
+        acc = np.zeros_like(preds[0])
+        for p_, a_ in zip(preds, areas):
+            acc = acc + p_ * (a_ / tot).astype(dt)[:, None]
+        out[b] = acc
+    return out
+
+
+def _liif_index_rel(coord_axis: np.ndarray, n: int, v: int):
+    """ensemble_index_rel for v in {-1, 0, +1}; v = 0 is local_ensemble=False: shift 0 AND eps_shift 0 (liif.py:76)."""
+    if v != 0:
+        return ensemble_index_rel(coord_axis, n, v)
+    c = coord_axis.astype(F32)
+    c_ = np.clip(c, F32(-1 + 1e-6), F32(1 - 1e-6)).astype(F32)
+    t = ((((c_ + F32(1.0)).astype(F32) * F32(n)).astype(F32) - F32(1.0)).astype(F32) * F32(0.5)).astype(F32)
+    idx = np.clip(np.rint(t).astype(np.int64), 0, n - 1)
+    rel = ((c - axis_centres(n)[idx]).astype(F32) * F32(n)).astype(F32)
+    return idx, rel
+
+
+def liif_make_coord(n: int) -> np.ndarray:
+    """One axis of LIIF.make_coord (liif.py:36-42): fl(fp32(-1 + 1/n) + fl(fp32(2/n) * i)) -- the same numbers as axis_centres."""
+    return axis_centres(n)
 
 
 def grid_coords(H_up: int, W_up: int):

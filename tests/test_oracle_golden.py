@@ -222,3 +222,30 @@ def test_init_q_weights_leave_the_other_streams_alone():
     a, b = synth.make_weights(seed=3, mode=3), synth.make_weights(seed=3, mode=3, init_q=True)
     assert set(b) - set(a) == {"first_layer.0.weight", "first_layer.0.bias"}
     assert all(np.array_equal(a[k], b[k]) for k in a if not k.startswith("Q.0.0."))
+
+
+# ---- LIIF-proper decoding: the unmodified reference LIIF.query_rgb with its own imnet
+@pytest.mark.parametrize("name,tol", [("sampled", 2e-6), ("sampled_gain", 2e-5), ("grid_x3", 2e-6), ("grid_odd", 5e-6)])
+@pytest.mark.parametrize("ens", [1, 0])
+def test_liif_query_rgb_matches_reference(golden_liif, name, tol, ens):
+    from conftest import liif_case, LIIF_CASES
+    import ast, os, re   # the generator and the tests must describe the same cases (read, not imported: it needs the reference)
+    src = open(os.path.join(os.path.dirname(__file__), "golden", "make_golden_liif.py")).read()
+    assert ast.literal_eval(re.search(r"^CASES = (\{.*?^\})", src, re.S | re.M).group(1)) == LIIF_CASES
+    weights, feat, coord, cell, ref = liif_case(golden_liif, name)
+    out = orc.liif_query_rgb(weights, feat, coord, cell, local_ensemble=bool(ens))
+    assert out.shape == ref[ens].shape and out.dtype == np.float32
+    assert float(np.abs(out - ref[ens]).max()) <= tol * max(1.0, float(np.abs(ref[ens]).max()))
+    # the fp64 evaluation of the same restatement agrees too: the pin is not an artefact of matching rounding
+    out64 = orc.liif_query_rgb(weights, feat, coord, cell, local_ensemble=bool(ens), fp64=True)
+    assert float(np.abs(out64 - ref[ens]).max()) <= 4 * tol * max(1.0, float(np.abs(ref[ens]).max()))
+
+
+def test_liif_grid_coordinates_bit_exact(golden_liif):
+    """LIIF.make_coord_and_cell (liif.py:32-57), as stored by the generator, equals the oracle's axis centres bit for bit."""
+    for name, (H_up, W_up) in (("grid_x3", (30, 39)), ("grid_odd", (16, 25))):
+        c = golden_liif[f"{name}.coord"].reshape(H_up, W_up, 2)
+        assert np.array_equal(c[:, 0, 0].view(np.uint32), orc.liif_make_coord(H_up).view(np.uint32))
+        assert np.array_equal(c[0, :, 1].view(np.uint32), orc.liif_make_coord(W_up).view(np.uint32))
+        ce = golden_liif[f"{name}.cell"]
+        assert np.all(ce[:, 0] == np.float32(2 / H_up)) and np.all(ce[:, 1] == np.float32(2 / W_up))

@@ -109,3 +109,31 @@ def test_local_ensemble_on_random_queries(ref_decoder_cls):
         got = orc.query_ensemble(w, feat, coord, cell)
         assert float(np.abs(got - ref).max()) <= 2e-6, (i, B, H, W)
     torch.set_grad_enabled(True)
+
+
+def test_liif_proper_on_random_queries(ref_decoder_cls):
+    """the UNMODIFIED reference LIIF (its own imnet, liif.py:9-127 + mlp.py) == oracle.liif_query_rgb on random feature-map
+    shapes, random coordinates (borders / exact cell centres / out-of-range values included), random cells, with and
+    without the local ensemble"""
+    torch.set_grad_enabled(False)
+    sys.path.insert(0, "/root/reference")
+    try:
+        from src.models.components.liif import LIIF
+    finally:
+        sys.path.remove("/root/reference")
+    rng = np.random.default_rng(8)
+    for i in range(6):
+        ens = i % 2 == 0
+        w = synth.make_liif_weights(20 + i, gain=1.0 + i)
+        liif = LIIF(local_ensemble=ens).eval()
+        liif.imnet.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in w.items()}, strict=True)
+        B, H, W, Q = 1 + i % 2, int(rng.integers(1, 24)), int(rng.integers(1, 24)), 300
+        feat = synth.make_feat(80 + i, B, H, W)
+        coord, cell = synth.make_query(90 + i, B, Q, (2.0 / float(rng.integers(H, 6 * H)), 2.0 / float(rng.integers(W, 6 * W))))
+        coord[:, :40, 0] = np.linspace(-1.05, 1.05, 40, dtype=np.float32)
+        coord[:, 40:80, 1] = (-1 + (2 * np.arange(40) + 1) / 40).astype(np.float32)
+        ref = liif.query_rgb(torch.from_numpy(feat), torch.from_numpy(coord), torch.from_numpy(cell)).numpy()
+        got = orc.liif_query_rgb(w, feat, coord, cell, local_ensemble=ens)
+        scale = max(1.0, float(np.abs(ref).max()))
+        assert float(np.abs(got - ref).max()) <= 4e-6 * scale, (i, B, H, W, ens)
+    torch.set_grad_enabled(True)
