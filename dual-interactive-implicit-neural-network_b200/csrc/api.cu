@@ -297,6 +297,7 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->WQ0_32);
   cudaFree(h->WAg16);
   cudaFree(h->WQ0g16);
+  cudaFree(h->WQ0A16);
   cudaFree(h->WH16);
   cudaFree(h->psnr_acc);
   cudaFree(h->host_feat_dev);
@@ -389,7 +390,7 @@ static int decode_impl(diinn_handle* h, const void* feat, int B, int C, int H, i
 
 // The LR-resolution half of a tensor-path decode: layout pass (skipped for a channels-last bf16 map, which stage A reads in
 // place as bf16 operands), stage A, and for modes 1 / 2 the K chain. nhwc / nhwc_lo / chain are workspace regions.
-// p16: P is written as fp16 (what stage B's select-MMA variant consumes, stage_b_wants_p16); never with the K chain.
+// p16: P is written as fp16 (what stage B's select-MMA variant consumes, stage_b_wants_p16); the K chain then updates it in fp16.
 static int run_lr_stages(Handle* h, const void* feat, int io_dtype, int fmt, int B, int H, int W, int fr0, int frows,
                          int lr_row0, int lr_rows, float* P, bool p16, char* nhwc, char* nhwc_lo, char* chain, cudaStream_t s,
                          cudaEvent_t ev_after_layout = nullptr) {
@@ -405,7 +406,7 @@ static int run_lr_stages(Handle* h, const void* feat, int io_dtype, int fmt, int
   if (rc) return rc;
   if (h->cfg.mode == 1 || h->cfg.mode == 2) {
     const int64_t M = static_cast<int64_t>(B) * lr_rows * W;
-    rc = fmt == kFmtSplit ? run_lr_chain_fp32(h, P, M, s) : run_lr_chain_umma(h, P, M, chain, s);
+    rc = fmt == kFmtSplit ? run_lr_chain_fp32(h, P, M, s) : run_lr_chain_umma(h, P, M, chain, s, p16);
   }
   return rc;
 }

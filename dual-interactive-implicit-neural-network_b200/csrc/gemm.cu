@@ -56,6 +56,10 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // LR chain launches are programmatic dependents of one another (PDL): the prologue above overlaps the predecessor's tail
+  // and nothing it wrote is touched before this wait (a no-op for ordinary launches)
+  grid_dep_launch();
+  grid_dep_wait();
   const int nk = K / 64;
 
   if (warp == 0 && lane == 0) {
@@ -106,6 +110,43 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             drow[c0 + 2 * j] = __low2float(hv);
             drow[c0 + 2 * j + 1] = __high2float(hv);
           }
+        }
+      }
+    } else if (ce.P != nullptr && ce.p16) {
+      // LR chain over the fp16 P of the select-MMA variant: P_layer = fp16(P_layer + acc), next A operand = bf16(relu(.)) of
+      // the unrounded sum. 64 columns (128 B) per pass, loads issued before the accumulators are read.
+      const bool valid = row < ce.rows;
+      __half* prow = reinterpret_cast<__half*>(ce.P) + (ce.m0 + row) * kPCols + ce.layer * kD + n0;
+      __nv_bfloat16* arow = ce.A_next ? ce.A_next + static_cast<size_t>(row) * kD + n0 : nullptr;
+      for (int c0 = 0; c0 < 256; c0 += 64) {
+        uint4 pv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          pv[j] = valid ? *reinterpret_cast<const uint4*>(prow + c0 + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+        uint32_t v[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0 + 16 * g, *reinterpret_cast<uint32_t(*)[16]>(&v[16 * g]));
+        tmem_ld_wait();
+        uint32_t pk[32], ph[32];
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pv);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a, b;
+          unpack_f16x2(pw[j], a, b);
+          a += __uint_as_float(v[2 * j]), b += __uint_as_float(v[2 * j + 1]);
+          ph[j] = pack_f16x2_sat(a, b);
+          pk[j] = pack_bf16x2(fmaxf(a, 0.f), fmaxf(b, 0.f));                   // padding rows of A_next stay zero
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(prow + c0 + 8 * j) = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+        }
+        if (arow && row < M) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(arow + c0 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
     } else if (ce.P != nullptr) {
@@ -356,13 +397,15 @@ int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int 
   cfg.blockDim = dim3(192, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cta_group;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (ce.P != nullptr && h->pdl) ? 2 : 1;  // the LR chain's kernels only (each waits on its predecessor, see the kernel)
   if (cta_group == 1) {
     DIINN_CUDA_OK(h, cudaFuncSetAttribute(umma_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem)));

@@ -68,6 +68,8 @@ struct Handle {
   float* WQ0_32 = nullptr;
   __nv_bfloat16* WAg16 = nullptr;
   __nv_bfloat16* WQ0g16 = nullptr;
+  __nv_bfloat16* WQ0A16 = nullptr;   // Q.0 (256,576) in stage A's (tap, row, channel) tile order: matrix-mode stage A on the gate
+  CUtensorMap tmapWQ0A[2]{};         // [cta_group - 1]
   SmallParams small{};            // host copy; passed by value to kernels
   diinn_output_transform out_tf{};  // eval glue fused into the output store (all zero = identity)
   int64_t bsize = 0;                // diinn_set_bsize: the reference's query-chunk size (0 = None); only mode 4 reads it
@@ -123,7 +125,7 @@ int launch_stage_a_fp32(Handle* h, const void* feat, int io_dtype, int B, int H,
                         float* P, cudaStream_t s);
 // LR-resolution K chain of modes 1 / 2: P[:, 256 i ..] += WH[i-1] . relu(P[:, 256 (i-1) ..]) for i = 1..3, M rows of P
 int run_lr_chain_fp32(Handle* h, float* P, int64_t M, cudaStream_t s);
-int run_lr_chain_umma(Handle* h, float* P, int64_t M, void* scratch, cudaStream_t s);
+int run_lr_chain_umma(Handle* h, float* P, int64_t M, void* scratch, cudaStream_t s, bool p16 = false);  // p16: fp16 P rows
 size_t lr_chain_scratch_bytes(int64_t M);
 // mode 4: 3x3 reflect-padded last conv over the dumped q_3 (csrc/mode4.cu)
 // tensor path: (pixels x 256) x (256 x 27) projection on mma.sync, then the 9-tap gather; T = (27, B*qrows*W_up) fp32 scratch
@@ -144,6 +146,8 @@ int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, con
 // stage_a_umma.cu / stage_b_umma.cu
 // feat_nhwc: (B, frows, W, 64) 16-bit elements in the operand format fmt; feat_lo: the fp16 residual plane (kFmtSplit only)
 // P: fp32 (B*lr_rows*W, 1024), or with p16 the same matrix in fp16 (what stage B's select-MMA variant consumes)
+int launch_stage_a_matrix(Handle* h, const void* A16, int64_t rows, int which, const float* q0_arg, void* out, bool p16,
+                          cudaStream_t s);
 int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, int fmt, int B, int H, int W, int fr0,
                         int frows, int lr_row0, int lr_rows, void* P, bool p16, cudaStream_t s);
 // P: fp32 rows, or fp16 rows when stage_b_wants_p16(h, src, fmt) (the select-MMA variant, which feeds P to the tensor core)

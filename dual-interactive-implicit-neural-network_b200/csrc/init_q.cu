@@ -18,6 +18,8 @@
 // (tap*64 + c, so the gate reads whole 128-byte channel vectors of the NHWC feature copy), the library's tcgen05 GEMM
 // (gemm.cu), fp32 PX / QS. Executed arithmetic: 2 264 064 FLOP per HR pixel (nothing is shared between pixels).
 // Correct and on the tensor cores, not tuned: PX / XG / S round-trip through L2 / HBM (about 10 KB per pixel).
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "handle.h"
@@ -103,6 +105,70 @@ __global__ void __launch_bounds__(192) initq_gate_kernel(PixelSource src, Feat f
         store_gate(srow + threadIdx.x + 192 * i, sv);
         store_gate(xrow + threadIdx.x + 192 * i, sv * xv);
       }
+    }
+  }
+}
+
+// Tensor-path gate, vectorised: 288 threads = 4 rows x 72 groups of 8 consecutive tap-major columns (one tap, channels
+// [c0, c0 + 8)): one 16-byte load of the NHWC feature vector, eight sines, two 16-byte stores (S, XG) per thread and row.
+// Same arithmetic per element as initq_gate_kernel<.., true, true>.
+__global__ void __launch_bounds__(288) initq_gate_vec_kernel(PixelSource src, FeatNHWC feat, const float4* __restrict__ wf4,
+                                                             __nv_bfloat16* __restrict__ S, __nv_bfloat16* __restrict__ XG,
+                                                             int64_t g1, int64_t rows_pad) {
+  __shared__ float s_syn[32][3];
+  __shared__ int s_loc[32][3];
+  const int grp = threadIdx.x % 72, rsub = threadIdx.x / 72;
+  const int j0 = grp * 8, tap = j0 >> 6, c0 = j0 & 63;
+  const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+  float4 w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = __ldg(wf4 + (c0 + e) * 9 + tap);
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * 32; base < rows_pad; base += static_cast<int64_t>(gridDim.x) * 32) {
+    __syncthreads();
+    if (threadIdx.x < 32 && base + threadIdx.x < g1) {
+      const PixInfo pi = pixel_info(src, base + threadIdx.x);
+      s_syn[threadIdx.x][0] = pi.rel_h, s_syn[threadIdx.x][1] = pi.rel_w, s_syn[threadIdx.x][2] = pi.ratio;
+      s_loc[threadIdx.x][0] = pi.b, s_loc[threadIdx.x][1] = pi.ih, s_loc[threadIdx.x][2] = pi.iw;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = rsub; r < 32; r += 4) {
+      const int64_t row = base + r;
+      if (row >= rows_pad) break;
+      uint4 so = make_uint4(0u, 0u, 0u, 0u), xo = so;
+      if (row < g1) {
+        const float rel_h = s_syn[r][0], rel_w = s_syn[r][1], ratio = s_syn[r][2];
+        const int b = s_loc[r][0], hh = s_loc[r][1] + dh, ww = s_loc[r][2] + dw;
+        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (hh >= 0 && hh < src.H && ww >= 0 && ww < src.W) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(
+              feat.ptr + ((static_cast<size_t>(b) * feat.frows + (hh - feat.fr0)) * src.W + ww) * kC + c0));
+          const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) x[2 * i] = __uint_as_float(uw[i] << 16), x[2 * i + 1] = __uint_as_float(uw[i] & 0xffff0000u);
+        }
+        uint32_t sp[4], xp[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          float sv[2];
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            float t = __fmul_rn(w[e + d].x, rel_h);
+            t = fmaf(w[e + d].y, rel_w, t);
+            t = fmaf(w[e + d].z, ratio, t);
+            t += w[e + d].w;
+            sv[d] = __sinf(t);
+          }
+          __nv_bfloat162 s2 = __floats2bfloat162_rn(sv[0], sv[1]);
+          __nv_bfloat162 x2 = __floats2bfloat162_rn(sv[0] * x[e], sv[1] * x[e + 1]);
+          sp[e >> 1] = *reinterpret_cast<uint32_t*>(&s2);
+          xp[e >> 1] = *reinterpret_cast<uint32_t*>(&x2);
+        }
+        so = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+        xo = make_uint4(xp[0], xp[1], xp[2], xp[3]);
+      }
+      *reinterpret_cast<uint4*>(S + row * kUnfold + j0) = so;
+      *reinterpret_cast<uint4*>(XG + row * kUnfold + j0) = xo;
     }
   }
 }
@@ -279,11 +345,38 @@ int run_initq_fp32(Handle* h, const void* feat, int io_dtype, const PixelSource&
   return DIINN_OK;
 }
 
+// q_0 of the chain modes on the tensor path: PX[r][f] (fp16) *= sin(QS[r][f]), f < 256 (QS already holds Q.0 s + bq_0)
+__global__ void __launch_bounds__(256) initq_q0_p16_kernel(__half* __restrict__ PX, const float* __restrict__ QS, int64_t M) {
+  const int64_t total = M * (kD / 4);
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / (kD / 4);
+    const int n = static_cast<int>(e % (kD / 4)) * 4;
+    uint2* p = reinterpret_cast<uint2*>(PX + r * kPCols + n);
+    const uint2 u = *p;
+    const float4 t = *reinterpret_cast<const float4*>(QS + r * kD + n);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    const __half2 lo = __floats2half2_rn(a.x * __sinf(t.x), a.y * __sinf(t.y));
+    const __half2 hi = __floats2half2_rn(b.x * __sinf(t.z), b.y * __sinf(t.w));
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo), o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *p = o;
+  }
+}
+
+// Tensor path, per chunk of HR pixels (whole patch rows of stage B):
+//   gate      S, XG (bf16, K tap-major)                                   initq_gate_vec_kernel
+//   QS      = Q.0 S + bq_0 (fp32)                                         stage-A kernel in matrix mode, one N-block
+//   PX      = [relu(K_0 XG + b_0) * sin(QS) | K_i[:, 256:] XG + b_i]      stage-A kernel in matrix mode, fp16 rows (2 KB / pixel);
+//             (modes 1 / 2: without the sine, then the k-fed chain over the fp16 rows, then q_0)
+//   stage B   kPix instantiation: one fp16 PX row per pixel, q_0 given
+// The 576-wide products use bf16 operands whatever the decode's operand format (the gate is written once, as bf16).
 int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, const PixelSource& src_in, const OutSpec& out,
                    char* ws, const InitQPlan& pl, int fmt, cudaStream_t s) {
   __nv_bfloat16* S = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_S);
   __nv_bfloat16* XG = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_XG);
-  float* PX = reinterpret_cast<float*>(ws + pl.off_PX);
+  __half* PX = reinterpret_cast<__half*>(ws + pl.off_PX);
   float* QS = reinterpret_cast<float*>(ws + pl.off_QS);
   const bool chain = h->cfg.mode == 1 || h->cfg.mode == 2;
   const FeatNHWC f{nhwc, fr0, frows};
@@ -295,20 +388,15 @@ int run_initq_umma(Handle* h, const __nv_bfloat16* nhwc, int fr0, int frows, con
     PixelSource src = src_in;
     src.row0 = a, src.row1 = b;
     src.per_pixel_p = 1, src.p_base = 0, src.out_row0 = src_in.row0;
-    initq_gate_kernel<FeatNHWC, __nv_bfloat16, true, true><<<capped_blocks(h, (Mp + 31) / 32), 192, 0, s>>>(src, f, wf4, S, XG, 0, M, Mp);
+    initq_gate_vec_kernel<<<capped_blocks(h, (Mp + 31) / 32), 288, 0, s>>>(src, f, wf4, S, XG, M, Mp);
     h->launches += 1;
     DIINN_CUDA_OK(h, cudaGetLastError());
     int rc;
-    // QS first: the big GEMM's epilogue finishes PX in registers -- bias, ReLU on block 0 and (modes 3 / 4) the q_0
-    // product with sin(QS + bq_0) -- so PX is written once and never re-read before stage B
-    if ((rc = launch_umma_selftest(h, S, h->WQ0g16, QS, static_cast<int>(Mp), kD, kUnfold, 2, s))) return rc;
-    ChainEpilogue ce{};
-    ce.add_bias = h->bA, ce.relu_cols = kD;
-    if (!chain) ce.q0_arg = QS, ce.q0_bias = h->bq_dev;
-    if ((rc = launch_umma_selftest(h, XG, h->WAg16, PX, static_cast<int>(Mp), kPCols, kUnfold, 2, s, &ce))) return rc;
+    if ((rc = launch_stage_a_matrix(h, S, Mp, 1, nullptr, QS, false, s))) return rc;
+    if ((rc = launch_stage_a_matrix(h, XG, Mp, 0, chain ? nullptr : QS, PX, true, s))) return rc;
     if (chain) {  // modes 1 / 2: q_0 only once the k-fed chain has read k_0
-      if ((rc = run_lr_chain_umma(h, PX, M, ws + pl.off_chain, s))) return rc;
-      initq_assemble_kernel<true><<<capped_blocks(h, (M * (kPCols / 4) + 255) / 256), 256, 0, s>>>(PX, QS, h->bA, h->bq_dev, M, 2);
+      if ((rc = run_lr_chain_umma(h, reinterpret_cast<float*>(PX), M, ws + pl.off_chain, s, true))) return rc;
+      initq_q0_p16_kernel<<<capped_blocks(h, (M * (kD / 4) + 255) / 256), 256, 0, s>>>(PX, QS, M);
       h->launches += 1;
       DIINN_CUDA_OK(h, cudaGetLastError());
     }

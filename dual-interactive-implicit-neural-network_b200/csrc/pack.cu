@@ -83,12 +83,18 @@ __global__ void pack_stage_b_kernel(RefPtrs r, int mode, float* __restrict__ WB3
 
 // init_q=True, tensor path: row-major bf16 operands of the library GEMM with the K index in tap-major channel order
 // (k' = tap*64 + c  <-  reference k = c*9 + tap): rows [0,1024) from WA32 (the x-facing K blocks), then Q.0's 256 rows
+// WQ0A16: Q.0 once more in stage A's tile order (tap, row, channel), for the matrix-mode stage A that evaluates Q.0 on the gate
 __global__ void pack_initq_kernel(const float* __restrict__ WA32, const float* __restrict__ q0w,
-                                  __nv_bfloat16* __restrict__ WAg16, __nv_bfloat16* __restrict__ WQ0g16) {
+                                  __nv_bfloat16* __restrict__ WAg16, __nv_bfloat16* __restrict__ WQ0g16,
+                                  __nv_bfloat16* __restrict__ WQ0A16) {
   const int n = blockIdx.x;  // 0..1279
   const float* src = n < kPCols ? WA32 + static_cast<size_t>(n) * kUnfold : q0w + static_cast<size_t>(n - kPCols) * kUnfold;
   __nv_bfloat16* dst = n < kPCols ? WAg16 + static_cast<size_t>(n) * kUnfold : WQ0g16 + static_cast<size_t>(n - kPCols) * kUnfold;
-  for (int j = threadIdx.x; j < kUnfold; j += blockDim.x) dst[j] = __float2bfloat16_rn(src[(j & 63) * 9 + (j >> 6)]);
+  for (int j = threadIdx.x; j < kUnfold; j += blockDim.x) {
+    const __nv_bfloat16 v = __float2bfloat16_rn(src[(j & 63) * 9 + (j >> 6)]);
+    dst[j] = v;
+    if (n >= kPCols) WQ0A16[(static_cast<size_t>(j >> 6) * kD + (n - kPCols)) * kC + (j & 63)] = v;
+  }
 }
 
 int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
@@ -204,10 +210,11 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
       DIINN_CUDA_OK(h, cudaMalloc(&h->WQ0_32, sizeof(float) * kD * kUnfold));
       DIINN_CUDA_OK(h, cudaMalloc(&h->WAg16, sizeof(__nv_bfloat16) * kPCols * kUnfold));
       DIINN_CUDA_OK(h, cudaMalloc(&h->WQ0g16, sizeof(__nv_bfloat16) * kD * kUnfold));
+      DIINN_CUDA_OK(h, cudaMalloc(&h->WQ0A16, sizeof(__nv_bfloat16) * kD * kUnfold));
     }
     DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WF4, wf4, sizeof(wf4), cudaMemcpyHostToDevice, s));
     DIINN_CUDA_OK(h, cudaMemcpyAsync(h->WQ0_32, r.qw[0], sizeof(float) * kD * kUnfold, cudaMemcpyDeviceToDevice, s));
-    pack_initq_kernel<<<kPCols + kD, 192, 0, s>>>(h->WA32, h->WQ0_32, h->WAg16, h->WQ0g16);
+    pack_initq_kernel<<<kPCols + kD, 192, 0, s>>>(h->WA32, h->WQ0_32, h->WAg16, h->WQ0g16, h->WQ0A16);
     h->launches += 1;
     DIINN_CUDA_OK(h, cudaGetLastError());
   }
@@ -301,6 +308,9 @@ int pack_weights(Handle* h, const diinn_weights_f32* w, cudaStream_t s) {
     const uint32_t ks = v == 0 ? 16 : 32;
     if ((rc = make_tmap_2d_bf16(h, &h->tmapSelB[v], h->WSel16[v], 64, 3 * 2 * 2 * ks, 64, ks))) return rc;
   }
+  if (init_q)
+    for (int cg = 0; cg < 2; ++cg)
+      if ((rc = make_tmap_2d_bf16(h, &h->tmapWQ0A[cg], h->WQ0A16, 64, 9 * 256, 64, cg == 0 ? 256 : 128))) return rc;
   h->has_weights = true;
   return DIINN_OK;
 }

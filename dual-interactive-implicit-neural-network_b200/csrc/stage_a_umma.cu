@@ -25,6 +25,7 @@
 // Small launches (an 8-way row shard of a DIV2K image has 96 pixel tiles for 74 CTA pairs) split every tile's four
 // N-blocks into 2 or 4 work items so that the last wave is not mostly idle (Geo::nsplit).
 #include <cstdlib>
+#include <cstring>
 
 #include "handle.h"
 #include "ptx.cuh"
@@ -69,6 +70,12 @@ struct Geo {
   int tiles_y, n_txp, n_work;  // n_work = pixel tiles x nsplit
   int nsplit;             // work items per pixel tile: each covers 4 / nsplit consecutive N-blocks (1, 2 or 4)
   int no_relu0;           // LIIF's imnet: block 0 is the feature part of the first Linear, its ReLU comes after the per-query part
+  // Matrix mode (init_q=True, csrc/init_q.cu): the A operand is an explicit (rows x 576) 16-bit matrix -- one row per HR pixel,
+  // K in tap-major order -- viewed as an "image" W pixels wide whose tap t is columns [64 t, 64 t + 64) of the same row
+  // instead of a neighbouring pixel; `nblocks` 256-column N-blocks (4: the x-facing K blocks, 1: Q.0 on the gate).
+  int matrix, nblocks;
+  // matrix mode, N-block 0: the finished q_0 = relu(.) * sin(q0_arg[row][col]) (q0_arg = Q.0 s + bq_0, fp32 (rows, 256))
+  const float* q0_arg;
 };
 
 template <int CG, int FMT, bool kP16>
@@ -114,7 +121,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_ptr;
   const int per_img = g.tiles_y * g.n_txp;
-  const int nb_cnt = 4 / g.nsplit;  // N-blocks per work item
+  const int nb_cnt = g.nblocks / g.nsplit;  // N-blocks per work item
   grid_dep_launch();  // stage B's CTAs may be scheduled as ours retire ...
   grid_dep_wait();    // ... and we read feat_nhwc only once the layout kernel has completed (PDL, see ptx.cuh)
 
@@ -138,7 +145,8 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
           const int nbq = sq / (9 * kTerms), rq = sq - nbq * 9 * kTerms;
           const int term = rq / 9, tap = rq - term * 9;
           const int s36 = nbq * 9 + tap;
-          const int c1 = w0 + tap % 3 - 1, c2 = h0 + tap / 3 - 1 - g.fr0;
+          const int c0 = g.matrix ? tap * kC : 0;
+          const int c1 = g.matrix ? w0 : w0 + tap % 3 - 1, c2 = g.matrix ? h0 : h0 + tap / 3 - 1 - g.fr0;
           {
             const CUtensorMap* mf = (kTerms == 3 && term == 0) ? &tmFlo : &tmF;
             const CUtensorMap* mw = (kTerms == 3 && term == 1) ? &tmWlo : &tmW;
@@ -148,10 +156,10 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
               if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
               uint8_t* dst = s_ring + st * C::kStageBytes;
               if constexpr (CG == 1) {
-                tma_load_4d(dst, mf, &sm.w_full[st], 0, c1, c2, b);
+                tma_load_4d(dst, mf, &sm.w_full[st], c0, c1, c2, b);
                 tma_load_2d(dst + kTapBytes, mw, &sm.w_full[st], 0, s36 * 256);
               } else {
-                tma_load_4d_2sm(dst, mf, &sm.w_full[st], 0, c1, c2, b);
+                tma_load_4d_2sm(dst, mf, &sm.w_full[st], c0, c1, c2, b);
                 tma_load_2d_2sm(dst + kTapBytes, mw, &sm.w_full[st], 0, s36 * 256 + rank * 128);
               }
             }
@@ -216,10 +224,18 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
         mbar_wait(&sm.tmem_full[slot], (slot_use >> 1) & 1);
         tc_fence_after();
         const uint32_t tslot = tmem_base + lane_bits + slot * 256;
+        // matrix mode, N-block 0: q_0 = k_0 * sin(Q.0 s + bq_0), the sine argument read from this pixel's row of q0_arg
+        const bool q0 = nb == 0 && g.q0_arg != nullptr;
+        const float* q0row = q0 ? g.q0_arg + (static_cast<size_t>(h0 + (lane >> 4)) * g.W + w0 + (lane & 15)) * kD : nullptr;
         if constexpr (!kP16) {
 #pragma unroll 1
           for (int c0 = 0; c0 < 256; c0 += 32) {
             uint32_t v[32];
+            float4 qa[8];
+            if (q0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) qa[j] = __ldg(reinterpret_cast<const float4*>(q0row + c0) + j);
+            }
             tmem_ld16(tslot + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
             tmem_ld16(tslot + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
             tmem_ld_wait();
@@ -228,6 +244,7 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
             for (int j = 0; j < 32; ++j) {
               float x = __uint_as_float(v[j]) + bias.b[n0 + j];
               if (nb == 0 && !g.no_relu0) x = fmaxf(x, 0.f);  // first 256 columns are k0 = relu(K0 x + b0)
+              if (q0) x *= __sinf(reinterpret_cast<const float*>(qa)[j]);
               v[j] = __float_as_uint(x);
             }
             // the previous TMA store of this warp must have finished reading the staging block
@@ -256,8 +273,21 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
             for (int j = 0; j < 64; j += 2) {
               float x0 = __uint_as_float(v[j]) + bias.b[n0 + j], x1 = __uint_as_float(v[j + 1]) + bias.b[n0 + j + 1];
               if (nb == 0 && !g.no_relu0) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
-              pk[j >> 1] = pack_f16x2_sat(x0, x1);
+              v[j] = __float_as_uint(x0), v[j + 1] = __float_as_uint(x1);
             }
+            if (q0) {  // (warp-uniform; 16 columns per load group keeps the register footprint flat)
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {
+                float4 qa[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) qa[j] = __ldg(reinterpret_cast<const float4*>(q0row + c0 + 16 * g4) + j);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  v[16 * g4 + j] = __float_as_uint(__uint_as_float(v[16 * g4 + j]) * __sinf(reinterpret_cast<const float*>(qa)[j]));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) pk[j >> 1] = pack_f16x2_sat(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
             if (lane == 0) bulk_wait_group_read0();
             __syncwarp();
 #pragma unroll
@@ -289,16 +319,89 @@ stage_a_umma_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_consta
 
 }  // namespace sa
 
-int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, int fmt, int B, int H, int W, int fr0,
-                        int frows, int lr_row0, int lr_rows, void* P, bool p16, cudaStream_t s) {
+namespace {
+
+// grid sizing (N-block split) + launch, shared by the image and the matrix entry
+int launch_sa_core(Handle* h, sa::Geo g, int n_tiles, int cta_group, int fmt, bool p16, const CUtensorMap& tmF,
+                   const CUtensorMap& tmFlo, const CUtensorMap& tmW, const CUtensorMap& tmWlo, const CUtensorMap& tmP,
+                   const sa::BiasParams& bias, cudaStream_t s) {
   using namespace sa;
+  int* err_flag = h->err_flag;
+  const int max_units = h->sm_count / cta_group;
+  // N-block split: the split with the fewest (fractional) waves wins, ties go to the coarser one (less A re-fetch set-up)
+  g.nsplit = 1;
+  {
+    static int env_ns = -1;
+    if (env_ns < 0) {
+      const char* e = getenv("DIINN_STAGE_A_NSPLIT");
+      env_ns = e ? atoi(e) : 0;
+    }
+    if ((env_ns == 1 || env_ns == 2 || env_ns == 4) && env_ns <= g.nblocks) {
+      g.nsplit = env_ns;
+    } else {
+      double best = 1e30;
+      for (int ns = 1; ns <= g.nblocks; ns *= 2) {
+        const int items = n_tiles * ns;
+        const double waves = static_cast<double>((items + max_units - 1) / max_units) / ns;
+        if (waves < best - 1e-9) best = waves, g.nsplit = ns;
+      }
+    }
+  }
+  g.n_work = n_tiles * g.nsplit;
+  int units = max_units;
+  if (units > g.n_work) units = g.n_work;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * cta_group, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = h->pdl ? 2 : 1;
+#define DIINN_SA_LAUNCH(CGv, FMTv, P16v)                                                                                   \
+  do {                                                                                                                     \
+    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<CGv, FMTv, P16v>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          static_cast<int>(kSmemBytes)));                                                  \
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<CGv, FMTv, P16v>, tmF, tmFlo, tmW, tmWlo, tmP, bias, g,   \
+                                        err_flag));                                                                        \
+  } while (0)
+#define DIINN_SA_PICK(CGv)                                                  \
+  do {                                                                      \
+    if (fmt == kFmtSplit) DIINN_SA_LAUNCH(CGv, kFmtSplit, false);           \
+    else if (fmt == kFmtBf16 && p16) DIINN_SA_LAUNCH(CGv, kFmtBf16, true);  \
+    else if (fmt == kFmtBf16) DIINN_SA_LAUNCH(CGv, kFmtBf16, false);        \
+    else if (p16) DIINN_SA_LAUNCH(CGv, kFmtF16, true);                      \
+    else DIINN_SA_LAUNCH(CGv, kFmtF16, false);                              \
+  } while (0)
+  if (cta_group == 1) DIINN_SA_PICK(1);
+  else DIINN_SA_PICK(2);
+#undef DIINN_SA_PICK
+#undef DIINN_SA_LAUNCH
+  h->launches += 1;
+  return DIINN_OK;
+}
+
+int stage_a_cta_group() {
   static int env_cg = -1;
   if (env_cg < 0) {
     const char* e = getenv("DIINN_CTA_GROUP_A");
     env_cg = (e && e[0] == '1') ? 1 : 2;
   }
-  const int cta_group = env_cg;
-  int* err_flag = h->err_flag;
+  return env_cg;
+}
+
+}  // namespace
+
+int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, int fmt, int B, int H, int W, int fr0,
+                        int frows, int lr_row0, int lr_rows, void* P, bool p16, cudaStream_t s) {
+  using namespace sa;
+  const int cta_group = stage_a_cta_group();
   if (fmt < 0 || fmt > kFmtSplit) return fail(h, DIINN_ERR_BAD_DTYPE, "stage A: unknown operand format");
   if (fmt == kFmtSplit && !feat_lo) return fail(h, DIINN_ERR_BAD_ARG, "stage A: the split format needs the residual plane");
   if (fmt == kFmtSplit && p16) return fail(h, DIINN_ERR_BAD_ARG, "stage A: the split format writes fp32 P");
@@ -328,69 +431,49 @@ int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, i
   const int tiles_x = (W + kPatchW - 1) / kPatchW;
   g.tiles_y = (lr_rows + kPatchH - 1) / kPatchH;
   g.n_txp = (tiles_x + cta_group - 1) / cta_group;
-  const int n_tiles = B * g.tiles_y * g.n_txp;
-  const int max_units = h->sm_count / cta_group;
-  // N-block split: the split with the fewest (fractional) waves wins, ties go to the coarser one (less A re-fetch set-up)
-  g.nsplit = 1;
   g.no_relu0 = h->liif ? 1 : 0;
-  {
-    static int env_ns = -1;
-    if (env_ns < 0) {
-      const char* e = getenv("DIINN_STAGE_A_NSPLIT");
-      env_ns = e ? atoi(e) : 0;
-    }
-    if (env_ns == 1 || env_ns == 2 || env_ns == 4) {
-      g.nsplit = env_ns;
-    } else {
-      double best = 1e30;
-      for (int ns = 1; ns <= 4; ns *= 2) {
-        const int items = n_tiles * ns;
-        const double waves = static_cast<double>((items + max_units - 1) / max_units) / ns;
-        if (waves < best - 1e-9) best = waves, g.nsplit = ns;
-      }
-    }
-  }
-  g.n_work = n_tiles * g.nsplit;
-  int units = max_units;
-  if (units > g.n_work) units = g.n_work;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(units * cta_group, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = kSmemBytes;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cta_group;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = h->pdl ? 2 : 1;
+  g.nblocks = 4;
   const int ci = cta_group - 1;
-  const CUtensorMap& tmW = h->tmapWA[fmt == kFmtBf16 ? 0 : 1][ci];
-  const CUtensorMap& tmWlo = h->tmapWAlo[ci];
-#define DIINN_SA_LAUNCH(CGv, FMTv, P16v)                                                                                   \
-  do {                                                                                                                     \
-    DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_a_umma_kernel<CGv, FMTv, P16v>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          static_cast<int>(kSmemBytes)));                                                  \
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(&cfg, stage_a_umma_kernel<CGv, FMTv, P16v>, tmF, tmFlo, tmW, tmWlo, tmP, bias, g,   \
-                                        err_flag));                                                                        \
-  } while (0)
-#define DIINN_SA_PICK(CGv)                                                  \
-  do {                                                                      \
-    if (fmt == kFmtSplit) DIINN_SA_LAUNCH(CGv, kFmtSplit, false);           \
-    else if (fmt == kFmtBf16 && p16) DIINN_SA_LAUNCH(CGv, kFmtBf16, true);  \
-    else if (fmt == kFmtBf16) DIINN_SA_LAUNCH(CGv, kFmtBf16, false);        \
-    else if (p16) DIINN_SA_LAUNCH(CGv, kFmtF16, true);                      \
-    else DIINN_SA_LAUNCH(CGv, kFmtF16, false);                              \
-  } while (0)
-  if (cta_group == 1) DIINN_SA_PICK(1);
-  else DIINN_SA_PICK(2);
-#undef DIINN_SA_PICK
-#undef DIINN_SA_LAUNCH
-  h->launches += 1;
-  return DIINN_OK;
+  return launch_sa_core(h, g, B * g.tiles_y * g.n_txp, cta_group, fmt, p16, tmF, tmFlo, h->tmapWA[fmt == kFmtBf16 ? 0 : 1][ci],
+                        h->tmapWAlo[ci], tmP, bias, s);
+}
+
+// Matrix mode (init_q=True): out (rows x 256 nblocks, fp32 or -- p16 -- fp16) = A (rows x 576, bf16, K tap-major) . W^T + bias, ReLU on N-block 0
+// if relu0, and N-block 0 multiplied by sin(q0_arg) if given. rows % 256 == 0 (the caller pads). which: 0 = the stacked
+// x-facing K blocks (N = 1024, bias b_k), 1 = Q.0 (N = 256, bias bq_0).
+int launch_stage_a_matrix(Handle* h, const void* A16, int64_t rows, int which, const float* q0_arg, void* out, bool p16,
+                          cudaStream_t s) {
+  using namespace sa;
+  const int cta_group = stage_a_cta_group();
+  const int wm = kPatchW * cta_group;  // "image" width: one CTA (pair) tile per row of tiles
+  if (rows <= 0 || rows % (kPatchH * wm) != 0) return fail(h, DIINN_ERR_BAD_SHAPE, "stage A (matrix): rows must be a multiple of the tile");
+  const int nblocks = which == 0 ? 4 : 1;
+  const int ci = cta_group - 1;
+  CUtensorMap tmF, tmP;
+  const uint64_t hrows = static_cast<uint64_t>(rows / wm);
+  const uint64_t dims[4] = {static_cast<uint64_t>(kUnfold), static_cast<uint64_t>(wm), hrows, 1};
+  const uint64_t strides[3] = {kUnfold * 2ull, static_cast<uint64_t>(wm) * kUnfold * 2ull, static_cast<uint64_t>(rows) * kUnfold * 2ull};
+  const uint32_t box[4] = {kC, kPatchW, kPatchH, 1};
+  int rc = make_tmap_4d_bf16(h, &tmF, A16, dims, strides, box);
+  if (rc) return rc;
+  const uint64_t ncols = static_cast<uint64_t>(nblocks) * 256;
+  const uint64_t pdims[4] = {ncols, static_cast<uint64_t>(wm), hrows, 1};
+  const uint64_t pesz = p16 ? 2 : 4;
+  const uint64_t pstrides[3] = {ncols * pesz, static_cast<uint64_t>(wm) * ncols * pesz, static_cast<uint64_t>(rows) * ncols * pesz};
+  const uint32_t pbox[4] = {p16 ? 64u : 32u, kPatchW, 2, 1};
+  rc = p16 ? make_tmap_4d_bf16(h, &tmP, out, pdims, pstrides, pbox) : make_tmap_4d_f32(h, &tmP, out, pdims, pstrides, pbox);
+  if (rc) return rc;
+  static thread_local BiasParams bias;
+  if (which == 0) memcpy(bias.b, h->bA_host, sizeof(float) * kPCols);
+  else memcpy(bias.b, h->small.bq[0], sizeof(float) * kD);
+  Geo g{};
+  g.B = 1, g.H = static_cast<int>(hrows), g.W = wm, g.fr0 = 0, g.lr_row0 = 0, g.lr_rows = static_cast<int>(hrows);
+  g.tiles_y = static_cast<int>(hrows / kPatchH);
+  g.n_txp = 1;
+  g.no_relu0 = which == 0 ? 0 : 1;
+  g.matrix = 1, g.nblocks = nblocks, g.q0_arg = q0_arg;
+  const CUtensorMap& tmW = which == 0 ? h->tmapWA[0][ci] : h->tmapWQ0A[ci];
+  return launch_sa_core(h, g, g.tiles_y, cta_group, kFmtBf16, p16, tmF, tmF, tmW, tmW, tmP, bias, s);
 }
 
 }  // namespace diinn

@@ -142,8 +142,8 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
     rc.valid = oh < s.row1 && ow < s.W_up;
     const int ohc = min(oh, s.row1 - 1), owc = min(ow, s.W_up - 1);
     const int ih = axis_index(s.ax_h, ohc), iw = axis_index(s.ax_w, owc);
-    if constexpr (kPix) {
-      rc.prow = P + (static_cast<size_t>(b * (s.row1 - s.row0) + (ohc - s.row0)) * s.W_up + owc) * kPCols;
+    if constexpr (kPix) {  // one fp16 row per HR pixel (float pointer, half the pitch: see load16h)
+      rc.prow = P + (static_cast<size_t>(b * (s.row1 - s.row0) + (ohc - s.row0)) * s.W_up + owc) * (kPCols / 2);
     } else if constexpr (kSel) {  // fp16 P: half the row pitch in bytes (kept as a float pointer; see p16row())
       rc.prow = P + static_cast<size_t>((b * s.lr_rows + (ih - s.lr_row0)) * s.W + iw) * (kPCols / 2);
       int ih0, iw0;
@@ -242,10 +242,11 @@ __device__ __forceinline__ void prefetch_tile_rows(const PixelSource& s, const v
   }
 }
 
-// kPix (init_q=True): the tile's own P rows -- 16 consecutive pixels x 4 KB per patch row -- in 16 KB pieces, one per lane
+// kPix (init_q=True): the tile's own P rows -- 16 consecutive pixels x 2 KB (fp16) per patch row -- in 8 KB pieces, one per lane
 template <int CG>
-__device__ __forceinline__ void prefetch_tile_pixels(const PixelSource& s, const float* __restrict__ P, const Work& wk,
+__device__ __forceinline__ void prefetch_tile_pixels(const PixelSource& s, const void* __restrict__ Pv, const Work& wk,
                                                      int work, int rank, int lane) {
+  const char* P = static_cast<const char*>(Pv);
   const int per_img = wk.tiles_y * wk.n_txp;
   const int b = work / per_img;
   const int rem = work - b * per_img;
@@ -258,8 +259,8 @@ __device__ __forceinline__ void prefetch_tile_pixels(const PixelSource& s, const
   for (int i = lane; i < nrows * segs; i += 32) {
     const int r = i / segs, c0 = (i % segs) * 4;
     const int nc = min(4, ncols - c0);
-    prefetch_l2_bulk(P + (static_cast<size_t>(b * (s.row1 - s.row0) + (oh0 + r - s.row0)) * s.W_up + ow0 + c0) * kPCols,
-                     static_cast<uint32_t>(nc) * kPCols * 4u);
+    prefetch_l2_bulk(P + (static_cast<size_t>(b * (s.row1 - s.row0) + (oh0 + r - s.row0)) * s.W_up + ow0 + c0) * (kPCols * 2u),
+                     static_cast<uint32_t>(nc) * kPCols * 2u);
   }
 }
 
@@ -358,9 +359,18 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
   }
   const float* k0 = kSel ? k0h : reinterpret_cast<const float*>(k0v);
   uint32_t pk[8], pl[8];
-  if constexpr (kPix) {  // init_q=True: Q.0 reads the 576-wide gate, so q_0 was finished per pixel by csrc/init_q.cu
+  if constexpr (kPix) {  // init_q=True: Q.0 reads the 576-wide gate, so q_0 was finished per pixel (fp16) by csrc/init_q.cu
+    const uint32_t* raw = reinterpret_cast<const uint32_t*>(k0v);
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_op<FMT>(k0[j], k0[j + 1]);
+    for (int j = 0; j < 8; ++j) {
+      if constexpr (FMT == 1) {
+        pk[j] = raw[j];
+      } else {
+        float a, b;
+        unpack_f16x2(raw[j], a, b);
+        pk[j] = pack_op<FMT>(a, b);
+      }
+    }
   } else if constexpr (kLiif) {
     // LIIF's imnet, first Linear(580, 256) + ReLU (mlp.py:9-12): the 576 feature columns were applied per LR cell by stage A
     // (k0 = W1[:, :576] x_l + b1, no ReLU there); the four coordinate columns (rel_h, rel_w, cell_h H, cell_w W) are per query
@@ -431,14 +441,21 @@ __device__ __forceinline__ void epi_load(uint32_t tslot, int col, Raw& raw) {  /
 // kx = the matching slice of P (prefetched). kLast: accumulate the RGB projection instead of writing the next A operand.
 // kDump (mode 4): q_3 goes to HBM for the 3x3 last conv -- bf16 (q3row) from the 16-bit-operand formats, fp32 (q3row_f) from
 // the split format.
-template <bool kLast, int FMT, bool kDump = false, bool kSel = false, bool kLiif = false>
+// kPix: the P slice arrives as 16 fp16 values (per-pixel fp16 rows of init_q=True) instead of 16 fp32.
+template <bool kLast, int FMT, bool kDump = false, bool kSel = false, bool kLiif = false, bool kPix = false>
 __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int layer, int h, int c, int wg, int r,
                                          const SmallParams& sp, const float4 (&kxv)[4], float (&rgb)[3],
                                          __nv_bfloat16* q3row = nullptr, float* q3row_f = nullptr) {
   constexpr bool kSplit = FMT == 2;
   const int col = c * 64 + wg * 16;
   const int f0 = h * 128 + col;
-  const float* kx = reinterpret_cast<const float*>(kxv);
+  float kxh[16];
+  if constexpr (kPix) {
+    const uint32_t* raw = reinterpret_cast<const uint32_t*>(kxv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) unpack_f16x2(raw[j], kxh[2 * j], kxh[2 * j + 1]);
+  }
+  const float* kx = kPix ? kxh : reinterpret_cast<const float*>(kxv);
   uint32_t pk[8], pl[8];
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
@@ -582,7 +599,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // ===================== weight producer (+ L2 prefetch of upcoming tiles' P rows) =====================
     uint32_t it = 0, sel_it = 0;
     auto prefetch = [&](int w_) {
-      if constexpr (kPix) prefetch_tile_pixels<CG>(src, static_cast<const float*>(P), wk, w_, rank, lane);
+      if constexpr (kPix) prefetch_tile_pixels<CG>(src, P, wk, w_, rank, lane);
       else prefetch_tile_rows<CG, kSel ? 2 : 4>(src, P, wk, w_, rank, lane);
     };
     // one weight stage: tile s24 of the (layer-1, half, kc) sequence out of map tm
@@ -792,10 +809,12 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // (select variant: nb counts fp16 elements of the P16 row, and asel >= 0 names the A_sel buffer this tile's one-hot
     // rows go to, written before K-chunk 0 is signalled)
     auto load_p = [&](const float* q, float4 (&v)[4]) {
-      if constexpr (kSel) load16h(reinterpret_cast<const uint16_t*>(q), v);
+      if constexpr (kSel || kPix) load16h(reinterpret_cast<const uint16_t*>(q), v);
       else load16(q, v);
     };
-    constexpr int kP64 = kSel ? 32 : 64;  // 64 P columns, in units of the float pointer that carries the row
+    constexpr bool kHalfP = kSel || kPix;     // fp16 P rows: every column offset of the float pointer halves
+    constexpr int kPD = kHalfP ? 2 : 1;
+    constexpr int kP64 = 64 / kPD;            // 64 P columns, in units of the float pointer that carries the row
     auto layer0_unit = [&](int bufidx, int kc0, const RowCtx& rcx, const float* nb, int asel = -1) {
       const uint32_t buf = act0 + bufidx * kActBytes;
       if constexpr (kSel) {
@@ -829,18 +848,18 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
     if (work < wk.n_work) {
       rc = make_row<CG, kPix, kSel, kLiif>(src, out, P, wk, work, rank, r, fg == 0);
-      const float* p0 = rc.prow + fg * (kSel ? 8 : 16);
+      const float* p0 = rc.prow + fg * (16 / kPD);
       load_p(p0, ka);
       load_p(p0 + kP64, kb);
       layer0_unit(0, 0, rc, p0 + 2 * kP64, 0);  // first tile -> buffer 0 (A_sel buffer 0)
-      layer0_unit(0, 2, rc, kSel ? nullptr : p0 + kD);
+      layer0_unit(0, 2, rc, kSel ? nullptr : p0 + kD / kPD);
     }
     for (; work < wk.n_work; work += n_units, ++t) {
       const int X = t & 1;
       const int next_work = work + n_units;
       const bool has_next = next_work < wk.n_work;
       RowCtx rc_next{};
-      const float* const pw = rc.prow + fg * (kSel ? 8 : 16);  // this warp's column of the tile row's P entry
+      const float* const pw = rc.prow + fg * (16 / kPD);  // this warp's column of the tile row's P entry
       const float* pn = nullptr;                               // same for the next tile
       float rgb[3] = {0.f, 0.f, 0.f};  // this warp's share of the RGB projection (scalar FFMA: measured faster than FFMA2 here)
       // mode 4: this row's q_3 vector in the dump buffer (rows outside the image / band get no store target)
@@ -856,7 +875,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         const bool last = layer == 3;
         if (layer == 2 && has_next) {
           rc_next = make_row<CG, kPix, kSel, kLiif>(src, out, P, wk, next_work, rank, r, fg == 0);
-          pn = rc_next.prow + fg * (kSel ? 8 : 16);
+          pn = rc_next.prow + fg * (16 / kPD);
           if constexpr (kSel) {  // only layer 0 reads P here: the next tile's first two k_0 slices, a whole layer ahead
             load_p(pn, ka);
             load_p(pn + kP64, kb);
@@ -874,13 +893,13 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           // this warp has itself consumed tmem_full[1] of layer 2. Its four chunks are interleaved with layer 3's halves.
           if (last && has_next) {
             if constexpr (kSel) layer0_unit(X ^ 1, 2 * h, rc_next, h == 0 ? pn + 2 * kP64 : nullptr, h == 0 ? ((t + 1) & 1) : -1);
-            else layer0_unit(kSplit ? 0 : (X ^ 1), 2 * h, rc_next, pw + 3 * kD + h * 128);
+            else layer0_unit(kSplit ? 0 : (X ^ 1), 2 * h, rc_next, pw + (3 * kD + h * 128) / kPD);
           }
           // unit after this one: the other half / the next layer / layer 0 of the next tile / the next tile's layer 1
           const float* nb;
           if constexpr (kSel) nb = nullptr;  // the accumulators arrive with P[l] and bq in them
-          else if (!last) nb = (h == 0) ? pw + layer * kD + 128 : (layer == 1 || !has_next) ? pw + (layer + 1) * kD : pn;
-          else nb = has_next ? (h == 0 ? pn + 128 : pn + kD) : (h == 0 ? pw + 3 * kD + 128 : nullptr);
+          else if (!last) nb = (h == 0) ? pw + (layer * kD + 128) / kPD : (layer == 1 || !has_next) ? pw + (layer + 1) * kD / kPD : pn;
+          else nb = has_next ? (h == 0 ? pn + 128 / kPD : pn + kD / kPD) : (h == 0 ? pw + (3 * kD + 128) / kPD : nullptr);
           const uint32_t tslot = tlane + h * 256;
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5);
           mbar_wait(&sm.tmem_full[h], full_uses & 1);
@@ -895,8 +914,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 0);
 #endif
-          if (last) epi_math<true, FMT, kDump, kSel, kLiif>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row, q3row_f);
-          else epi_math<false, FMT, false, kSel, kLiif>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
+          if (last) epi_math<true, FMT, kDump, kSel, kLiif, kPix>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb, q3row, q3row_f);
+          else epi_math<false, FMT, false, kSel, kLiif, kPix>(ra, out_base, layer, h, 0, fg, r, sp, ka, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 1);
 #endif
@@ -906,7 +925,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             __syncwarp();
             if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h]);
           }
-          if (nb) load16(nb, ka);  // after the fence (see layer0_unit)
+          if (nb) load_p(nb, ka);  // after the fence (see layer0_unit)
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 2);
           tmem_ld_wait();
 #if DIINN_FINE_TRACE
@@ -916,8 +935,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
           __syncwarp();
           if (lane == 0) signal<CG>(&sm.tmem_empty[h]);
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 4);
-          if (last) epi_math<true, FMT, kDump, kSel, kLiif>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row, q3row_f);
-          else epi_math<false, FMT, false, kSel, kLiif>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
+          if (last) epi_math<true, FMT, kDump, kSel, kLiif, kPix>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb, q3row, q3row_f);
+          else epi_math<false, FMT, false, kSel, kLiif, kPix>(rb, out_base, layer, h, 1, fg, r, sp, kb, rgb);
 #if DIINN_FINE_TRACE
           if (tracer && layer == 2) DIINN_TR(t, 96 + h * 8 + 3);
 #endif
@@ -926,7 +945,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             __syncwarp();
             if (lane == 0) signal<CG>(&sm.act_ready[bout][2 * h + 1]);
           }
-          if (nb) load16(nb + 64, kb);
+          if (nb) load_p(nb + kP64, kb);
           if (tracer) DIINN_TR(t, 64 + (layer - 1) * 10 + h * 5 + 3);
         }
         ++full_uses;
@@ -1044,14 +1063,14 @@ Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, 
     wk.n_work = static_cast<int>((total + kTileM * cta_group - 1) / (kTileM * cta_group));
     return pl;
   }
-  // Select variant: CTA pairs, 16-bit formats, LR-resolution P that no LR chain rewrites, and a pair patch of <= 30 LR cells.
+  // Select variant: CTA pairs, 16-bit formats, LR-resolution P (modes 1 / 2: the K chain updates the fp16 P), a pair patch of <= 30 LR cells.
   // Whether it applies must NOT depend on the row range or the patch shape a launch ends up with: row tiles of one image
   // have to be bit-identical to the full decode, and the two variants differ in the last bits (fp16 P added inside the
   // tensor core vs fp32 P added by the epilogue). So the decision is taken for the DEFAULT patch shape from a bound that
   // only knows the scale factors -- n pixels of an axis touch at most floor((n - 1) * n_in / n_up) + 2 source cells -- and
   // the wave-count search below only considers shapes on the same side of it.
   static const int env_nosel = env_int("DIINN_NO_SEL", 0);
-  const bool sel_candidate = cta_group == 2 && fmt != kFmtSplit && !pix && !chain_mode && !env_nosel;
+  const bool sel_candidate = cta_group == 2 && fmt != kFmtSplit && !pix && !env_nosel;
   auto box_of = [&](int l2, int max_rows, int& br, int& bc) {
     const int pw = 1 << l2, ph = kTileM >> l2;
     br = static_cast<int>(floor(static_cast<double>(ph - 1) * src.H / src.H_up)) + 2;
