@@ -295,8 +295,6 @@ void diinn_destroy(diinn_handle* h) {
   cudaFree(h->WL27frag);
   cudaFree(h->WF4);
   cudaFree(h->WQ0_32);
-  cudaFree(h->WAg16);
-  cudaFree(h->WQ0g16);
   cudaFree(h->WQ0A16);
   cudaFree(h->WH16);
   cudaFree(h->psnr_acc);

@@ -172,12 +172,6 @@ struct ChainEpilogue {
   long long m0, rows;       // first P row of this chunk / valid rows in it
   int layer;
   int p16;                  // P holds fp16 rows (stage B's select-MMA variant): read-modify-write in fp16
-  // init_q=True (csrc/init_q.cu), plain D output: D[r][n] = acc + add_bias[n], ReLU on columns < relu_cols, and with q0_arg
-  // the first 256 columns are multiplied by sin(q0_arg[r][n] + q0_bias[n])  (q_0 = k_0 * sin(Q.0 s + bq_0))
-  const float* add_bias;    // nullptr: D = acc
-  int relu_cols;
-  const float* q0_arg;      // (M, 256) or nullptr
-  const float* q0_bias;
 };
 
 struct Handle;  // defined in handle.h

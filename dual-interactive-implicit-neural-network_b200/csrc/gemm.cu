@@ -184,44 +184,17 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             *reinterpret_cast<uint4*>(arow + c0 + 8 * j) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
       }
-    } else
-    {
-      // init_q=True (ce.add_bias): the per-pixel pre-activations are finished here -- bias, ReLU on the k_0 block and, in
-      // the first N tile, the product with sin(QS + bq_0). All of it warp-uniform; the operand loads of a 16-column step
-      // are issued while its TMEM load is in flight.
-      const bool fuse = ce.add_bias != nullptr;
-      const bool q0 = fuse && ce.q0_arg != nullptr && n0 < kD;
-      const size_t rq = static_cast<size_t>(row < M ? row : M - 1) * kD;
+    } else {
+      // plain GEMM (the tcgen05 self-test / probe entry): D = acc
       for (int c0 = 0; c0 < 256; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-        float4 bv[4], tv[4];
-        if (fuse) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bv[j] = __ldg(reinterpret_cast<const float4*>(ce.add_bias + n0 + c0) + j);
-        }
-        if (q0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(ce.q0_arg + rq + c0) + j);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(ce.q0_bias + c0) + j);
-            tv[j] = make_float4(t.x + b.x, t.y + b.y, t.z + b.z, t.w + b.w);
-          }
-        }
         tmem_ld_wait();
         if (row < M) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                   __uint_as_float(v[4 * j + 3]));
-            if (fuse) {
-              o.x += bv[j].x, o.y += bv[j].y, o.z += bv[j].z, o.w += bv[j].w;
-              if (n0 + c0 < ce.relu_cols)
-                o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            }
-            if (q0) o.x *= __sinf(tv[j].x), o.y *= __sinf(tv[j].y), o.z *= __sinf(tv[j].z), o.w *= __sinf(tv[j].w);
-            *reinterpret_cast<float4*>(drow + c0 + 4 * j) = o;
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(drow + c0 + 4 * j) = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
       }
     }

@@ -66,8 +66,6 @@ struct Handle {
   // channel order (k' = tap*64 + c): the x-facing K blocks (1024, 576) and Q.0 (256, 576)
   float* WF4 = nullptr;
   float* WQ0_32 = nullptr;
-  __nv_bfloat16* WAg16 = nullptr;
-  __nv_bfloat16* WQ0g16 = nullptr;
   __nv_bfloat16* WQ0A16 = nullptr;   // Q.0 (256,576) in stage A's (tap, row, channel) tile order: matrix-mode stage A on the gate
   CUtensorMap tmapWQ0A[2]{};         // [cta_group - 1]
   SmallParams small{};            // host copy; passed by value to kernels

@@ -8,16 +8,18 @@
 //   gate     S  = s_p,  XG = s_p * x_l(p)                          (chunk x 576 each; x gathered with the nearest-exact
 //                                                                   index, zero-padded 3x3 neighbourhood)
 //   GEMM     PX = XG . WA^T   (chunk x 1024: the x-facing blocks of K.0..3)      QS = S . Q0^T   (chunk x 256)
-//   assemble PX += bk;  PX[:, :256] = relu(.) = k_0        (tensor path: fused into the GEMM's epilogue, with q_0 below)
-//   (modes 1 / 2: the k-fed chain of csrc/lr_chain.cu, now over HR pixels:  PX_i += WH_i . relu(PX_{i-1}))
-//   q_0      PX[:, :256] *= sin(QS + bq_0)
+//   assemble PX += bk;  PX[:, :256] = relu(.) = k_0;  q_0: PX[:, :256] *= sin(QS + bq_0)
+//   (modes 1 / 2: the k-fed chain of csrc/lr_chain.cu, now over HR pixels:  PX_i += WH_i . relu(PX_{i-1}), before q_0)
 //   stage B  layers 1..3 and the last layer exactly as without init_q, reading ONE PX ROW PER PIXEL (kPix variants of
 //            stage_b_umma_kernel / per_pixel_p in the fp32 kernels) and taking q_0 as given.
 //
-// fp32 path: CUDA-core SGEMMs in the reference's channel order (c*9 + tap). Tensor path: bf16 operands in tap-major order
-// (tap*64 + c, so the gate reads whole 128-byte channel vectors of the NHWC feature copy), the library's tcgen05 GEMM
-// (gemm.cu), fp32 PX / QS. Executed arithmetic: 2 264 064 FLOP per HR pixel (nothing is shared between pixels).
-// Correct and on the tensor cores, not tuned: PX / XG / S round-trip through L2 / HBM (about 10 KB per pixel).
+// fp32 path: CUDA-core SGEMMs in the reference's channel order (c*9 + tap), separate assemble / q_0 kernels. Tensor path
+// (run_initq_umma): bf16 gate operands in tap-major order (tap*64 + c, so the gate reads whole 128-byte channel vectors of
+// the NHWC feature copy and stage A's weight tiles serve unchanged); both products run on the STAGE-A KERNEL in matrix mode
+// (stage_a_umma.cu: persistent, 6-stage TMA ring, TMA-store epilogue) with bias, ReLU and the q_0 product fused into the
+// epilogue; PX is written once, as fp16 rows (2 KB per pixel), QS as fp32. Executed arithmetic: 2 264 064 FLOP per HR pixel
+// (nothing is shared between pixels). What still round-trips through L2 / HBM per pixel: S, XG (1.1 KB each), PX (2 KB),
+// QS (1 KB) -- a single persistent kernel that keeps XG in shared memory is the remaining step.
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -27,7 +29,8 @@
 
 namespace diinn {
 
-constexpr int64_t kInitQChunkUmma = 148 * 128 * 2;  // HR pixels per tensor-path chunk: two waves of stage-B tiles
+constexpr int64_t kInitQChunkUmma = 148 * 128 * 8;  // HR pixels per tensor-path chunk: eight waves of stage-B tiles (measured on
+                                                    // c3: 2 waves 11.4 ms, 4: 10.4, 8: 8.9, 16: 9.6 -- launch tails vs L2 residency of PX)
 constexpr int64_t kInitQChunkFp32 = 1 << 15;        // HR pixels per fp32-path chunk
 
 // ---------------------------------------------------------------------------------------------------------
@@ -295,7 +298,7 @@ InitQPlan plan_initq(int B, int W_up, int rows, int compute, int mode, size_t of
   p.off_XG = off;
   off += align_up(static_cast<size_t>(p.rows_pad) * kUnfold * el);
   p.off_PX = off;
-  off += align_up(static_cast<size_t>(p.rows_pad) * kPCols * sizeof(float));
+  off += align_up(static_cast<size_t>(p.rows_pad) * kPCols * (fp32 ? sizeof(float) : sizeof(__half)));  // tensor path: fp16 rows
   p.off_QS = off;
   off += align_up(static_cast<size_t>(p.rows_pad) * kD * sizeof(float));
   if (fp32) {

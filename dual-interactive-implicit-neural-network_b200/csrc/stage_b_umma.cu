@@ -34,9 +34,10 @@
 // Select-MMA variant (template kSel; grid decodes whose CTA-pair patch touches at most 30 LR cells, i.e. scale factors from
 // about x3.6 up -- c1, c2x4, c3, c4): the two ADDS of every epilogue element move into the tensor core. relu(accK + P[l]) needs
 // the LR cell's hoisted row P[l]; sin(accQ + bq) needs the Q bias. Both are linear in a one-hot row vector: with
-//   A_sel[row]  = e_slot(l(row)) + e_bias_hi + e_bias_lo                 (128 x K_sel fp16, K_sel = 16 or 32, built per tile)
-//   B_sel       = [ P16 rows of the pair's LR patch ; 0 ; 0 ]  for the K-branch columns (one TMA 4-D box out of the fp16 P
-//                 stage A writes for this variant), [ 0 ; bq_hi ; bq_lo ] for the Q-branch columns (constant table)
+//   A_sel[row]  = e_slot(l(row))                                         (128 x K_sel fp16, K_sel = 16 or 32, built per tile)
+//   B_sel       = [ P16 rows of the pair's LR patch ]  for the K-branch columns (one TMA 4-D box out of the fp16 P stage A
+//                 writes for this variant), [ fp16(bq) in EVERY row ] for the Q-branch columns (constant table: whichever slot
+//                 a row selects, it picks up the bias once)
 // one or two extra K = 16 MMAs per half slot (MN-major B: a P row IS a row of N values) pre-load the accumulators with
 // P[l] and bq, and the epilogue shrinks to relu(accK) * sin(accQ): no P loads, no bias loads, two adds fewer per pair.
 //
@@ -97,7 +98,7 @@ struct Work {
   int n_work;          // work items per CTA pair (CG=2) / CTA (CG=1)
   int tiles_y, n_txp;  // grid mode
   int pw_log2;         // log2 of the patch width in pixels (3..6); patch height = 128 >> pw_log2
-  int ksel;            // select variant: K_sel (16 or 32); slots [0, box_r*box_c) = LR cells of the pair's patch, the last two = bias
+  int ksel;            // select variant: K_sel (16 or 32) >= box_r*box_c; slot = LR cell of the pair's patch
   int box_r, box_c;    // select variant: LR rows x columns of the TMA box that fetches a pair's P16 patch
   uint32_t sel_lbo, sel_sbo, sel_kstep;  // select variant: B_sel descriptor strides (bytes): 64-feature blocks, 8-row K groups,
                                          // and the start-address step of the second K = 16 MMA
@@ -819,15 +820,14 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       const uint32_t buf = act0 + bufidx * kActBytes;
       if constexpr (kSel) {
         if (asel >= 0) {
-          // this row's A_sel: 1.0 at its LR cell's slot and at the two bias slots (K_sel-2: bq_hi, K_sel-1: bq_lo); this
-          // warp writes 16-byte unit fg = slots [8 fg, 8 fg + 8) of the 64-byte row (64B swizzle: unit ^= (row >> 1) & 3)
+          // this row's A_sel: 1.0 at its LR cell's slot; this warp writes 16-byte unit fg = slots [8 fg, 8 fg + 8) of the
+          // 64-byte row (64B swizzle: unit ^= (row >> 1) & 3)
           uint32_t w[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int s0 = 8 * fg + 2 * j;
             w[j] = (rcx.slot == s0 ? 0x3C00u : 0u) | (rcx.slot == s0 + 1 ? 0x3C000000u : 0u);
           }
-          if (fg == (wk.ksel >> 3) - 1) w[3] = 0x3C003C00u;
           st_shared_v4(asel0 + asel * kASelBytes + r * 64 + ((fg ^ ((r >> 1) & 3)) << 4), w[0], w[1], w[2], w[3]);
         }
       }
@@ -1034,6 +1034,13 @@ static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap&
 
 namespace {
 
+// host twin of axis_index() (common.cuh): one rounded fp32 multiply, then floorf
+inline int host_axis_index(const AxisParams& p, int j) {
+  volatile float t = (static_cast<float>(j) + 0.5f) * p.scale;
+  const int i = static_cast<int>(floorf(t));
+  return i < p.n_in - 1 ? i : p.n_in - 1;
+}
+
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -1107,7 +1114,24 @@ Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, 
   wk.n_work = src.B * wk.tiles_y * wk.n_txp;
   if (pl.sel) {
     box_of(wk.pw_log2, src.lr_rows, wk.box_r, wk.box_c);  // (the P16 tensor of this launch holds lr_rows LR rows)
-    wk.ksel = wk.box_r * wk.box_c + 2 <= 16 ? 16 : 32;
+    // The bound above decides WHETHER the variant runs; the box itself is the exact extent of this launch's patches (x4 with
+    // aligned 8 x 32 patches: 2 x 8 = 16 cells where the bound says 27), which is what picks one or two K = 16 select MMAs.
+    // Unselected slots multiply zeros, so K_sel does not change a single bit of the result.
+    int er = 1, ec = 1;
+    for (int ty = 0; ty < wk.tiles_y; ++ty) {
+      const int a = src.row0 + ty * ph, b = (a + ph - 1 < src.row1 - 1) ? a + ph - 1 : src.row1 - 1;
+      const int n = host_axis_index(src.ax_h, b) - host_axis_index(src.ax_h, a) + 1;
+      er = n > er ? n : er;
+    }
+    for (int tx = 0; tx < wk.n_txp; ++tx) {
+      const int a = (tx * cta_group * pw < src.W_up - 1) ? tx * cta_group * pw : src.W_up - 1;
+      const int b = (a + cta_group * pw - 1 < src.W_up - 1) ? a + cta_group * pw - 1 : src.W_up - 1;
+      const int n = host_axis_index(src.ax_w, b) - host_axis_index(src.ax_w, a) + 1;
+      ec = n > ec ? n : ec;
+    }
+    wk.box_r = er < wk.box_r ? er : wk.box_r;
+    wk.box_c = ec < wk.box_c ? ec : wk.box_c;
+    wk.ksel = wk.box_r * wk.box_c <= 16 ? 16 : 32;
     // B_sel tile of one CTA: two 64-feature blocks of K_sel rows x 128 B; MN-major SWIZZLE_128B atoms are 8 K-rows (1 KB)
     wk.sel_lbo = static_cast<uint32_t>(env_int("DIINN_SEL_LBO", wk.ksel * 128));
     wk.sel_sbo = static_cast<uint32_t>(env_int("DIINN_SEL_SBO", 1024));
