@@ -460,6 +460,22 @@ def main():
                 extra[f"{args.workload}_mode{mode}_init_q{int(init_q)}"] = time_decoder(d2, args.workload, n_it=3)
                 d2.release()
                 del d2
+            # LIIF-proper decoding (the reference's own LIIF imnet on the same kernels): LIIF.forward from the encoder output
+            # on, local ensemble (4 evaluations per query) and plain, on a 256x256 -> 1024x1024 grid (informative)
+            for ens in (True, False):
+                lq = diinn_b200.load_liif_imnet(diinn_b200.FusedLIIFQuery(local_ensemble=ens, precision=args.precision if
+                                                args.precision != "fp32_simt" else "fp32"),
+                                                {"imnet." + k: v for k, v in synth.make_liif_weights(1).items()}).to(dev)
+                b, h, w, hu, wu = synth.CONFIGS["c2x4"]
+                xl = torch.from_numpy(synth.make_feat(1, b, h, w)).to(dev)
+                coord, cell = lq.make_coord_and_cell(xl, (hu, wu))
+                for _ in range(2):
+                    lq.query_rgb(xl, coord, cell)
+                ms = timed(lambda: lq.query_rgb(xl, coord, cell), 5, torch.cuda.synchronize)
+                extra["liif_c2x4_ensemble" if ens else "liif_c2x4_plain"] = {
+                    "ms": round(ms, 4), "queries_per_s": b * hu * wu / ms * 1e3, "imnet_evals_per_s": b * hu * wu * (4 if ens else 1) / ms * 1e3}
+                lq.release()
+                del lq, xl, coord, cell
         torch.cuda.empty_cache()
 
     if rank != 0:
@@ -484,8 +500,9 @@ def main():
                             "symmetric-memory image buffers + 1 barrier per step)" if args.assembly == "fused" else
                             "assembly by in-place NCCL all_gather_into_tensor per channel"))
                         if world > 1 else "single GPU, whole image",
-            "l2": "no explicit flush: each step writes then re-reads the 708 MB fp32 LR pre-activation tensor P "
-                  "(5.6x the 126 MB L2) plus 33 MB of output, so no step finds its working set in L2",
+            "l2": ("no explicit flush: each step writes then re-reads the LR pre-activation tensor P (c3: 354 MB as fp16 on the "
+                   "16-bit operand paths, 708 MB as fp32 on the fp32 path: 2.8x / 5.6x the 126 MB L2) plus 33 MB of output, so "
+                   "no step finds its working set in L2"),
         },
         "ms_per_div2k_x4_image": ms_step if args.workload == "c3" else None,
         "ms_per_step_best": per_step[0], "ms_per_step_median": per_step[len(per_step) // 2],
@@ -517,7 +534,9 @@ def main():
         peak = peaks["bf16_burst"] if burst else peaks["bf16_sustained"]
         fmt = {"fp16": 1, "bf16": 0, "fp32": 2}[args.precision]
         line["roofline"] = {
-            "bound": "tensor", "kernel": f"stage_b_umma_kernel<2, {fmt}, false, false>", "achieved": ach, "peak": peak,
+            "bound": "tensor",
+            "kernel": f"stage_b_umma_kernel<CG=2, FMT={fmt}, kDump=0, kPix=0, kSel={int(terms == 1 and args.workload != 'c2x2' and args.workload != 'c2x3')}, kLiif=0>",
+            "achieved": ach, "peak": peak,
             "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": prof.get("dram_bytes_per_launch_c3") if args.workload == "c3" and world == 1 and terms == 1 else None,
             "traffic_source": prof.get("source"),
@@ -525,6 +544,7 @@ def main():
                                               "; sustained cuBLAS bf16 figure: the timed region lasts %.1f s" % (ms_total / 1e3)),
             "frac_of_burst_peak": ach / peaks["bf16_burst"], "frac_of_sustained_peak": ach / peaks["bf16_sustained"],
             "algorithmic_flop_per_px": FLOP_STAGE_B_PER_PX, "executed_tensor_flop_per_px": terms * FLOP_STAGE_B_PER_PX,
+            "select_mma_flop_per_px": (6 * 2 * 256 * 16 if terms == 1 and args.workload in ("c3", "c2x4") else None),
             "avg_launch_ms": ms_b,
             "kernel_share_of_step": {"layout_nhwc": kt["layout_ms"] / n / ms_step,
                                      "stage_a_umma": kt["stage_a_ms"] / n / ms_step,
