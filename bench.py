@@ -226,6 +226,17 @@ def time_eager_gpu_port(workload, steps=5, warmup=2, bsize=30000 * 16):
             "what": f"{what}, fp32 (cudnn TF32 convs at PyTorch's default), bsize={bsize}; not the product path"}
 
 
+L2_NOTE = ("no explicit flush: each step writes then re-reads the LR pre-activation tensor P (c3: 354 MB as fp16 on the 16-bit "
+           "operand paths, 708 MB as fp32 on the fp32 path: 2.8x / 5.6x the 126 MB L2) plus 33 MB of output, so no step finds its "
+           "working set in L2")
+
+
+def bench_config(workload):
+    """the `config` object -- identical for both arms (the reference arm runs on OUR arm's config) and for every N; what is
+    specific to an arm or to N (compute path, sharding) lives in the line's `path` object"""
+    return {"workload": workload_desc(workload), "io_dtype": "fp32 feature map in, fp32 image out", "l2": L2_NOTE}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -235,9 +246,9 @@ def run_reference(args):
         "impl": "reference", "metric": "HR query pixels/s", "value": r["mean_px_per_s"], "unit": "px/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": workload_desc(args.workload),
-                   "note": "CPU arm: each step is a bounded sample of the workload (see cpu_baseline.sample); px/s is the "
-                           "metric and the per-pixel work is uniform over the image"},
+        "config": bench_config(args.workload),
+        "path": {"note": "CPU arm: each step is a bounded sample of the workload (see cpu_baseline.sample); px/s is the metric "
+                         "and the per-pixel work is uniform over the image"},
         "cpu_baseline": {"value": r["mean_px_per_s"], "unit": "px/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"], "host_cpus": r["host_cpus"]},
         "e2e": {"value": r["mean_px_per_s"], "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -491,18 +502,14 @@ def main():
         "metric": "HR query pixels/s", "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {
-            "workload": workload_desc(args.workload),
-            "io_dtype": "fp32 feature map in, fp32 image out",
+        "config": bench_config(args.workload),
+        "path": {
             "compute": COMPUTE_DESC[args.precision],
             "sharding": (f"HR row tiles over {world} ranks, feature map and weights replicated, no data-path collective; "
                          + (f"assembly fused into stage B ({diinn_b200.sharding.last_fused_mode} over NVLink, two alternating "
                             "symmetric-memory image buffers + 1 barrier per step)" if args.assembly == "fused" else
                             "assembly by in-place NCCL all_gather_into_tensor per channel"))
                         if world > 1 else "single GPU, whole image",
-            "l2": ("no explicit flush: each step writes then re-reads the LR pre-activation tensor P (c3: 354 MB as fp16 on the "
-                   "16-bit operand paths, 708 MB as fp32 on the fp32 path: 2.8x / 5.6x the 126 MB L2) plus 33 MB of output, so "
-                   "no step finds its working set in L2"),
         },
         "ms_per_div2k_x4_image": ms_step if args.workload == "c3" else None,
         "ms_per_step_best": per_step[0], "ms_per_step_median": per_step[len(per_step) // 2],

@@ -27,6 +27,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["cores"] >= 1 and "c3" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "c3" in d["config"]["workload"]
+    # the reference arm runs on OUR arm's config: the same object, whatever the arm, the precision or N
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config("c3") and set(d["config"]) == {"workload", "io_dtype", "l2"}
 
 
 def test_reference_arm_other_ranks_exit_quietly():

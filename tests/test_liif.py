@@ -152,3 +152,21 @@ def test_handle_switches_between_liif_and_diinn_weights():
     bad = diinn_b200.FusedImplicitDecoder(mode=1).cuda()
     _, hb = bad._ensure_handle(x.device)
     assert lib.diinn_set_weights_liif(hb, C.byref(w), None) == -4      # hosted by a mode-3 handle only
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a GPU")
+@pytest.mark.parametrize("shape", [(1, 1, 1), (1, 1, 5), (2, 3, 1), (1, 2, 2)])
+def test_tiny_feature_maps(shape):
+    """degenerate LR grids (a single cell, single rows / columns): every shifted lookup clamps into the map"""
+    B, H, W = shape
+    weights = synth.make_liif_weights(4)
+    feat = synth.make_feat(51, B, H, W)
+    coord, cell = synth.make_query(53, B, 200, cell_hw=(2.0 / (3 * H), 2.0 / (3 * W)))
+    coord[:, :2] = np.float32([[-1.0, -1.0], [1.0, 1.0]])
+    for ens in (True, False):
+        want = orc.liif_query_rgb(weights, feat, coord, cell, local_ensemble=ens)
+        m = _module(weights, "fp32", ens).cuda()
+        with torch.no_grad():
+            out = m.query_rgb(torch.from_numpy(feat).cuda(), torch.from_numpy(coord).cuda(), torch.from_numpy(cell).cuda())
+        assert float(np.abs(out.cpu().numpy() - want).max()) <= TOL["fp32"], (shape, ens)
