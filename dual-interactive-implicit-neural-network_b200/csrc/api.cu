@@ -2,6 +2,7 @@
 // sits between them and the kernels: argument validation, workspace carving, TMA descriptor encoding.
 #include <cmath>
 #include <cstring>
+#include <exception>
 #include <new>
 #include <vector>
 
@@ -335,7 +336,7 @@ int diinn_set_weights(diinn_handle* h, const diinn_weights_f32* w, void* stream)
 //                       the four per-feature constants of stage B's layer 0 (SmallParams::wq0_p)
 //   Linear i (256,256), i = 1..3: the q-facing block of K.i, with zero x-facing columns, so P block i = b_i for every LR cell
 //   Q.1..3 = 0 (the kLiif instantiation of stage B ignores the gate), Linear 4 (3,256) = last_layer.
-int diinn_set_weights_liif(diinn_handle* h, const diinn_liif_weights_f32* w, void* stream) {
+static int set_weights_liif_impl(diinn_handle* h, const diinn_liif_weights_f32* w, void* stream) {
   if (!h || !w) return DIINN_ERR_BAD_ARG;
   for (int i = 0; i < 5; ++i)
     if (!w->weight[i] || !w->bias[i]) return fail(h, DIINN_ERR_BAD_ARG, "null weight pointer");
@@ -374,6 +375,14 @@ int diinn_set_weights_liif(diinn_handle* h, const diinn_liif_weights_f32* w, voi
   const int rc = pack_weights(h, &v, s);  // synchronises the stream before it returns: the host vectors may go
   h->liif = rc == DIINN_OK;
   return rc;
+}
+
+int diinn_set_weights_liif(diinn_handle* h, const diinn_liif_weights_f32* w, void* stream) {
+  try {  // the host-side repacking allocates: nothing may throw across the C ABI
+    return set_weights_liif_impl(h, w, stream);
+  } catch (const std::exception& e) {
+    return h ? fail(h, DIINN_ERR_BAD_ARG, std::string("diinn_set_weights_liif: ") + e.what()) : DIINN_ERR_BAD_ARG;
+  }
 }
 
 size_t diinn_workspace_bytes(const diinn_handle* h, int B, int H, int W, int H_up, int W_up, int row0, int row1,
