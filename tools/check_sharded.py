@@ -56,6 +56,31 @@ for name in ("c1", "c3"):
         same = bool(torch.equal(full, sh)) and bool(torch.equal(full, sh2)) and bool(torch.equal(x, src))
         ok &= same
         print(f"rank {rank}/{world} broadcast hand-off {name} {fmt}: bit-identical={same}", flush=True)
+# CUDA-graph replay of the fused sharded step (what bench.py's timed loop does at N > 1): two consecutive steps -- one per
+# symmetric image buffer -- captured once, replayed with NEW feature values in the same buffer
+B, H, W, H_up, W_up = synth.CONFIGS["c1"]
+x = torch.from_numpy(synth.make_feat(1, B, H, W)).to(dev)
+with torch.no_grad():
+    for _ in range(2):
+        diinn_b200.decode_sharded_fused(dec, x, (H_up, W_up), clone=False)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    g = torch.cuda.CUDAGraph()
+    try:
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+            diinn_b200.decode_sharded_fused(dec, x, (H_up, W_up), clone=False)
+            img = diinn_b200.decode_sharded_fused(dec, x, (H_up, W_up), clone=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        x.copy_(torch.from_numpy(synth.make_feat(2, B, H, W)))
+        dist.barrier()
+        g.replay()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(img, dec(x, (H_up, W_up))))
+    except Exception as e:  # report, do not hide
+        same = False
+        print(f"rank {rank} graph replay: EXCEPTION {type(e).__name__}: {e}", flush=True)
+ok &= same
+print(f"rank {rank}/{world} fused step replayed from a CUDA graph (new input values): bit-identical={same}", flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
