@@ -94,6 +94,16 @@ template <int CG, bool kSel>
 constexpr size_t smem_bytes() { return Cfg<CG, kSel>::kCtrlOff + sizeof(Smem); }
 static_assert(smem_bytes<2, true>() <= 232448 && smem_bytes<2, false>() <= 232448, "exceeds 227 KB of dynamic shared memory");
 
+// Layer-0 sine table (template kTab; integer scale factors with at most 16 phases, see Work::canon): up to 16 rows of
+// 256 fp16 values sin(Wq0 s_phase + bq0), 512 B each, in two 4 KB halves. The select variant with K_sel = 16 leaves the
+// upper half of its B_sel stage unused (the tile is 2 x 16 rows x 128 B), which holds phases 0..7; phases 8..15 (and, in
+// the classic variant, all of them) live behind struct Smem.
+constexpr int kTabHalf = 4096;
+template <int CG, bool kSel, bool kTab>
+constexpr size_t smem_bytes_tab() { return smem_bytes<CG, kSel>() + (kTab ? (kSel ? kTabHalf : 2 * kTabHalf) : 0); }
+static_assert(sizeof(Smem) % 16 == 0, "the sine table behind struct Smem is read with 16-byte loads");
+static_assert(smem_bytes_tab<2, true, true>() <= 232448 && smem_bytes_tab<2, false, true>() <= 232448, "exceeds 227 KB of dynamic shared memory");
+
 struct Work {
   int n_work;          // work items per CTA pair (CG=2) / CTA (CG=1)
   int tiles_y, n_txp;  // grid mode
@@ -102,6 +112,12 @@ struct Work {
   int box_r, box_c;    // select variant: LR rows x columns of the TMA box that fetches a pair's P16 patch
   uint32_t sel_lbo, sel_sbo, sel_kstep;  // select variant: B_sel descriptor strides (bytes): 64-feature blocks, 8-row K groups,
                                          // and the start-address step of the second K = 16 MMA
+  // Integer scale factors (H_up = s_h H, W_up = s_w W, 16-bit formats, grid decodes, s_h s_w <= 16): every HR pixel of
+  // phase (p_h, p_w) = (oh - s_h ih, ow - s_w iw) has the same relative coordinate (2p + 1)/s - 1 in exact arithmetic; the
+  // reference's fp32 values scatter around it by the rounding of its coordinate grids (5e-5 on a DIV2K image). With `canon`
+  // every pixel uses that closed form (canon_rel), so sin(Wq0 s_p + bq0) takes s_h s_w distinct rows, which the kTab
+  // instantiation evaluates ONCE per CTA into shared memory: layer 0 shrinks to q_0 = k_0 * table[phase] (no MUFU, no FMA).
+  int canon, s_h, s_w;
   int4* tap;           // debug (diinn_debug_stage_b_rows): per output pixel (ih, iw, bits(rel_h), bits(rel_w)) as THIS kernel
                        // derives them, indexed by the pixel's channel-0 output offset; nullptr in product calls
 };
@@ -109,12 +125,18 @@ struct Work {
 struct RowCtx {
   const float* prow;  // P row of this pixel's LR cell (select variant: the fp16 row, see p16row())
   int slot;           // select variant: index of the LR cell inside the pair's patch box
+  int phase;          // Work::canon: p_h * s_w + p_w
   float rel_h, rel_w, ratio;
   float area;  // ensemble rows: |rel_h * rel_w| + 1e-9
   float cell_w;  // kLiif only: rel_cell = cell * (H, W) (liif.py:107-110) travels as (ratio, cell_w)
   int64_t out_off;  // offset of channel 0
   bool valid;
 };
+
+// the relative coordinate of phase p of an integer scale factor s (Work::canon): fl(fl((2p + 1) / s) - 1)
+__device__ __forceinline__ float canon_rel(int p, int s) {
+  return __fadd_rn(__fdiv_rn(static_cast<float>(2 * p + 1), static_cast<float>(s)), -1.0f);
+}
 
 // kPix (init_q=True, csrc/init_q.cu): P holds one row per HR pixel of the launch's rows [row0,row1) -- pixel-major
 // (b, row, col) -- instead of one per LR cell, and the launch covers a chunk of the band whose first row is out_row0.
@@ -132,6 +154,7 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
   RowCtx rc;
   const float* P = static_cast<const float*>(Pv);
   rc.slot = 0;
+  rc.phase = 0;
   if (s.mode == 0) {
     const int per_img = wk.tiles_y * wk.n_txp;
     const int b = work / per_img;
@@ -156,8 +179,15 @@ __device__ __forceinline__ RowCtx make_row(const PixelSource& s, const OutSpec& 
 #if DIINN_ABL & 1
     rc.prow = P;
 #endif
-    rc.rel_h = axis_rel(s.ax_h, ohc, ih);
-    rc.rel_w = axis_rel(s.ax_w, owc, iw);
+    if (!kPix && wk.canon) {
+      const int p_h = ohc - ih * wk.s_h, p_w = owc - iw * wk.s_w;
+      rc.rel_h = canon_rel(p_h, wk.s_h);
+      rc.rel_w = canon_rel(p_w, wk.s_w);
+      rc.phase = p_h * wk.s_w + p_w;
+    } else {
+      rc.rel_h = axis_rel(s.ax_h, ohc, ih);
+      rc.rel_w = axis_rel(s.ax_w, owc, iw);
+    }
     rc.ratio = s.ratio;
     rc.out_off = b * o.batch_stride + static_cast<int64_t>(ohc - (kPix ? s.out_row0 : s.row0)) * o.row_stride + owc;
     if (wk.tap != nullptr && write_tap && rc.valid)
@@ -289,6 +319,10 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
 #ifndef DIINN_TRACE_BUILD
 #define DIINN_TRACE_BUILD DIINN_FINE_TRACE
 #endif
+// order of layer 0's stores, fences and k_0 fetches inside one unit (two K-chunks); see layer0_unit
+#ifndef DIINN_L0V
+#define DIINN_L0V 1
+#endif
 
 // 16 fp32 values (64 B) of a P row as two 256-bit loads (LDG.E.256): a warp's 32 rows sit in ~8 LR cells 4 KB apart, so every
 // load instruction costs ~8 L1 wavefronts whatever its width -- half the instructions of four 128-bit loads
@@ -346,9 +380,14 @@ __device__ __forceinline__ uint32_t pack_residual(float a, float b, uint32_t hi1
 
 // layer 0 for K-chunk kc, features [64kc + 16wg, +16) of row r -> act buffer. k0 = P[l][those features] (prefetched).
 // Split formats write the fp16 residual into the lo half of the buffer (same swizzled position, kActBytes further on).
-template <int FMT, bool kPix = false, bool kSel = false, bool kLiif = false>
+// kTab: sin(Wq0 s_p + bq0) comes out of the CTA's phase table (tab_row = this pixel's 512-byte row, tab_key = phase & 7: the
+// 16-byte units of a row are XOR-swizzled by the phase so that the 8 phases a warp touches hit 8 different bank groups).
+// canon (kSel, bf16 operands only): the sine is rounded to fp16 first, as the table holds it, so that row tiles which must
+// compute (K_sel = 32: no room for the table) stay bit-identical to those which look it up.
+template <int FMT, bool kPix = false, bool kSel = false, bool kLiif = false, bool kTab = false>
 __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, int r, const RowCtx& rc,
-                                            const SmallParams& sp, const float4 (&k0v)[4]) {
+                                            const SmallParams& sp, const float4 (&k0v)[4], uint32_t tab_row = 0,
+                                            int tab_key = 0, bool canon = false) {
   constexpr bool kSplit = FMT == 2;
   const uint32_t chunk_base = act_base + kc * kChunkBytes;
   const int f0 = kc * 64 + wg * 16;
@@ -388,6 +427,23 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
       pk[j >> 1] = pack_op<FMT>(qx, qy);
       if constexpr (kSplit) pl[j >> 1] = pack_residual(qx, qy, pk[j >> 1]);
     }
+  } else if constexpr (kTab) {
+    uint32_t tv[8];
+    const int u0 = kc * 8 + wg * 2;  // first 16-byte unit (8 features) of this step's 16 features
+    ld_shared_v4(tab_row + (((u0) ^ tab_key) << 4), tv[0], tv[1], tv[2], tv[3]);
+    ld_shared_v4(tab_row + (((u0 + 1) ^ tab_key) << 4), tv[4], tv[5], tv[6], tv[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if constexpr (kSel && FMT == 1) {
+        const uint32_t k0raw = reinterpret_cast<const uint32_t*>(k0v)[j];
+        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pk[j]) : "r"(k0raw), "r"(tv[j]));
+      } else {
+        float sx, sy;
+        unpack_f16x2(tv[j], sx, sy);
+        const float2 q = __fmul2_rn(make_float2(k0[2 * j], k0[2 * j + 1]), make_float2(sx, sy));
+        pk[j] = pack_op<FMT>(q.x, q.y);
+      }
+    }
   } else {
     // Layer 0 is bound by the FMA pipe (packed FFMA2 / FMUL2 and the fp16 -> fp32 unpacks all issue there), so:
     //  * grid decodes fold the per-image constant w_ratio * ratio + b into the bias on the host (sp.q0_folded): two FFMA2
@@ -403,7 +459,10 @@ __device__ __forceinline__ void layer0_step(uint32_t act_base, int kc, int wg, i
       float2 t = __ffma2_rn(w[0], rh, w[3]);
       t = __ffma2_rn(w[1], rw, t);
       if (!folded) t = __ffma2_rn(w[2], ra, t);
-      const float2 sn = make_float2(act_sin<kSplit>(t.x), act_sin<kSplit>(t.y));
+      float2 sn = make_float2(act_sin<kSplit>(t.x), act_sin<kSplit>(t.y));
+      if constexpr (!kSplit && !(kSel && FMT == 1)) {
+        if (canon) unpack_f16x2(pack_f16x2_sat(sn.x, sn.y), sn.x, sn.y);
+      }
       if constexpr (kSel && FMT == 1) {
         const uint32_t k0raw = reinterpret_cast<const uint32_t*>(k0v)[j >> 1];
         const uint32_t s16 = pack_f16x2_sat(sn.x, sn.y);
@@ -519,7 +578,8 @@ __device__ __forceinline__ void epi_math(const Raw& raw, uint32_t out_base, int 
 // tmWlo: the fp16 residual weights (split format). tmSelP / tmSelB (select variant): the 4-D map of the fp16 P whose box is
 // one pair's LR patch x 64 features, and the 2-D map of the constant Q-bias tiles. P: fp32 rows, fp16 rows with kSel.
 // kLiif: LIIF's imnet (ReLU MLP 580 -> 256^4 -> 3, liif.py:26 / mlp.py) instead of the dual-interactive layers, query lists only.
-template <int CG, int FMT, bool kDump, bool kPix, bool kSel, bool kLiif>
+// kTab: layer 0's sines come out of a per-CTA phase table (Work::canon, layer0_step).
+template <int CG, int FMT, bool kDump, bool kPix, bool kSel, bool kLiif, bool kTab>
 __global__ void __launch_bounds__(kThreads, 1)
 stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmWlo,
                     const __grid_constant__ CUtensorMap tmSelP, const __grid_constant__ CUtensorMap tmSelB,
@@ -532,11 +592,16 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   static_assert(!(kSplit && kPix), "the split format is not wired for per-pixel P (init_q=True runs on the fp32 CUDA-core path)");
   static_assert(!kSel || (CG == 2 && !kSplit && !kPix), "select variant: CTA pairs, 16-bit operand formats, LR-resolution P");
   static_assert(!kLiif || (!kSel && !kPix && !kDump), "LIIF's imnet runs on the classic kernel (query lists, fp32 P)");
+  static_assert(!kTab || (CG == 2 && !kSplit && !kPix && !kLiif), "phase table: CTA pairs, 16-bit operand formats, grid decodes");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_act = smem;                     // 2 x 64 KB
   uint8_t* s_w = smem + 2 * kActBytes;       // weight stages
   Smem& sm = *reinterpret_cast<Smem*>(smem + C::kCtrlOff);
   const uint32_t sel0 = smem_u32(smem + C::kSelOff), asel0 = smem_u32(smem + C::kASelOff);  // select variant only
+  // phase table (kTab): rows 0..7 at tab_lo, rows 8..15 at tab_hi (see kTabHalf)
+  const uint32_t tab_tail = smem_u32(smem + C::kCtrlOff + sizeof(Smem));
+  const uint32_t tab_lo = kSel ? sel0 + kTabHalf : tab_tail;
+  const uint32_t tab_hi = kSel ? tab_tail : tab_tail + kTabHalf;
 
   // warp index through a shuffle: ptxas then knows it is warp-uniform, so everything indexed by it (feature offsets
   // into the constant-bank parameters, TMEM columns) goes through uniform registers / LDCU instead of the ADU
@@ -582,8 +647,25 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   if constexpr (kSel) {
     // the B_sel stage starts all-zero: the P16 box fills rows [0, box_r*box_c) of the K-branch CTA's tile and nothing ever
     // writes the rows behind them (the bias slots and the padding up to K_sel must multiply to zero there)
-    for (int i = threadIdx.x; i < kSelBytes / 16; i += kThreads) st_shared_v4(sel0 + i * 16, 0u, 0u, 0u, 0u);
+    // (kTab: K_sel = 16, the tile is the lower half of the stage and the upper half holds phase-table rows)
+    for (int i = threadIdx.x; i < (kTab ? kTabHalf : kSelBytes) / 16; i += kThreads) st_shared_v4(sel0 + i * 16, 0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
+  }
+  if constexpr (kTab) {
+    // sin(Wq0 (rel_h, rel_w, ratio) + bq0) for every phase x feature pair, with exactly the operations of layer0_step's
+    // compute path (the launcher folded w_ratio * ratio + b into the bias: grid decode), rounded to fp16
+    const int n = wk.s_h * wk.s_w * (kD / 2);
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      const int phase = i >> 7, fp = i & 127;
+      const int p_h = phase / wk.s_w, p_w = phase - p_h * wk.s_w;
+      const float rel_h = canon_rel(p_h, wk.s_h), rel_w = canon_rel(p_w, wk.s_w);
+      const float2* w = &sp.wq0_p[fp][0];
+      float2 t = __ffma2_rn(w[0], make_float2(rel_h, rel_h), w[3]);
+      t = __ffma2_rn(w[1], make_float2(rel_w, rel_w), t);
+      const uint32_t s16 = pack_f16x2_sat(act_sin<false>(t.x), act_sin<false>(t.y));
+      const uint32_t row = (phase < 8 ? tab_lo : tab_hi) + static_cast<uint32_t>(phase & 7) * 512u;
+      st_shared_b32(row + ((((fp >> 2) ^ (phase & 7))) << 4) + (fp & 3) * 4, s16);
+    }
   }
   if (warp == 2) tmem_alloc<CG>(&sm.tmem_ptr, 512);
   tc_fence_before();
@@ -604,10 +686,16 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       else prefetch_tile_rows<CG, kSel ? 2 : 4>(src, P, wk, w_, rank, lane);
     };
     // one weight stage: tile s24 of the (layer-1, half, kc) sequence out of map tm
+    int tr_tile = 0;  // (timeline builds) tile counter of this producer
     auto load_w = [&](const CUtensorMap* tm, int s24) {
       const int st = it % C::kStages;
       const uint32_t ph = (it / C::kStages) & 1;
       mbar_wait(&sm.w_empty[st], ph ^ 1);
+#if DIINN_TRACE_BUILD
+      // the stage came free = the MMAs of the weight tile kStages earlier have RETIRED: the tensor pipe's own timeline, as
+      // long as the producer was already waiting here (16 + 4 + 4 slots: 96..111, 124..127, 60..63)
+      if (!kSplit && lane == 0) DIINN_TR(tr_tile, s24 < 16 ? 96 + s24 : s24 < 20 ? 124 + (s24 - 16) : 60 + (s24 - 20));
+#endif
       if (elect_one()) {
         if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
         void* dst = s_w + st * C::kStageBytes;
@@ -620,7 +708,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       ++it;
     };
     if (unit_id + n_units < wk.n_work) prefetch(unit_id + n_units);
-    for (int work = unit_id; work < wk.n_work; work += n_units) {
+    for (int work = unit_id; work < wk.n_work; work += n_units, ++tr_tile) {
       if (work + 2 * n_units < wk.n_work) prefetch(work + 2 * n_units);
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
@@ -834,16 +922,43 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       // (the P prefetch is issued AFTER the proxy fence: fence.proxy.async lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
       // which waits for every outstanding global load of the thread -- a prefetch issued just before it exposes its
       // whole L2 latency in every step; measured)
-      layer0_step<FMT, kPix, kSel, kLiif>(buf, kc0, fg, r, rcx, sp, ka);
+      const uint32_t trow = (rcx.phase < 8 ? tab_lo : tab_hi) + static_cast<uint32_t>(rcx.phase & 7) * 512u;
+      const int tkey = rcx.phase & 7;
+      const bool canon = wk.canon != 0;
+#if DIINN_L0V == 0
+      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0, fg, r, rcx, sp, ka, trow, tkey, canon);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
       if (nb) load_p(nb, ka);
-      layer0_step<FMT, kPix, kSel, kLiif>(buf, kc0 + 1, fg, r, rcx, sp, kb);
+      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0 + 1, fg, r, rcx, sp, kb, trow, tkey, canon);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
       if (nb) load_p(nb + kP64, kb);
+#elif DIINN_L0V == 1   // both next slices fetched behind the unit's LAST fence (no load in flight at a fence)
+      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0, fg, r, rcx, sp, ka, trow, tkey, canon);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
+      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0 + 1, fg, r, rcx, sp, kb, trow, tkey, canon);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
+      if (nb) load_p(nb, ka);
+      if (nb) load_p(nb + kP64, kb);
+#else                  // one fence for the two chunks of the unit
+      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0, fg, r, rcx, sp, ka, trow, tkey, canon);
+      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0 + 1, fg, r, rcx, sp, kb, trow, tkey, canon);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        signal<CG>(&sm.act_ready[bufidx][kc0]);
+        signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
+      }
+      if (nb) load_p(nb, ka);
+      if (nb) load_p(nb + kP64, kb);
+#endif
     };
 
     if (work < wk.n_work) {
@@ -999,18 +1114,18 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 
 }  // namespace sb
 
-template <int CG, int FMT, bool kDump, bool kPix, bool kSel, bool kLiif = false>
+template <int CG, int FMT, bool kDump, bool kPix, bool kSel, bool kLiif = false, bool kTab = false>
 static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap& tm, const CUtensorMap& tm_lo,
                           const CUtensorMap& tm_selp, const CUtensorMap& tm_selb, const PixelSource& src, const OutSpec& out,
                           const void* P, const sb::Work& wk, int* err_flag, long long* trace) {
   using namespace sb;
-  constexpr int kBytes = static_cast<int>(smem_bytes<CG, kSel>());
+  constexpr int kBytes = static_cast<int>(smem_bytes_tab<CG, kSel, kTab>());
   cfg->dynamicSmemBytes = kBytes;
-  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>,
+  DIINN_CUDA_OK(h, cudaFuncSetAttribute(stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif, kTab>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes));
   if (getenv("DIINN_DEBUG_OCC")) {
     int nc = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>, cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif, kTab>, cfg);
     fprintf(stderr, "[diinn] stage B: grid %u CTAs, cluster %d, max active clusters %d (%s)\n", cfg->gridDim.x, CG, nc,
             cudaGetErrorString(e));
   }
@@ -1023,11 +1138,11 @@ static int launch_variant(Handle* h, cudaLaunchConfig_t* cfg, const CUtensorMap&
       spf.wq0_p[i][3].y = fmaf(spf.wq0_p[i][2].y, src.ratio, spf.wq0_p[i][3].y);
     }
     spf.q0_folded = 1;
-    DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>, tm, tm_lo, tm_selp, tm_selb, spf,
+    DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif, kTab>, tm, tm_lo, tm_selp, tm_selb, spf,
                                         src, out, P, wk, err_flag, trace));
     return DIINN_OK;
   }
-  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif>, tm, tm_lo, tm_selp, tm_selb,
+  DIINN_CUDA_OK(h, cudaLaunchKernelEx(cfg, stage_b_umma_kernel<CG, FMT, kDump, kPix, kSel, kLiif, kTab>, tm, tm_lo, tm_selp, tm_selb,
                                       h->small, src, out, P, wk, err_flag, trace));
   return DIINN_OK;
 }
@@ -1051,6 +1166,7 @@ struct Plan {
   sb::Work wk{};
   int cta_group = 2;
   bool sel = false;
+  bool tab = false;  // layer 0 from the phase table (Work::canon and room for the table)
 };
 
 Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, bool chain_mode) {
@@ -1137,6 +1253,19 @@ Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, 
     wk.sel_sbo = static_cast<uint32_t>(env_int("DIINN_SEL_SBO", 1024));
     wk.sel_kstep = static_cast<uint32_t>(env_int("DIINN_SEL_KSTEP", 2048));
   }
+  // Canonical relative coordinates + phase table (Work::canon). Decided from the image geometry and the format alone, so every
+  // row tile of an image agrees; only whether the table fits (select variant: K_sel = 16) may differ between launches, and
+  // the computing and the looking-up kernels are bit-identical (layer0_step). nearest-exact picks floor(j / s) exactly as long
+  // as the fp32 rounding of (j + 0.5) * fl(1/s) (<= n_in * 2^-23) stays below the 1/(2s) distance to the next integer.
+  static const int env_nocanon = env_int("DIINN_NO_CANON", 0), env_notab = env_int("DIINN_NO_TAB", 0);
+  if (cta_group == 2 && fmt != kFmtSplit && !pix && !src.liif && !env_nocanon && src.H_up % src.H == 0 &&
+      src.W_up % src.W == 0 && src.H_up <= (1 << 20) && src.W_up <= (1 << 20)) {
+    const int s_h = src.H_up / src.H, s_w = src.W_up / src.W;
+    if (s_h * s_w <= 16) {
+      wk.canon = 1, wk.s_h = s_h, wk.s_w = s_w;
+      pl.tab = !env_notab && (!pl.sel || wk.ksel == 16);
+    }
+  }
   return pl;
 }
 
@@ -1203,6 +1332,11 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   (dump ? (pix ? DIINN_SB_LAUNCH(CGv, FMTv, true, true, false) : DIINN_SB_LAUNCH(CGv, FMTv, true, false, false))       \
         : (pix ? DIINN_SB_LAUNCH(CGv, FMTv, false, true, false) : DIINN_SB_LAUNCH(CGv, FMTv, false, false, false)))
 #define DIINN_SB_PICK_SEL(FMTv) (dump ? DIINN_SB_LAUNCH(2, FMTv, true, false, true) : DIINN_SB_LAUNCH(2, FMTv, false, false, true))
+#define DIINN_SB_TAB(FMTv, DUMPv, SELv) \
+  launch_variant<2, FMTv, DUMPv, false, SELv, false, true>(h, &cfg, tm, tm_lo, tm_selp, tm_selb, src, out, P, wk, err_flag, trace)
+#define DIINN_SB_PICK_TAB(FMTv)                                                                    \
+  (pl.sel ? (dump ? DIINN_SB_TAB(FMTv, true, true) : DIINN_SB_TAB(FMTv, false, true))              \
+          : (dump ? DIINN_SB_TAB(FMTv, true, false) : DIINN_SB_TAB(FMTv, false, false)))
 #define DIINN_SB_PICK_SPLIT(CGv) \
   (dump ? DIINN_SB_LAUNCH(CGv, 2, true, false, false) : DIINN_SB_LAUNCH(CGv, 2, false, false, false))
   if (src.liif) {
@@ -1212,10 +1346,13 @@ int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, c
   launch_variant<2, FMTv, false, false, false, true>(h, &cfg, tm, tm_lo, tm_selp, tm_selb, src, out, P, wk, err_flag, trace)
     rc = fmt == kFmtSplit ? DIINN_SB_LIIF(2) : fmt == kFmtF16 ? DIINN_SB_LIIF(1) : DIINN_SB_LIIF(0);
 #undef DIINN_SB_LIIF
-  } else if (pl.sel) rc = fmt == kFmtF16 ? DIINN_SB_PICK_SEL(1) : DIINN_SB_PICK_SEL(0);
+  } else if (pl.tab) rc = fmt == kFmtF16 ? DIINN_SB_PICK_TAB(1) : DIINN_SB_PICK_TAB(0);
+  else if (pl.sel) rc = fmt == kFmtF16 ? DIINN_SB_PICK_SEL(1) : DIINN_SB_PICK_SEL(0);
   else if (cta_group == 1) rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(1) : fmt == kFmtF16 ? DIINN_SB_PICK(1, 1) : DIINN_SB_PICK(1, 0);
   else rc = fmt == kFmtSplit ? DIINN_SB_PICK_SPLIT(2) : fmt == kFmtF16 ? DIINN_SB_PICK(2, 1) : DIINN_SB_PICK(2, 0);
 #undef DIINN_SB_PICK_SPLIT
+#undef DIINN_SB_PICK_TAB
+#undef DIINN_SB_TAB
 #undef DIINN_SB_PICK_SEL
 #undef DIINN_SB_PICK
 #undef DIINN_SB_LAUNCH

@@ -195,18 +195,73 @@ def test_siren_strength_weights_route_to_the_fp32_path():
     assert float(np.abs(o - orc.decoder_forward(w0_, feat, size)).max()) <= TIGHT["fp16"]
 
 
+def _canonical_rel(n_in, n_up):
+    """Integer scale s = n_up / n_in: every pixel of phase p = j - s * floor(j / s) sits at (2p + 1)/s - 1 in exact arithmetic;
+    the kernel uses fl(fl((2p + 1)/s) - 1) (stage_b_umma.cu: canon_rel)."""
+    s = n_up // n_in
+    p = np.arange(n_up) % s
+    return ((2 * p + 1).astype(np.float32) / np.float32(s) + np.float32(-1.0)).astype(np.float32)
+
+
 @pytest.mark.parametrize("name", ["c1", "c2x3", "c3", "odd1", "odd2", "odd3", "down"])
 def test_fused_kernel_indices_and_coordinates_bit_exact(golden_posenc, w0, name):
     """(ih, iw, rel_h, rel_w) as make_row() INSIDE the fused stage-B kernel derives them for every output pixel
-    (diinn_debug_set_tap), against the reference's _make_pos_encoding fixtures: bit for bit."""
+    (diinn_debug_set_tap), against the reference's _make_pos_encoding fixtures. Gather indices: bit for bit, always. Relative
+    coordinates: bit for bit, except on INTEGER scale factors with <= 16 phases (c1, c2x3, c3), where the 16-bit paths use the
+    exact closed form of the phase -- the value the reference's fp32 coordinate grids scatter around by their own rounding
+    (measured 5e-5 on c3; bound: a few ulps of a [-1, 1] coordinate times n_in) -- so that layer 0's sines form a table."""
     H, W, H_up, W_up = (int(v) for v in golden_posenc[f"{name}.shape"])
     dec = _decoder(w0, "fp16")
     x = torch.from_numpy(synth.make_feat(3, 1, H, W)).cuda()
     ih, iw, rh, rw = (t.cpu().numpy() for t in dec.debug_rows(x, (H_up, W_up)))
     assert np.array_equal(ih, np.broadcast_to(golden_posenc[f"{name}.ih"][:, None], (H_up, W_up)))
     assert np.array_equal(iw, np.broadcast_to(golden_posenc[f"{name}.iw"][None, :], (H_up, W_up)))
-    assert np.array_equal(rh.view(np.uint32), np.broadcast_to(golden_posenc[f"{name}.rel_h"].view(np.uint32)[:, None], (H_up, W_up)))
-    assert np.array_equal(rw.view(np.uint32), np.broadcast_to(golden_posenc[f"{name}.rel_w"].view(np.uint32)[None, :], (H_up, W_up)))
+    ref_h, ref_w = golden_posenc[f"{name}.rel_h"], golden_posenc[f"{name}.rel_w"]
+    canon = H_up % H == 0 and W_up % W == 0 and (H_up // H) * (W_up // W) <= 16
+    assert canon == (name in ("c1", "c2x3", "c3"))
+    if canon:
+        can_h, can_w = _canonical_rel(H, H_up), _canonical_rel(W, W_up)
+        assert float(np.abs(can_h - ref_h).max()) <= 4 * 2.0 ** -23 * H and float(np.abs(can_w - ref_w).max()) <= 4 * 2.0 ** -23 * W
+        ref_h, ref_w = can_h, can_w
+    assert np.array_equal(rh.view(np.uint32), np.broadcast_to(ref_h.view(np.uint32)[:, None], (H_up, W_up)))
+    assert np.array_equal(rw.view(np.uint32), np.broadcast_to(ref_w.view(np.uint32)[None, :], (H_up, W_up)))
+
+
+def test_phase_table_is_bit_identical_to_computing_and_close_to_per_pixel_coordinates():
+    """Integer scale factors: layer 0's sines come out of a per-CTA phase table. DIINN_NO_TAB=1 computes them per pixel from
+    the same canonical coordinates and must not change a bit (row tiles whose patches need K_sel = 32 have no room for the
+    table and compute); DIINN_NO_CANON=1 uses the reference's per-pixel fp32 coordinates (the kernel before the table) and
+    may differ by the coordinate noise only. The switches are read once per process, hence subprocesses."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch, numpy as np; sys.path.insert(0, %r)\n"
+        "import diinn_b200; from diinn_b200 import synth\n"
+        "outs = []\n"
+        "for mode in (3, 2, 4):\n"
+        "    w = synth.make_weights(seed=mode, mode=mode)\n"
+        "    for (B, H, W, sh, sw) in ((1, 24, 24, 4, 4), (2, 13, 17, 2, 2), (1, 11, 9, 3, 3), (1, 10, 12, 2, 8), (1, 7, 9, 1, 1)):\n"
+        "        x = torch.from_numpy(synth.make_feat(6, B, H, W)).cuda()\n"
+        "        for prec in ('fp16', 'bf16'):\n"
+        "            d = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=mode, precision=prec), w).cuda()\n"
+        "            with torch.no_grad():\n"
+        "                o = d(x, (H * sh, W * sw))\n"
+        "                t = torch.cat([d.forward_rows(x, (H * sh, W * sw), a, b) for a, b in ((0, 5), (5, 6), (6, H * sh))], dim=2)\n"
+        "            assert torch.equal(o, t), (mode, H, W, sh, sw, prec)\n"
+        "            outs.append(o.float().cpu().numpy().ravel())\n"
+        "np.save(sys.argv[1], np.concatenate(outs))\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    got = {}
+    with tempfile.TemporaryDirectory() as td:
+        for leg, env in (("table", {}), ("no_tab", {"DIINN_NO_TAB": "1"}), ("no_canon", {"DIINN_NO_CANON": "1"})):
+            path = os.path.join(td, leg + ".npy")
+            r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True, text=True,
+                               timeout=600)
+            assert r.returncode == 0, (leg, r.stderr[-2000:])
+            got[leg] = np.load(path)
+    assert np.array_equal(got["table"].view(np.uint32), got["no_tab"].view(np.uint32))
+    # (a coordinate that moves by 5e-5 can flip the 16-bit rounding of a q_0 value: bounded by the operand noise of the format)
+    assert float(np.abs(got["table"] - got["no_canon"]).max()) <= 1e-4
 
 
 def test_bf16_io(golden_decoder):
