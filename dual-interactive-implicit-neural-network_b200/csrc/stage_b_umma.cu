@@ -319,10 +319,7 @@ __device__ __forceinline__ void signal(uint64_t* bar) {
 #ifndef DIINN_TRACE_BUILD
 #define DIINN_TRACE_BUILD DIINN_FINE_TRACE
 #endif
-// order of layer 0's stores, fences and k_0 fetches inside one unit (two K-chunks); see layer0_unit
-#ifndef DIINN_L0V
-#define DIINN_L0V 1
-#endif
+
 
 // 16 fp32 values (64 B) of a P row as two 256-bit loads (LDG.E.256): a warp's 32 rows sit in ~8 LR cells 4 KB apart, so every
 // load instruction costs ~8 L1 wavefronts whatever its width -- half the instructions of four 128-bit loads
@@ -679,12 +676,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
   if (warp < 4) {
   setmaxnreg_dec<kRegsCtrl>();
   if (warp == 0) {
-    // ===================== weight producer (+ L2 prefetch of upcoming tiles' P rows) =====================
+    // ===================== weight producer =====================
     uint32_t it = 0, sel_it = 0;
-    auto prefetch = [&](int w_) {
-      if constexpr (kPix) prefetch_tile_pixels<CG>(src, P, wk, w_, rank, lane);
-      else prefetch_tile_rows<CG, kSel ? 2 : 4>(src, P, wk, w_, rank, lane);
-    };
     // one weight stage: tile s24 of the (layer-1, half, kc) sequence out of map tm
     int tr_tile = 0;  // (timeline builds) tile counter of this producer
     auto load_w = [&](const CUtensorMap* tm, int s24) {
@@ -694,7 +687,8 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
 #if DIINN_TRACE_BUILD
       // the stage came free = the MMAs of the weight tile kStages earlier have RETIRED: the tensor pipe's own timeline, as
       // long as the producer was already waiting here (16 + 4 + 4 slots: 96..111, 124..127, 60..63)
-      if (!kSplit && lane == 0) DIINN_TR(tr_tile, s24 < 16 ? 96 + s24 : s24 < 20 ? 124 + (s24 - 16) : 60 + (s24 - 20));
+      if (!kSplit && lane == 0 && (s24 & 3) == 0) DIINN_TR(tr_tile, 96 + (s24 >> 2) * 2);
+      if (!kSplit && lane == 0 && s24 == 23) DIINN_TR(tr_tile, 110);
 #endif
       if (elect_one()) {
         if (leader) mbar_arrive_expect_tx(&sm.w_full[st], C::kStageBytes * CG);
@@ -707,9 +701,10 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       __syncwarp();
       ++it;
     };
-    if (unit_id + n_units < wk.n_work) prefetch(unit_id + n_units);
     for (int work = unit_id; work < wk.n_work; work += n_units, ++tr_tile) {
-      if (work + 2 * n_units < wk.n_work) prefetch(work + 2 * n_units);
+#if DIINN_TRACE_BUILD
+      if (lane == 0) DIINN_TR(tr_tile, 109);
+#endif
       __syncwarp();
       // the whole warp walks the ring (so the stage index and barrier addresses stay in uniform registers and the
       // TMA / mbarrier instructions are issued without a per-lane broadcast loop); one elected lane issues
@@ -736,6 +731,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
             // fetches the pair's LR patch out of the fp16 P, the Q-branch CTA the constant bias tile
             const uint32_t fb_stride = static_cast<uint32_t>(wk.ksel) * 128u;
             mbar_wait(&sm.sel_empty, (sel_it & 1) ^ 1);
+#if DIINN_TRACE_BUILD
+            if (lane == 0) DIINN_TR(tr_tile, 97 + lh * 2);
+#endif
             if (elect_one()) {
               if (leader)
                 mbar_arrive_expect_tx(&sm.sel_full, 2u * 128u * static_cast<uint32_t>(wk.box_r * wk.box_c + wk.ksel));
@@ -869,6 +867,25 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ===================== L2 prefetcher =====================
+    // P is produced by stage A right before this kernel and is far larger than L2, so a tile's first touch of its P rows would
+    // be an HBM-latency fetch in the middle of the pipeline. This warp pulls the rows of the tile TWO work items ahead into L2
+    // (cp.async.bulk.prefetch.L2). It used to be the weight producer's job at the top of its tile loop, where the ~1 900 clk the
+    // prefetch instructions take (timeline: tools/trace_stage_b.py) delayed the next tile's first B_sel / weight requests and
+    // left the tensor pipe idle at every tile boundary. Paced by TMEM slot 1's `full` barrier: three phases per tile.
+    auto prefetch = [&](int w_) {
+      if constexpr (kPix) prefetch_tile_pixels<CG>(src, P, wk, w_, rank, lane);
+      else prefetch_tile_rows<CG, kSel ? 2 : 4>(src, P, wk, w_, rank, lane);
+    };
+    if (unit_id + n_units < wk.n_work) prefetch(unit_id + n_units);
+    uint32_t uses = 0;
+    for (int work = unit_id; work < wk.n_work; work += n_units) {
+      if (work + 2 * n_units < wk.n_work) prefetch(work + 2 * n_units);
+      __syncwarp();
+      for (int k = 0; k < 3; ++k, ++uses) mbar_wait(&sm.tmem_full[1], uses & 1);
+    }
+    __syncwarp();
   }
   } else {
     // ===================== epilogue warps =====================
@@ -925,18 +942,9 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       const uint32_t trow = (rcx.phase < 8 ? tab_lo : tab_hi) + static_cast<uint32_t>(rcx.phase & 7) * 512u;
       const int tkey = rcx.phase & 7;
       const bool canon = wk.canon != 0;
-#if DIINN_L0V == 0
-      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0, fg, r, rcx, sp, ka, trow, tkey, canon);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0]);
-      if (nb) load_p(nb, ka);
-      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0 + 1, fg, r, rcx, sp, kb, trow, tkey, canon);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
-      if (nb) load_p(nb + kP64, kb);
-#elif DIINN_L0V == 1   // both next slices fetched behind the unit's LAST fence (no load in flight at a fence)
+      // Both k_0 slices of the NEXT unit are fetched behind this unit's LAST proxy fence: fence.proxy.async drains the thread's
+      // outstanding global loads, so a load issued between the two steps exposed its whole L2 latency at the second fence
+      // (timeline: 1 750 clk per unit against 760 for the unit without loads; same-box A/B 1.680 -> 1.663 ms on c3).
       layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0, fg, r, rcx, sp, ka, trow, tkey, canon);
       fence_proxy_async_smem();
       __syncwarp();
@@ -947,18 +955,6 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       if (lane == 0) signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
       if (nb) load_p(nb, ka);
       if (nb) load_p(nb + kP64, kb);
-#else                  // one fence for the two chunks of the unit
-      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0, fg, r, rcx, sp, ka, trow, tkey, canon);
-      layer0_step<FMT, kPix, kSel, kLiif, kTab>(buf, kc0 + 1, fg, r, rcx, sp, kb, trow, tkey, canon);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        signal<CG>(&sm.act_ready[bufidx][kc0]);
-        signal<CG>(&sm.act_ready[bufidx][kc0 + 1]);
-      }
-      if (nb) load_p(nb, ka);
-      if (nb) load_p(nb + kP64, kb);
-#endif
     };
 
     if (work < wk.n_work) {

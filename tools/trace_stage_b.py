@@ -41,11 +41,12 @@ for t in range(1, 5):
             print(f" L{layer + 1}.h{h} MMA slot_free {m[0]:7d} | act ready / issued kc0 {m[1]:7d}/{m[2]:7d} kc1 {m[3]:7d}/{m[4]:7d} "
                   f"kc2 {m[5]:7d}/{m[6]:7d} kc3 {m[7]:7d}/{m[8]:7d} issued {m[9]:7d} || EPI wait {e[0]:7d} full {e[1]:7d} "
                   f"c0 {e[2]:7d} c1 {e[3]:7d} freed {e[4]:7d}")
-    # producer side: when each weight stage came free = when the MMAs of the tile 4 stages earlier retired (24 per tile)
-    ws = np.concatenate([tr[t, 96:112], tr[t, 124:128], tr[t, 60:64]]) - t0
-    for lh in range(6):
-        print(f" producer: stage free before loading L{lh // 2 + 1}.h{lh % 2} kc0..3 (= MMAs of the previous half slot's kc retired): "
-              + " ".join(f"{v:7d}" for v in ws[lh * 4: lh * 4 + 4]))
+    # producer side (leader CTA): when it entered the tile's loop, and per half slot when the
+    # B_sel stage came free (= the previous half slot's select MMA retired) and when the first weight stage came free
+    pr = tr[t, 96:112] - t0
+    print(f" producer: tile loop entered {pr[13]:7d} | last weight stage of L3.h1 requested {pr[14]:7d}")
+    print(" producer: per half slot  B_sel stage free / kc0 stage free: "
+          + "  ".join(f"L{lh // 2 + 1}.h{lh % 2} {pr[lh * 2 + 1]:7d}/{pr[lh * 2]:7d}" for lh in range(6)))
     for h in range(2) if os.environ.get("DIINN_FINE") else []:
         f = tr[t, 96 + h * 8: 96 + h * 8 + 8] - t0
         print(f" L2.h{h} fine (needs -DDIINN_FINE_TRACE=1): ld0 landed {f[0]} math0 done {f[1]} ld1 landed {f[2]} math1 done {f[3]}")
