@@ -592,7 +592,7 @@ def main():
         fmt = {"fp16": 1, "bf16": 0, "fp32": 2}[args.precision]
         line["roofline"] = {
             "bound": "tensor",
-            "kernel": f"stage_b_umma_kernel<CG=2, FMT={fmt}, kDump=0, kPix=0, kSel={int(terms == 1 and args.workload != 'c2x2' and args.workload != 'c2x3')}, kLiif=0>",
+            "kernel": f"stage_b_umma_kernel<CG=2, FMT={fmt}, kDump=0, kPix=0, kSel={int(terms == 1 and args.workload != 'c2x2' and args.workload != 'c2x3')}, kLiif=0, kTab={int(terms == 1 and args.workload in ('c1', 'c2x2', 'c2x3', 'c2x4', 'c3', 'c5'))}>",
             "achieved": ach, "peak": peak,
             "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": prof.get("dram_bytes_per_launch_c3") if args.workload == "c3" and world == 1 and terms == 1 else None,

@@ -87,7 +87,7 @@ struct Smem {  // after the big buffers
   uint64_t a01_free;   // split format: the layer's MMAs no longer read K-chunks 0, 1 of the (in-place) activation buffer
   uint64_t sel_full, sel_empty;  // select variant: the B_sel stage
   uint32_t tmem_ptr;
-  uint32_t pad[1];
+  uint32_t pf_tile;    // index of the tile the weight producer has started (paces the L2 prefetcher warp)
   float partial[3][kTileM][3];  // RGB partial sums of the three non-reducing warp sets
 };
 template <int CG, bool kSel>
@@ -632,6 +632,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       mbar_init(&sm.tmem_full[i], 1);
       mbar_init(&sm.tmem_empty[i], kEpiWarps * CG);
     }
+    sm.pf_tile = 0;
     mbar_init(&sm.a01_free, 1);
     mbar_init(&sm.sel_full, 1);
     mbar_init(&sm.sel_empty, 1);
@@ -679,7 +680,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // ===================== weight producer =====================
     uint32_t it = 0, sel_it = 0;
     // one weight stage: tile s24 of the (layer-1, half, kc) sequence out of map tm
-    int tr_tile = 0;  // (timeline builds) tile counter of this producer
+    int tr_tile = 0;  // tile counter of this producer
     auto load_w = [&](const CUtensorMap* tm, int s24) {
       const int st = it % C::kStages;
       const uint32_t ph = (it / C::kStages) & 1;
@@ -702,6 +703,7 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
       ++it;
     };
     for (int work = unit_id; work < wk.n_work; work += n_units, ++tr_tile) {
+      if (lane == 0) st_shared_volatile_u32(smem_u32(&sm.pf_tile), static_cast<uint32_t>(tr_tile));
 #if DIINN_TRACE_BUILD
       if (lane == 0) DIINN_TR(tr_tile, 109);
 #endif
@@ -873,17 +875,20 @@ stage_b_umma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
     // be an HBM-latency fetch in the middle of the pipeline. This warp pulls the rows of the tile TWO work items ahead into L2
     // (cp.async.bulk.prefetch.L2). It used to be the weight producer's job at the top of its tile loop, where the ~1 900 clk the
     // prefetch instructions take (timeline: tools/trace_stage_b.py) delayed the next tile's first B_sel / weight requests and
-    // left the tensor pipe idle at every tile boundary. Paced by TMEM slot 1's `full` barrier: three phases per tile.
+    // left the tensor pipe idle at every tile boundary.
     auto prefetch = [&](int w_) {
       if constexpr (kPix) prefetch_tile_pixels<CG>(src, P, wk, w_, rank, lane);
       else prefetch_tile_rows<CG, kSel ? 2 : 4>(src, P, wk, w_, rank, lane);
     };
+    // Pacing: the weight producer publishes the index of the tile it has started (a plain shared-memory counter, polled
+    // here). Deliberately NOT an mbarrier phase: a prefetcher that falls two phases behind (query lists issue 128 prefetches per
+    // tile) would wait for a parity that never comes back; with a counter it simply stops waiting until it has caught up.
     if (unit_id + n_units < wk.n_work) prefetch(unit_id + n_units);
-    uint32_t uses = 0;
-    for (int work = unit_id; work < wk.n_work; work += n_units) {
+    int t3 = 0;
+    for (int work = unit_id; work < wk.n_work; work += n_units, ++t3) {
+      while (ld_shared_volatile_u32(smem_u32(&sm.pf_tile)) < static_cast<uint32_t>(t3)) nanosleep_ns(200);
       if (work + 2 * n_units < wk.n_work) prefetch(work + 2 * n_units);
       __syncwarp();
-      for (int k = 0; k < 3; ++k, ++uses) mbar_wait(&sm.tmem_full[1], uses & 1);
     }
     __syncwarp();
   }
