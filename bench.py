@@ -121,7 +121,7 @@ def h2d_bytes_all_ranks(H, W, H_up, world, B, C=64):
     (nearest-exact rows of the tile +-1 for the 3x3 unfold), fp32."""
     import diinn_b200
     total = 0
-    for r0, r1 in diinn_b200.row_partition(H_up, world):
+    for r0, r1 in diinn_b200.tile_partition(H, H_up, world):
         lo = max(min(int((r0 + 0.5) * H / H_up), H - 1) - 1, 0)
         hi = min(min(int((r1 - 0.5) * H / H_up), H - 1) + 2, H)
         total += B * C * (hi - lo) * W * 4
@@ -303,7 +303,7 @@ def main():
     feat_host = torch.from_numpy(synth.make_feat(1, B, H, W)).pin_memory()
     feat = feat_host.to(dev)
     npx = B * H_up * W_up
-    parts = diinn_b200.row_partition(H_up, world)
+    parts = diinn_b200.tile_partition(H, H_up, world)
     r0, r1 = parts[rank]
 
     def step(assembly=args.assembly, d=dec, x=feat, size=(H_up, W_up)):
@@ -441,7 +441,7 @@ def main():
                 # tile alone (compute only), max over ranks
                 b4, h4, w4, hu4, wu4 = synth.CONFIGS["c4"]
                 x4 = torch.from_numpy(synth.make_feat(1, b4, h4, w4)).to(dev)
-                a4, c4 = diinn_b200.row_partition(hu4, world)[rank]
+                a4, c4 = diinn_b200.tile_partition(h4, hu4, world)[rank]
                 legs = {"fused": lambda: step("fused", dec, x4, (hu4, wu4)), "nccl": lambda: step("nccl", dec, x4, (hu4, wu4)),
                         "compute_only": lambda: dec.forward_rows(x4, (hu4, wu4), a4, c4)}
                 single4 = dec(x4, (hu4, wu4))

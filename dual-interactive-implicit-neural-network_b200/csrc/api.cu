@@ -647,6 +647,12 @@ int diinn_decode_host(diinn_handle* h, const void* feat_host, int B, int C, int 
   for (int k = 0, acc = 0; k < bands; ++k) {
     acc += weights[k];
     edge[k + 1] = k + 1 == bands ? row1 : row0 + static_cast<int>(static_cast<int64_t>(nrows) * acc / wsum);
+    // integer scale factor s <= 16: interior edges on multiples of s keep stage B's 8-row patches on whole LR cells (fewest
+    // cells per patch: one select MMA per half slot and room for the phase table, stage_b_umma.cu); any split is bit-identical
+    if (k + 1 < bands && H_up % H == 0 && H_up / H <= 16) {
+      const int al = edge[k + 1] / (H_up / H) * (H_up / H);
+      if (al > edge[k]) edge[k + 1] = al;
+    }
     if (edge[k + 1] <= edge[k]) edge[k + 1] = edge[k] + 1 <= row1 ? edge[k] + 1 : row1;
   }
   edge[bands] = row1;

@@ -13,23 +13,43 @@ import torch
 import torch.distributed as dist
 
 
-def row_partition(n_rows: int, world: int) -> List[Tuple[int, int]]:
+def row_partition(n_rows: int, world: int, align: int = 1) -> List[Tuple[int, int]]:
     """Contiguous, balanced [row0,row1) per rank; the first n_rows % world ranks get one extra row
-    (1356 rows on 8 ranks -> 170,170,170,170,169,169,169,169). Ranks beyond n_rows get empty ranges."""
-    base, extra = divmod(n_rows, world)
-    out, r0 = [], 0
+    (1356 rows on 8 ranks -> 170,170,170,170,169,169,169,169). Ranks beyond n_rows get empty ranges.
+    align > 1: every boundary is a multiple of `align` rows (the image is dealt out in units of `align` rows:
+    1356 rows, 8 ranks, align 4 -> 172,172,172,168,168,168,168,168)."""
+    align = max(int(align), 1)
+    units = -(-n_rows // align)
+    base, extra = divmod(units, world)
+    out, u0 = [], 0
     for r in range(world):
         n = base + (1 if r < extra else 0)
-        out.append((r0, r0 + n))
-        r0 += n
+        out.append((min(u0 * align, n_rows), min((u0 + n) * align, n_rows)))
+        u0 += n
     return out
 
 
-def band_partition(n_rows: int, world: int, bands: int) -> Tuple[int, List[List[Tuple[int, int]]]]:
+def row_align(H: int, H_up: int) -> int:
+    """Row granularity of a sharded decode. On an integer scale factor s (<= 16) tile boundaries on multiples of s keep every
+    8-row patch of stage B on whole LR cells, so a row tile's patches touch as few cells as the full image's (x4: 2 x 8 = 16,
+    one select MMA per half slot and room for the phase table; an unaligned tile touches 3 x 8 = 24 and computes layer 0's
+    sines). Any partition is bit-identical to the full decode -- this only picks the fast one."""
+    s = H_up // H if H > 0 and H_up % H == 0 else 1
+    return s if 1 <= s <= 16 else 1
+
+
+def tile_partition(H: int, H_up: int, world: int) -> List[Tuple[int, int]]:
+    """The row tiles decode_sharded_fused / decode_sharded(gather="none") give the ranks."""
+    return row_partition(H_up, world, row_align(H, H_up))
+
+
+def band_partition(n_rows: int, world: int, bands: int, align: int = 1) -> Tuple[int, List[List[Tuple[int, int]]]]:
     """Block-cyclic row bands for pipelined assembly: the image is cut into `bands` super-bands of world*sub rows, and
     inside super-band k rank r owns rows [(k*world + r)*sub, +sub) (clipped to n_rows). Returns (sub, per-rank lists).
-    With bands=1 this is the plain contiguous split with equal (padded) tiles."""
+    With bands=1 this is the plain contiguous split with equal (padded) tiles. align: `sub` is rounded up to a multiple of it
+    (see row_align)."""
     sub = -(-n_rows // (world * bands))
+    sub = -(-sub // max(int(align), 1)) * max(int(align), 1)
     out = []
     for r in range(world):
         mine = []
@@ -103,7 +123,7 @@ def decode_sharded_fused(decoder, x: torch.Tensor, size, group: Optional[dist.Pr
     slot = _symm_turn.get(tkey, 0)
     _symm_turn[tkey] = slot ^ 1
     buf, hdl = _symmetric_image((B, 3, H_up, W_up), odt, x.device, group, slot)
-    r0, r1 = row_partition(H_up, world)[rank]
+    r0, r1 = tile_partition(x.shape[2], H_up, world)[rank]
     if multicast == "auto":
         multicast = B * (r1 - r0) * W_up < (1 << 21)
     mc = int(hdl.multicast_ptr) if (multicast and odt == torch.float32) else 0  # 0 when the fabric has no multicast
@@ -134,7 +154,7 @@ def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessG
     H_up, W_up = int(size[0]), int(size[1])
     B = x.shape[0]
     if gather == "none":
-        r0, r1 = row_partition(H_up, world)[rank]
+        r0, r1 = tile_partition(x.shape[2], H_up, world)[rank]
         if r1 > r0:
             return decoder.forward_rows(x, (H_up, W_up), r0, r1)
         return torch.empty((B, 3, 0, W_up), dtype=_out_dtype(decoder, x), device=x.device)
@@ -142,7 +162,7 @@ def decode_sharded(decoder, x: torch.Tensor, size, group: Optional[dist.ProcessG
         return decoder.forward_rows(x, (H_up, W_up), 0, H_up)
     if bands is None:
         bands = 4 if (H_up // world) * W_up * B >= (1 << 21) else 1
-    sub, parts = band_partition(H_up, world, bands)
+    sub, parts = band_partition(H_up, world, bands, row_align(x.shape[2], H_up))
     H_pad = world * bands * sub
     out = torch.empty((B, 3, H_pad, W_up), dtype=_out_dtype(decoder, x), device=x.device)
     on_gpu = x.is_cuda

@@ -49,7 +49,12 @@ typedef enum diinn_status {
  *   default-init weights (|out| < 0.06)      FP32 <= 2e-6    FP16 ~3e-6    BF16 ~2e-5
  *   gain-scaled weights, O(1) activations    FP32 <= 1e-4    FP16 ~2e-3    BF16 ~1.6e-2  (K x3, Q x10: bf16 misses the 1e-2
  *   contract there, fp16 operands keep it -- which is why FP16 is the default 16-bit mode of the Python layer)
- * Sine arguments: MUFU.SIN's error grows as ~6e-8 |x|; DIINN_COMPUTE_FP32 range-reduces first (error ~5e-7 for |x| < 1e5). */
+ * Sine arguments: MUFU.SIN's error grows as ~6e-8 |x|; DIINN_COMPUTE_FP32 range-reduces first (error ~5e-7 for |x| < 1e5).
+ * Coordinates (diinn.py:94-110): gather indices are bit-exact in every mode; relative coordinates are the reference's fp32
+ * values bit for bit, except that the 16-bit modes, on INTEGER scale factors with at most 16 phases (s_h * s_w <= 16), use the
+ * exact value of the pixel's phase, (2p + 1)/s - 1 -- the number the reference's rounded coordinate grids scatter around by a
+ * few ulps of a [-1, 1] coordinate times the axis length (5e-5 on a 339 x 510 map) -- so that Q.0's sines form a small table
+ * (DESIGN.md section 4.1d). DIINN_COMPUTE_FP32 / _FP32_SIMT never do; DIINN_NO_CANON=1 in the environment turns it off. */
 typedef enum diinn_compute {
   DIINN_COMPUTE_FP32 = 0, /* fp32 PRECISION on the tensor cores: every operand is an fp16 hi + lo pair (22 mantissa bits) and
                              every product three MMAs (hi.hi + lo.hi + hi.lo). init_q=True decodes fall back to _FP32_SIMT. */

@@ -178,6 +178,16 @@ def test_row_partition():
     assert all(parts[i][1] == parts[i + 1][0] for i in range(7))
     assert diinn_b200.row_partition(4320, 8) == [(540 * i, 540 * (i + 1)) for i in range(8)]
     assert diinn_b200.row_partition(3, 8)[3:] == [(3, 3)] * 5
+    # aligned tiles: every boundary on a multiple of the (integer) scale factor, still contiguous, balanced in units
+    al = diinn_b200.tile_partition(339, 1356, 8)
+    assert [b - a for a, b in al] == [172, 172, 172, 168, 168, 168, 168, 168] and al[-1][1] == 1356
+    assert all(a % 4 == 0 for a, _ in al) and all(al[i][1] == al[i + 1][0] for i in range(7))
+    assert diinn_b200.tile_partition(360, 4320, 8) == [(540 * i, 540 * (i + 1)) for i in range(8)]   # x12: already aligned
+    assert diinn_b200.tile_partition(16, 37, 3) == diinn_b200.row_partition(37, 3)                  # non-integer scale
+    assert diinn_b200.tile_partition(4, 1356, 2) == diinn_b200.row_partition(1356, 2)               # x339: no alignment
+    assert diinn_b200.row_partition(10, 4, 4) == [(0, 4), (4, 8), (8, 10), (10, 10)]
+    sub, parts = diinn_b200.band_partition(1356, 8, 1, 4)
+    assert sub == 172 and parts[0] == [(0, 172)] and parts[7] == [(1204, 1356)]
 
 
 @pytest.mark.skipif(not __import__("shutil").which("gcc"), reason="needs gcc")

@@ -57,7 +57,7 @@ def _worker(rank, world, port, sizes, results):
                 full = diinn_b200.decode_sharded(StandInDecoder(), xb, (H_up, W_up), feat_src=0)
                 ok &= bool(torch.equal(xb, real)) and bool(torch.equal(full, StandInDecoder.full(B, H_up, W_up, x.dtype)))
             tile = diinn_b200.decode_sharded(StandInDecoder(), x, (H_up, W_up), gather="none")
-            r0, r1 = diinn_b200.row_partition(H_up, world)[rank]
+            r0, r1 = diinn_b200.tile_partition(x.shape[2], H_up, world)[rank]
             ok &= bool(torch.equal(tile, StandInDecoder.full(B, H_up, W_up, x.dtype)[:, :, r0:r1]))
         results[rank] = ok
     finally:

@@ -17,7 +17,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 dec = diinn_b200.load_numpy_weights(diinn_b200.FusedImplicitDecoder(mode=3, precision="fp16"), synth.make_weights(seed=0)).to(dev)
 B, H, W, H_up, W_up = synth.CONFIGS[name]
 x = torch.from_numpy(synth.make_feat(1, B, H, W)).to(dev)
-r0, r1 = diinn_b200.row_partition(H_up, world)[rank]
+r0, r1 = diinn_b200.tile_partition(H, H_up, world)[rank]
 
 
 def timed(fn, n=10):
@@ -42,7 +42,7 @@ with torch.no_grad():
     res = {}
     for bands in (1, 4):
         res[bands] = timed(lambda: diinn_b200.decode_sharded(dec, x, (H_up, W_up), bands=bands))
-    parts = diinn_b200.row_partition(H_up, world)
+    parts = diinn_b200.tile_partition(H, H_up, world)
     if len({b - a for a, b in parts}) == 1:   # the bare all-gather timing needs equal tiles (c3 at 8 ranks is 170/169 rows)
         buf = torch.empty((B, 3, world * (r1 - r0), W_up), device=dev)
         t_gather = timed(lambda: [dist.all_gather_into_tensor(buf[0, c], buf[0, c, rank * (r1 - r0):(rank + 1) * (r1 - r0)]) for c in range(3)])
