@@ -1199,13 +1199,16 @@ Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, 
     const int pw = 1 << l2, ph = kTileM >> l2;
     br = static_cast<int>(floor(static_cast<double>(ph - 1) * src.H / src.H_up)) + 2;
     bc = static_cast<int>(floor(static_cast<double>(2 * pw - 1) * src.W / src.W_up)) + 2;
+    // columns always start at 0: on an integer scale factor that divides the pair's width every pair covers exactly
+    // 2 pw / s_w cells (x4, 4x32 patches: 16, where the bound says 17). Rows start wherever the caller's tile does: bound kept.
+    if (src.W_up % src.W == 0 && (2 * pw) % (src.W_up / src.W) == 0) bc = 2 * pw / (src.W_up / src.W);
     br = br < max_rows ? br : max_rows;
     bc = bc < src.W ? bc : src.W;
   };
   auto sel_ok = [&](int l2) {
     int br, bc;
     box_of(l2, src.H, br, bc);  // (whole-image extents: the same answer for every row tile)
-    return sel_candidate && br * bc + 2 <= 32;
+    return sel_candidate && br * bc <= 32;  // every B_sel row may hold a cell (the Q bias rides in all of them)
   };
   pl.sel = sel_ok(kPatchWLog2Default);
   // patch shape: fewest waves over the launch's CTA (pair)s; ties keep the default 8x16 (DIINN_PATCH_W_LOG2 pins it)
@@ -1222,7 +1225,8 @@ Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, 
     const long long n = static_cast<long long>(src.B) * ((src.row1 - src.row0 + ph - 1) / ph) *
                         (((src.W_up + pw - 1) / pw + cta_group - 1) / cta_group);
     const long long waves = (n + max_units - 1) / max_units;
-    if (best_waves < 0 || waves < best_waves) best_waves = waves, wk.pw_log2 = l2;
+    // (another shape must save at least 2 % of the waves: the default's timings are the measured ones)
+    if (best_waves < 0 || waves * 50 <= best_waves * 49) best_waves = waves, wk.pw_log2 = l2;
   }
   const int pw = 1 << wk.pw_log2, ph = kTileM >> wk.pw_log2;
   const int tiles_x = (src.W_up + pw - 1) / pw;

@@ -542,6 +542,21 @@ def test_config_c3_div2k(w0):
         tiled = torch.empty_like(o16)
         for r0, r1 in diinn_b200.row_partition(H_up, 8):
             dec16.forward_rows(x, (H_up, W_up), r0, r1, out=tiled)
+        # and so are the tiles the sharded decodes actually use: boundaries on multiples of the scale factor (172 / 168 rows;
+        # these take the 4x32 patch shape, one select MMA and the phase table, the unaligned ones above K_sel = 32 and no
+        # table), for 2, 4 and 8 ranks and for bf16 operands
+        aligned = torch.empty_like(o16)
+        parts = diinn_b200.tile_partition(H, H_up, 8)
+        assert [b - a for a, b in parts] == [172] * 3 + [168] * 5
+        for world in (8, 4, 2):
+            aligned.fill_(-7.0)
+            for r0, r1 in diinn_b200.tile_partition(H, H_up, world):
+                dec16.forward_rows(x, (H_up, W_up), r0, r1, out=aligned)
+            assert torch.equal(o16, aligned), world
+        dbf = _decoder(w0, "bf16")
+        for r0, r1 in parts:
+            dbf.forward_rows(x, (H_up, W_up), r0, r1, out=aligned)
+        assert torch.equal(obf, aligned)
     assert torch.equal(o16, tiled)
     # host entry at full size: 4 pipelined row bands (upload / decode / download on three streams)
     host = dec16.decode_host(torch.from_numpy(feat).pin_memory(), (H_up, W_up))
