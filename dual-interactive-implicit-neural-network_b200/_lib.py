@@ -30,7 +30,7 @@ SYMBOLS = [
 ]
 DEBUG_SYMBOLS = [
     "diinn_debug_gather", "diinn_debug_query_gather", "diinn_debug_set_tap", "diinn_debug_stage_a", "diinn_debug_umma_gemm",
-    "diinn_debug_umma_pace", "diinn_debug_read_trace",
+    "diinn_debug_umma_pace", "diinn_debug_read_trace", "diinn_debug_plan_stage_b",
 ]
 
 
@@ -95,6 +95,8 @@ def load() -> C.CDLL:
     lib.diinn_debug_gather.restype = i
     lib.diinn_debug_query_gather.argtypes = [vp, i, i, i, vp, vp, i, vp, vp, vp, vp]
     lib.diinn_debug_query_gather.restype = i
+    lib.diinn_debug_plan_stage_b.argtypes = [i] * 10 + [vp]
+    lib.diinn_debug_plan_stage_b.restype = i
     lib.diinn_debug_set_tap.argtypes = [vp, vp]
     lib.diinn_debug_set_tap.restype = i
     lib.diinn_debug_stage_a.argtypes = [vp, vp, i, i, i, i, vp, vp, sz, i, i, vp]

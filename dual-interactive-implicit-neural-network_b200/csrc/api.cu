@@ -935,6 +935,15 @@ int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n) {
   return DIINN_OK;
 }
 
+int diinn_debug_plan_stage_b(int sm_count, int decoder_mode, int B, int H, int W, int H_up, int W_up, int row0, int row1,
+                             int compute, int32_t* out12) {
+  if (!out12 || sm_count < 1 || B < 1 || H < 1 || W < 1 || H_up < 1 || W_up < 1 || row0 < 0 || row1 > H_up || row0 >= row1 ||
+      compute < DIINN_COMPUTE_FP32 || compute > DIINN_COMPUTE_FP16)
+    return DIINN_ERR_BAD_ARG;
+  plan_stage_b_probe(sm_count, decoder_mode, B, H, W, H_up, W_up, row0, row1, fmt_of(compute), out12);
+  return DIINN_OK;
+}
+
 int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* D, int M, int N, int K,
                           int cta_group, void* stream) {
   if (!h || !A || !B || !D) return DIINN_ERR_BAD_ARG;

@@ -152,6 +152,8 @@ int launch_stage_a_umma(Handle* h, const void* feat_nhwc, const void* feat_lo, i
 int launch_stage_b_umma(Handle* h, const PixelSource& src, const OutSpec& out, const void* P, int cta_group, int fmt,
                         cudaStream_t s, int4* tap = nullptr);
 bool stage_b_wants_p16(const Handle* h, const PixelSource& src, int fmt);
+void plan_stage_b_probe(int sm_count, int decoder_mode, int B, int H, int W, int H_up, int W_up, int row0, int row1, int fmt,
+                        int* out);
 // gemm.cu
 int launch_umma_selftest(Handle* h, const void* A, const void* B, float* D, int M, int N, int K, int cta_group,
                          cudaStream_t s, const ChainEpilogue* chain = nullptr);

@@ -1276,6 +1276,26 @@ Plan make_plan(const Handle* h, const PixelSource& src, int cta_group, int fmt, 
 
 }  // namespace
 
+// Host-only view of make_plan for tests (diinn_debug_plan_stage_b): which kernel a launch would take, without a device.
+// out[12] = {select variant, phase table, canonical coordinates, s_h, s_w, log2 patch width, K_sel, box rows, box columns,
+//            work items, tiles_y, pairs per patch row}
+void plan_stage_b_probe(int sm_count, int decoder_mode, int B, int H, int W, int H_up, int W_up, int row0, int row1, int fmt,
+                        int* out) {
+  Handle h;
+  h.sm_count = sm_count;
+  h.cfg.mode = decoder_mode;
+  PixelSource src{};
+  src.mode = 0;
+  src.ax_h = make_axis(H, H_up);
+  src.ax_w = make_axis(W, W_up);
+  src.B = B, src.H = H, src.W = W, src.H_up = H_up, src.W_up = W_up, src.row0 = row0, src.row1 = row1;
+  src.lr_row0 = 0, src.lr_rows = H;
+  const Plan pl = make_plan(&h, src, 0, fmt, decoder_mode == 1 || decoder_mode == 2);
+  const int v[12] = {pl.sel, pl.tab, pl.wk.canon, pl.wk.s_h, pl.wk.s_w, pl.wk.pw_log2, pl.sel ? pl.wk.ksel : 0,
+                     pl.sel ? pl.wk.box_r : 0, pl.sel ? pl.wk.box_c : 0, pl.wk.n_work, pl.wk.tiles_y, pl.wk.n_txp};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+}
+
 // Does the stage-B launch for this source take the select-MMA variant, i.e. must stage A write P as fp16?
 bool stage_b_wants_p16(const Handle* h, const PixelSource& src, int fmt) {
   return make_plan(h, src, 0, fmt, h->cfg.mode == 1 || h->cfg.mode == 2).sel;

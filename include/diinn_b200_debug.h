@@ -38,6 +38,13 @@ int diinn_debug_umma_gemm(diinn_handle* h, const void* A, const void* B, float* 
  * noise: 16 extra warps per CTA hammer the idle TMEM half (bit 0), shared memory (bit 1) or the MUFU (bit 2) meanwhile. */
 int diinn_debug_umma_pace(diinn_handle* h, int cta_group, int n_cols, int iters, int n_ctas, float* cyc_per_mma,
                           int noise, void* stream);
+/* Host-only: which stage-B kernel a grid decode of rows [row0,row1) would launch on a device with sm_count SMs (no device, no
+ * handle needed; compute = DIINN_COMPUTE_FP32 | _BF16 | _FP16). out12 = {select-MMA variant, phase table, canonical relative
+ * coordinates, s_h, s_w, log2 of the patch width, K_sel, LR rows and columns of a pair's P box, work items, patch rows, CTA pairs
+ * per patch row}. The first three must not depend on the row range (row tiles are bit-identical to the full decode); tested on
+ * the CPU by tests/test_plan.py. */
+int diinn_debug_plan_stage_b(int sm_count, int decoder_mode, int B, int H, int W, int H_up, int W_up, int row0, int row1,
+                             int compute, int32_t* out12);
 /* DIINN_TRACE=1 in the environment makes the fused stage-B kernel record clock64() at its pipeline events (leader
  * CTA of the first CTA pair, first 8 tiles); this copies the first n (<=1024) samples to host_out. */
 int diinn_debug_read_trace(diinn_handle* h, int64_t* host_out, int n);
