@@ -17,7 +17,8 @@
 // running, and layer 0 of the NEXT tile is interleaved into the epilogue warps during layer 3.
 //
 // Warp roles (640 threads): warp 0 = TMA producer (streams the 3 x 2 x 4 weight stages of [256 x 64] bf16 from L2),
-// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warps 4..19 = 16 epilogue warps. ALL of them drain
+// warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM allocator, warp 3 = L2 prefetcher of upcoming tiles' P rows,
+// warps 4..19 = 16 epilogue warps. ALL of them drain
 // half slot 0, then half slot 1, of every layer: a warp owns one TMEM lane quarter and one 16-feature group of every
 // 64-feature chunk, so a half slot is two steps per warp and every step completes one K-chunk of the next layer's A
 // operand (the chunk that gates the next layer is one step behind the layer's last MMA). The control warpgroup gives
@@ -40,6 +41,11 @@
 //                 a row selects, it picks up the bias once)
 // one or two extra K = 16 MMAs per half slot (MN-major B: a P row IS a row of N values) pre-load the accumulators with
 // P[l] and bq, and the epilogue shrinks to relu(accK) * sin(accQ): no P loads, no bias loads, two adds fewer per pair.
+//
+// Phase table (template kTab; integer scale factors with at most 16 phases, 16-bit formats): every HR pixel of phase
+// (p_h, p_w) has the relative coordinate (2p + 1)/s - 1, so sin(Wq0 s_p + bq0) is one of s_h s_w rows, evaluated once per CTA
+// into shared memory; layer 0 is then q_0 = k_0 * table[phase] -- two LDS.128 and eight HMUL2 per step, no MUFU (Work::canon,
+// layer0_step).
 //
 // Measured alternatives that did NOT pay: two 8-warp groups (one per half slot), four 128-column
 // slots with per-slot groups, three slots (256|128|128), fp16 accumulators, packed FFMA2 for the RGB projection.
