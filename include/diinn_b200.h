@@ -54,7 +54,9 @@ typedef enum diinn_status {
  * values bit for bit, except that the 16-bit modes, on INTEGER scale factors with at most 16 phases (s_h * s_w <= 16), use the
  * exact value of the pixel's phase, (2p + 1)/s - 1 -- the number the reference's rounded coordinate grids scatter around by a
  * few ulps of a [-1, 1] coordinate times the axis length (5e-5 on a 339 x 510 map) -- so that Q.0's sines form a small table
- * (DESIGN.md section 4.1d). DIINN_COMPUTE_FP32 / _FP32_SIMT never do; DIINN_NO_CANON=1 in the environment turns it off. */
+ * (DESIGN.md section 4.1d). Effect on the image, fp32 oracle with either set of coordinates: < 1e-8 on default-init weights, up to
+ * 8e-4 on the gain-scaled set at the 339 x 510 geometry (tests/test_canonical_coords.py) -- the reference's own sensitivity to
+ * that rounding. DIINN_COMPUTE_FP32 / _FP32_SIMT never do this; DIINN_NO_CANON=1 in the environment turns it off. */
 typedef enum diinn_compute {
   DIINN_COMPUTE_FP32 = 0, /* fp32 PRECISION on the tensor cores: every operand is an fp16 hi + lo pair (22 mantissa bits) and
                              every product three MMAs (hi.hi + lo.hi + hi.lo). init_q=True decodes fall back to _FP32_SIMT. */

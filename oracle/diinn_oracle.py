@@ -66,6 +66,20 @@ def rel_axis(n_in: int, n_out: int):
     return idx, rel
 
 
+def canonical_rel_axis(n_in: int, n_out: int):
+    """NOT the reference's arithmetic -- the yardstick for one documented deviation of the product. On an integer scale
+    factor s = n_out / n_in the HR sample j = s*i + p sits at (2p + 1)/s - 1 of its source cell in exact arithmetic; the
+    reference's rel (rel_axis above) is that value plus the rounding of its two fp32 coordinate grids (diinn.py:98-108). The
+    16-bit tensor paths use the closed form, fl(fl((2p + 1)/s) - 1), so that Q.0's sines form a table (stage_b_umma.cu:
+    canon_rel); tests bound its distance to the reference's values and its effect on the output."""
+    assert n_out % n_in == 0
+    s = n_out // n_in
+    idx = nearest_exact_index(n_in, n_out)
+    p = np.arange(n_out, dtype=np.int64) - idx * s
+    rel = ((2 * p + 1).astype(F32) / F32(s) + F32(-1.0)).astype(F32)
+    return idx, rel
+
+
 def make_pos_encoding(H: int, W: int, H_up: int, W_up: int) -> np.ndarray:
     """(2, H_up, W_up) fp32: channel 0 = rel_h (varies along rows), channel 1 = rel_w."""
     _, rh = rel_axis(H, H_up)
@@ -175,8 +189,9 @@ def last_conv3x3_reflect(weights: dict, q3: np.ndarray, fp64: bool = False, rows
 # forward (diinn.py:163-173) and the row-band form used for sharding / large configs
 # --------------------------------------------------------------------------------------------------
 def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool = False,
-                    chunk: int = 1 << 16, mode: int = 3, bsize=None) -> np.ndarray:
+                    chunk: int = 1 << 16, mode: int = 3, bsize=None, canonical_rel: bool = False) -> np.ndarray:
     """(B,64,H,W), size=(H_up,W_up) -> (B,3,rows,W_up); rows=(r0,r1) restricts to an HR row band.
+    canonical_rel (modes 1-3, integer scale factors): canonical_rel_axis instead of the reference's rel -- a deviation study.
 
     bsize matters in mode 4 only: batched_step (diinn.py:149-160) applies `step`, hence the reflect-padded 3x3 last
     conv, to column strips of bsize // H_up columns one at a time."""
@@ -192,8 +207,8 @@ def decoder_forward(weights: dict, feat: np.ndarray, size, rows=None, fp64: bool
         outs = [last_conv3x3_reflect(weights, q3[:, :, a:a + strip], fp64=fp64, rows=(r0, r1), row_base=lo, H_up=H_up)
                 for a in range(0, W_up, strip)]
         return np.concatenate(outs, axis=-1)
-    ih, rh = rel_axis(H, H_up)
-    iw, rw = rel_axis(W, W_up)
+    ih, rh = (canonical_rel_axis if canonical_rel else rel_axis)(H, H_up)
+    iw, rw = (canonical_rel_axis if canonical_rel else rel_axis)(W, W_up)
     ratio = ratio_value(H, W, H_up, W_up)
     u = unfold3x3(feat)                                   # (B,576,H,W)
     u = np.ascontiguousarray(u.transpose(0, 2, 3, 1))     # (B,H,W,576)
